@@ -1,0 +1,165 @@
+/* b200optas.h -- C ABI of libb200optas.so, the B200 (sm_100a) batched NLP/QP solver back-end
+ * that sits behind the OpTaS solver interface.
+ *
+ * The reference (cmower/optas) has no C ABI: its solver plug-in boundary is the Python ABC
+ * optas/solver.py:61-315 (`Solver`), whose concrete CasADiSolver crosses into native code at
+ *     optas/solver.py:382   self._solver = cs.nlpsol/qpsol("solver", name, {x,p,f,g}, opts)   (create)
+ *     optas/solver.py:395   self._solution = self._solver(x0=, p=, lbg=, ubg=)                (solve)
+ *     optas/solver.py:396   self._stats = self._solver.stats()                                (status)
+ * and whose model functions cross at
+ *     optas/models.py:786-787   cs.Function(label,[q],[expr]).map(n)                          (batched FK eval)
+ * Each entry point below replaces exactly one of those crossings; the comment on each says
+ * which.  The binding a maintainer of the reference would add is shown in INTEGRATION.md.
+ *
+ * Conventions
+ *   - every function returns BO_OK (0) or a negative bo_status; none throws, none calls back
+ *     into the host language; bo_last_error() gives the message for the calling thread.
+ *   - all numeric data is IEEE binary64, row-major with the INSTANCE index slowest:
+ *     p[B][np], x[B][nx] ... (one OpTaS problem instance per row).
+ *   - data pointers may be host or device memory (detected with cudaPointerGetAttributes);
+ *     a call whose buffers are all device memory is asynchronous on `stream`, a call with any
+ *     host buffer stages through pinned memory and returns after the results are on the host.
+ *   - buffers are BORROWED for the duration of the call; nothing is retained.
+ *   - a handle is bound to the CUDA device current at creation; handles are not thread-safe,
+ *     distinct handles may be used from distinct threads / processes (one per GPU).
+ *   - there is NO CPU fallback: without a usable sm_100-class device the solve/eval calls
+ *     fail with BO_ERR_NO_DEVICE.  (bo_*_create with BO_FLAG_COMPILE_ONLY only needs NVRTC.)
+ */
+#ifndef B200OPTAS_H
+#define B200OPTAS_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define BO_ABI_VERSION 1
+
+typedef enum bo_status {
+  BO_OK = 0,
+  BO_ERR_INVALID = -1,   /* bad argument / malformed tape            */
+  BO_ERR_COMPILE = -2,   /* NVRTC rejected the generated kernel       */
+  BO_ERR_CUDA = -3,      /* CUDA runtime / driver error               */
+  BO_ERR_NO_DEVICE = -4, /* no CUDA device (there is no CPU path)     */
+  BO_ERR_UNSUPPORTED = -5/* problem too large for the tiers built     */
+} bo_status;
+
+/* Per-instance solver outcome written to status[B] by bo_solve. */
+typedef enum bo_instance_status {
+  BO_CONVERGED = 0,      /* scaled KKT error <= tol                                    */
+  BO_ACCEPTABLE = 1,     /* stalled with KKT error <= acceptable_tol                   */
+  BO_MAX_ITER = 2,       /* iteration cap reached                                      */
+  BO_LINE_SEARCH = 3,    /* no acceptable step found                                   */
+  BO_NUMERICAL = 4       /* NaN/Inf in function values or unfactorable KKT system      */
+} bo_instance_status;
+
+/* ---------------------------------------------------------------------------------------
+ * Expression tape: the lowered form of one CasADi-style Function (what the SX virtual
+ * machine interprets inside nlpsol on the reference path).  SSA-with-slot-reuse rows
+ *     instr[i] = { op | (c << 8), dst, a, b }
+ *   BO_OP_INPUT   work[dst] = in[b][a]            BO_OP_CONST  work[dst] = consts[a]
+ *   BO_OP_OUTPUT  out[b][a] = work[dst]           BO_OP_IF_ELSE work[dst] = work[c] ? work[a] : work[b]
+ *   unary/binary  work[dst] = op(work[a], work[b])
+ * Opcode numbers are in bo_opcodes.h (shared with the Python front-end and the CPU oracle).
+ * ------------------------------------------------------------------------------------- */
+typedef struct bo_tape {
+  const int32_t* instr;     /* [n_instr][4]                          */
+  int64_t n_instr;
+  const double* consts;     /* [n_consts]                            */
+  int32_t n_consts;
+  int32_t n_work;           /* work slots (after liveness reuse)     */
+  int32_t n_in;
+  const int32_t* in_sizes;  /* [n_in]  elements per input segment    */
+  int32_t n_out;
+  const int32_t* out_sizes; /* [n_out] elements per output segment   */
+} bo_tape;
+
+typedef struct bo_sparsity {  /* coordinate list of structural non-zeros */
+  int32_t nnz;
+  const int32_t* row;
+  const int32_t* col;
+} bo_sparsity;
+
+/* Problem: min f(x,p)  s.t.  c_eq(x,p) = 0,  c_ineq(x,p) >= 0.
+ * For an OpTaS `Optimization` object: c_eq = [a; h] (optimization.py:249-260,283-290),
+ * c_ineq = [k; g] (optimization.py:225-247,262-281) -- NOT the +-pair stacking `v`
+ * (optimization.py:27-51) the reference hands to IPOPT.
+ *   fc   : (x, p)        -> f[1], c_eq[n_eq], c_ineq[n_ineq]
+ *   kkt  : (x, p, y, z)  -> f[1], grad_f[nx], c_eq, c_ineq, jac_eq nz, jac_ineq nz, hess nz
+ *          where hess = lower triangle of  d2/dx2 ( f - y'c_eq - z'c_ineq ).            */
+typedef struct bo_problem_desc {
+  int32_t nx, np, n_eq, n_ineq;
+  bo_tape fc;
+  bo_tape kkt;
+  bo_sparsity jac_eq;    /* n_eq   x nx */
+  bo_sparsity jac_ineq;  /* n_ineq x nx */
+  bo_sparsity hess;      /* nx x nx, row >= col */
+} bo_problem_desc;
+
+#define BO_FLAG_COMPILE_ONLY 1u /* generate + compile (fills the cubin cache), never touch a GPU */
+#define BO_FLAG_VERBOSE 2u      /* print ptxas info / cache hits to stderr                      */
+#define BO_FLAG_NO_CACHE 4u     /* ignore and do not write the on-disk cubin cache              */
+#define BO_FLAG_TIMING 8u       /* bracket every kernel launch with CUDA events (see *_kernel_time) */
+
+typedef struct bo_options {
+  uint32_t flags;
+  int32_t max_iter;        /* <=0: default 200                                              */
+  double tol;              /* <=0: default 1e-8  (scaled KKT error, as IPOPT's `tol`)      */
+  double acceptable_tol;   /* <=0: default 1e-6                                             */
+  double mu_init;          /* <=0: default 0.1   (as IPOPT's `mu_init`)                    */
+  const char* cache_dir;   /* NULL: <directory of libb200optas.so>/_jitcache               */
+  const char* include_dir; /* NULL: <directory of libb200optas.so>/csrc/jit                */
+  int32_t threads_per_block; /* <=0: tier default                                           */
+  int32_t reserved[7];
+} bo_options;
+
+typedef struct bo_problem bo_problem;   /* opaque, owned by the library */
+typedef struct bo_function bo_function; /* opaque, owned by the library */
+
+/* Library identity. */
+int bo_abi_version(void);
+const char* bo_last_error(void);        /* thread-local; valid until the next call on this thread */
+int bo_device_count(void);              /* number of usable CUDA devices (0 => solve/eval fail)   */
+
+/* Replaces optas/solver.py:382 (nlpsol/qpsol factory): lowers the tapes to a fused sm_100a
+ * solver kernel (NVRTC), loads it on the current device.                                    */
+int bo_problem_create(const bo_problem_desc* desc, const bo_options* opts, bo_problem** out);
+int bo_problem_destroy(bo_problem* prob);
+
+/* Generated CUDA source of the problem's kernels (for inspection, offline nvcc checks and
+ * the host-compiled test harness).  Returns the length; copies at most cap-1 bytes + NUL.  */
+int64_t bo_problem_source(const bo_problem* prob, char* buf, int64_t cap);
+/* Resource usage of the compiled solver kernel: regs/thread, bytes local (spill), static smem. */
+int bo_problem_kernel_info(const bo_problem* prob, int32_t* regs, int32_t* local_bytes, int32_t* smem_bytes);
+
+/* Replaces optas/solver.py:395-396 (one nlpsol call + stats) for B instances at once.
+ *   p   [B][np]        parameters                      (may be NULL iff np == 0)
+ *   x0  [B][nx]        initial seed, NULL = zeros      (optas/solver.py:76)
+ *   x   [B][nx]   out  solution
+ *   lam [B][n_eq+n_ineq] out, multipliers [y; z] of c_eq / c_ineq, or NULL
+ *   f   [B]       out  cost at x, or NULL
+ *   status, iters [B] out (bo_instance_status / iteration count), or NULL
+ *   kkt_res [B]   out  scaled KKT error at x, or NULL                                       */
+int bo_solve(bo_problem* prob, int64_t B, const double* p, const double* x0, double* x, double* lam,
+             double* f, int32_t* status, int32_t* iters, double* kkt_res, void* cuda_stream);
+
+/* Average device time (ms) of the solver-kernel launches since the last call, measured with
+ * CUDA events on the launching stream; resets the counters.  n_launches may be NULL.       */
+int bo_problem_kernel_time(bo_problem* prob, double* ms_total, int64_t* n_launches);
+
+/* Replaces optas/models.py:786-787 (`Function.map(n)` evaluation of an FK / Jacobian / cost
+ * expression graph over n columns): a streaming kernel, one instance per thread, inputs and
+ * outputs staged through shared memory with bulk async copies (TMA).
+ *   in[k]  [B][in_sizes[k]]   out[k]  [B][out_sizes[k]]                                     */
+int bo_function_create(const bo_tape* tape, const bo_options* opts, bo_function** out);
+int bo_function_destroy(bo_function* fn);
+int bo_function_eval(bo_function* fn, int64_t B, const double* const* in, double* const* out, void* cuda_stream);
+int64_t bo_function_source(const bo_function* fn, char* buf, int64_t cap);
+int bo_function_kernel_info(const bo_function* fn, int32_t* regs, int32_t* local_bytes, int32_t* smem_bytes);
+int bo_function_kernel_time(bo_function* fn, double* ms_total, int64_t* n_launches);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B200OPTAS_H */

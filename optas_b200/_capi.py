@@ -1,0 +1,266 @@
+"""ctypes binding of libb200optas.so (include/b200optas.h).  Thin on purpose: every structure
+here is a field-for-field image of the C header, and every call releases the GIL.
+
+The library is built in-tree by ``__graft_entry__.build()`` / ``make -C optas_b200/csrc``; if it
+is missing, importing this module raises -- there is no Python or CPU fallback.
+"""
+
+from __future__ import annotations
+
+import ctypes as C
+import os
+from typing import List, Optional, Sequence
+
+import numpy as np
+
+from .tape import Tape
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libb200optas.so")
+
+BO_ABI_VERSION = 1
+BO_OK, BO_ERR_INVALID, BO_ERR_COMPILE, BO_ERR_CUDA, BO_ERR_NO_DEVICE, BO_ERR_UNSUPPORTED = 0, -1, -2, -3, -4, -5
+BO_FLAG_COMPILE_ONLY, BO_FLAG_VERBOSE, BO_FLAG_NO_CACHE, BO_FLAG_TIMING = 1, 2, 4, 8
+STATUS_NAMES = {0: "converged", 1: "acceptable", 2: "max_iter", 3: "line_search", 4: "numerical"}
+
+EXPORTS = [
+    "bo_abi_version", "bo_last_error", "bo_device_count",
+    "bo_problem_create", "bo_problem_destroy", "bo_problem_source", "bo_problem_kernel_info",
+    "bo_solve", "bo_problem_kernel_time",
+    "bo_function_create", "bo_function_destroy", "bo_function_eval", "bo_function_source",
+    "bo_function_kernel_info", "bo_function_kernel_time",
+]
+
+
+class BoError(RuntimeError):
+    def __init__(self, code: int, message: str):
+        super().__init__(f"libb200optas error {code}: {message}")
+        self.code = code
+
+
+class bo_tape(C.Structure):
+    _fields_ = [
+        ("instr", C.POINTER(C.c_int32)), ("n_instr", C.c_int64),
+        ("consts", C.POINTER(C.c_double)), ("n_consts", C.c_int32),
+        ("n_work", C.c_int32),
+        ("n_in", C.c_int32), ("in_sizes", C.POINTER(C.c_int32)),
+        ("n_out", C.c_int32), ("out_sizes", C.POINTER(C.c_int32)),
+    ]
+
+
+class bo_sparsity(C.Structure):
+    _fields_ = [("nnz", C.c_int32), ("row", C.POINTER(C.c_int32)), ("col", C.POINTER(C.c_int32))]
+
+
+class bo_problem_desc(C.Structure):
+    _fields_ = [
+        ("nx", C.c_int32), ("np", C.c_int32), ("n_eq", C.c_int32), ("n_ineq", C.c_int32),
+        ("fc", bo_tape), ("kkt", bo_tape),
+        ("jac_eq", bo_sparsity), ("jac_ineq", bo_sparsity), ("hess", bo_sparsity),
+    ]
+
+
+class bo_options(C.Structure):
+    _fields_ = [
+        ("flags", C.c_uint32), ("max_iter", C.c_int32),
+        ("tol", C.c_double), ("acceptable_tol", C.c_double), ("mu_init", C.c_double),
+        ("cache_dir", C.c_char_p), ("include_dir", C.c_char_p),
+        ("threads_per_block", C.c_int32), ("reserved", C.c_int32 * 7),
+    ]
+
+
+_lib: Optional[C.CDLL] = None
+
+
+def load() -> C.CDLL:
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise ImportError(
+            f"{LIB_PATH} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+            "or `make -C optas_b200/csrc` (there is no fallback path)")
+    lib = C.CDLL(LIB_PATH)
+    vp, i32p, f64p = C.c_void_p, C.POINTER(C.c_int32), C.POINTER(C.c_double)
+    lib.bo_abi_version.restype = C.c_int
+    lib.bo_last_error.restype = C.c_char_p
+    lib.bo_device_count.restype = C.c_int
+    lib.bo_problem_create.argtypes = [C.POINTER(bo_problem_desc), C.POINTER(bo_options), C.POINTER(vp)]
+    lib.bo_problem_destroy.argtypes = [vp]
+    lib.bo_problem_source.argtypes = [vp, C.c_char_p, C.c_int64]
+    lib.bo_problem_source.restype = C.c_int64
+    lib.bo_problem_kernel_info.argtypes = [vp, i32p, i32p, i32p]
+    lib.bo_solve.argtypes = [vp, C.c_int64] + [vp] * 8 + [vp]
+    lib.bo_problem_kernel_time.argtypes = [vp, f64p, C.POINTER(C.c_int64)]
+    lib.bo_function_create.argtypes = [C.POINTER(bo_tape), C.POINTER(bo_options), C.POINTER(vp)]
+    lib.bo_function_destroy.argtypes = [vp]
+    lib.bo_function_eval.argtypes = [vp, C.c_int64, C.POINTER(vp), C.POINTER(vp), vp]
+    lib.bo_function_source.argtypes = [vp, C.c_char_p, C.c_int64]
+    lib.bo_function_source.restype = C.c_int64
+    lib.bo_function_kernel_info.argtypes = [vp, i32p, i32p, i32p]
+    lib.bo_function_kernel_time.argtypes = [vp, f64p, C.POINTER(C.c_int64)]
+    if lib.bo_abi_version() != BO_ABI_VERSION:
+        raise ImportError(f"libb200optas ABI {lib.bo_abi_version()} != binding ABI {BO_ABI_VERSION}")
+    _lib = lib
+    return lib
+
+
+def check(code: int) -> None:
+    if code != BO_OK:
+        raise BoError(code, load().bo_last_error().decode(errors="replace"))
+
+
+def device_count() -> int:
+    return int(load().bo_device_count())
+
+
+class _Keep:
+    """Keeps the numpy arrays behind a C structure alive."""
+
+    def __init__(self):
+        self.refs: List = []
+
+    def i32(self, a) -> C.POINTER(C.c_int32):
+        arr = np.ascontiguousarray(a, dtype=np.int32)
+        self.refs.append(arr)
+        return arr.ctypes.data_as(C.POINTER(C.c_int32))
+
+    def f64(self, a) -> C.POINTER(C.c_double):
+        arr = np.ascontiguousarray(a, dtype=np.float64)
+        self.refs.append(arr)
+        return arr.ctypes.data_as(C.POINTER(C.c_double))
+
+
+def tape_struct(t: Tape, keep: _Keep) -> bo_tape:
+    return bo_tape(
+        instr=keep.i32(t.instr.reshape(-1)), n_instr=t.n_instr,
+        consts=keep.f64(t.consts), n_consts=int(t.consts.shape[0]),
+        n_work=int(t.n_work),
+        n_in=len(t.in_sizes), in_sizes=keep.i32(t.in_sizes),
+        n_out=len(t.out_sizes), out_sizes=keep.i32(t.out_sizes),
+    )
+
+
+def options_struct(flags: int = 0, max_iter: int = 0, tol: float = 0.0, acceptable_tol: float = 0.0,
+                   mu_init: float = 0.0, cache_dir: Optional[str] = None, include_dir: Optional[str] = None,
+                   threads_per_block: int = 0) -> bo_options:
+    return bo_options(
+        flags=flags, max_iter=max_iter, tol=tol, acceptable_tol=acceptable_tol, mu_init=mu_init,
+        cache_dir=cache_dir.encode() if cache_dir else None,
+        include_dir=include_dir.encode() if include_dir else None,
+        threads_per_block=threads_per_block,
+    )
+
+
+def _source(getter, handle) -> str:
+    n = getter(handle, None, 0)
+    buf = C.create_string_buffer(int(n) + 1)
+    getter(handle, buf, int(n) + 1)
+    return buf.value.decode()
+
+
+def _kernel_info(getter, handle) -> dict:
+    r, l, s = C.c_int32(-1), C.c_int32(-1), C.c_int32(-1)
+    check(getter(handle, C.byref(r), C.byref(l), C.byref(s)))
+    return {"registers": r.value, "local_bytes": l.value, "smem_bytes": s.value}
+
+
+def _ptr(a) -> Optional[int]:
+    """Raw address of a numpy array / torch tensor / None."""
+    if a is None:
+        return None
+    if isinstance(a, np.ndarray):
+        return a.ctypes.data
+    if hasattr(a, "data_ptr"):
+        return int(a.data_ptr())
+    raise TypeError(f"cannot take the address of {type(a)}")
+
+
+class ProblemHandle:
+    """Owns a ``bo_problem*``."""
+
+    def __init__(self, lowered, **opts):
+        lib = load()
+        keep = _Keep()
+        desc = bo_problem_desc(
+            nx=lowered.nx, np=lowered.np_, n_eq=lowered.n_eq, n_ineq=lowered.n_ineq,
+            fc=tape_struct(lowered.fc, keep), kkt=tape_struct(lowered.kkt, keep),
+            jac_eq=bo_sparsity(lowered.jac_eq.nnz, keep.i32(lowered.jac_eq.row), keep.i32(lowered.jac_eq.col)),
+            jac_ineq=bo_sparsity(lowered.jac_ineq.nnz, keep.i32(lowered.jac_ineq.row), keep.i32(lowered.jac_ineq.col)),
+            hess=bo_sparsity(lowered.hess.nnz, keep.i32(lowered.hess.row), keep.i32(lowered.hess.col)),
+        )
+        o = options_struct(**opts)
+        h = C.c_void_p()
+        check(lib.bo_problem_create(C.byref(desc), C.byref(o), C.byref(h)))
+        self._h = h
+        self.lowered = lowered
+
+    def source(self) -> str:
+        return _source(load().bo_problem_source, self._h)
+
+    def kernel_info(self) -> dict:
+        return _kernel_info(load().bo_problem_kernel_info, self._h)
+
+    def solve(self, B: int, p, x0, x, lam=None, f=None, status=None, iters=None, kkt=None, stream: int = 0) -> None:
+        check(load().bo_solve(self._h, B, _ptr(p), _ptr(x0), _ptr(x), _ptr(lam), _ptr(f), _ptr(status), _ptr(iters),
+                              _ptr(kkt), stream or None))
+
+    def kernel_time(self):
+        ms, n = C.c_double(0.0), C.c_int64(0)
+        check(load().bo_problem_kernel_time(self._h, C.byref(ms), C.byref(n)))
+        return ms.value, n.value
+
+    def close(self) -> None:
+        if getattr(self, "_h", None):
+            load().bo_problem_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class FunctionHandle:
+    """Owns a ``bo_function*`` (streaming evaluation of one tape)."""
+
+    def __init__(self, tape: Tape, **opts):
+        lib = load()
+        keep = _Keep()
+        ts = tape_struct(tape, keep)
+        o = options_struct(**opts)
+        h = C.c_void_p()
+        check(lib.bo_function_create(C.byref(ts), C.byref(o), C.byref(h)))
+        self._h = h
+        self.tape = tape
+
+    def source(self) -> str:
+        return _source(load().bo_function_source, self._h)
+
+    def kernel_info(self) -> dict:
+        return _kernel_info(load().bo_function_kernel_info, self._h)
+
+    def eval(self, B: int, ins: Sequence, outs: Sequence, stream: int = 0) -> None:
+        n_in, n_out = len(self.tape.in_sizes), len(self.tape.out_sizes)
+        if len(ins) != n_in or len(outs) != n_out:
+            raise ValueError(f"expected {n_in} inputs and {n_out} outputs")
+        in_arr = (C.c_void_p * n_in)(*[_ptr(a) for a in ins])
+        out_arr = (C.c_void_p * n_out)(*[_ptr(a) for a in outs])
+        check(load().bo_function_eval(self._h, B, in_arr, out_arr, stream or None))
+
+    def kernel_time(self):
+        ms, n = C.c_double(0.0), C.c_int64(0)
+        check(load().bo_function_kernel_time(self._h, C.byref(ms), C.byref(n)))
+        return ms.value, n.value
+
+    def close(self) -> None:
+        if getattr(self, "_h", None):
+            load().bo_function_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

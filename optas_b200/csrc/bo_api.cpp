@@ -1,0 +1,789 @@
+// bo_api.cpp -- C ABI of libb200optas.so (see include/b200optas.h).
+//
+// Host side only: validates the tapes, generates the CUDA source (bo_codegen.cpp), compiles it
+// for sm_100a with NVRTC (cubins cached on disk, keyed by a hash of source + headers + compiler
+// version), loads it through the CUDA driver API and launches it.  libcuda.so.1 is opened lazily
+// with dlopen so that the library itself loads (and can compile) on a GPU-less machine; every
+// entry point that needs a device fails with BO_ERR_NO_DEVICE there -- there is no CPU fallback.
+#include <cuda.h>
+#include <dlfcn.h>
+#include <nvrtc.h>
+#include <sys/stat.h>
+#include <unistd.h>
+
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <fstream>
+#include <memory>
+#include <sstream>
+#include <string>
+#include <vector>
+
+#include "b200optas.h"
+#include "bo_codegen.h"
+
+namespace {
+
+thread_local std::string g_err;
+
+int set_err(int code, const char* fmt, ...) {
+  char buf[4096];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof buf, fmt, ap);
+  va_end(ap);
+  g_err = buf;
+  return code;
+}
+
+// ------------------------------------------------------------------------------------------
+// CUDA driver API, resolved at run time
+// ------------------------------------------------------------------------------------------
+struct Driver {
+  void* lib = nullptr;
+  bool tried = false;
+  std::string why;
+#define BO_DRV(name) decltype(&::name) name = nullptr;
+  BO_DRV(cuInit)
+  BO_DRV(cuDeviceGetCount)
+  BO_DRV(cuDeviceGet)
+  BO_DRV(cuDeviceGetAttribute)
+  BO_DRV(cuCtxGetCurrent)
+  BO_DRV(cuCtxSetCurrent)
+  BO_DRV(cuCtxGetDevice)
+  BO_DRV(cuDevicePrimaryCtxRetain)
+  BO_DRV(cuModuleLoadData)
+  BO_DRV(cuModuleUnload)
+  BO_DRV(cuModuleGetFunction)
+  BO_DRV(cuFuncGetAttribute)
+  BO_DRV(cuFuncSetAttribute)
+  BO_DRV(cuOccupancyMaxActiveBlocksPerMultiprocessor)
+  BO_DRV(cuLaunchKernel)
+  BO_DRV(cuMemAlloc_v2)
+  BO_DRV(cuMemFree_v2)
+  BO_DRV(cuMemcpyHtoDAsync_v2)
+  BO_DRV(cuMemcpyDtoHAsync_v2)
+  BO_DRV(cuMemsetD8Async)
+  BO_DRV(cuStreamSynchronize)
+  BO_DRV(cuPointerGetAttribute)
+  BO_DRV(cuEventCreate)
+  BO_DRV(cuEventDestroy_v2)
+  BO_DRV(cuEventRecord)
+  BO_DRV(cuEventSynchronize)
+  BO_DRV(cuEventElapsedTime)
+  BO_DRV(cuGetErrorString)
+#undef BO_DRV
+};
+
+Driver g_drv;
+
+bool load_driver() {
+  if (g_drv.tried) return g_drv.lib != nullptr;
+  g_drv.tried = true;
+  void* lib = dlopen("libcuda.so.1", RTLD_NOW | RTLD_GLOBAL);
+  if (!lib) {
+    g_drv.why = "libcuda.so.1 not found (no NVIDIA driver on this machine)";
+    return false;
+  }
+  bool ok = true;
+#define BO_SYM(field, sym)                                          \
+  g_drv.field = reinterpret_cast<decltype(g_drv.field)>(dlsym(lib, sym)); \
+  if (!g_drv.field) { ok = false; g_drv.why = std::string("missing driver symbol ") + sym; }
+  BO_SYM(cuInit, "cuInit")
+  BO_SYM(cuDeviceGetCount, "cuDeviceGetCount")
+  BO_SYM(cuDeviceGet, "cuDeviceGet")
+  BO_SYM(cuDeviceGetAttribute, "cuDeviceGetAttribute")
+  BO_SYM(cuCtxGetCurrent, "cuCtxGetCurrent")
+  BO_SYM(cuCtxSetCurrent, "cuCtxSetCurrent")
+  BO_SYM(cuCtxGetDevice, "cuCtxGetDevice")
+  BO_SYM(cuDevicePrimaryCtxRetain, "cuDevicePrimaryCtxRetain")
+  BO_SYM(cuModuleLoadData, "cuModuleLoadData")
+  BO_SYM(cuModuleUnload, "cuModuleUnload")
+  BO_SYM(cuModuleGetFunction, "cuModuleGetFunction")
+  BO_SYM(cuFuncGetAttribute, "cuFuncGetAttribute")
+  BO_SYM(cuFuncSetAttribute, "cuFuncSetAttribute")
+  BO_SYM(cuOccupancyMaxActiveBlocksPerMultiprocessor, "cuOccupancyMaxActiveBlocksPerMultiprocessor")
+  BO_SYM(cuLaunchKernel, "cuLaunchKernel")
+  BO_SYM(cuMemAlloc_v2, "cuMemAlloc_v2")
+  BO_SYM(cuMemFree_v2, "cuMemFree_v2")
+  BO_SYM(cuMemcpyHtoDAsync_v2, "cuMemcpyHtoDAsync_v2")
+  BO_SYM(cuMemcpyDtoHAsync_v2, "cuMemcpyDtoHAsync_v2")
+  BO_SYM(cuMemsetD8Async, "cuMemsetD8Async")
+  BO_SYM(cuStreamSynchronize, "cuStreamSynchronize")
+  BO_SYM(cuPointerGetAttribute, "cuPointerGetAttribute")
+  BO_SYM(cuEventCreate, "cuEventCreate")
+  BO_SYM(cuEventDestroy_v2, "cuEventDestroy_v2")
+  BO_SYM(cuEventRecord, "cuEventRecord")
+  BO_SYM(cuEventSynchronize, "cuEventSynchronize")
+  BO_SYM(cuEventElapsedTime, "cuEventElapsedTime")
+  BO_SYM(cuGetErrorString, "cuGetErrorString")
+#undef BO_SYM
+  if (!ok) {
+    dlclose(lib);
+    return false;
+  }
+  if (g_drv.cuInit(0) != CUDA_SUCCESS) {
+    g_drv.why = "cuInit failed (no usable CUDA device)";
+    dlclose(lib);
+    return false;
+  }
+  g_drv.lib = lib;
+  return true;
+}
+
+const char* cu_err(CUresult r) {
+  const char* s = nullptr;
+  if (g_drv.cuGetErrorString && g_drv.cuGetErrorString(r, &s) == CUDA_SUCCESS && s) return s;
+  return "unknown CUDA error";
+}
+
+#define BO_CU(call)                                                                       \
+  do {                                                                                    \
+    CUresult _r = (call);                                                                 \
+    if (_r != CUDA_SUCCESS) return set_err(BO_ERR_CUDA, "%s failed: %s", #call, cu_err(_r)); \
+  } while (0)
+
+// Make sure a context is current on this thread (torch's primary context if it exists).
+int ensure_context(CUdevice* dev_out) {
+  if (!load_driver()) return set_err(BO_ERR_NO_DEVICE, "%s", g_drv.why.c_str());
+  int n = 0;
+  if (g_drv.cuDeviceGetCount(&n) != CUDA_SUCCESS || n == 0) return set_err(BO_ERR_NO_DEVICE, "no CUDA device");
+  CUcontext ctx = nullptr;
+  g_drv.cuCtxGetCurrent(&ctx);
+  if (!ctx) {
+    CUdevice dev;
+    BO_CU(g_drv.cuDeviceGet(&dev, 0));
+    BO_CU(g_drv.cuDevicePrimaryCtxRetain(&ctx, dev));
+    BO_CU(g_drv.cuCtxSetCurrent(ctx));
+  }
+  if (dev_out) BO_CU(g_drv.cuCtxGetDevice(dev_out));
+  return BO_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// paths, hashing, files
+// ------------------------------------------------------------------------------------------
+std::string lib_dir() {
+  Dl_info info;
+  if (dladdr(reinterpret_cast<void*>(&bo_abi_version), &info) && info.dli_fname) {
+    std::string p(info.dli_fname);
+    const size_t k = p.find_last_of('/');
+    return k == std::string::npos ? "." : p.substr(0, k);
+  }
+  return ".";
+}
+
+uint64_t fnv1a(const std::string& s, uint64_t h = 1469598103934665603ULL) {
+  for (unsigned char c : s) {
+    h ^= c;
+    h *= 1099511628211ULL;
+  }
+  return h;
+}
+
+bool read_file(const std::string& path, std::string* out) {
+  std::ifstream f(path, std::ios::binary);
+  if (!f) return false;
+  std::ostringstream ss;
+  ss << f.rdbuf();
+  *out = ss.str();
+  return true;
+}
+
+bool write_file(const std::string& path, const std::string& data) {
+  const std::string tmp = path + ".tmp" + std::to_string((long)getpid());
+  {
+    std::ofstream f(tmp, std::ios::binary);
+    if (!f) return false;
+    f.write(data.data(), (std::streamsize)data.size());
+    if (!f) return false;
+  }
+  return std::rename(tmp.c_str(), path.c_str()) == 0;
+}
+
+// ------------------------------------------------------------------------------------------
+// JIT: source -> cubin (NVRTC, sm_100a), with an on-disk cache
+// ------------------------------------------------------------------------------------------
+struct Compiled {
+  std::string cubin;
+  std::string log;
+  int regs = -1, local_bytes = -1, smem_bytes = -1;  // parsed from the ptxas -v log when available
+  bool from_cache = false;
+};
+
+void parse_ptxas(const std::string& log, const char* kernel, Compiled* c) {
+  // "ptxas info    : Compiling entry function 'bo_solve_kernel' for 'sm_100a'" ... "Used N registers"
+  const size_t at = log.find(std::string("'") + kernel + "'");
+  if (at == std::string::npos) return;
+  const size_t used = log.find("Used ", at);
+  if (used != std::string::npos) c->regs = atoi(log.c_str() + used + 5);
+  const size_t fr = log.find("bytes stack frame", at);
+  if (fr != std::string::npos) {
+    size_t b = fr;
+    while (b > 0 && (isdigit((unsigned char)log[b - 1]) || log[b - 1] == ' ')) --b;
+    c->local_bytes = atoi(log.c_str() + b);
+  }
+  const size_t sm = log.find(" bytes smem", at);
+  if (sm != std::string::npos) {
+    size_t b = sm;
+    while (b > 0 && isdigit((unsigned char)log[b - 1])) --b;
+    c->smem_bytes = atoi(log.c_str() + b);
+  } else {
+    c->smem_bytes = 0;
+  }
+}
+
+int jit_compile(const std::string& source, const char* unit_name, const char* kernel, const bo_options& opts,
+                Compiled* out) {
+  const std::string inc = opts.include_dir ? opts.include_dir : lib_dir() + "/csrc/jit";
+  const std::string cache = opts.cache_dir ? opts.cache_dir : lib_dir() + "/_jitcache";
+  int major = 0, minor = 0;
+  nvrtcVersion(&major, &minor);
+
+  // hash = source + every header it may include + compiler version
+  uint64_t h = fnv1a(source);
+  for (const char* hdr : {"bo_common.cuh", "bo_ipm_reg.cuh", "bo_stream_eval.cuh"}) {
+    std::string text;
+    if (!read_file(inc + "/" + hdr, &text)) return set_err(BO_ERR_INVALID, "JIT header %s/%s not found", inc.c_str(), hdr);
+    h = fnv1a(text, h);
+  }
+  h = fnv1a("nvrtc" + std::to_string(major) + "." + std::to_string(minor) + "sm_100a-lineinfo", h);
+  char hex[32];
+  snprintf(hex, sizeof hex, "%016llx", (unsigned long long)h);
+  const std::string stem = cache + "/" + unit_name + "_" + hex;
+  const bool use_cache = !(opts.flags & BO_FLAG_NO_CACHE);
+
+  if (use_cache && read_file(stem + ".cubin", &out->cubin) && !out->cubin.empty()) {
+    read_file(stem + ".log", &out->log);
+    out->from_cache = true;
+    parse_ptxas(out->log, kernel, out);
+    if (opts.flags & BO_FLAG_VERBOSE) fprintf(stderr, "[b200optas] cubin cache hit %s.cubin\n", stem.c_str());
+    return BO_OK;
+  }
+
+  nvrtcProgram prog;
+  const std::string file = std::string(unit_name) + ".cu";
+  if (nvrtcCreateProgram(&prog, source.c_str(), file.c_str(), 0, nullptr, nullptr) != NVRTC_SUCCESS)
+    return set_err(BO_ERR_COMPILE, "nvrtcCreateProgram failed");
+  const std::string iflag = "-I" + inc;
+  const char* flags[] = {"--gpu-architecture=sm_100a", "--std=c++17", "-lineinfo", "--ptxas-options=-v", iflag.c_str()};
+  const nvrtcResult res = nvrtcCompileProgram(prog, (int)(sizeof flags / sizeof flags[0]), flags);
+  size_t log_size = 0;
+  nvrtcGetProgramLogSize(prog, &log_size);
+  out->log.assign(log_size, '\0');
+  if (log_size) nvrtcGetProgramLog(prog, &out->log[0]);
+  if (res != NVRTC_SUCCESS) {
+    nvrtcDestroyProgram(&prog);
+    return set_err(BO_ERR_COMPILE, "NVRTC: %s\n%s", nvrtcGetErrorString(res), out->log.c_str());
+  }
+  size_t sz = 0;
+  if (nvrtcGetCUBINSize(prog, &sz) != NVRTC_SUCCESS || sz == 0) {
+    nvrtcDestroyProgram(&prog);
+    return set_err(BO_ERR_COMPILE, "NVRTC produced no cubin");
+  }
+  out->cubin.assign(sz, '\0');
+  nvrtcGetCUBIN(prog, &out->cubin[0]);
+  nvrtcDestroyProgram(&prog);
+  parse_ptxas(out->log, kernel, out);
+  if (opts.flags & BO_FLAG_VERBOSE) fprintf(stderr, "[b200optas] compiled %s: %s\n", unit_name, out->log.c_str());
+  if (use_cache) {
+    mkdir(cache.c_str(), 0755);
+    if (write_file(stem + ".cubin", out->cubin)) {
+      write_file(stem + ".log", out->log);
+      write_file(stem + ".cu", source);
+    }
+  }
+  return BO_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// device helpers
+// ------------------------------------------------------------------------------------------
+struct LoadedKernel {
+  CUmodule mod = nullptr;
+  CUfunction fn = nullptr;
+  int regs = -1, local_bytes = -1, smem_bytes = -1;
+};
+
+int load_kernel(const Compiled& c, const char* name, LoadedKernel* k) {
+  BO_CU(g_drv.cuModuleLoadData(&k->mod, c.cubin.data()));
+  BO_CU(g_drv.cuModuleGetFunction(&k->fn, k->mod, name));
+  g_drv.cuFuncGetAttribute(&k->regs, CU_FUNC_ATTRIBUTE_NUM_REGS, k->fn);
+  g_drv.cuFuncGetAttribute(&k->local_bytes, CU_FUNC_ATTRIBUTE_LOCAL_SIZE_BYTES, k->fn);
+  g_drv.cuFuncGetAttribute(&k->smem_bytes, CU_FUNC_ATTRIBUTE_SHARED_SIZE_BYTES, k->fn);
+  return BO_OK;
+}
+
+bool is_device_ptr(const void* p) {
+  if (!p) return false;
+  unsigned int type = 0;
+  const CUresult r = g_drv.cuPointerGetAttribute(&type, CU_POINTER_ATTRIBUTE_MEMORY_TYPE, (CUdeviceptr)(uintptr_t)p);
+  if (r != CUDA_SUCCESS) return false;  // plain (unregistered) host memory
+  return type == CU_MEMORYTYPE_DEVICE || type == CU_MEMORYTYPE_UNIFIED;
+}
+
+// grow-only device scratch buffer
+struct DevBuf {
+  CUdeviceptr ptr = 0;
+  size_t cap = 0;
+  int reserve(size_t bytes) {
+    if (bytes <= cap) return BO_OK;
+    if (ptr) g_drv.cuMemFree_v2(ptr);
+    ptr = 0;
+    cap = 0;
+    BO_CU(g_drv.cuMemAlloc_v2(&ptr, bytes));
+    cap = bytes;
+    return BO_OK;
+  }
+  void release() {
+    if (ptr && g_drv.cuMemFree_v2) g_drv.cuMemFree_v2(ptr);
+    ptr = 0;
+    cap = 0;
+  }
+};
+
+struct Timer {
+  bool enabled = false;
+  std::vector<std::pair<CUevent, CUevent>> pool;
+  size_t used = 0;
+  double carried_ms = 0.0;
+  int64_t carried_n = 0;
+  int begin(CUstream s, size_t* slot) {
+    if (!enabled) return BO_OK;
+    if (used == pool.size()) {
+      if (pool.size() >= 4096) {
+        double ms = 0.0;
+        int64_t n = 0;
+        collect(&ms, &n);
+        carried_ms += ms;
+        carried_n += n;
+      } else {
+        CUevent a, b;
+        BO_CU(g_drv.cuEventCreate(&a, CU_EVENT_DEFAULT));
+        BO_CU(g_drv.cuEventCreate(&b, CU_EVENT_DEFAULT));
+        pool.emplace_back(a, b);
+      }
+    }
+    *slot = used++;
+    BO_CU(g_drv.cuEventRecord(pool[*slot].first, s));
+    return BO_OK;
+  }
+  int end(CUstream s, size_t slot) {
+    if (!enabled) return BO_OK;
+    BO_CU(g_drv.cuEventRecord(pool[slot].second, s));
+    return BO_OK;
+  }
+  int collect(double* ms_total, int64_t* n) {
+    double tot = carried_ms;
+    int64_t cnt = carried_n;
+    for (size_t i = 0; i < used; ++i) {
+      float ms = 0.f;
+      BO_CU(g_drv.cuEventSynchronize(pool[i].second));
+      BO_CU(g_drv.cuEventElapsedTime(&ms, pool[i].first, pool[i].second));
+      tot += ms;
+      ++cnt;
+    }
+    used = 0;
+    carried_ms = 0.0;
+    carried_n = 0;
+    *ms_total = tot;
+    *n = cnt;
+    return BO_OK;
+  }
+  void release() {
+    for (auto& p : pool) {
+      g_drv.cuEventDestroy_v2(p.first);
+      g_drv.cuEventDestroy_v2(p.second);
+    }
+    pool.clear();
+  }
+};
+
+bo_options normalise(const bo_options* in) {
+  bo_options o;
+  memset(&o, 0, sizeof o);
+  if (in) o = *in;
+  if (o.max_iter <= 0) o.max_iter = 200;
+  if (!(o.tol > 0)) o.tol = 1e-8;
+  if (!(o.acceptable_tol > 0)) o.acceptable_tol = 1e-6;
+  if (!(o.mu_init > 0)) o.mu_init = 0.1;
+  return o;
+}
+
+struct SolverParams {  // must match bo_solver_params in csrc/jit/bo_common.cuh
+  int32_t max_iter;
+  double tol;
+  double acceptable_tol;
+  double mu_init;
+};
+
+}  // namespace
+
+struct bo_problem {
+  bo::ProblemSource ps;
+  bo_options opts;
+  std::string cache_dir, include_dir;
+  std::string source;
+  Compiled compiled;
+  LoadedKernel kernel;
+  bool loaded = false;
+  int tpb = 64;
+  DevBuf d_p, d_x0, d_x, d_lam, d_f, d_status, d_iters, d_kkt;
+  Timer timer;
+};
+
+struct bo_function {
+  bo::Tape tape;
+  bo_options opts;
+  std::string cache_dir, include_dir;
+  std::string source;
+  Compiled compiled;
+  LoadedKernel kernel;
+  bool loaded = false;
+  int tpb = 128;
+  int smem_dynamic = 0;
+  int blocks_per_sm = 1, n_sm = 1;
+  std::vector<DevBuf> d_in, d_out;
+  Timer timer;
+};
+
+extern "C" {
+
+int bo_abi_version(void) { return BO_ABI_VERSION; }
+
+const char* bo_last_error(void) { return g_err.c_str(); }
+
+int bo_device_count(void) {
+  if (!load_driver()) return 0;
+  int n = 0;
+  if (g_drv.cuDeviceGetCount(&n) != CUDA_SUCCESS) return 0;
+  return n;
+}
+
+// ------------------------------------------------------------------------------------------
+// solver
+// ------------------------------------------------------------------------------------------
+int bo_problem_create(const bo_problem_desc* desc, const bo_options* opts_in, bo_problem** out) {
+  if (!desc || !out) return set_err(BO_ERR_INVALID, "bo_problem_create: null argument");
+  *out = nullptr;
+  if (desc->nx <= 0 || desc->np < 0 || desc->n_eq < 0 || desc->n_ineq < 0)
+    return set_err(BO_ERR_INVALID, "bo_problem_create: bad dimensions");
+  std::unique_ptr<bo_problem> pr(new bo_problem);
+  pr->opts = normalise(opts_in);
+  if (pr->opts.cache_dir) { pr->cache_dir = pr->opts.cache_dir; pr->opts.cache_dir = pr->cache_dir.c_str(); }
+  if (pr->opts.include_dir) { pr->include_dir = pr->opts.include_dir; pr->opts.include_dir = pr->include_dir.c_str(); }
+  bo::ProblemSource& ps = pr->ps;
+  ps.nx = desc->nx;
+  ps.np = desc->np;
+  ps.n_eq = desc->n_eq;
+  ps.n_ineq = desc->n_ineq;
+  std::string err;
+  if (!bo::copy_tape(desc->fc, &ps.fc, &err) || !bo::copy_tape(desc->kkt, &ps.kkt, &err) ||
+      !bo::copy_sparsity(desc->jac_eq, ps.n_eq, ps.nx, false, &ps.jac_eq, &err) ||
+      !bo::copy_sparsity(desc->jac_ineq, ps.n_ineq, ps.nx, false, &ps.jac_ineq, &err) ||
+      !bo::copy_sparsity(desc->hess, ps.nx, ps.nx, true, &ps.hess, &err))
+    return set_err(BO_ERR_INVALID, "bo_problem_create: %s", err.c_str());
+  auto expect = [&](const bo::Tape& t, std::vector<int32_t> in, std::vector<int32_t> outs, const char* nm) {
+    if (t.in_sizes != in || t.out_sizes != outs) {
+      err = std::string(nm) + " tape has the wrong input/output segment sizes";
+      return false;
+    }
+    return true;
+  };
+  if (!expect(ps.fc, {ps.nx, ps.np}, {1, ps.n_eq, ps.n_ineq}, "fc") ||
+      !expect(ps.kkt, {ps.nx, ps.np, ps.n_eq, ps.n_ineq},
+              {1, ps.nx, ps.n_eq, ps.n_ineq, ps.jac_eq.nnz(), ps.jac_ineq.nnz(), ps.hess.nnz()}, "kkt"))
+    return set_err(BO_ERR_INVALID, "bo_problem_create: %s", err.c_str());
+  if (ps.nx + ps.n_eq > 40 || ps.n_ineq > 128)
+    return set_err(BO_ERR_UNSUPPORTED,
+                   "bo_problem_create: nx+n_eq=%d, n_ineq=%d exceeds the register-resident tier (nx+n_eq<=40, n_ineq<=128)",
+                   ps.nx + ps.n_eq, ps.n_ineq);
+  pr->tpb = pr->opts.threads_per_block > 0 ? pr->opts.threads_per_block : 64;
+  if (getenv("BO_DEBUG")) fprintf(stderr, "[bo] emitting source\n");
+  pr->source = bo::emit_problem_source(ps, pr->tpb);
+  if (getenv("BO_DEBUG")) fprintf(stderr, "[bo] source %zu bytes\n", pr->source.size());
+  int rc = jit_compile(pr->source, "bo_solve", "bo_solve_kernel", pr->opts, &pr->compiled);
+  if (rc != BO_OK) return rc;
+  pr->kernel.regs = pr->compiled.regs;
+  pr->kernel.local_bytes = pr->compiled.local_bytes;
+  pr->kernel.smem_bytes = pr->compiled.smem_bytes;
+  if (!(pr->opts.flags & BO_FLAG_COMPILE_ONLY)) {
+    rc = ensure_context(nullptr);
+    if (rc != BO_OK) return rc;
+    rc = load_kernel(pr->compiled, "bo_solve_kernel", &pr->kernel);
+    if (rc != BO_OK) return rc;
+    pr->loaded = true;
+    pr->timer.enabled = (pr->opts.flags & BO_FLAG_TIMING) != 0;
+  }
+  *out = pr.release();
+  return BO_OK;
+}
+
+int bo_problem_destroy(bo_problem* pr) {
+  if (!pr) return BO_OK;
+  if (pr->loaded) {
+    for (DevBuf* b : {&pr->d_p, &pr->d_x0, &pr->d_x, &pr->d_lam, &pr->d_f, &pr->d_status, &pr->d_iters, &pr->d_kkt})
+      b->release();
+    pr->timer.release();
+    if (pr->kernel.mod) g_drv.cuModuleUnload(pr->kernel.mod);
+  }
+  delete pr;
+  return BO_OK;
+}
+
+static int64_t copy_out(const std::string& s, char* buf, int64_t cap) {
+  if (buf && cap > 0) {
+    const int64_t n = (int64_t)s.size() < cap - 1 ? (int64_t)s.size() : cap - 1;
+    memcpy(buf, s.data(), (size_t)n);
+    buf[n] = '\0';
+  }
+  return (int64_t)s.size();
+}
+
+int64_t bo_problem_source(const bo_problem* pr, char* buf, int64_t cap) {
+  if (!pr) return set_err(BO_ERR_INVALID, "null problem");
+  return copy_out(pr->source, buf, cap);
+}
+
+int bo_problem_kernel_info(const bo_problem* pr, int32_t* regs, int32_t* local_bytes, int32_t* smem_bytes) {
+  if (!pr) return set_err(BO_ERR_INVALID, "null problem");
+  if (regs) *regs = pr->kernel.regs;
+  if (local_bytes) *local_bytes = pr->kernel.local_bytes;
+  if (smem_bytes) *smem_bytes = pr->kernel.smem_bytes;
+  return BO_OK;
+}
+
+int bo_solve(bo_problem* pr, int64_t B, const double* p, const double* x0, double* x, double* lam, double* f,
+             int32_t* status, int32_t* iters, double* kkt_res, void* cuda_stream) {
+  if (!pr || !x || B < 0) return set_err(BO_ERR_INVALID, "bo_solve: bad argument");
+  if (!pr->loaded) return set_err(BO_ERR_NO_DEVICE, "bo_solve: problem was created compile-only or without a device");
+  if (pr->ps.np > 0 && !p) return set_err(BO_ERR_INVALID, "bo_solve: p is NULL but np > 0");
+  if (B == 0) return BO_OK;
+  int rc = ensure_context(nullptr);
+  if (rc != BO_OK) return rc;
+  CUstream st = (CUstream)cuda_stream;
+  const size_t nx = pr->ps.nx, np = pr->ps.np, nl = pr->ps.n_eq + pr->ps.n_ineq;
+  bool any_host = false;
+
+  auto stage_in = [&](const double* src, size_t n, DevBuf& buf, CUdeviceptr* dptr) -> int {
+    *dptr = 0;
+    if (!src || n == 0) return BO_OK;
+    if (is_device_ptr(src)) {
+      *dptr = (CUdeviceptr)(uintptr_t)src;
+      return BO_OK;
+    }
+    any_host = true;
+    const size_t bytes = (size_t)B * n * sizeof(double);
+    int r = buf.reserve(bytes);
+    if (r != BO_OK) return r;
+    BO_CU(g_drv.cuMemcpyHtoDAsync_v2(buf.ptr, src, bytes, st));
+    *dptr = buf.ptr;
+    return BO_OK;
+  };
+  struct Out {
+    void* host;
+    CUdeviceptr dev;
+    size_t bytes;
+  };
+  std::vector<Out> outs;
+  auto stage_out = [&](void* dst, size_t bytes_per, DevBuf& buf, CUdeviceptr* dptr) -> int {
+    *dptr = 0;
+    if (!dst || bytes_per == 0) return BO_OK;
+    if (is_device_ptr(dst)) {
+      *dptr = (CUdeviceptr)(uintptr_t)dst;
+      return BO_OK;
+    }
+    any_host = true;
+    const size_t bytes = (size_t)B * bytes_per;
+    int r = buf.reserve(bytes);
+    if (r != BO_OK) return r;
+    *dptr = buf.ptr;
+    outs.push_back({dst, buf.ptr, bytes});
+    return BO_OK;
+  };
+
+  CUdeviceptr dp, dx0, dx, dlam, df, dstat, dit, dkkt;
+  if ((rc = stage_in(p, np, pr->d_p, &dp)) != BO_OK) return rc;
+  if ((rc = stage_in(x0, nx, pr->d_x0, &dx0)) != BO_OK) return rc;
+  if ((rc = stage_out(x, nx * sizeof(double), pr->d_x, &dx)) != BO_OK) return rc;
+  if ((rc = stage_out(lam, nl * sizeof(double), pr->d_lam, &dlam)) != BO_OK) return rc;
+  if ((rc = stage_out(f, sizeof(double), pr->d_f, &df)) != BO_OK) return rc;
+  if ((rc = stage_out(status, sizeof(int32_t), pr->d_status, &dstat)) != BO_OK) return rc;
+  if ((rc = stage_out(iters, sizeof(int32_t), pr->d_iters, &dit)) != BO_OK) return rc;
+  if ((rc = stage_out(kkt_res, sizeof(double), pr->d_kkt, &dkkt)) != BO_OK) return rc;
+
+  long long Bll = B;
+  SolverParams prm{pr->opts.max_iter, pr->opts.tol, pr->opts.acceptable_tol, pr->opts.mu_init};
+  void* args[] = {&Bll, &dp, &dx0, &dx, &dlam, &df, &dstat, &dit, &dkkt, &prm};
+  const unsigned grid = (unsigned)((B + pr->tpb - 1) / pr->tpb);
+  size_t slot = 0;
+  if ((rc = pr->timer.begin(st, &slot)) != BO_OK) return rc;
+  BO_CU(g_drv.cuLaunchKernel(pr->kernel.fn, grid, 1, 1, (unsigned)pr->tpb, 1, 1, 0, st, args, nullptr));
+  if ((rc = pr->timer.end(st, slot)) != BO_OK) return rc;
+
+  for (const Out& o : outs) BO_CU(g_drv.cuMemcpyDtoHAsync_v2(o.host, o.dev, o.bytes, st));
+  if (any_host) BO_CU(g_drv.cuStreamSynchronize(st));
+  return BO_OK;
+}
+
+int bo_problem_kernel_time(bo_problem* pr, double* ms_total, int64_t* n_launches) {
+  if (!pr || !ms_total) return set_err(BO_ERR_INVALID, "null argument");
+  if (!pr->loaded) return set_err(BO_ERR_NO_DEVICE, "problem not loaded on a device");
+  int64_t n = 0;
+  int rc = pr->timer.collect(ms_total, &n);
+  if (n_launches) *n_launches = n;
+  return rc;
+}
+
+// ------------------------------------------------------------------------------------------
+// streaming function evaluation
+// ------------------------------------------------------------------------------------------
+int bo_function_create(const bo_tape* tape, const bo_options* opts_in, bo_function** out) {
+  if (!tape || !out) return set_err(BO_ERR_INVALID, "bo_function_create: null argument");
+  *out = nullptr;
+  std::unique_ptr<bo_function> fn(new bo_function);
+  fn->opts = normalise(opts_in);
+  if (fn->opts.cache_dir) { fn->cache_dir = fn->opts.cache_dir; fn->opts.cache_dir = fn->cache_dir.c_str(); }
+  if (fn->opts.include_dir) { fn->include_dir = fn->opts.include_dir; fn->opts.include_dir = fn->include_dir.c_str(); }
+  std::string err;
+  if (!bo::copy_tape(*tape, &fn->tape, &err)) return set_err(BO_ERR_INVALID, "bo_function_create: %s", err.c_str());
+  if (fn->tape.in_sizes.empty() || fn->tape.out_sizes.empty())
+    return set_err(BO_ERR_INVALID, "bo_function_create: need at least one input and one output segment");
+  if (fn->tape.in_sizes.size() > 16 || fn->tape.out_sizes.size() > 16)
+    return set_err(BO_ERR_UNSUPPORTED, "bo_function_create: at most 16 input and 16 output segments");
+  size_t per_instance = 0;
+  for (int s : fn->tape.in_sizes) per_instance += (size_t)s;
+  for (int s : fn->tape.out_sizes) per_instance += (size_t)s;
+  // two pipeline stages of BO_TPB instances must fit in shared memory (227 KB per CTA on sm_100)
+  int tpb = fn->opts.threads_per_block > 0 ? fn->opts.threads_per_block : 128;
+  while (tpb > 32 && 2 * (size_t)tpb * per_instance * sizeof(double) + 64 > 200 * 1024) tpb /= 2;
+  if (2 * (size_t)tpb * per_instance * sizeof(double) + 64 > 220 * 1024)
+    return set_err(BO_ERR_UNSUPPORTED, "bo_function_create: %zu doubles per instance do not fit the shared-memory pipeline",
+                   per_instance);
+  fn->tpb = tpb;
+  fn->smem_dynamic = (int)(2 * (size_t)tpb * per_instance * sizeof(double) + 64);
+  fn->source = bo::emit_function_source(fn->tape, tpb);
+  int rc = jit_compile(fn->source, "bo_eval", "bo_eval_kernel", fn->opts, &fn->compiled);
+  if (rc != BO_OK) return rc;
+  fn->kernel.regs = fn->compiled.regs;
+  fn->kernel.local_bytes = fn->compiled.local_bytes;
+  fn->kernel.smem_bytes = fn->compiled.smem_bytes;
+  if (!(fn->opts.flags & BO_FLAG_COMPILE_ONLY)) {
+    CUdevice dev;
+    rc = ensure_context(&dev);
+    if (rc != BO_OK) return rc;
+    rc = load_kernel(fn->compiled, "bo_eval_kernel", &fn->kernel);
+    if (rc != BO_OK) return rc;
+    BO_CU(g_drv.cuFuncSetAttribute(fn->kernel.fn, CU_FUNC_ATTRIBUTE_MAX_DYNAMIC_SHARED_SIZE_BYTES, fn->smem_dynamic));
+    BO_CU(g_drv.cuDeviceGetAttribute(&fn->n_sm, CU_DEVICE_ATTRIBUTE_MULTIPROCESSOR_COUNT, dev));
+    BO_CU(g_drv.cuOccupancyMaxActiveBlocksPerMultiprocessor(&fn->blocks_per_sm, fn->kernel.fn, tpb, fn->smem_dynamic));
+    if (fn->blocks_per_sm < 1) fn->blocks_per_sm = 1;
+    fn->d_in.resize(fn->tape.in_sizes.size());
+    fn->d_out.resize(fn->tape.out_sizes.size());
+    fn->loaded = true;
+    fn->timer.enabled = (fn->opts.flags & BO_FLAG_TIMING) != 0;
+  }
+  *out = fn.release();
+  return BO_OK;
+}
+
+int bo_function_destroy(bo_function* fn) {
+  if (!fn) return BO_OK;
+  if (fn->loaded) {
+    for (auto& b : fn->d_in) b.release();
+    for (auto& b : fn->d_out) b.release();
+    fn->timer.release();
+    if (fn->kernel.mod) g_drv.cuModuleUnload(fn->kernel.mod);
+  }
+  delete fn;
+  return BO_OK;
+}
+
+int64_t bo_function_source(const bo_function* fn, char* buf, int64_t cap) {
+  if (!fn) return set_err(BO_ERR_INVALID, "null function");
+  return copy_out(fn->source, buf, cap);
+}
+
+int bo_function_kernel_info(const bo_function* fn, int32_t* regs, int32_t* local_bytes, int32_t* smem_bytes) {
+  if (!fn) return set_err(BO_ERR_INVALID, "null function");
+  if (regs) *regs = fn->kernel.regs;
+  if (local_bytes) *local_bytes = fn->kernel.local_bytes;
+  if (smem_bytes) *smem_bytes = fn->loaded ? fn->kernel.smem_bytes + fn->smem_dynamic : fn->smem_dynamic;
+  return BO_OK;
+}
+
+int bo_function_eval(bo_function* fn, int64_t B, const double* const* in, double* const* out, void* cuda_stream) {
+  if (!fn || !in || !out || B < 0) return set_err(BO_ERR_INVALID, "bo_function_eval: bad argument");
+  if (!fn->loaded) return set_err(BO_ERR_NO_DEVICE, "bo_function_eval: function was created compile-only or without a device");
+  if (B == 0) return BO_OK;
+  int rc = ensure_context(nullptr);
+  if (rc != BO_OK) return rc;
+  CUstream st = (CUstream)cuda_stream;
+  const size_t n_in = fn->tape.in_sizes.size(), n_out = fn->tape.out_sizes.size();
+  // kernel argument block: must match bo_eval_args in csrc/jit/bo_stream_eval.cuh
+  std::vector<unsigned char> argbuf((n_in + n_out) * sizeof(void*) + sizeof(int) + 8, 0);
+  CUdeviceptr* ptrs = reinterpret_cast<CUdeviceptr*>(argbuf.data());
+  bool any_host = false, aligned = true;
+  struct Out {
+    void* host;
+    CUdeviceptr dev;
+    size_t bytes;
+  };
+  std::vector<Out> outs;
+  for (size_t k = 0; k < n_in; ++k) {
+    const size_t bytes = (size_t)B * fn->tape.in_sizes[k] * sizeof(double);
+    if (bytes == 0) continue;
+    if (!in[k]) return set_err(BO_ERR_INVALID, "bo_function_eval: input %zu is NULL", k);
+    if (is_device_ptr(in[k])) {
+      ptrs[k] = (CUdeviceptr)(uintptr_t)in[k];
+    } else {
+      any_host = true;
+      if ((rc = fn->d_in[k].reserve(bytes)) != BO_OK) return rc;
+      BO_CU(g_drv.cuMemcpyHtoDAsync_v2(fn->d_in[k].ptr, in[k], bytes, st));
+      ptrs[k] = fn->d_in[k].ptr;
+    }
+    if (ptrs[k] & 15) aligned = false;
+  }
+  for (size_t k = 0; k < n_out; ++k) {
+    const size_t bytes = (size_t)B * fn->tape.out_sizes[k] * sizeof(double);
+    if (bytes == 0) continue;
+    if (!out[k]) return set_err(BO_ERR_INVALID, "bo_function_eval: output %zu is NULL", k);
+    if (is_device_ptr(out[k])) {
+      ptrs[n_in + k] = (CUdeviceptr)(uintptr_t)out[k];
+    } else {
+      any_host = true;
+      if ((rc = fn->d_out[k].reserve(bytes)) != BO_OK) return rc;
+      ptrs[n_in + k] = fn->d_out[k].ptr;
+      outs.push_back({out[k], fn->d_out[k].ptr, bytes});
+    }
+    if (ptrs[n_in + k] & 15) aligned = false;
+  }
+  *reinterpret_cast<int*>(argbuf.data() + (n_in + n_out) * sizeof(void*)) = aligned ? 1 : 0;
+
+  long long Bll = B;
+  void* args[] = {&Bll, argbuf.data()};
+  const long long n_tiles = (B + fn->tpb - 1) / fn->tpb;
+  long long grid = (long long)fn->n_sm * fn->blocks_per_sm;
+  if (grid > n_tiles) grid = n_tiles;
+  size_t slot = 0;
+  if ((rc = fn->timer.begin(st, &slot)) != BO_OK) return rc;
+  BO_CU(g_drv.cuLaunchKernel(fn->kernel.fn, (unsigned)grid, 1, 1, (unsigned)fn->tpb, 1, 1, (unsigned)fn->smem_dynamic, st, args,
+                             nullptr));
+  if ((rc = fn->timer.end(st, slot)) != BO_OK) return rc;
+  for (const Out& o : outs) BO_CU(g_drv.cuMemcpyDtoHAsync_v2(o.host, o.dev, o.bytes, st));
+  if (any_host) BO_CU(g_drv.cuStreamSynchronize(st));
+  return BO_OK;
+}
+
+int bo_function_kernel_time(bo_function* fn, double* ms_total, int64_t* n_launches) {
+  if (!fn || !ms_total) return set_err(BO_ERR_INVALID, "null argument");
+  if (!fn->loaded) return set_err(BO_ERR_NO_DEVICE, "function not loaded on a device");
+  int64_t n = 0;
+  int rc = fn->timer.collect(ms_total, &n);
+  if (n_launches) *n_launches = n;
+  return rc;
+}
+
+}  // extern "C"

@@ -1,0 +1,50 @@
+// bo_codegen.h -- expression tape -> straight-line CUDA C++ (host side of libb200optas).
+#pragma once
+#include <string>
+#include <vector>
+
+#include "b200optas.h"
+
+namespace bo {
+
+// Owning copy of a bo_tape (the C struct only borrows caller memory).
+struct Tape {
+  std::vector<int32_t> instr;  // [n][4]
+  std::vector<double> consts;
+  int32_t n_work = 0;
+  std::vector<int32_t> in_sizes, out_sizes;
+  int64_t n_instr() const { return (int64_t)instr.size() / 4; }
+};
+
+struct Sparsity {
+  std::vector<int32_t> row, col;
+  int32_t nnz() const { return (int32_t)row.size(); }
+};
+
+// Validate and copy.  Returns false and fills err on a malformed tape.
+bool copy_tape(const bo_tape& in, Tape* out, std::string* err);
+bool copy_sparsity(const bo_sparsity& in, int32_t n_rows, int32_t n_cols, bool lower_only, Sparsity* out,
+                   std::string* err);
+
+// Emit `BO_DEVICE void <name>(const double* i0, ..., double* o0, ...)` evaluating the tape.
+// sin/cos of the same operand are fused into one sincos.
+std::string emit_tape_function(const Tape& tape, const std::string& name);
+
+// Count of floating-point operations (adds, muls, ... 1 each; sincos counted as 2 calls).
+struct TapeStats {
+  int64_t n_arith = 0, n_div_sqrt = 0, n_trig = 0, n_other = 0;
+};
+TapeStats tape_stats(const Tape& tape);
+
+struct ProblemSource {
+  int32_t nx, np, n_eq, n_ineq;
+  Tape fc, kkt;
+  Sparsity jac_eq, jac_ineq, hess;
+};
+
+// Full translation unit of the tier-S (thread-per-instance) solver for this problem.
+std::string emit_problem_source(const ProblemSource& ps, int threads_per_block);
+// Full translation unit of the streaming evaluation kernel for one tape.
+std::string emit_function_source(const Tape& tape, int threads_per_block);
+
+}  // namespace bo

@@ -1,0 +1,415 @@
+"""Solver front: the plug-in boundary of OpTaS, with the B200 back-end behind it.
+
+``Solver`` restates the reference's abstract base (optas/solver.py:61-315): same members, same
+argument meaning, same error behaviour.  ``B200Solver`` is the drop-in for the concrete
+``CasADiSolver`` (ref :321-419) and ``ScipyMinimizeSolver`` (ref :587-813): construct it with a
+built ``Optimization``, call ``setup(...)`` with either spelling, then ``reset_parameters`` /
+``reset_initial_seed`` / ``solve`` exactly as task scripts do (example/example.py:40-60).
+
+Batch extension (the reason this back-end exists): any value handed to ``reset_parameters`` /
+``reset_initial_seed`` may carry a leading batch axis -- ``[B, m, n]`` or ``[B, m*n]`` for an
+``m x n`` label -- and then ``solve()`` returns ``[B, m, n]`` arrays and ``stats()`` per-instance
+status / iteration / KKT-error arrays.  Without a batch axis everything behaves (and is typed)
+like the reference: ``solve()`` returns a dict of ``DM``.
+
+All numerical work goes through libb200optas.so (ctypes, GIL released); there is no CPU solve
+path in this module -- without the library or without a GPU ``setup`` / ``solve`` raise.
+"""
+
+from __future__ import annotations
+
+from abc import ABC, abstractmethod
+from dataclasses import dataclass
+from typing import Dict, List, Optional, Tuple
+
+import numpy as np
+
+from . import sym as cs
+from .lowering import LoweredProblem, lower_problem
+from .models import RobotModel
+from .optimization import CONSTRAINED_OPT, MixedIntegerNonlinearCostNonlinearConstrained, Optimization
+from .spatialmath import ArrayType, CasADiArrayType
+
+
+class Solver(ABC):
+    """Abstract solver (reference: optas/solver.py:61-315)."""
+
+    def __init__(self, optimization: Optimization, error_on_fail: bool = False):
+        self.opt = optimization
+        self.x0 = cs.DM.zeros(optimization.nx)  # ref :76 -- an unset seed is zeros
+        self.p = cs.DM.zeros(optimization.np)
+        self._p_dict: Dict = {}
+        self._error_on_fail = error_on_fail
+        self._solution = None
+
+    @property
+    def opt_type(self) -> type:
+        return type(self.opt)
+
+    @abstractmethod
+    def setup(self, *args, **kwargs):
+        """Must return ``self`` (ref :98-101)."""
+
+    def reset_initial_seed(self, x0: Dict[str, ArrayType]) -> None:
+        """Missing labels become zeros, unknown labels are ignored (ref :103-108)."""
+        self.x0 = self.opt.decision_variables.dict2vec(x0)
+
+    def reset_parameters(self, p: Dict[str, ArrayType]) -> None:
+        self.p = self.opt.parameters.dict2vec(p)
+        self._p_dict = self.opt.parameters.vec2dict(self.p)
+
+    @abstractmethod
+    def _solve(self) -> CasADiArrayType:
+        pass
+
+    def _with_full_states(self, solution: Dict, p_dict: Dict, zeros, take_rows) -> Dict:
+        """Add ``name/q`` entries rebuilt from ``name/q/x`` and ``name/q/p`` (ref :137-155)."""
+        for model in self.opt.models or []:
+            for d in model.time_derivs:
+                full, opt_name = model.state_name(d), model.state_optimized_name(d)
+                if isinstance(model, RobotModel) and model.num_param_joints > 0:
+                    par_name = model.state_parameter_name(d)
+                    merged = zeros(model.dim, solution[opt_name])
+                    take_rows(merged, model.optimized_joint_indexes, solution[opt_name])
+                    take_rows(merged, model.parameter_joint_indexes, p_dict[par_name])
+                    solution[full] = merged
+                else:
+                    solution[full] = solution[opt_name]
+        return solution
+
+    def solve(self) -> Dict[str, CasADiArrayType]:
+        solution = self.opt.decision_variables.vec2dict(self._solve())
+        if self._error_on_fail and not self.did_solve():
+            raise RuntimeError("Solver failed!")
+
+        def zeros(dim, like):
+            return cs.DM.zeros(dim, like.shape[1])
+
+        def take_rows(dst, rows, src):
+            dst[rows, :] = src
+
+        return self._with_full_states(solution, self._p_dict, zeros, take_rows)
+
+    @abstractmethod
+    def stats(self):
+        pass
+
+    @abstractmethod
+    def did_solve(self) -> bool:
+        pass
+
+    @abstractmethod
+    def number_of_iterations(self) -> int:
+        pass
+
+    # -- diagnostics (ref :167-314) -----------------------------------------------------------
+    def violated_constraints(self, x: Dict[str, ArrayType], p: Dict[str, ArrayType]) -> Tuple:
+        xv = self.opt.decision_variables.dict2vec(x)
+        pv = self.opt.parameters.dict2vec(p)
+
+        @dataclass
+        class ViolatedConstraint:
+            label: str
+            ctype: str
+            diff: cs.DM
+            pattern: cs.DM
+
+            def __str__(self):
+                return f"\n{self.label} [{self.ctype}]:\n{self.pattern}\n"
+
+            def __repr__(self):
+                info = str(self)
+                width = max(len(line) for line in info.split("\n"))
+                return "=" * width + info + "-" * width + "\n"
+
+            @property
+            def verbose_info(self):
+                return str(self) + f"{self.diff}\n"
+
+        def family(container, ctype) -> List:
+            out = []
+            for label, expr in container.items():
+                diff = cs.Function("fun", [self.opt.x, self.opt.p], [expr])(xv, pv)
+                out.append(ViolatedConstraint(label, ctype, diff, diff >= 0.0))
+            return out
+
+        return (family(self.opt.lin_eq_constraints, "lin_eq"), family(self.opt.eq_constraints, "eq"),
+                family(self.opt.lin_ineq_constraints, "lin_ineq"), family(self.opt.ineq_constraints, "ineq"))
+
+    @staticmethod
+    def interpolate(traj: cs.DM, T: float, **interp_args):
+        from scipy.interpolate import interp1d
+
+        assert isinstance(traj, cs.DM), f"traj is incorrect type, got '{type(traj)}', expected casadi.DM'"
+        return interp1d(np.linspace(0, T, traj.shape[1]), traj.toarray(), **interp_args)
+
+    def evaluate_cost(self, x: Dict[str, ArrayType], p: Dict[str, ArrayType]) -> CasADiArrayType:
+        return self.opt.f(self.opt.decision_variables.dict2vec(x), self.opt.parameters.dict2vec(p))
+
+    def evaluate_cost_terms(self, x: Dict[str, ArrayType], p: Dict[str, ArrayType]) -> List:
+        xv = self.opt.decision_variables.dict2vec(x)
+        pv = self.opt.parameters.dict2vec(p)
+        return [cs.Function("fun", [self.opt.x, self.opt.p], [expr])(xv, pv) for expr in self.opt.cost_terms.values()]
+
+
+# ----------------------------------------------------------------------------------------------
+# batched marshalling: dict of (possibly batched) arrays <-> [B, n] row-major matrix
+# ----------------------------------------------------------------------------------------------
+
+
+def _as_numpy(v) -> np.ndarray:
+    if isinstance(v, (cs.DM,)):
+        return v.toarray()
+    if isinstance(v, cs.SX):
+        return cs.DM(v).toarray()
+    if hasattr(v, "detach") and hasattr(v, "cpu"):  # torch tensor
+        return v.detach().cpu().numpy()
+    return np.asarray(v, dtype=float)
+
+
+def _batch_of(value: np.ndarray, m: int, n: int) -> Optional[int]:
+    """Batch size carried by ``value`` for an m x n label, or None when it is one instance."""
+    if value.ndim == 3:
+        return int(value.shape[0])
+    if value.ndim == 2 and value.shape != (m, n) and value.size != m * n and value.shape[1] == m * n:
+        return int(value.shape[0])
+    return None
+
+
+def pack_batch(container, d: Dict[str, ArrayType]) -> Tuple[np.ndarray, Optional[int]]:
+    """Vectorised ``SXContainer.dict2vec`` (ref sx_container.py:113-123) over a batch.
+
+    Returns ``(M, B)``: ``M`` is ``[B or 1, numel]`` float64 C-contiguous, every row the
+    column-major flattening ``vec()`` layout of one instance; ``B`` is None when no value was batched.
+    """
+    layout = container.offsets()
+    total = container.numel()
+    values, B = {}, None
+    for label, (off, m, n) in layout.items():
+        if label not in d or d[label] is None:
+            continue
+        v = _as_numpy(d[label])
+        b = _batch_of(v, m, n)
+        if b is not None:
+            if B is not None and b != B:
+                raise ValueError(f"'{label}': batch size {b} does not match {B}")
+            B = b
+        values[label] = (v, b)
+    out = np.zeros((B or 1, total))
+    for label, (v, b) in values.items():
+        off, m, n = layout[label]
+        if m * n == 0:
+            continue
+        if b is None:
+            if v.size != m * n:
+                raise ValueError(f"'{label}': expected {m * n} elements, got {v.size}")
+            flat = v.reshape(-1, order="F") if v.ndim == 2 else v.reshape(-1)
+            out[:, off:off + m * n] = flat[None, :]
+        elif v.ndim == 3:
+            if v.shape[1:] != (m, n):
+                raise ValueError(f"'{label}': expected [B, {m}, {n}], got {list(v.shape)}")
+            out[:, off:off + m * n] = v.transpose(0, 2, 1).reshape(B, m * n)
+        else:
+            out[:, off:off + m * n] = v
+    return out, B
+
+
+def unpack_batch(container, M: np.ndarray) -> Dict[str, np.ndarray]:
+    """Vectorised ``vec2dict``: ``[B, numel]`` -> label -> ``[B, m, n]``."""
+    out = {}
+    B = M.shape[0]
+    for label, (off, m, n) in container.offsets().items():
+        out[label] = M[:, off:off + m * n].reshape(B, n, m).transpose(0, 2, 1)
+    return out
+
+
+# ----------------------------------------------------------------------------------------------
+# the B200 back-end
+# ----------------------------------------------------------------------------------------------
+
+_NLP_NAMES = {"ipopt", "knitro", "snopt", "worhp", "scpgen", "sqpmethod", "b200"}
+_QP_NAMES = {"cplex", "gurobi", "ooqp", "qpoases", "sqic", "nlp", "osqp", "cvxopt"}
+_MI_NAMES = {"bonmin", "knitro"}
+_SCIPY_CONSTRAINED = {"COBYLA", "SLSQP", "trust-constr"}
+_SCIPY_METHODS = {"Nelder-Mead", "Powell", "CG", "BFGS", "Newton-CG", "L-BFGS-B", "TNC", "COBYLA", "SLSQP",
+                  "trust-constr", "dogleg", "trust-ncg", "trust-exact", "trust-krylov"}
+
+
+class B200Solver(Solver):
+    """Batched interior-point / Newton-KKT solver on B200 (libb200optas.so) behind the OpTaS API.
+
+    ``setup`` accepts both reference spellings:
+      * ``setup("ipopt", {"ipopt.max_iter": 100, ...})``  (CasADiSolver.setup, ref :333)
+      * ``setup(method="SLSQP", tol=1e-6, options={"maxiter": 100})``  (ScipyMinimizeSolver.setup, ref :619)
+    The solver name / method selects nothing but option parsing: every problem class runs the
+    same fused GPU kernel.  Returns ``self``.
+    """
+
+    def __init__(self, optimization: Optimization, error_on_fail: bool = False):
+        super().__init__(optimization, error_on_fail)
+        self._handle = None
+        self._lowered: Optional[LoweredProblem] = None
+        self._stats: Optional[Dict] = None
+        self._batch: Optional[int] = None
+        self._X0 = np.zeros((1, optimization.nx))
+        self._P = np.zeros((1, optimization.np))
+        self._x0_batched = self._p_batched = None
+
+    # -- setup --------------------------------------------------------------------------------
+    def setup(self, solver_name: Optional[str] = None, solver_options: Optional[Dict] = None, *,
+              method: Optional[str] = None, tol: Optional[float] = None, options: Optional[Dict] = None,
+              compile_only: bool = False, timing: bool = False, threads_per_block: int = 0):
+        from . import _capi
+
+        name = solver_name if solver_name is not None else (method if method is not None else "ipopt")
+        solver_options = dict(solver_options or {})  # never mutate the caller's dict
+        if name in _SCIPY_METHODS:
+            # ScipyMinimizeSolver.setup semantics (ref :619-639)
+            if self.opt_type in CONSTRAINED_OPT and name not in _SCIPY_CONSTRAINED:
+                raise TypeError(f"optimization problem has constraints, the method '{name}' is not suitable")
+        elif name not in _NLP_NAMES | _QP_NAMES | _MI_NAMES:
+            raise ValueError(f"solver '{name}' does not support this problem type")
+        if self.opt.has_discrete_variables() or isinstance(self.opt, MixedIntegerNonlinearCostNonlinearConstrained):
+            raise NotImplementedError("mixed-integer problems are out of scope for the B200 back-end")
+
+        max_iter, acc_tol, mu_init = 0, 0.0, 0.0
+        tol_use = float(tol) if tol is not None else 0.0
+        for key, val in solver_options.items():
+            leaf = key.split(".")[-1]
+            if leaf == "max_iter":
+                max_iter = int(val)
+            elif leaf == "tol":
+                tol_use = float(val)
+            elif leaf == "acceptable_tol":
+                acc_tol = float(val)
+            elif leaf == "mu_init":
+                mu_init = float(val)
+        for key, val in (options or {}).items():
+            if key == "maxiter":
+                max_iter = int(val)
+            elif key in ("ftol", "gtol", "xtol") and tol is None:
+                pass  # scipy's per-method tolerances have no KKT-error equivalent; `tol` is honoured
+
+        self._lowered = lower_problem(self.opt)
+        flags = (_capi.BO_FLAG_COMPILE_ONLY if compile_only else 0) | (_capi.BO_FLAG_TIMING if timing else 0)
+        self._handle = _capi.ProblemHandle(self._lowered, flags=flags, max_iter=max_iter, tol=tol_use,
+                                           acceptable_tol=acc_tol, mu_init=mu_init,
+                                           threads_per_block=threads_per_block)
+        self._stats = None
+        return self
+
+    # -- inputs -------------------------------------------------------------------------------
+    def reset_initial_seed(self, x0: Dict[str, ArrayType]) -> None:
+        self._X0, self._x0_batched = pack_batch(self.opt.decision_variables, x0)
+        self.x0 = cs.DM(self._X0[0])
+
+    def reset_parameters(self, p: Dict[str, ArrayType]) -> None:
+        self._P, self._p_batched = pack_batch(self.opt.parameters, p)
+        self.p = cs.DM(self._P[0])
+        self._p_dict = self.opt.parameters.vec2dict(self.p)
+
+    # -- raw batched call (numpy or torch tensors, host or device) ---------------------------
+    def solve_raw(self, P, X0, X, lam=None, f=None, status=None, iters=None, kkt=None, stream: int = 0) -> None:
+        """Direct ``bo_solve``: ``P [B, np]``, ``X0 [B, nx]`` (or None), ``X [B, nx]`` out, all float64
+        C-contiguous; numpy arrays (host) or torch tensors (host or cuda).  No copies are made here."""
+        if self._handle is None:
+            raise RuntimeError("call setup() first")
+        B = int(X.shape[0])
+        self._handle.solve(B, P, X0, X, lam, f, status, iters, kkt, stream)
+
+    # -- solve --------------------------------------------------------------------------------
+    def _run(self) -> np.ndarray:
+        if self._handle is None:
+            raise RuntimeError("call setup() first")
+        B = self._x0_batched or self._p_batched
+        if self._x0_batched and self._p_batched and self._x0_batched != self._p_batched:
+            raise ValueError(f"seed batch {self._x0_batched} != parameter batch {self._p_batched}")
+        self._batch = B
+        n = B or 1
+        X0 = np.ascontiguousarray(np.broadcast_to(self._X0, (n, self.opt.nx)))
+        P = np.ascontiguousarray(np.broadcast_to(self._P, (n, self.opt.np)))
+        lo = self._lowered
+        X = np.empty((n, lo.nx))
+        lam = np.empty((n, lo.n_eq + lo.n_ineq))
+        f = np.empty(n)
+        status = np.empty(n, dtype=np.int32)
+        iters = np.empty(n, dtype=np.int32)
+        kkt = np.empty(n)
+        self._handle.solve(n, P if lo.np_ else None, X0, X, lam, f, status, iters, kkt)
+        ok = status <= 1
+        self._stats = {
+            "success": bool(ok.all()),
+            "iter_count": int(iters.max()),
+            "return_status": "Solve_Succeeded" if ok.all() else "Solve_Failed",
+            "n_instances": n,
+            "n_converged": int(ok.sum()),
+            "status": status,
+            "iterations": iters,
+            "kkt_error": kkt,
+            "solution": {"x": X if B else cs.DM(X[0]), "f": f if B else cs.DM(f[0]),
+                         "lam_eq": lam[:, :lo.n_eq], "lam_ineq": lam[:, lo.n_eq:]},
+        }
+        self._solution = self._stats["solution"]
+        return X
+
+    def _solve(self):
+        X = self._run()
+        return X if self._batch else X[0]
+
+    def solve(self) -> Dict:
+        X = self._run()
+        if self._batch is None:
+            solution = self.opt.decision_variables.vec2dict(X[0])
+            if self._error_on_fail and not self.did_solve():
+                raise RuntimeError("Solver failed!")
+
+            def zeros(dim, like):
+                return cs.DM.zeros(dim, like.shape[1])
+
+            def take_rows(dst, rows, src):
+                dst[rows, :] = src
+
+            return self._with_full_states(solution, self._p_dict, zeros, take_rows)
+
+        if self._error_on_fail and not self.did_solve():
+            raise RuntimeError("Solver failed!")
+        solution = unpack_batch(self.opt.decision_variables, X)
+        p_dict = unpack_batch(self.opt.parameters, np.broadcast_to(self._P, (X.shape[0], self.opt.np)))
+
+        def zeros(dim, like):
+            return np.zeros((like.shape[0], dim, like.shape[2]))
+
+        def take_rows(dst, rows, src):
+            dst[:, rows, :] = src
+
+        return self._with_full_states(solution, p_dict, zeros, take_rows)
+
+    # -- outcome ------------------------------------------------------------------------------
+    def stats(self) -> Dict:
+        return self._stats
+
+    def did_solve(self) -> bool:
+        return bool(self._stats["success"])
+
+    def number_of_iterations(self) -> int:
+        return int(self._stats["iter_count"])
+
+    def kernel_info(self) -> Dict:
+        return self._handle.kernel_info()
+
+    def kernel_source(self) -> str:
+        return self._handle.source()
+
+
+class CasADiSolver(B200Solver):
+    """Name-compatible drop-in for ``optas.CasADiSolver`` (ref :321-419): same constructor, same
+    ``setup(solver_name, solver_options)``; the work runs on the B200 back-end."""
+
+
+class ScipyMinimizeSolver(B200Solver):
+    """Name-compatible drop-in for ``optas.ScipyMinimizeSolver`` (ref :587-813): same constructor,
+    same ``setup(method, tol, options)``; the work runs on the B200 back-end.  (The CPU restatement
+    of the reference's scipy path lives in oracle/slsqp_driver.py and is test infrastructure.)"""
+
+    def setup(self, method: str = "SLSQP", tol: Optional[float] = None, options: Optional[Dict] = None, **kw):
+        return super().setup(method=method, tol=tol, options=options, **kw)

@@ -1,0 +1,181 @@
+"""SSA tapes: the lowered form of expression graphs that the CUDA virtual machine executes.
+
+CasADi evaluates ``Function`` objects by interpreting an instruction tape over a scalar work
+vector (the "SX virtual machine" that runs inside ``nlpsol`` on the reference path,
+reference: optas/solver.py:395 -> casadi).  This module lowers `optas_b200.sym` graphs to the
+equivalent structure for this backend:
+
+* ``instr``  int32 [n, 4] rows ``(op | c << 8, dst, a, b)``; opcodes are `sym.OP_*`.
+  - ``OP_INPUT``:  ``work[dst] = inputs[segment b][element a]``
+  - ``OP_CONST``:  ``work[dst] = consts[a]``
+  - ``OP_OUTPUT``: ``outputs[segment b][element a] = work[dst]``
+  - unary/binary:  ``work[dst] = op(work[a], work[b])``
+  - ``OP_IF_ELSE``: ``work[dst] = work[c] != 0 ? work[a] : work[b]`` (``c`` in the high bits)
+* ``consts`` float64 [n_const]
+* ``n_work`` number of work slots after liveness-based slot reuse.
+
+A tape may be split into *groups* (independent sub-tapes that each write a disjoint part of
+the outputs) so that the GPU can run one thread per (instance, group).
+"""
+
+from __future__ import annotations
+
+from dataclasses import dataclass, field
+from typing import Dict, List, Optional, Sequence
+
+import numpy as np
+
+from . import sym as S
+
+
+@dataclass
+class Tape:
+    instr: np.ndarray  # int32 [n, 4]
+    consts: np.ndarray  # float64 [n_const]
+    n_work: int
+    in_sizes: List[int]
+    out_sizes: List[int]
+    # instruction ranges of the groups: group g is instr[group_ptr[g]:group_ptr[g+1]]
+    group_ptr: np.ndarray = field(default_factory=lambda: np.zeros(2, dtype=np.int32))
+
+    @property
+    def n_instr(self) -> int:
+        return int(self.instr.shape[0])
+
+    @property
+    def n_groups(self) -> int:
+        return int(self.group_ptr.shape[0] - 1)
+
+    # ---------------------------------------------------------------------------------------
+    @staticmethod
+    def from_function(f: "S.Function") -> "Tape":
+        ins = [i.nodes() for i in f._in]
+        outs = []
+        for o in f._out:
+            outs.append(o.nodes() if isinstance(o, S.SX) else [S.const(v) for v in o._a.flatten(order="F")])
+        return Tape.lower(ins, outs)
+
+    @staticmethod
+    def lower(inputs: Sequence[Sequence[S.Node]], outputs: Sequence[Sequence[S.Node]],
+              groups: Optional[Sequence[Sequence[tuple]]] = None) -> "Tape":
+        """Lower to a tape.
+
+        inputs:  per input segment, the list of symbol nodes (position = element index).
+        outputs: per output segment, the list of nodes to store.
+        groups:  optional partition of the outputs: a list of groups, each a list of
+                 ``(segment, element)`` pairs.  Default: one group holding everything.
+        """
+        in_pos: Dict[int, tuple] = {}
+        for s, seg in enumerate(inputs):
+            for e, nd in enumerate(seg):
+                if nd.op != S.OP_SYM:
+                    raise ValueError("tape inputs must be symbols")
+                in_pos[nd.idx] = (s, e)
+        if groups is None:
+            groups = [[(s, e) for s, seg in enumerate(outputs) for e in range(len(seg))]]
+
+        const_index: Dict[int, int] = {}
+        consts: List[float] = []
+        rows: List[tuple] = []
+        group_ptr = [0]
+        n_work = 0
+
+        for grp in groups:
+            out_nodes = [outputs[s][e] for (s, e) in grp]
+            order = S.topo_sort(out_nodes)
+            # last use (position in `order`) of every node, outputs live until stored
+            last_use: Dict[int, int] = {}
+            for k, nd in enumerate(order):
+                for ch in (nd.a, nd.b, nd.c):
+                    if ch is not None:
+                        last_use[ch.idx] = k
+            stores: Dict[int, List[tuple]] = {}
+            for (s, e), nd in zip(grp, out_nodes):
+                stores.setdefault(nd.idx, []).append((s, e))
+            slot_of: Dict[int, int] = {}
+            free: List[int] = []
+            high = 0
+            for k, nd in enumerate(order):
+                # operands' slots (read before the destination is chosen)
+                ops = [slot_of[ch.idx] if ch is not None else 0 for ch in (nd.a, nd.b, nd.c)]
+                # release operand slots whose last use is this instruction
+                released = []
+                for ch in {c.idx: c for c in (nd.a, nd.b, nd.c) if c is not None}.values():
+                    if last_use.get(ch.idx) == k and ch.idx not in stores:
+                        released.append(slot_of[ch.idx])
+                    elif last_use.get(ch.idx) == k and ch.idx in stores:
+                        released.append(slot_of[ch.idx])  # already stored when it was produced
+                free.extend(released)
+                if free:
+                    dst = free.pop()
+                else:
+                    dst = high
+                    high += 1
+                slot_of[nd.idx] = dst
+                if nd.op == S.OP_CONST:
+                    ci = const_index.get(nd.idx)
+                    if ci is None:
+                        ci = len(consts)
+                        consts.append(nd.val)
+                        const_index[nd.idx] = ci
+                    rows.append((S.OP_CONST, dst, ci, 0))
+                elif nd.op == S.OP_SYM:
+                    if nd.idx not in in_pos:
+                        raise ValueError(f"free symbol '{nd.name}' is not an input of the tape")
+                    s, e = in_pos[nd.idx]
+                    rows.append((S.OP_INPUT, dst, e, s))
+                elif nd.op == S.OP_IF_ELSE:
+                    # node operands are (cond, then, else)
+                    rows.append((S.OP_IF_ELSE | (ops[0] << 8), dst, ops[1], ops[2]))
+                else:
+                    rows.append((nd.op, dst, ops[0], ops[1]))
+                for (s, e) in stores.get(nd.idx, ()):
+                    rows.append((S.OP_OUTPUT, dst, e, s))
+                if nd.idx not in last_use:
+                    free.append(dst)  # value is never read again (pure output)
+            n_work = max(n_work, high)
+            group_ptr.append(len(rows))
+
+        instr = np.array(rows, dtype=np.int64).reshape(-1, 4)
+        if instr.size and (instr[:, 0] >> 8).max() >= (1 << 23):
+            raise ValueError("tape too large for the if_else operand encoding")
+        return Tape(
+            instr=instr.astype(np.int32),
+            consts=np.array(consts, dtype=np.float64),
+            n_work=max(1, n_work),
+            in_sizes=[len(s) for s in inputs],
+            out_sizes=[len(s) for s in outputs],
+            group_ptr=np.array(group_ptr, dtype=np.int32),
+        )
+
+    # ---------------------------------------------------------------------------------------
+    def eval_numpy(self, inputs: Sequence[np.ndarray]) -> List[np.ndarray]:
+        """Reference interpreter.  Each input is [n] (one instance) or [n, B] (batched)."""
+        ins = [np.asarray(v, dtype=float) for v in inputs]
+        batched = any(v.ndim == 2 for v in ins)
+        B = max((v.shape[1] for v in ins if v.ndim == 2), default=1)
+        shape = (B,) if batched else ()
+        outs = [np.zeros((n,) + shape) for n in self.out_sizes]
+        work: List = [None] * self.n_work
+        UN, BI = S._NUM_UNARY, S._NUM_BINARY
+        with np.errstate(all="ignore"):
+            for op, dst, a, b in self.instr.tolist():
+                c = op >> 8
+                op &= 0xFF
+                if op == S.OP_INPUT:
+                    work[dst] = ins[b][a]
+                elif op == S.OP_CONST:
+                    work[dst] = self.consts[a]
+                elif op == S.OP_OUTPUT:
+                    outs[b][a] = work[dst]
+                elif op == S.OP_IF_ELSE:
+                    work[dst] = np.where(np.asarray(work[c]) != 0.0, work[a], work[b])
+                elif op in UN:
+                    work[dst] = UN[op](work[a])
+                else:
+                    work[dst] = BI[op](work[a], work[b])
+        return outs
+
+    def op_histogram(self) -> Dict[str, int]:
+        ops, counts = np.unique(self.instr[:, 0] & 0xFF, return_counts=True)
+        return {S.OP_NAMES.get(int(o), str(o)): int(c) for o, c in zip(ops, counts)}

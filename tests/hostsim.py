@@ -1,0 +1,77 @@
+"""Host-compiled build of the GENERATED solver source -- a test harness, not a product path.
+
+The tier-S solver template (optas_b200/csrc/jit/bo_ipm_reg.cuh) and the code generated from a
+problem's tapes are plain C++ apart from the kernel entry point, so with ``-DBO_HOST_SIM`` the very
+same text compiles with g++.  GPU-less CI uses this to exercise the solver *logic* (convergence,
+inertia correction, line search) on the exact source that NVRTC compiles for sm_100a.  Nothing in
+``optas_b200`` imports this module; ``B200Solver`` never runs on the CPU.
+"""
+
+from __future__ import annotations
+
+import ctypes as C
+import hashlib
+import os
+import subprocess
+import tempfile
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_JIT_INC = os.path.join(_HERE, "..", "optas_b200", "csrc", "jit")
+
+_WRAPPER = r"""
+#define BO_HOST_SIM 1
+#include <cstdio>
+%(trace)s
+#include "%(gen)s"
+extern "C" void hostsim_solve(long long B, const double* p, const double* x0, double* x, double* lam, double* f,
+                              int* status, int* iters, double* kkt, int max_iter, double tol, double acc_tol,
+                              double mu_init) {
+  bo_solver_params prm;
+  prm.max_iter = max_iter; prm.tol = tol; prm.acceptable_tol = acc_tol; prm.mu_init = mu_init;
+  for (long long b = 0; b < B; ++b) {
+    double pp[BO_DIM(BO_NP)], xx[BO_NX], y[BO_DIM(BO_ME)], z[BO_DIM(BO_MI)];
+    for (int i = 0; i < BO_NP; ++i) pp[i] = p[b * BO_NP + i];
+    for (int i = 0; i < BO_NX; ++i) xx[i] = x0 ? x0[b * BO_NX + i] : 0.0;
+    double ff, err; int it;
+    status[b] = bo_ipm_solve(pp, xx, y, z, prm, &ff, &it, &err);
+    for (int i = 0; i < BO_NX; ++i) x[b * BO_NX + i] = xx[i];
+    for (int j = 0; j < BO_ME; ++j) lam[b * (BO_ME + BO_MI) + j] = y[j];
+    for (int i = 0; i < BO_MI; ++i) lam[b * (BO_ME + BO_MI) + BO_ME + i] = z[i];
+    f[b] = ff; iters[b] = it; kkt[b] = err;
+  }
+}
+"""
+
+
+class HostSim:
+    def __init__(self, generated_source: str, nx: int, np_: int, n_eq: int, n_ineq: int, trace: bool = False):
+        self.nx, self.np_, self.nl = nx, np_, n_eq + n_ineq
+        key = hashlib.sha1(generated_source.encode()).hexdigest()[:16] + str(trace)
+        for name in ("bo_common.cuh", "bo_ipm_reg.cuh"):
+            key += hashlib.sha1(open(os.path.join(_JIT_INC, name), "rb").read()).hexdigest()[:8]
+        d = os.path.join(tempfile.gettempdir(), "b200optas_hostsim")
+        os.makedirs(d, exist_ok=True)
+        so = os.path.join(d, f"hostsim_{hashlib.sha1(key.encode()).hexdigest()[:16]}.so")
+        if not os.path.exists(so):
+            gen = os.path.join(d, f"gen_{os.getpid()}.cu")
+            wrap = os.path.join(d, f"wrap_{os.getpid()}.cpp")
+            open(gen, "w").write(generated_source)
+            open(wrap, "w").write(_WRAPPER % {"gen": gen, "trace": "#define BO_HOST_TRACE 1" if trace else ""})
+            subprocess.run(["/usr/bin/g++", "-O1", "-shared", "-fPIC", "-std=c++17", "-I", _JIT_INC, wrap, "-o", so + ".tmp"],
+                           check=True)
+            os.replace(so + ".tmp", so)
+        self.lib = C.CDLL(so)
+        vp = C.c_void_p
+        self.lib.hostsim_solve.argtypes = [C.c_longlong] + [vp] * 8 + [C.c_int, C.c_double, C.c_double, C.c_double]
+
+    def solve(self, P, X0, max_iter=200, tol=1e-8, acc_tol=1e-6, mu_init=0.1):
+        B = X0.shape[0]
+        P = np.ascontiguousarray(P, dtype=float)
+        X0 = np.ascontiguousarray(X0, dtype=float)
+        X = np.empty((B, self.nx)); lam = np.empty((B, max(self.nl, 1))); f = np.empty(B)
+        st = np.empty(B, dtype=np.int32); it = np.empty(B, dtype=np.int32); kkt = np.empty(B)
+        self.lib.hostsim_solve(B, P.ctypes.data, X0.ctypes.data, X.ctypes.data, lam.ctypes.data, f.ctypes.data,
+                               st.ctypes.data, it.ctypes.data, kkt.ctypes.data, max_iter, tol, acc_tol, mu_init)
+        return {"x": X, "lam": lam[:, :self.nl], "f": f, "status": st, "iters": it, "kkt": kkt}
