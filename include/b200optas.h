@@ -108,6 +108,7 @@ typedef struct bo_options {
   double tol;              /* <=0: default 1e-8  (scaled KKT error, as IPOPT's `tol`)      */
   double acceptable_tol;   /* <=0: default 1e-6                                             */
   double mu_init;          /* <=0: default 0.1   (as IPOPT's `mu_init`)                    */
+  double max_step;         /* cap on ||alpha*dx||_inf per iteration; 0: default 0.5, <0: unlimited */
   const char* cache_dir;   /* NULL: <directory of libb200optas.so>/_jitcache               */
   const char* include_dir; /* NULL: <directory of libb200optas.so>/csrc/jit                */
   int32_t threads_per_block; /* <=0: tier default                                           */

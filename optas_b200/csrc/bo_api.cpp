@@ -409,6 +409,7 @@ bo_options normalise(const bo_options* in) {
   if (!(o.tol > 0)) o.tol = 1e-8;
   if (!(o.acceptable_tol > 0)) o.acceptable_tol = 1e-6;
   if (!(o.mu_init > 0)) o.mu_init = 0.1;
+  if (o.max_step == 0.0) o.max_step = 0.5;
   return o;
 }
 
@@ -417,6 +418,7 @@ struct SolverParams {  // must match bo_solver_params in csrc/jit/bo_common.cuh
   double tol;
   double acceptable_tol;
   double mu_init;
+  double max_step;
 };
 
 }  // namespace
@@ -615,7 +617,7 @@ int bo_solve(bo_problem* pr, int64_t B, const double* p, const double* x0, doubl
   if ((rc = stage_out(kkt_res, sizeof(double), pr->d_kkt, &dkkt)) != BO_OK) return rc;
 
   long long Bll = B;
-  SolverParams prm{pr->opts.max_iter, pr->opts.tol, pr->opts.acceptable_tol, pr->opts.mu_init};
+  SolverParams prm{pr->opts.max_iter, pr->opts.tol, pr->opts.acceptable_tol, pr->opts.mu_init, pr->opts.max_step};
   void* args[] = {&Bll, &dp, &dx0, &dx, &dlam, &df, &dstat, &dit, &dkkt, &prm};
   const unsigned grid = (unsigned)((B + pr->tpb - 1) / pr->tpb);
   size_t slot = 0;

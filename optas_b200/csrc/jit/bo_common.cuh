@@ -42,6 +42,7 @@ struct bo_solver_params {
   double tol;
   double acceptable_tol;
   double mu_init;
+  double max_step;  // <= 0: unlimited
 };
 
 // per-instance status codes (mirror bo_instance_status in include/b200optas.h)

@@ -34,10 +34,9 @@
 // inertia; returns false if a pivot block is numerically singular.
 BO_DEVICE bool bo_bk_factor(double* BO_RESTRICT A, int* BO_RESTRICT ipiv, int* n_neg_out) {
   const double alpha = 0.6403882032022076;  // (1 + sqrt(17)) / 8
-  double amax = 0.0;
-  for (int i = 0; i < BO_NK; ++i)
-    for (int j = 0; j <= i; ++j) amax = fmax(amax, fabs(A[BO_KIDX(i, j)]));
-  const double tiny = 1e-14 * fmax(amax, 1e-300);
+  // Like LAPACK, only an exactly (here: denormal-small) zero pivot is "singular"; near-singular
+  // systems show up as a wrong inertia count and are handled by the caller's regularisation.
+  const double tiny = 1e-250;
   int n_neg = 0;
   bool ok = true;
   int k = 0;
@@ -239,8 +238,40 @@ BO_DEVICE int bo_ipm_solve(const double* BO_RESTRICT p, double* BO_RESTRICT x, d
   BO_UNROLL
   for (int j = 0; j < BO_ME; ++j) y[j] = 0.0;
 
+  bool recalc_y = false;
   for (it = 0;; ++it) {
     bo_tape_kkt(x, p, y, z, &f, g, cE, cI, JE, JI, H);
+    if (recalc_y && BO_ME > 0) {
+      // The last step needed Hessian convexification (dw > 0): its Newton multipliers scale with dw
+      // and feed back into the Hessian.  Replace y by the least-squares estimate
+      //   [ I  JE' ; JE  -dc ] [ r ; y ] = [ grad f - JI' z ; 0 ]
+      // and re-evaluate the Hessian with it.
+      recalc_y = false;
+      BO_UNROLL
+      for (int i = 0; i < BO_DIM(BO_NNZ_H); ++i) H[i] = 0.0;
+      BO_UNROLL
+      for (int i = 0; i < BO_MI; ++i) sigma[i] = 0.0;
+      bo_kkt_fill(H, JE, JI, sigma, K);
+      if (bo_kkt_factor(K, 1.0, 1e-10, LD, ipiv) == 0) {
+        double nz[BO_DIM(BO_MI)];
+        BO_UNROLL
+        for (int i = 0; i < BO_MI; ++i) nz[i] = -z[i];
+        BO_UNROLL
+        for (int i = 0; i < BO_NX; ++i) sol[i] = g[i];
+        bo_JIt_acc(JI, nz, sol);
+        BO_UNROLL
+        for (int j = 0; j < BO_ME; ++j) sol[BO_NX + j] = 0.0;
+        bo_bk_solve(LD, ipiv, sol);
+        bool fin = true;
+        BO_UNROLL
+        for (int j = 0; j < BO_ME; ++j) fin = fin && bo_isfinite(sol[BO_NX + j]);
+        if (fin) {
+          BO_UNROLL
+          for (int j = 0; j < BO_ME; ++j) y[j] = sol[BO_NX + j];
+        }
+      }
+      bo_tape_kkt(x, p, y, z, &f, g, cE, cI, JE, JI, H);
+    }
 
     // ---- residuals and the scaled optimality error (IPOPT's E_mu, Waechter & Biegler eq. 5) ----
     BO_UNROLL
@@ -388,6 +419,14 @@ BO_DEVICE int bo_ipm_solve(const double* BO_RESTRICT p, double* BO_RESTRICT x, d
       for (int i = 0; i < BO_MI; ++i) dphi -= mu * ds[i] / s[i];
 
       double a = a_p;
+      if (prm.max_step > 0.0) {
+        // step-length cap (cf. SNOPT's "major step limit"): Newton steps of several radians through
+        // trigonometric kinematics are meaningless and wreck the multipliers
+        double dxn = 0.0;
+        BO_UNROLL
+        for (int i = 0; i < BO_NX; ++i) dxn = fmax(dxn, fabs(dx[i]));
+        if (a * dxn > prm.max_step) a = prm.max_step / dxn;
+      }
       for (int ls = 0; ls < 40 && !accepted; ++ls) {
         BO_UNROLL
         for (int i = 0; i < BO_NX; ++i) xt[i] = x[i] + a * dx[i];
@@ -504,6 +543,7 @@ BO_DEVICE int bo_ipm_solve(const double* BO_RESTRICT p, double* BO_RESTRICT x, d
     }
     BO_UNROLL
     for (int j = 0; j < BO_ME; ++j) y[j] += a_used * y_step[j];
+    recalc_y = dw > 0.0;
   }
   *f_out = f;
   *iters_out = it;

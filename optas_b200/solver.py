@@ -272,7 +272,7 @@ class B200Solver(Solver):
         if self.opt.has_discrete_variables() or isinstance(self.opt, MixedIntegerNonlinearCostNonlinearConstrained):
             raise NotImplementedError("mixed-integer problems are out of scope for the B200 back-end")
 
-        max_iter, acc_tol, mu_init = 0, 0.0, 0.0
+        max_iter, acc_tol, mu_init, max_step = 0, 0.0, 0.0, 0.0
         tol_use = float(tol) if tol is not None else 0.0
         for key, val in solver_options.items():
             leaf = key.split(".")[-1]
@@ -284,6 +284,8 @@ class B200Solver(Solver):
                 acc_tol = float(val)
             elif leaf == "mu_init":
                 mu_init = float(val)
+            elif leaf == "max_step":
+                max_step = float(val)
         for key, val in (options or {}).items():
             if key == "maxiter":
                 max_iter = int(val)
@@ -293,7 +295,7 @@ class B200Solver(Solver):
         self._lowered = lower_problem(self.opt)
         flags = (_capi.BO_FLAG_COMPILE_ONLY if compile_only else 0) | (_capi.BO_FLAG_TIMING if timing else 0)
         self._handle = _capi.ProblemHandle(self._lowered, flags=flags, max_iter=max_iter, tol=tol_use,
-                                           acceptable_tol=acc_tol, mu_init=mu_init,
+                                           acceptable_tol=acc_tol, mu_init=mu_init, max_step=max_step,
                                            threads_per_block=threads_per_block)
         self._stats = None
         return self

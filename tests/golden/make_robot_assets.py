@@ -1,0 +1,62 @@
+"""Derive kinematics-only robot descriptions from the reference's URDF files.
+
+Run in the build container only (reads /root/reference, which does not exist on the GPU box):
+
+    python tests/golden/make_robot_assets.py
+
+For each robot the config scripts use (KUKA LWR for C1/C2/C5, LBR Med7 for
+C4) it parses the reference URDF with this repo's reader and re-emits ONLY what forward kinematics
+needs -- joint name / type / parent / child / origin / axis / limits -- as a minimal URDF under
+optas_b200/robots/.  Meshes, inertias, visuals, collision geometry, transmissions and gazebo tags
+are dropped.  The numbers are printed with repr() so they round-trip exactly; tests/test_models.py
+checks that FK on the derived file is bit-identical to FK on the original when that is present.
+"""
+
+import os
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, ROOT)
+
+from optas_b200.urdf import URDF  # noqa: E402
+
+REF = "/root/reference/example/robots"
+SOURCES = {
+    "kuka_lwr.urdf": os.path.join(REF, "kuka_lwr", "kuka_lwr.urdf"),
+    "med7.urdf": os.path.join(REF, "kuka_lbr", "med7.urdf"),
+}
+
+
+def fmt(vals):
+    return " ".join(repr(float(v)) for v in vals)
+
+
+def emit(urdf: URDF) -> str:
+    out = ['<?xml version="1.0"?>',
+           "<!-- kinematics-only description derived by tests/golden/make_robot_assets.py -->",
+           f'<robot name="{urdf.name}">']
+    for link in urdf.links:
+        out.append(f'  <link name="{link.name}"/>')
+    for j in urdf.joints:
+        out.append(f'  <joint name="{j.name}" type="{j.type}">')
+        out.append(f'    <parent link="{j.parent}"/>')
+        out.append(f'    <child link="{j.child}"/>')
+        if j.origin is not None:
+            out.append(f'    <origin xyz="{fmt(j.origin.xyz)}" rpy="{fmt(j.origin.rpy)}"/>')
+        if j.axis is not None:
+            out.append(f'    <axis xyz="{fmt(j.axis)}"/>')
+        if j.limit is not None:
+            out.append(f'    <limit lower="{j.limit.lower!r}" upper="{j.limit.upper!r}" '
+                       f'velocity="{j.limit.velocity!r}" effort="{j.limit.effort!r}"/>')
+        out.append("  </joint>")
+    out.append("</robot>")
+    return "\n".join(out) + "\n"
+
+
+if __name__ == "__main__":
+    for name, src in SOURCES.items():
+        urdf = URDF.from_xml_file(src)
+        dst = os.path.join(ROOT, "optas_b200", "robots", name)
+        with open(dst, "w") as fh:
+            fh.write(emit(urdf))
+        print(f"{src} -> {dst}: {len(urdf.links)} links, {len(urdf.joints)} joints")

@@ -27,9 +27,9 @@ _WRAPPER = r"""
 #include "%(gen)s"
 extern "C" void hostsim_solve(long long B, const double* p, const double* x0, double* x, double* lam, double* f,
                               int* status, int* iters, double* kkt, int max_iter, double tol, double acc_tol,
-                              double mu_init) {
+                              double mu_init, double max_step) {
   bo_solver_params prm;
-  prm.max_iter = max_iter; prm.tol = tol; prm.acceptable_tol = acc_tol; prm.mu_init = mu_init;
+  prm.max_iter = max_iter; prm.tol = tol; prm.acceptable_tol = acc_tol; prm.mu_init = mu_init; prm.max_step = max_step;
   for (long long b = 0; b < B; ++b) {
     double pp[BO_DIM(BO_NP)], xx[BO_NX], y[BO_DIM(BO_ME)], z[BO_DIM(BO_MI)];
     for (int i = 0; i < BO_NP; ++i) pp[i] = p[b * BO_NP + i];
@@ -46,9 +46,9 @@ extern "C" void hostsim_solve(long long B, const double* p, const double* x0, do
 
 
 class HostSim:
-    def __init__(self, generated_source: str, nx: int, np_: int, n_eq: int, n_ineq: int, trace: bool = False):
+    def __init__(self, generated_source: str, nx: int, np_: int, n_eq: int, n_ineq: int, trace: bool = False, defines: str = ""):
         self.nx, self.np_, self.nl = nx, np_, n_eq + n_ineq
-        key = hashlib.sha1(generated_source.encode()).hexdigest()[:16] + str(trace)
+        key = hashlib.sha1(generated_source.encode()).hexdigest()[:16] + str(trace) + defines
         for name in ("bo_common.cuh", "bo_ipm_reg.cuh"):
             key += hashlib.sha1(open(os.path.join(_JIT_INC, name), "rb").read()).hexdigest()[:8]
         d = os.path.join(tempfile.gettempdir(), "b200optas_hostsim")
@@ -58,20 +58,20 @@ class HostSim:
             gen = os.path.join(d, f"gen_{os.getpid()}.cu")
             wrap = os.path.join(d, f"wrap_{os.getpid()}.cpp")
             open(gen, "w").write(generated_source)
-            open(wrap, "w").write(_WRAPPER % {"gen": gen, "trace": "#define BO_HOST_TRACE 1" if trace else ""})
+            open(wrap, "w").write(_WRAPPER % {"gen": gen, "trace": ("#define BO_HOST_TRACE 1\n" if trace else "") + defines})
             subprocess.run(["/usr/bin/g++", "-O1", "-shared", "-fPIC", "-std=c++17", "-I", _JIT_INC, wrap, "-o", so + ".tmp"],
                            check=True)
             os.replace(so + ".tmp", so)
         self.lib = C.CDLL(so)
         vp = C.c_void_p
-        self.lib.hostsim_solve.argtypes = [C.c_longlong] + [vp] * 8 + [C.c_int, C.c_double, C.c_double, C.c_double]
+        self.lib.hostsim_solve.argtypes = [C.c_longlong] + [vp] * 8 + [C.c_int, C.c_double, C.c_double, C.c_double, C.c_double]
 
-    def solve(self, P, X0, max_iter=200, tol=1e-8, acc_tol=1e-6, mu_init=0.1):
+    def solve(self, P, X0, max_iter=200, tol=1e-8, acc_tol=1e-6, mu_init=0.1, max_step=0.5):
         B = X0.shape[0]
         P = np.ascontiguousarray(P, dtype=float)
         X0 = np.ascontiguousarray(X0, dtype=float)
         X = np.empty((B, self.nx)); lam = np.empty((B, max(self.nl, 1))); f = np.empty(B)
         st = np.empty(B, dtype=np.int32); it = np.empty(B, dtype=np.int32); kkt = np.empty(B)
         self.lib.hostsim_solve(B, P.ctypes.data, X0.ctypes.data, X.ctypes.data, lam.ctypes.data, f.ctypes.data,
-                               st.ctypes.data, it.ctypes.data, kkt.ctypes.data, max_iter, tol, acc_tol, mu_init)
+                               st.ctypes.data, it.ctypes.data, kkt.ctypes.data, max_iter, tol, acc_tol, mu_init, max_step)
         return {"x": X, "lam": lam[:, :self.nl], "f": f, "status": st, "iters": it, "kkt": kkt}
