@@ -432,7 +432,8 @@ struct bo_problem {
   LoadedKernel kernel;
   bool loaded = false;
   int tpb = 64;
-  DevBuf d_p, d_x0, d_x, d_lam, d_f, d_status, d_iters, d_kkt;
+  DevBuf d_p, d_x0, d_x, d_lam, d_f, d_status, d_iters, d_kkt, d_counter;
+  int blocks_per_sm = 1, n_sm = 1;
   Timer timer;
 };
 
@@ -514,8 +515,15 @@ int bo_problem_create(const bo_problem_desc* desc, const bo_options* opts_in, bo
   if (!(pr->opts.flags & BO_FLAG_COMPILE_ONLY)) {
     rc = ensure_context(nullptr);
     if (rc != BO_OK) return rc;
+    CUdevice dev;
+    rc = ensure_context(&dev);
+    if (rc != BO_OK) return rc;
     rc = load_kernel(pr->compiled, "bo_solve_kernel", &pr->kernel);
     if (rc != BO_OK) return rc;
+    BO_CU(g_drv.cuDeviceGetAttribute(&pr->n_sm, CU_DEVICE_ATTRIBUTE_MULTIPROCESSOR_COUNT, dev));
+    BO_CU(g_drv.cuOccupancyMaxActiveBlocksPerMultiprocessor(&pr->blocks_per_sm, pr->kernel.fn, pr->tpb, 0));
+    if (pr->blocks_per_sm < 1) pr->blocks_per_sm = 1;
+    if ((rc = pr->d_counter.reserve(sizeof(unsigned long long))) != BO_OK) return rc;
     pr->loaded = true;
     pr->timer.enabled = (pr->opts.flags & BO_FLAG_TIMING) != 0;
   }
@@ -526,7 +534,7 @@ int bo_problem_create(const bo_problem_desc* desc, const bo_options* opts_in, bo
 int bo_problem_destroy(bo_problem* pr) {
   if (!pr) return BO_OK;
   if (pr->loaded) {
-    for (DevBuf* b : {&pr->d_p, &pr->d_x0, &pr->d_x, &pr->d_lam, &pr->d_f, &pr->d_status, &pr->d_iters, &pr->d_kkt})
+    for (DevBuf* b : {&pr->d_p, &pr->d_x0, &pr->d_x, &pr->d_lam, &pr->d_f, &pr->d_status, &pr->d_iters, &pr->d_kkt, &pr->d_counter})
       b->release();
     pr->timer.release();
     if (pr->kernel.mod) g_drv.cuModuleUnload(pr->kernel.mod);
@@ -618,8 +626,14 @@ int bo_solve(bo_problem* pr, int64_t B, const double* p, const double* x0, doubl
 
   long long Bll = B;
   SolverParams prm{pr->opts.max_iter, pr->opts.tol, pr->opts.acceptable_tol, pr->opts.mu_init, pr->opts.max_step};
-  void* args[] = {&Bll, &dp, &dx0, &dx, &dlam, &df, &dstat, &dit, &dkkt, &prm};
-  const unsigned grid = (unsigned)((B + pr->tpb - 1) / pr->tpb);
+  // persistent lanes: one wave of CTAs (multiple of the SM count), instances fetched from a counter
+  CUdeviceptr dcounter = pr->d_counter.ptr;
+  BO_CU(g_drv.cuMemsetD8Async(dcounter, 0, sizeof(unsigned long long), st));
+  void* args[] = {&Bll, &dp, &dx0, &dx, &dlam, &df, &dstat, &dit, &dkkt, &dcounter, &prm};
+  long long grid_ll = (long long)pr->n_sm * pr->blocks_per_sm;
+  const long long need = (B + pr->tpb - 1) / pr->tpb;
+  if (grid_ll > need) grid_ll = need;
+  const unsigned grid = (unsigned)grid_ll;
   size_t slot = 0;
   if ((rc = pr->timer.begin(st, &slot)) != BO_OK) return rc;
   BO_CU(g_drv.cuLaunchKernel(pr->kernel.fn, grid, 1, 1, (unsigned)pr->tpb, 1, 1, 0, st, args, nullptr));

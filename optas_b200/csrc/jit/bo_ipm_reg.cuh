@@ -201,45 +201,69 @@ BO_DEVICE void bo_measures(double f, const double* cE, const double* cI, const d
 }
 
 #define BO_NFILTER 8
+#define BO_LS_MAX 16    /* backtracking halvings per direction (alpha >= 1.5e-5 alpha_max) */
+#define BO_HEAVY_MAX 5  /* re-solves with dw = 1, 1e2, 1e4, 1e6 when no step is acceptable */
 
-// Solve one instance.  x: in = seed, out = solution.  y[BO_ME], z[BO_MI]: out multipliers.
+// Everything an instance carries from one iteration to the next.  A GPU lane owns one of these and
+// re-uses it for instance after instance (see bo_solve_kernel).
+struct bo_ipm_state {
+  double p[BO_DIM(BO_NP)], x[BO_NX], s[BO_DIM(BO_MI)], y[BO_DIM(BO_ME)], z[BO_DIM(BO_MI)];
+  double fth[BO_NFILTER], fph[BO_NFILTER];
+  double f, mu, dw_last, err0, theta_max, theta_min;
+  int nf, it, n_acceptable;
+  bool recalc_y;
+};
+
+// Start an instance: S.p and S.x hold the parameters and the seed.
+BO_DEVICE void bo_ipm_init(bo_ipm_state& S, const bo_solver_params prm) {
+  double cE[BO_DIM(BO_ME)], cI[BO_DIM(BO_MI)];
+  S.mu = prm.mu_init;
+  S.dw_last = 0.0;
+  S.err0 = BO_INF;
+  S.theta_max = BO_INF;
+  S.theta_min = 0.0;
+  S.nf = 0;
+  S.it = 0;
+  S.n_acceptable = 0;
+  S.recalc_y = false;
+  bo_tape_fc(S.x, S.p, &S.f, cE, cI);
+  BO_UNROLL
+  for (int i = 0; i < BO_MI; ++i) {
+    S.s[i] = fmax(cI[i], 1e-2 * fmax(1.0, fabs(cI[i])));
+    S.z[i] = S.mu / S.s[i];
+  }
+  BO_UNROLL
+  for (int j = 0; j < BO_ME; ++j) S.y[j] = 0.0;
+}
+
+// One interior-point iteration.  Returns -1 to continue, or the final BO_ST_* status.
 //
 // Globalisation is IPOPT's filter line search (Waechter & Biegler 2006, section 2.3, with their
 // default constants) on the pair (theta = ||c||_1, phi = barrier objective), plus a second-order
 // correction for the first trial step.  IPOPT's restoration phase is replaced by re-solving the
 // step with a heavily convexified Hessian (dw -> large turns the step into the minimum-norm
 // feasibility step), accepted on constraint-violation decrease.
-BO_DEVICE int bo_ipm_solve(const double* BO_RESTRICT p, double* BO_RESTRICT x, double* BO_RESTRICT y,
-                           double* BO_RESTRICT z, const bo_solver_params prm, double* f_out, int* iters_out,
-                           double* err_out) {
+BO_DEVICE int bo_ipm_iterate(bo_ipm_state& S, const bo_solver_params prm) {
   const double kappa_eps = 10.0, kappa_mu = 0.2, theta_mu = 1.5, tau_min = 0.99, s_max = 100.0;
   const double kappa_sigma = 1e10, gamma_theta = 1e-5, gamma_phi = 1e-5, eta_phi = 1e-8;
   const double s_phi = 2.3, s_theta = 1.1, kappa_soc = 0.99;
   const double mu_min = prm.tol * 0.1;
 
-  double s[BO_DIM(BO_MI)], cE[BO_DIM(BO_ME)], cI[BO_DIM(BO_MI)];
+  double *const p = S.p, *const x = S.x, *const s = S.s, *const y = S.y, *const z = S.z;
+  double *const fth = S.fth, *const fph = S.fph;
+  double &f = S.f, &mu = S.mu, &dw_last = S.dw_last, &err0 = S.err0, &theta_max = S.theta_max, &theta_min = S.theta_min;
+  int &nf = S.nf, &n_acceptable = S.n_acceptable;
+  bool& recalc_y = S.recalc_y;
+  const int it = S.it;
+
+  double cE[BO_DIM(BO_ME)], cI[BO_DIM(BO_MI)];
   double g[BO_NX], JE[BO_DIM(BO_NNZ_JE)], JI[BO_DIM(BO_NNZ_JI)], H[BO_DIM(BO_NNZ_H)];
   double K[BO_KSZ], LD[BO_KSZ], sol[BO_NK];
   int ipiv[BO_NK];
   double dx[BO_NX], ds[BO_DIM(BO_MI)], dz[BO_DIM(BO_MI)], sigma[BO_DIM(BO_MI)];
   double xt[BO_NX], st[BO_DIM(BO_MI)], cEt[BO_DIM(BO_ME)], cIt[BO_DIM(BO_MI)], rd[BO_NX];
   double rE[BO_DIM(BO_ME)], rI[BO_DIM(BO_MI)];  // constraint residuals the step is asked to remove
-  double fth[BO_NFILTER], fph[BO_NFILTER];
-  int nf = 0;
-  double f = 0.0, mu = prm.mu_init, dw_last = 0.0, err0 = BO_INF, theta_max = BO_INF, theta_min = 0.0;
-  int status = BO_ST_MAX_ITER, it = 0, n_acceptable = 0;
-
-  bo_tape_fc(x, p, &f, cE, cI);
-  BO_UNROLL
-  for (int i = 0; i < BO_MI; ++i) {
-    s[i] = fmax(cI[i], 1e-2 * fmax(1.0, fabs(cI[i])));
-    z[i] = mu / s[i];
-  }
-  BO_UNROLL
-  for (int j = 0; j < BO_ME; ++j) y[j] = 0.0;
-
-  bool recalc_y = false;
-  for (it = 0;; ++it) {
+  {
     bo_tape_kkt(x, p, y, z, &f, g, cE, cI, JE, JI, H);
     if (recalc_y && BO_ME > 0) {
       // The last step needed Hessian convexification (dw > 0): its Newton multipliers scale with dw
@@ -307,11 +331,11 @@ BO_DEVICE int bo_ipm_solve(const double* BO_RESTRICT p, double* BO_RESTRICT x, d
     printf("it %3d f %.6e err0 %.3e (dual %.3e prim %.3e comp %.3e) mu %.2e nf %d dw_last %.2e\n", it, f, err0, e_dual / s_d,
            e_prim, e_comp0 / s_c, mu, nf, dw_last);
 #endif
-    if (!bo_isfinite(err0) || !bo_isfinite(f)) { status = BO_ST_NUMERICAL; break; }
-    if (err0 <= prm.tol) { status = BO_ST_CONVERGED; break; }
+    if (!bo_isfinite(err0) || !bo_isfinite(f)) return BO_ST_NUMERICAL;
+    if (err0 <= prm.tol) return BO_ST_CONVERGED;
     n_acceptable = (err0 <= prm.acceptable_tol) ? n_acceptable + 1 : 0;
-    if (n_acceptable >= 15) { status = BO_ST_ACCEPTABLE; break; }
-    if (it >= prm.max_iter) { status = BO_ST_MAX_ITER; break; }
+    if (n_acceptable >= 15) return BO_ST_ACCEPTABLE;
+    if (it >= prm.max_iter) return BO_ST_MAX_ITER;
 
     // ---- barrier parameter update (monotone Fiacco-McCormick, IPOPT eq. 7); resets the filter ----
     if (BO_MI > 0) {
@@ -353,7 +377,7 @@ BO_DEVICE int bo_ipm_solve(const double* BO_RESTRICT p, double* BO_RESTRICT x, d
       }
       if (dw > 1e40) break;
     }
-    if (inertia != 0) { status = BO_ST_NUMERICAL; break; }
+    if (inertia != 0) return BO_ST_NUMERICAL;
     if (dw > 0.0) dw_last = dw;
 
     // current measures, filter thresholds
@@ -396,7 +420,7 @@ BO_DEVICE int bo_ipm_solve(const double* BO_RESTRICT p, double* BO_RESTRICT x, d
 
     bool accepted = false;
     double a_used = 0.0, y_step[BO_DIM(BO_ME)];
-    for (int heavy = 0; heavy < 8 && !accepted; ++heavy) {
+    for (int heavy = 0; heavy < BO_HEAVY_MAX && !accepted; ++heavy) {
       if (heavy > 0) {
         // no acceptable step: convexify harder (dw large => minimum-norm feasibility step); this
         // stands in for IPOPT's restoration phase on these small problems
@@ -427,7 +451,7 @@ BO_DEVICE int bo_ipm_solve(const double* BO_RESTRICT p, double* BO_RESTRICT x, d
         for (int i = 0; i < BO_NX; ++i) dxn = fmax(dxn, fabs(dx[i]));
         if (a * dxn > prm.max_step) a = prm.max_step / dxn;
       }
-      for (int ls = 0; ls < 40 && !accepted; ++ls) {
+      for (int ls = 0; ls < BO_LS_MAX && !accepted; ++ls) {
         BO_UNROLL
         for (int i = 0; i < BO_NX; ++i) xt[i] = x[i] + a * dx[i];
         BO_UNROLL
@@ -525,7 +549,7 @@ BO_DEVICE int bo_ipm_solve(const double* BO_RESTRICT p, double* BO_RESTRICT x, d
         if (a < 1e-12) break;
       }
     }
-    if (!accepted) { status = BO_ST_LINE_SEARCH; break; }
+    if (!accepted) return BO_ST_LINE_SEARCH;
 
     // ---- accept: primal, slack reset, duals with their own fraction-to-the-boundary step ----
     double a_d = 1.0;
@@ -545,40 +569,70 @@ BO_DEVICE int bo_ipm_solve(const double* BO_RESTRICT p, double* BO_RESTRICT x, d
     for (int j = 0; j < BO_ME; ++j) y[j] += a_used * y_step[j];
     recalc_y = dw > 0.0;
   }
-  *f_out = f;
-  *iters_out = it;
-  *err_out = err0;
+  S.it = it + 1;
+  return -1;
+}
+
+// Convenience driver for one instance (used by the host-compiled test harness).
+BO_DEVICE int bo_ipm_solve(bo_ipm_state& S, const bo_solver_params prm) {
+  bo_ipm_init(S, prm);
+  int status;
+  do {
+    status = bo_ipm_iterate(S, prm);
+  } while (status < 0);
   return status;
 }
 
 #ifndef BO_HOST_SIM
-// One thread per instance.  Global layout: row-major [B][n] (instance-major), see b200optas.h.
+// Persistent lanes with per-lane work fetching.  Iteration counts differ widely between instances
+// (mean ~17, tail > 100 on the IK workload); a one-instance-per-thread launch would idle 31 lanes of
+// a warp while its slowest instance finishes.  Instead every lane runs a small state machine:
+// fetch an instance index from a global counter, initialise, then execute ONE interior-point
+// iteration per trip round the loop; all lanes of a warp reconverge at the top of the loop, so the
+// iteration body (the expensive, straight-line part) always runs warp-wide, and a lane whose
+// instance has finished picks up the next one instead of waiting.
+// Global layout: row-major [B][n] (instance-major), see b200optas.h.
 extern "C" __global__ void __launch_bounds__(BO_TPB)
 bo_solve_kernel(long long B, const double* __restrict__ p_all, const double* __restrict__ x0_all,
                 double* __restrict__ x_all, double* __restrict__ lam_all, double* __restrict__ f_all,
                 int* __restrict__ status_all, int* __restrict__ iters_all, double* __restrict__ kkt_all,
-                const bo_solver_params prm) {
-  const long long b = (long long)blockIdx.x * BO_TPB + threadIdx.x;
-  if (b >= B) return;
-  double p[BO_DIM(BO_NP)], x[BO_NX], y[BO_DIM(BO_ME)], z[BO_DIM(BO_MI)];
-  BO_UNROLL
-  for (int i = 0; i < BO_NP; ++i) p[i] = p_all[b * BO_NP + i];
-  BO_UNROLL
-  for (int i = 0; i < BO_NX; ++i) x[i] = x0_all ? x0_all[b * BO_NX + i] : 0.0;
-  double f, err;
-  int iters;
-  const int status = bo_ipm_solve(p, x, y, z, prm, &f, &iters, &err);
-  BO_UNROLL
-  for (int i = 0; i < BO_NX; ++i) x_all[b * BO_NX + i] = x[i];
-  if (lam_all) {
-    BO_UNROLL
-    for (int j = 0; j < BO_ME; ++j) lam_all[b * (BO_ME + BO_MI) + j] = y[j];
-    BO_UNROLL
-    for (int i = 0; i < BO_MI; ++i) lam_all[b * (BO_ME + BO_MI) + BO_ME + i] = z[i];
+                unsigned long long* __restrict__ work_counter, const bo_solver_params prm) {
+  bo_ipm_state S;
+  long long b = -1;
+  bool active = false, exhausted = false;
+  while (true) {
+    if (!active && !exhausted) {
+      b = (long long)atomicAdd(work_counter, 1ULL);
+      if (b < B) {
+        BO_UNROLL
+        for (int i = 0; i < BO_NP; ++i) S.p[i] = p_all[b * BO_NP + i];
+        BO_UNROLL
+        for (int i = 0; i < BO_NX; ++i) S.x[i] = x0_all ? x0_all[b * BO_NX + i] : 0.0;
+        bo_ipm_init(S, prm);
+        active = true;
+      } else {
+        exhausted = true;
+      }
+    }
+    if (!__any_sync(0xffffffffu, active)) break;
+    if (active) {
+      const int status = bo_ipm_iterate(S, prm);
+      if (status >= 0) {
+        BO_UNROLL
+        for (int i = 0; i < BO_NX; ++i) x_all[b * BO_NX + i] = S.x[i];
+        if (lam_all) {
+          BO_UNROLL
+          for (int j = 0; j < BO_ME; ++j) lam_all[b * (BO_ME + BO_MI) + j] = S.y[j];
+          BO_UNROLL
+          for (int i = 0; i < BO_MI; ++i) lam_all[b * (BO_ME + BO_MI) + BO_ME + i] = S.z[i];
+        }
+        if (f_all) f_all[b] = S.f;
+        if (status_all) status_all[b] = status;
+        if (iters_all) iters_all[b] = S.it;
+        if (kkt_all) kkt_all[b] = S.err0;
+        active = false;
+      }
+    }
   }
-  if (f_all) f_all[b] = f;
-  if (status_all) status_all[b] = status;
-  if (iters_all) iters_all[b] = iters;
-  if (kkt_all) kkt_all[b] = err;
 }
 #endif

@@ -31,15 +31,14 @@ extern "C" void hostsim_solve(long long B, const double* p, const double* x0, do
   bo_solver_params prm;
   prm.max_iter = max_iter; prm.tol = tol; prm.acceptable_tol = acc_tol; prm.mu_init = mu_init; prm.max_step = max_step;
   for (long long b = 0; b < B; ++b) {
-    double pp[BO_DIM(BO_NP)], xx[BO_NX], y[BO_DIM(BO_ME)], z[BO_DIM(BO_MI)];
-    for (int i = 0; i < BO_NP; ++i) pp[i] = p[b * BO_NP + i];
-    for (int i = 0; i < BO_NX; ++i) xx[i] = x0 ? x0[b * BO_NX + i] : 0.0;
-    double ff, err; int it;
-    status[b] = bo_ipm_solve(pp, xx, y, z, prm, &ff, &it, &err);
-    for (int i = 0; i < BO_NX; ++i) x[b * BO_NX + i] = xx[i];
-    for (int j = 0; j < BO_ME; ++j) lam[b * (BO_ME + BO_MI) + j] = y[j];
-    for (int i = 0; i < BO_MI; ++i) lam[b * (BO_ME + BO_MI) + BO_ME + i] = z[i];
-    f[b] = ff; iters[b] = it; kkt[b] = err;
+    bo_ipm_state S;
+    for (int i = 0; i < BO_NP; ++i) S.p[i] = p[b * BO_NP + i];
+    for (int i = 0; i < BO_NX; ++i) S.x[i] = x0 ? x0[b * BO_NX + i] : 0.0;
+    status[b] = bo_ipm_solve(S, prm);
+    for (int i = 0; i < BO_NX; ++i) x[b * BO_NX + i] = S.x[i];
+    for (int j = 0; j < BO_ME; ++j) lam[b * (BO_ME + BO_MI) + j] = S.y[j];
+    for (int i = 0; i < BO_MI; ++i) lam[b * (BO_ME + BO_MI) + BO_ME + i] = S.z[i];
+    f[b] = S.f; iters[b] = S.it; kkt[b] = S.err0;
   }
 }
 """

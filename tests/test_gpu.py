@@ -1,0 +1,227 @@
+"""GPU parity tests (run with -m gpu on the B200 box).  Everything goes through the C ABI
+(libb200optas.so via optas_b200._capi); the oracle (oracle/) is only the checker.
+
+Tolerances: all arithmetic is IEEE binary64.  FK / Jacobian values must agree with the numpy
+restatement to 1e-12 absolute (a few ulp of O(1) quantities: FMA contraction and the device sincos
+differ from libm in the last bits).  Converged decision variables must agree with the oracle's
+polished solution to 1e-6 relative and have oracle KKT residual <= 1e-6 (north_star: "1e-6 rel-tol
+on decision variables and KKT residual")."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+FK_TOL = 1e-12
+X_RTOL = 1e-6
+KKT_TOL = 1e-6
+
+
+@pytest.fixture(scope="module")
+def torch_cuda():
+    import torch
+
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    torch.cuda.set_device(0)
+    return torch
+
+
+@pytest.fixture(scope="module")
+def ik(torch_cuda):
+    import optas_b200
+    from optas_b200 import problems
+
+    prob = problems.lwr_ik()
+    solver = optas_b200.B200Solver(prob.opt).setup("ipopt")
+    return prob, solver
+
+
+def _solve_host(solver, P, X0):
+    B = X0.shape[0]
+    lo = solver._lowered
+    out = dict(x=np.empty((B, lo.nx)), lam=np.empty((B, lo.n_eq + lo.n_ineq)), f=np.empty(B),
+               status=np.empty(B, dtype=np.int32), iters=np.empty(B, dtype=np.int32), kkt=np.empty(B))
+    solver.solve_raw(np.ascontiguousarray(P), np.ascontiguousarray(X0), out["x"], out["lam"], out["f"], out["status"],
+                     out["iters"], out["kkt"])
+    return out
+
+
+def test_fk_jacobian_matches_oracle_full_batch(ik):
+    import fk_ref
+    from optas_b200.function import B200Function
+
+    prob, _ = ik
+    fk = B200Function(prob.functions["fk_jac"])
+    rng = np.random.default_rng(0)
+    for B in (65536, 1000, 129, 1):  # full tiles, ragged tail, single instance
+        q = rng.uniform(-2.9, 2.9, (B, 7))
+        p, J = fk(q)
+        p_ref, J_ref = fk_ref.lwr_position_and_jacobian(q)
+        assert np.abs(p - p_ref).max() < FK_TOL
+        assert np.abs(J - J_ref).max() < FK_TOL
+
+
+def test_fk_device_pointers_and_unaligned_views(ik, torch_cuda):
+    import fk_ref
+    from optas_b200.function import B200Function
+
+    torch = torch_cuda
+    prob, _ = ik
+    fk = B200Function(prob.functions["fk_jac"])
+    B = 4096 + 37
+    q = torch.rand((B + 1, 7), dtype=torch.float64, device="cuda") * 4 - 2
+    p = torch.empty((B, 3), dtype=torch.float64, device="cuda")
+    J = torch.empty((B, 21), dtype=torch.float64, device="cuda")
+    qv = q[1:]  # starts 56 bytes into the allocation: only 8-byte aligned -> non-bulk path
+    fk.eval_raw(B, [qv], [p, J], stream=torch.cuda.current_stream().cuda_stream)
+    torch.cuda.synchronize()
+    p_ref, J_ref = fk_ref.lwr_position_and_jacobian(qv.cpu().numpy())
+    assert np.abs(p.cpu().numpy() - p_ref).max() < FK_TOL
+    assert np.abs(J.cpu().numpy() - J_ref).max() < FK_TOL
+
+
+def test_booth_known_answer(torch_cuda):
+    """Reference tests/test_solver.py:45-54, through the drop-in classes and both setup spellings."""
+    import optas_b200
+    from optas_b200 import problems
+
+    prob = problems.booth()
+    for cls, setup in ((optas_b200.CasADiSolver, lambda s: s.setup("ipopt")),
+                       (optas_b200.CasADiSolver, lambda s: s.setup("qpoases")),
+                       (optas_b200.ScipyMinimizeSolver, lambda s: s.setup(method="SLSQP", tol=1e-6))):
+        solver = setup(cls(prob.opt))
+        solver.reset_parameters({"a": 2.0, "b": 7.0})
+        solution = solver.solve()
+        assert solver.did_solve()
+        xy = solution["booth/y"].toarray().flatten()
+        assert np.isclose(xy[0], 1.0) and np.isclose(xy[1], 3.0)
+        assert solver.number_of_iterations() >= 1 and solver.stats()["success"]
+
+
+def test_c1_example_script_flow(torch_cuda):
+    """example/example.py:40-60 with the reference's seed-key quirk and with the
+    correct key; the latter must reproduce the golden q*."""
+    import optas_b200 as optas
+    from optas_b200 import problems
+
+    prob = problems.lwr_ik()
+    robot = prob.models["robot"]
+    name = robot.get_name()
+    solver = optas.CasADiSolver(prob.opt).setup("ipopt")
+    q_nominal = optas.deg2rad([0, 45, 0, -90, 0, -45, 0])
+    p_goal = robot.get_global_link_position(problems.LWR_EE, q_nominal) + optas.DM([0.0, 0.3, -0.2])
+    solver.reset_parameters({"q_nominal": q_nominal, "p_goal": p_goal})
+    solver.reset_initial_seed({f"{name}/q/x": q_nominal})
+    solution = solver.solve()
+    assert solver.did_solve()
+    q = solution[f"{name}/q"].toarray().flatten()
+    golden = np.array([-0.24904555, 1.14296583, -0.12385623, -1.29959808, 0.03860145, -0.66073211, 0.0])
+    assert np.abs(q - golden).max() < 1e-7
+    assert isinstance(solution[f"{name}/q"], optas.DM) and solution[f"{name}/q"].shape == (7, 1)
+    # the script's own (wrong) key is ignored -> seed zeros, exactly as in the reference
+    solver.reset_initial_seed({f"{name}/q": q_nominal})
+    assert not np.asarray(solver._X0).any()
+
+
+def test_c2_batch_parity_protocol(ik):
+    import kkt_check
+    import slsqp_driver
+
+    prob, solver = ik
+    B = 4096
+    P, X0 = prob.sample(B, seed=11)
+    r = _solve_host(solver, P, X0)
+    ok = r["status"] <= 1
+    assert ok.mean() >= 0.995, ok.mean()
+    lo = solver._lowered
+    idx = np.where(ok)[0][:512]
+    res = kkt_check.kkt_residual(prob, r["x"][idx], P[idx], r["lam"][idx][:, :lo.n_eq], r["lam"][idx][:, lo.n_eq:])
+    assert res.max() < KKT_TOL, res.max()
+    op = slsqp_driver.OracleProblem(prob.opt)
+    worst = 0.0
+    for i in idx[:96]:
+        pol = slsqp_driver.solve_slsqp(op, P[i], r["x"][i], form="split", options={"ftol": 1e-15, "maxiter": 200})
+        worst = max(worst, np.abs(pol.x - r["x"][i]).max() / max(1.0, np.abs(pol.x).max()))
+    assert worst < X_RTOL, worst
+
+
+def test_c2_full_size_properties(ik, torch_cuda):
+    """65536 instances: size-independent properties -- FK(q*) == p_goal (round trip through the
+    streaming kernel), joint limits, finite outputs, f == ||q* - q_nominal||^2."""
+    from optas_b200.function import B200Function
+
+    prob, solver = ik
+    B = 65536
+    P, X0 = prob.sample(B, seed=0)
+    r = _solve_host(solver, P, X0)
+    ok = r["status"] <= 1
+    assert ok.mean() >= 0.995
+    assert np.isfinite(r["x"]).all()
+    fk = B200Function(prob.functions["fk_jac"])
+    p, _ = fk(r["x"])
+    assert np.abs(p[ok] - P[ok, 7:]).max() < 1e-7
+    robot = prob.models["robot"]
+    lo = robot.lower_actuated_joint_limits.toarray().flatten()
+    up = robot.upper_actuated_joint_limits.toarray().flatten()
+    assert (r["x"][ok] >= lo - 1e-9).all() and (r["x"][ok] <= up + 1e-9).all()
+    assert np.abs(r["f"][ok] - ((r["x"][ok] - P[ok, :7]) ** 2).sum(1)).max() < 1e-9
+    assert (r["iters"][ok] <= 200).all() and (r["kkt"][ok] <= 1e-6).all()
+
+
+def test_shard_equivalence_and_device_pointers(ik, torch_cuda):
+    """Per-instance results do not depend on how the batch is sharded or where the buffers live
+    (no cross-instance arithmetic): bitwise equality."""
+    torch = torch_cuda
+    prob, solver = ik
+    B = 3000  # not a multiple of the block size
+    P, X0 = prob.sample(B, seed=21)
+    whole = _solve_host(solver, P, X0)
+    parts = [_solve_host(solver, P[a:b], X0[a:b]) for a, b in ((0, 1), (1, 1501), (1501, 3000))]
+    for key in ("x", "lam", "f", "status", "iters", "kkt"):
+        glued = np.concatenate([p[key] for p in parts])
+        assert np.array_equal(glued, whole[key]), key
+    Pd, X0d = torch.from_numpy(P).cuda(), torch.from_numpy(X0).cuda()
+    Xd = torch.empty_like(X0d)
+    st = torch.empty(B, dtype=torch.int32, device="cuda")
+    solver.solve_raw(Pd, X0d, Xd, None, None, st, None, None, stream=torch.cuda.current_stream().cuda_stream)
+    torch.cuda.synchronize()
+    assert np.array_equal(Xd.cpu().numpy(), whole["x"]) and np.array_equal(st.cpu().numpy(), whole["status"])
+
+
+def test_batched_dict_api(ik):
+    prob, solver = ik
+    B = 257
+    P, X0 = prob.sample(B, seed=4)
+    solver.reset_parameters(prob.param_dict(P))
+    solver.reset_initial_seed(prob.seed_dict(X0))
+    sol = solver.solve()
+    name = prob.models["robot"].get_name()
+    assert sol[f"{name}/q"].shape == (B, 7, 1) and sol[f"{name}/q/x"].shape == (B, 7, 1)
+    st = solver.stats()
+    assert st["status"].shape == (B,) and st["n_converged"] >= 0.99 * B
+    ref = _solve_host(solver, P, X0)
+    assert np.array_equal(sol[f"{name}/q"][:, :, 0], ref["x"])
+    # zero seed default (solver.py:76) and empty batch
+    solver.reset_initial_seed({})
+    solver.reset_parameters({"q_nominal": P[0, :7], "p_goal": P[0, 7:]})
+    one = solver.solve()
+    assert one[f"{name}/q"].shape == (7, 1)
+
+
+def test_error_on_fail(torch_cuda):
+    import optas_b200
+    from optas_b200 import problems
+
+    prob = problems.lwr_ik()
+    solver = optas_b200.B200Solver(prob.opt, error_on_fail=True).setup("ipopt")
+    p, x0 = problems.lwr_ik_example_instance()
+    solver.reset_parameters({"q_nominal": p[:7], "p_goal": [5.0, 5.0, 5.0]})
+    solver.reset_initial_seed({"kuka/q/x": x0})
+    with pytest.raises(RuntimeError, match="Solver failed!"):
+        solver.solve()
+
+
+def test_smoke_entry_point(torch_cuda):
+    import __graft_entry__
+
+    __graft_entry__.smoke()

@@ -1,0 +1,161 @@
+"""Pins the CPU oracle (oracle/) against every known answer the reference's tests hold for this
+path, and against itself (two tape interpreters, closed forms).  No GPU needed.
+
+Reference anchors replayed here:
+  tests/test_solver.py:19-54        Booth function -> x = 1, y = 3, did_solve
+  tests/test_spatialmath.py:123-129 angvec2r vs scipy Rotation.from_rotvec
+  tests/test_spatialmath.py:217-223 rpy2r (6 orders) vs scipy Rotation.from_euler
+  tests/test_spatialmath.py:415-425 quaternion product order
+  tests/test_spatialmath.py:484-489 Quaternion.fromrpy
+  tests/tester_robot.urdf:10-37     closed form eff = [2c0 + c01, 2s0 + s01, q2 + 0.5]
+"""
+import os
+
+import numpy as np
+import pytest
+from scipy.spatial.transform import Rotation as Rot
+
+import fk_ref
+import kkt_check
+import slsqp_driver
+import tape_vm
+from optas_b200 import problems
+from optas_b200.tape import Tape
+
+NUM_RANDOM = 100
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+def test_angvec2r_matches_scipy():
+    rng = np.random.default_rng(0)
+    for _ in range(NUM_RANDOM):
+        theta = rng.uniform(-2 * np.pi, 2 * np.pi)
+        v = rng.uniform(-1, 1, 3)
+        v /= np.linalg.norm(v)
+        assert np.allclose(fk_ref.angvec2r(theta, v), Rot.from_rotvec(theta * v).as_matrix())
+
+
+@pytest.mark.parametrize("opt,seq", [("zyx", "xyz"), ("vehicle", "xyz"), ("xyz", "zyx"), ("arm", "zyx"),
+                                     ("yxz", "zxy"), ("camera", "zxy")])
+def test_rpy2r_matches_scipy(opt, seq):
+    # rpy2r('zyx') = Rz(yaw) Ry(pitch) Rx(roll) = scipy extrinsic 'xyz' applied to (roll, pitch, yaw), etc.
+    rng = np.random.default_rng(1)
+    for _ in range(NUM_RANDOM):
+        rpy = rng.uniform(-np.pi, np.pi, 3)
+        assert np.allclose(fk_ref.rpy2r(rpy, opt), Rot.from_euler(seq, rpy).as_matrix())
+
+
+def test_quaternion_product_and_fromrpy_match_scipy():
+    rng = np.random.default_rng(2)
+    for _ in range(NUM_RANDOM):
+        q0, q1 = Rot.random(random_state=int(rng.integers(1 << 30))), Rot.random(random_state=int(rng.integers(1 << 30)))
+        prod = fk_ref.quat_mul(q0.as_quat(), q1.as_quat())
+        ref = (q1 * q0).as_quat()  # reference test: Rot(q1) * Rot(q0)
+        assert np.allclose(prod, ref) or np.allclose(prod, -ref)
+        rpy = rng.uniform(-np.pi, np.pi, 3)
+        q = fk_ref.quat_fromrpy(rpy)
+        ref = Rot.from_euler("xyz", rpy).as_quat()
+        assert np.allclose(q, ref) or np.allclose(q, -ref)
+
+
+def test_quaternion_chain_agrees_with_rotation_chain():
+    chain = fk_ref.lwr_chain()
+    q = np.random.default_rng(3).uniform(-2, 2, (NUM_RANDOM, 7))
+    R, _ = chain.fk(q)
+    quat = chain.quaternion(q)
+    Rq = Rot.from_quat(quat).as_matrix()
+    assert np.abs(R - Rq).max() < 1e-12
+
+
+def test_tester_robot_closed_form():
+    """FK of the reference's test robot (continuous + revolute + prismatic + fixed) has a closed form."""
+    chain = fk_ref.Chain(os.path.join(GOLDEN, "tester_robot.urdf"), "eff")
+    q = np.random.default_rng(4).uniform(-1.5, 1.5, (NUM_RANDOM, 3))
+    _, p = chain.fk(q)
+    ref = np.stack([2 * np.cos(q[:, 0]) + np.cos(q[:, 0] + q[:, 1]), 2 * np.sin(q[:, 0]) + np.sin(q[:, 0] + q[:, 1]),
+                    q[:, 2] + 0.5], axis=1)
+    assert np.abs(p - ref).max() < 1e-12
+
+
+def test_survey_golden_positions():
+    p = fk_ref.lwr_chain().fk(problems.LWR_Q_NOMINAL)[1][0]
+    assert np.allclose(p, [-0.8689143571374, 0.0, 0.3170710678119], atol=1e-12)
+    med7 = fk_ref.Chain(problems.MED7_URDF, "lbr_link_ee")
+    p = med7.fk(np.deg2rad([0, 30, 0, -90, 0, -30, 0]))[1][0]
+    assert np.allclose(p, [0.672410161513775, 0.0, 0.486410161513775], atol=1e-12)
+    quat = med7.quaternion(np.deg2rad([0, 30, 0, -90, 0, -30, 0]))[0]
+    assert np.allclose(quat, [0, 0.70710678, 0, 0.70710678], atol=1e-8)
+
+
+def test_linear_jacobian_is_the_derivative_of_position():
+    chain = fk_ref.lwr_chain()
+    q = np.random.default_rng(5).uniform(-2, 2, (8, 7))
+    p, J = chain.position_and_linear_jacobian(q)
+    h = 1e-6
+    for j in range(7):
+        dq = np.zeros(7)
+        dq[j] = h
+        num = (chain.fk(q + dq)[1] - chain.fk(q - dq)[1]) / (2 * h)
+        assert np.abs(J[:, :, j] - num).max() < 1e-8
+
+
+def test_front_end_tapes_match_the_numpy_restatement():
+    """The expression-graph FK (what the GPU kernels are generated from) against the independent
+    numpy restatement of models.py / spatialmath.py."""
+    prob = problems.lwr_ik()
+    tape = Tape.from_function(prob.functions["fk_jac"])
+    q = np.random.default_rng(6).uniform(-2.9, 2.9, (NUM_RANDOM, 7))
+    p_ref, J_ref = fk_ref.lwr_position_and_jacobian(q)
+    for vm in (tape_vm.eval_numpy, lambda t, ins: tape_vm.CTape(t)(*ins)):
+        p, J = vm(tape, [q])
+        assert np.abs(p - p_ref).max() < 1e-14
+        assert np.abs(J - J_ref).max() < 1e-14
+
+
+def test_two_tape_interpreters_agree_bitwise_on_arithmetic():
+    prob = problems.lwr_ik()
+    from optas_b200.lowering import lower_problem
+
+    lo = lower_problem(prob.opt)
+    P, X0 = prob.sample(64, seed=7)
+    rng = np.random.default_rng(7)
+    y, z = rng.normal(size=(64, lo.n_eq)), rng.uniform(0.1, 1, (64, lo.n_ineq))
+    a = tape_vm.eval_numpy(lo.kkt, [X0, P, y, z])
+    b = tape_vm.CTape(lo.kkt)(X0, P, y, z)
+    for u, v in zip(a, b):
+        assert np.abs(u - v).max() <= 1e-13 * max(1.0, np.abs(u).max())  # numpy vs libm sin/cos may differ by an ulp
+
+
+def test_slsqp_driver_booth_known_answer():
+    """tests/test_solver.py:45-54 of the reference: Booth function, a=2, b=7, seed (0,0) -> (1,3)."""
+    prob = problems.booth()
+    op = slsqp_driver.OracleProblem(prob.opt)
+    r = slsqp_driver.solve_slsqp(op, [2.0, 7.0], [0.0, 0.0], tol=1e-6)
+    assert r.success
+    assert np.isclose(r.x[0], 1.0) and np.isclose(r.x[1], 3.0)
+
+
+def test_slsqp_driver_c1_survey_golden():
+    """C1 (example/example.py) from seed q_nominal: the survey's provisional golden."""
+    prob = problems.lwr_ik()
+    op = slsqp_driver.OracleProblem(prob.opt)
+    p, x0 = problems.lwr_ik_example_instance()
+    golden = np.array([-0.24904555, 1.14296583, -0.12385623, -1.29959808, 0.03860145, -0.66073211, 0.0])
+    for form in ("v", "split"):
+        r = slsqp_driver.solve_slsqp(op, p, x0, form=form, options={"ftol": 1e-15, "maxiter": 500})
+        assert r.success
+        assert np.abs(r.x - golden).max() < 5e-8
+        assert abs(r.fun - 0.29579887518014) < 1e-10
+        assert max(kkt_check.kkt_terms(op, r.x, p).values()) < 1e-8
+
+
+def test_v_stacking_order():
+    """v = [k; g; a; -a; h; -h] (reference tests/test_optimization.py:289-292)."""
+    prob = problems.lwr_ik()
+    op = slsqp_driver.OracleProblem(prob.opt)
+    p, x0 = problems.lwr_ik_example_instance()
+    v = op.v(x0, p)
+    ci, _ = op.c_ineq(x0, p)
+    ce, _ = op.c_eq(x0, p)
+    assert np.allclose(v, np.concatenate([ci, ce, -ce]))
+    assert v.shape == (20,)
