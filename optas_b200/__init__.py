@@ -21,6 +21,7 @@ from .models import RobotModel, TaskModel, Model
 from .builder import OptimizationBuilder
 from .optimization import Optimization
 from .solver import B200Solver, CasADiSolver, ScipyMinimizeSolver, Solver
+from .nlpsol import nlpsol, qpsol
 
 __version__ = "0.1.0"
 

@@ -203,20 +203,46 @@ BO_DEVICE void bo_measures(double f, const double* cE, const double* cI, const d
 #define BO_NFILTER 8
 #define BO_LS_MAX 16    /* backtracking halvings per direction (alpha >= 1.5e-5 alpha_max) */
 #define BO_HEAVY_MAX 5  /* re-solves with dw = 1, 1e2, 1e4, 1e6 when no step is acceptable */
+#define BO_IC_MAX 60    /* inertia-correction attempts per iteration */
 
-// Everything an instance carries from one iteration to the next.  A GPU lane owns one of these and
-// re-uses it for instance after instance (see bo_solve_kernel).
+#define BO_PH_EVAL 0    /* evaluate f, grad, c, J, H at x; test convergence; assemble K */
+#define BO_PH_FACTOR 1  /* factor K + regularisation; on success compute the step */
+#define BO_PH_TRIAL 2   /* evaluate one trial point; accept / correct / backtrack */
+
+// Everything an instance carries between trips of the solver loop.  A GPU lane owns one of these
+// and re-uses it for instance after instance (see bo_solve_kernel).
+//
+// The interior-point iteration is written as a *flattened state machine*: one call of
+// bo_ipm_trip() runs at most ONE evaluation of the big tape, ONE factorisation and ONE trial-point
+// evaluation, in that order, and every data-dependent retry loop of the algorithm (inertia
+// correction, backtracking, second-order correction, convexified re-solve) is a transition that
+// takes effect on the NEXT trip instead of an inner loop.  On the GPU all lanes of a warp execute
+// trips in lock step, so the three heavy code blocks always run warp-wide: a lane that is
+// backtracking costs its neighbours nothing, it simply uses the TRIAL block of the following trip
+// while they are already in their next iteration.
 struct bo_ipm_state {
+  // instance data and iterate
   double p[BO_DIM(BO_NP)], x[BO_NX], s[BO_DIM(BO_MI)], y[BO_DIM(BO_ME)], z[BO_DIM(BO_MI)];
   double fth[BO_NFILTER], fph[BO_NFILTER];
-  double f, mu, dw_last, err0, theta_max, theta_min;
-  int nf, it, n_acceptable;
-  bool recalc_y;
+  double f, mu, tau, dw_last, err0, theta_max, theta_min;
+  int nf, it, n_acceptable, phase;
+  bool recalc_y, ls_mode;
+  // evaluation at x (valid from PH_EVAL to the end of the iteration)
+  double g[BO_NX], cE[BO_DIM(BO_ME)], cI[BO_DIM(BO_MI)], rd[BO_NX], sigma[BO_DIM(BO_MI)];
+  double JE[BO_DIM(BO_NNZ_JE)], JI[BO_DIM(BO_NNZ_JI)], H[BO_DIM(BO_NNZ_H)];
+  double K[BO_KSZ], LD[BO_KSZ];
+  int ipiv[BO_NK];
+  double phi0, theta0, dw, dc;
+  int attempt, heavy;
+  // step and line search
+  double sol[BO_NK], dx[BO_NX], ds[BO_DIM(BO_MI)], y_step[BO_DIM(BO_ME)];
+  double dx0[BO_NX], ds0[BO_DIM(BO_MI)], rE[BO_DIM(BO_ME)], rI[BO_DIM(BO_MI)];
+  double a, a_trial, dphi, th_soc;
+  int ls, soc;  // soc: 0 = plain trial, k > 0 = k-th second-order-corrected trial
 };
 
 // Start an instance: S.p and S.x hold the parameters and the seed.
 BO_DEVICE void bo_ipm_init(bo_ipm_state& S, const bo_solver_params prm) {
-  double cE[BO_DIM(BO_ME)], cI[BO_DIM(BO_MI)];
   S.mu = prm.mu_init;
   S.dw_last = 0.0;
   S.err0 = BO_INF;
@@ -226,350 +252,329 @@ BO_DEVICE void bo_ipm_init(bo_ipm_state& S, const bo_solver_params prm) {
   S.it = 0;
   S.n_acceptable = 0;
   S.recalc_y = false;
-  bo_tape_fc(S.x, S.p, &S.f, cE, cI);
+  S.ls_mode = false;
+  S.phase = BO_PH_EVAL;
+  bo_tape_fc(S.x, S.p, &S.f, S.cE, S.cI);
   BO_UNROLL
   for (int i = 0; i < BO_MI; ++i) {
-    S.s[i] = fmax(cI[i], 1e-2 * fmax(1.0, fabs(cI[i])));
+    S.s[i] = fmax(S.cI[i], 1e-2 * fmax(1.0, fabs(S.cI[i])));
     S.z[i] = S.mu / S.s[i];
   }
   BO_UNROLL
   for (int j = 0; j < BO_ME; ++j) S.y[j] = 0.0;
 }
 
-// One interior-point iteration.  Returns -1 to continue, or the final BO_ST_* status.
+// Step for the constraint residuals (S.rE, S.rI) with the current factorisation: fills S.sol
+// (dx, -dy), S.dx, S.ds and returns the fraction-to-the-boundary primal step length.
+BO_DEVICE double bo_ipm_step(bo_ipm_state& S) {
+  double tvec[BO_DIM(BO_MI)];
+  BO_UNROLL
+  for (int i = 0; i < BO_MI; ++i) tvec[i] = -(S.z[i] - S.mu / S.s[i] + S.sigma[i] * S.rI[i]);
+  BO_UNROLL
+  for (int i = 0; i < BO_NX; ++i) S.sol[i] = -S.rd[i];
+  bo_JIt_acc(S.JI, tvec, S.sol);
+  BO_UNROLL
+  for (int j = 0; j < BO_ME; ++j) S.sol[BO_NX + j] = -S.rE[j];
+  bo_bk_solve(S.LD, S.ipiv, S.sol);
+  BO_UNROLL
+  for (int i = 0; i < BO_NX; ++i) S.dx[i] = S.sol[i];
+  bo_JI_mul(S.JI, S.dx, S.ds);
+  double ap = 1.0;
+  BO_UNROLL
+  for (int i = 0; i < BO_MI; ++i) {
+    S.ds[i] += S.rI[i];
+    if (S.ds[i] < 0.0) ap = fmin(ap, -S.tau * S.s[i] / S.ds[i]);
+  }
+  return ap;
+}
+
+// One trip of the solver state machine.  Returns -1 to continue, or the final BO_ST_* status.
 //
-// Globalisation is IPOPT's filter line search (Waechter & Biegler 2006, section 2.3, with their
-// default constants) on the pair (theta = ||c||_1, phi = barrier objective), plus a second-order
-// correction for the first trial step.  IPOPT's restoration phase is replaced by re-solving the
-// step with a heavily convexified Hessian (dw -> large turns the step into the minimum-norm
-// feasibility step), accepted on constraint-violation decrease.
-BO_DEVICE int bo_ipm_iterate(bo_ipm_state& S, const bo_solver_params prm) {
+// Algorithm: primal-dual interior point with IPOPT's filter line search (Waechter & Biegler 2006,
+// section 2.3, their default constants) on (theta = ||c||_1, phi = barrier objective), second-order
+// correction of the first trial step (section 2.4), inertia-correcting regularisation (Algorithm
+// IC).  IPOPT's restoration phase is replaced by re-solving the step with a heavily convexified
+// Hessian (dw -> large turns it into the minimum-norm feasibility step).
+BO_DEVICE int bo_ipm_trip(bo_ipm_state& S, const bo_solver_params prm) {
   const double kappa_eps = 10.0, kappa_mu = 0.2, theta_mu = 1.5, tau_min = 0.99, s_max = 100.0;
   const double kappa_sigma = 1e10, gamma_theta = 1e-5, gamma_phi = 1e-5, eta_phi = 1e-8;
   const double s_phi = 2.3, s_theta = 1.1, kappa_soc = 0.99;
   const double mu_min = prm.tol * 0.1;
 
-  double *const p = S.p, *const x = S.x, *const s = S.s, *const y = S.y, *const z = S.z;
-  double *const fth = S.fth, *const fph = S.fph;
-  double &f = S.f, &mu = S.mu, &dw_last = S.dw_last, &err0 = S.err0, &theta_max = S.theta_max, &theta_min = S.theta_min;
-  int &nf = S.nf, &n_acceptable = S.n_acceptable;
-  bool& recalc_y = S.recalc_y;
-  const int it = S.it;
-
-  double cE[BO_DIM(BO_ME)], cI[BO_DIM(BO_MI)];
-  double g[BO_NX], JE[BO_DIM(BO_NNZ_JE)], JI[BO_DIM(BO_NNZ_JI)], H[BO_DIM(BO_NNZ_H)];
-  double K[BO_KSZ], LD[BO_KSZ], sol[BO_NK];
-  int ipiv[BO_NK];
-  double dx[BO_NX], ds[BO_DIM(BO_MI)], dz[BO_DIM(BO_MI)], sigma[BO_DIM(BO_MI)];
-  double xt[BO_NX], st[BO_DIM(BO_MI)], cEt[BO_DIM(BO_ME)], cIt[BO_DIM(BO_MI)], rd[BO_NX];
-  double rE[BO_DIM(BO_ME)], rI[BO_DIM(BO_MI)];  // constraint residuals the step is asked to remove
-  {
-    bo_tape_kkt(x, p, y, z, &f, g, cE, cI, JE, JI, H);
-    if (recalc_y && BO_ME > 0) {
+  // =========================== PH_EVAL ===========================
+  if (S.phase == BO_PH_EVAL) {
+    bo_tape_kkt(S.x, S.p, S.y, S.z, &S.f, S.g, S.cE, S.cI, S.JE, S.JI, S.H);
+    if (S.recalc_y && BO_ME > 0) {
       // The last step needed Hessian convexification (dw > 0): its Newton multipliers scale with dw
       // and feed back into the Hessian.  Replace y by the least-squares estimate
       //   [ I  JE' ; JE  -dc ] [ r ; y ] = [ grad f - JI' z ; 0 ]
-      // and re-evaluate the Hessian with it.
-      recalc_y = false;
+      // (factor + solve in the FACTOR block below), then re-evaluate on the next trip.
+      S.recalc_y = false;
+      S.ls_mode = true;
       BO_UNROLL
-      for (int i = 0; i < BO_DIM(BO_NNZ_H); ++i) H[i] = 0.0;
+      for (int i = 0; i < BO_DIM(BO_NNZ_H); ++i) S.H[i] = 0.0;
       BO_UNROLL
-      for (int i = 0; i < BO_MI; ++i) sigma[i] = 0.0;
-      bo_kkt_fill(H, JE, JI, sigma, K);
-      if (bo_kkt_factor(K, 1.0, 1e-10, LD, ipiv) == 0) {
-        double nz[BO_DIM(BO_MI)];
+      for (int i = 0; i < BO_MI; ++i) S.sigma[i] = 0.0;
+      bo_kkt_fill(S.H, S.JE, S.JI, S.sigma, S.K);
+      S.dw = 1.0;
+      S.dc = 1e-10;
+      S.phase = BO_PH_FACTOR;
+    } else {
+      // ---- residuals and the scaled optimality error (IPOPT's E_mu, Waechter & Biegler eq. 5) ----
+      BO_UNROLL
+      for (int i = 0; i < BO_NX; ++i) S.rd[i] = S.g[i];
+      {
+        double ny[BO_DIM(BO_ME)], nz[BO_DIM(BO_MI)];
         BO_UNROLL
-        for (int i = 0; i < BO_MI; ++i) nz[i] = -z[i];
+        for (int j = 0; j < BO_ME; ++j) ny[j] = -S.y[j];
         BO_UNROLL
-        for (int i = 0; i < BO_NX; ++i) sol[i] = g[i];
-        bo_JIt_acc(JI, nz, sol);
-        BO_UNROLL
-        for (int j = 0; j < BO_ME; ++j) sol[BO_NX + j] = 0.0;
-        bo_bk_solve(LD, ipiv, sol);
-        bool fin = true;
-        BO_UNROLL
-        for (int j = 0; j < BO_ME; ++j) fin = fin && bo_isfinite(sol[BO_NX + j]);
-        if (fin) {
-          BO_UNROLL
-          for (int j = 0; j < BO_ME; ++j) y[j] = sol[BO_NX + j];
-        }
+        for (int i = 0; i < BO_MI; ++i) nz[i] = -S.z[i];
+        bo_JEt_acc(S.JE, ny, S.rd);
+        bo_JIt_acc(S.JI, nz, S.rd);
       }
-      bo_tape_kkt(x, p, y, z, &f, g, cE, cI, JE, JI, H);
-    }
-
-    // ---- residuals and the scaled optimality error (IPOPT's E_mu, Waechter & Biegler eq. 5) ----
-    BO_UNROLL
-    for (int i = 0; i < BO_NX; ++i) rd[i] = g[i];
-    {
-      double ny[BO_DIM(BO_ME)], nz[BO_DIM(BO_MI)];
+      double e_dual = 0.0, e_prim = 0.0, e_comp0 = 0.0, sum_mult = 0.0, sum_z = 0.0;
       BO_UNROLL
-      for (int j = 0; j < BO_ME; ++j) ny[j] = -y[j];
+      for (int i = 0; i < BO_NX; ++i) e_dual = fmax(e_dual, fabs(S.rd[i]));
       BO_UNROLL
-      for (int i = 0; i < BO_MI; ++i) nz[i] = -z[i];
-      bo_JEt_acc(JE, ny, rd);
-      bo_JIt_acc(JI, nz, rd);
-    }
-    double e_dual = 0.0, e_prim = 0.0, e_comp0 = 0.0, sum_mult = 0.0, sum_z = 0.0;
-    BO_UNROLL
-    for (int i = 0; i < BO_NX; ++i) e_dual = fmax(e_dual, fabs(rd[i]));
-    BO_UNROLL
-    for (int j = 0; j < BO_ME; ++j) {
-      e_prim = fmax(e_prim, fabs(cE[j]));
-      sum_mult += fabs(y[j]);
-    }
-    BO_UNROLL
-    for (int i = 0; i < BO_MI; ++i) {
-      e_prim = fmax(e_prim, fabs(cI[i] - s[i]));
-      e_comp0 = fmax(e_comp0, s[i] * z[i]);
-      sum_z += fabs(z[i]);
-    }
-    sum_mult += sum_z;
-    const double s_d = (BO_ME + BO_MI) > 0 ? fmax(s_max, sum_mult / (double)BO_DIM(BO_ME + BO_MI)) / s_max : 1.0;
-    const double s_c = BO_MI > 0 ? fmax(s_max, sum_z / (double)BO_DIM(BO_MI)) / s_max : 1.0;
-    err0 = fmax(fmax(e_dual / s_d, e_prim), e_comp0 / s_c);
-#ifdef BO_HOST_TRACE
-    printf("it %3d f %.6e err0 %.3e (dual %.3e prim %.3e comp %.3e) mu %.2e nf %d dw_last %.2e\n", it, f, err0, e_dual / s_d,
-           e_prim, e_comp0 / s_c, mu, nf, dw_last);
-#endif
-    if (!bo_isfinite(err0) || !bo_isfinite(f)) return BO_ST_NUMERICAL;
-    if (err0 <= prm.tol) return BO_ST_CONVERGED;
-    n_acceptable = (err0 <= prm.acceptable_tol) ? n_acceptable + 1 : 0;
-    if (n_acceptable >= 15) return BO_ST_ACCEPTABLE;
-    if (it >= prm.max_iter) return BO_ST_MAX_ITER;
-
-    // ---- barrier parameter update (monotone Fiacco-McCormick, IPOPT eq. 7); resets the filter ----
-    if (BO_MI > 0) {
-      for (int rep = 0; rep < 8; ++rep) {
-        double e_comp = 0.0;
-        BO_UNROLL
-        for (int i = 0; i < BO_MI; ++i) e_comp = fmax(e_comp, fabs(s[i] * z[i] - mu));
-        const double err_mu = fmax(fmax(e_dual / s_d, e_prim), e_comp / s_c);
-        if (err_mu <= kappa_eps * mu && mu > mu_min) {
-          mu = fmax(mu_min, fmin(kappa_mu * mu, pow(mu, theta_mu)));
-          nf = 0;
-        } else {
-          break;
-        }
+      for (int j = 0; j < BO_ME; ++j) {
+        e_prim = fmax(e_prim, fabs(S.cE[j]));
+        sum_mult += fabs(S.y[j]);
       }
-    }
-    const double tau = fmax(tau_min, 1.0 - mu);
-
-    // ---- assemble and factor the reduced KKT system, with inertia correction (IPOPT Alg. IC) ----
-    BO_UNROLL
-    for (int i = 0; i < BO_MI; ++i) sigma[i] = z[i] / s[i];
-    bo_kkt_fill(H, JE, JI, sigma, K);
-    double dw = 0.0, dc = 0.0;
-    int inertia = 1;
-    for (int attempt = 0; attempt < 60; ++attempt) {
-      inertia = bo_kkt_factor(K, dw, dc, LD, ipiv);
-#ifdef BO_HOST_TRACE
-      if (inertia != 0) printf("     inertia %d at dw %.3e dc %.3e\n", inertia, dw, dc);
-#endif
-      if (inertia == 0) break;
-      if (inertia < 0 && BO_ME > 0 && dc == 0.0) {
-        dc = 1e-8 * pow(mu, 0.25);  // singular: perturb the constraint block first
-        continue;
-      }
-      if (dw == 0.0) {
-        dw = (dw_last == 0.0) ? 1e-4 : fmax(1e-20, dw_last / 3.0);
-      } else {
-        dw *= (dw_last == 0.0) ? 100.0 : 8.0;
-      }
-      if (dw > 1e40) break;
-    }
-    if (inertia != 0) return BO_ST_NUMERICAL;
-    if (dw > 0.0) dw_last = dw;
-
-    // current measures, filter thresholds
-    double phi0, theta0;
-    bo_measures(f, cE, cI, s, mu, &phi0, &theta0);
-    if (it == 0) {
-      theta_max = 1e4 * fmax(1.0, theta0);
-      theta_min = 1e-4 * fmax(1.0, theta0);
-    }
-
-    // step for given constraint residuals (rE, rI): fills sol (dx, -dy), dx, ds and returns the
-    // fraction-to-the-boundary primal step length
-    auto compute_step = [&]() -> double {
-      double tvec[BO_DIM(BO_MI)];
-      BO_UNROLL
-      for (int i = 0; i < BO_MI; ++i) tvec[i] = -(z[i] - mu / s[i] + sigma[i] * rI[i]);
-      BO_UNROLL
-      for (int i = 0; i < BO_NX; ++i) sol[i] = -rd[i];
-      bo_JIt_acc(JI, tvec, sol);
-      BO_UNROLL
-      for (int j = 0; j < BO_ME; ++j) sol[BO_NX + j] = -rE[j];
-      bo_bk_solve(LD, ipiv, sol);
-      BO_UNROLL
-      for (int i = 0; i < BO_NX; ++i) dx[i] = sol[i];
-      bo_JI_mul(JI, dx, ds);
-      double ap = 1.0;
       BO_UNROLL
       for (int i = 0; i < BO_MI; ++i) {
-        ds[i] += rI[i];
-        if (ds[i] < 0.0) ap = fmin(ap, -tau * s[i] / ds[i]);
+        e_prim = fmax(e_prim, fabs(S.cI[i] - S.s[i]));
+        e_comp0 = fmax(e_comp0, S.s[i] * S.z[i]);
+        sum_z += fabs(S.z[i]);
       }
-      return ap;
-    };
-    auto filter_ok = [&](double th, double ph) -> bool {
-      if (!(th <= theta_max)) return false;
-      for (int j = 0; j < nf; ++j)
-        if (!(th <= (1.0 - gamma_theta) * fth[j] || ph <= fph[j] - gamma_phi * fth[j])) return false;
-      return true;
-    };
+      sum_mult += sum_z;
+      const double s_d = (BO_ME + BO_MI) > 0 ? fmax(s_max, sum_mult / (double)BO_DIM(BO_ME + BO_MI)) / s_max : 1.0;
+      const double s_c = BO_MI > 0 ? fmax(s_max, sum_z / (double)BO_DIM(BO_MI)) / s_max : 1.0;
+      S.err0 = fmax(fmax(e_dual / s_d, e_prim), e_comp0 / s_c);
+#ifdef BO_HOST_TRACE
+      printf("it %3d f %.6e err0 %.3e (dual %.3e prim %.3e comp %.3e) mu %.2e nf %d dw_last %.2e\n", S.it, S.f, S.err0,
+             e_dual / s_d, e_prim, e_comp0 / s_c, S.mu, S.nf, S.dw_last);
+#endif
+      if (!bo_isfinite(S.err0) || !bo_isfinite(S.f)) return BO_ST_NUMERICAL;
+      if (S.err0 <= prm.tol) return BO_ST_CONVERGED;
+      S.n_acceptable = (S.err0 <= prm.acceptable_tol) ? S.n_acceptable + 1 : 0;
+      if (S.n_acceptable >= 15) return BO_ST_ACCEPTABLE;
+      if (S.it >= prm.max_iter) return BO_ST_MAX_ITER;
 
-    bool accepted = false;
-    double a_used = 0.0, y_step[BO_DIM(BO_ME)];
-    for (int heavy = 0; heavy < BO_HEAVY_MAX && !accepted; ++heavy) {
-      if (heavy > 0) {
-        // no acceptable step: convexify harder (dw large => minimum-norm feasibility step); this
-        // stands in for IPOPT's restoration phase on these small problems
-        dw = fmax(dw * 100.0, 1.0);
-        if (bo_kkt_factor(K, dw, dc, LD, ipiv) != 0) continue;
-      }
-      BO_UNROLL
-      for (int j = 0; j < BO_ME; ++j) rE[j] = cE[j];
-      BO_UNROLL
-      for (int i = 0; i < BO_MI; ++i) rI[i] = cI[i] - s[i];
-      const double a_p = compute_step();
-      BO_UNROLL
-      for (int i = 0; i < BO_MI; ++i) dz[i] = -z[i] + mu / s[i] - sigma[i] * ds[i];
-      BO_UNROLL
-      for (int j = 0; j < BO_ME; ++j) y_step[j] = -sol[BO_NX + j];
-      double dphi = 0.0;  // directional derivative of the barrier objective
-      BO_UNROLL
-      for (int i = 0; i < BO_NX; ++i) dphi += g[i] * dx[i];
-      BO_UNROLL
-      for (int i = 0; i < BO_MI; ++i) dphi -= mu * ds[i] / s[i];
-
-      double a = a_p;
-      if (prm.max_step > 0.0) {
-        // step-length cap (cf. SNOPT's "major step limit"): Newton steps of several radians through
-        // trigonometric kinematics are meaningless and wreck the multipliers
-        double dxn = 0.0;
-        BO_UNROLL
-        for (int i = 0; i < BO_NX; ++i) dxn = fmax(dxn, fabs(dx[i]));
-        if (a * dxn > prm.max_step) a = prm.max_step / dxn;
-      }
-      for (int ls = 0; ls < BO_LS_MAX && !accepted; ++ls) {
-        BO_UNROLL
-        for (int i = 0; i < BO_NX; ++i) xt[i] = x[i] + a * dx[i];
-        BO_UNROLL
-        for (int i = 0; i < BO_MI; ++i) st[i] = s[i] + a * ds[i];
-        double ft, phit, thetat;
-        bo_tape_fc(xt, p, &ft, cEt, cIt);
-        bo_measures(ft, cEt, cIt, st, mu, &phit, &thetat);
-        const bool finite = bo_isfinite(phit) && bo_isfinite(thetat);
-        const bool ftype = dphi < 0.0 && a * pow(-dphi, s_phi) > pow(theta0, s_theta) && theta0 <= theta_min;
-        const double slack = 10.0 * 2.2e-16 * fabs(phi0);
-        bool ok = false, armijo = false;
-        if (finite && filter_ok(thetat, phit)) {
-          if (ftype) {
-            armijo = phit - phi0 - slack <= eta_phi * a * dphi;
-            ok = armijo;
+      // ---- barrier parameter update (monotone Fiacco-McCormick, IPOPT eq. 7); resets the filter ----
+      if (BO_MI > 0) {
+        for (int rep = 0; rep < 8; ++rep) {
+          double e_comp = 0.0;
+          BO_UNROLL
+          for (int i = 0; i < BO_MI; ++i) e_comp = fmax(e_comp, fabs(S.s[i] * S.z[i] - S.mu));
+          const double err_mu = fmax(fmax(e_dual / s_d, e_prim), e_comp / s_c);
+          if (err_mu <= kappa_eps * S.mu && S.mu > mu_min) {
+            S.mu = fmax(mu_min, fmin(kappa_mu * S.mu, pow(S.mu, theta_mu)));
+            S.nf = 0;
           } else {
-            ok = thetat <= (1.0 - gamma_theta) * theta0 || phit - slack <= phi0 - gamma_phi * theta0;
+            break;
           }
         }
+      }
+      S.tau = fmax(tau_min, 1.0 - S.mu);
+      BO_UNROLL
+      for (int i = 0; i < BO_MI; ++i) S.sigma[i] = S.z[i] / S.s[i];
+      bo_kkt_fill(S.H, S.JE, S.JI, S.sigma, S.K);
+      bo_measures(S.f, S.cE, S.cI, S.s, S.mu, &S.phi0, &S.theta0);
+      if (S.it == 0) {
+        S.theta_max = 1e4 * fmax(1.0, S.theta0);
+        S.theta_min = 1e-4 * fmax(1.0, S.theta0);
+      }
+      S.dw = 0.0;
+      S.dc = 0.0;
+      S.attempt = 0;
+      S.heavy = 0;
+      S.ls_mode = false;
+      S.phase = BO_PH_FACTOR;
+    }
+  }
+
+  // =========================== PH_FACTOR ===========================
+  if (S.phase == BO_PH_FACTOR) {
+    const int inertia = bo_kkt_factor(S.K, S.dw, S.dc, S.LD, S.ipiv);
+    if (S.ls_mode) {
+      if (inertia == 0) {
+        double nz[BO_DIM(BO_MI)];
+        BO_UNROLL
+        for (int i = 0; i < BO_MI; ++i) nz[i] = -S.z[i];
+        BO_UNROLL
+        for (int i = 0; i < BO_NX; ++i) S.sol[i] = S.g[i];
+        bo_JIt_acc(S.JI, nz, S.sol);
+        BO_UNROLL
+        for (int j = 0; j < BO_ME; ++j) S.sol[BO_NX + j] = 0.0;
+        bo_bk_solve(S.LD, S.ipiv, S.sol);
+        bool fin = true;
+        BO_UNROLL
+        for (int j = 0; j < BO_ME; ++j) fin = fin && bo_isfinite(S.sol[BO_NX + j]);
+        if (fin) {
+          BO_UNROLL
+          for (int j = 0; j < BO_ME; ++j) S.y[j] = S.sol[BO_NX + j];
+        }
+      }
+      S.ls_mode = false;
+      S.phase = BO_PH_EVAL;  // re-evaluate the Hessian with the new multipliers on the next trip
+      return -1;
+    }
 #ifdef BO_HOST_TRACE
-        if (ls == 0 || ok)
-          printf("     heavy %d ls %d a %.3e ok %d ftype %d theta %.3e->%.3e phi %.8e->%.8e dphi %.3e dw %.2e\n", heavy, ls, a,
-                 (int)ok, (int)ftype, theta0, thetat, phi0, phit, dphi, dw);
+    if (inertia != 0) printf("     inertia %d at dw %.3e dc %.3e\n", inertia, S.dw, S.dc);
 #endif
-        if (!ok && ls == 0 && finite && thetat >= theta0 && (BO_ME + BO_MI) > 0) {
-          // ---- second-order correction (Waechter & Biegler section 2.4) ----
-          double theta_old = theta0, th_soc = thetat;
-          double dx0[BO_NX], ds0[BO_DIM(BO_MI)];
-          BO_UNROLL
-          for (int i = 0; i < BO_NX; ++i) dx0[i] = dx[i];
-          BO_UNROLL
-          for (int i = 0; i < BO_MI; ++i) ds0[i] = ds[i];
-          BO_UNROLL
-          for (int j = 0; j < BO_ME; ++j) rE[j] = a * cE[j] + cEt[j];
-          BO_UNROLL
-          for (int i = 0; i < BO_MI; ++i) rI[i] = a * (cI[i] - s[i]) + (cIt[i] - st[i]);
-          for (int soc = 0; soc < 4; ++soc) {
-            const double a_soc = compute_step();
-            BO_UNROLL
-            for (int i = 0; i < BO_NX; ++i) xt[i] = x[i] + a_soc * dx[i];
-            BO_UNROLL
-            for (int i = 0; i < BO_MI; ++i) st[i] = s[i] + a_soc * ds[i];
-            bo_tape_fc(xt, p, &ft, cEt, cIt);
-            bo_measures(ft, cEt, cIt, st, mu, &phit, &thetat);
-            bool ok_soc = false;
-            if (bo_isfinite(phit) && bo_isfinite(thetat) && filter_ok(thetat, phit)) {
-              if (ftype) {
-                armijo = phit - phi0 - slack <= eta_phi * a * dphi;
-                ok_soc = armijo;
-              } else {
-                ok_soc = thetat <= (1.0 - gamma_theta) * theta0 || phit - slack <= phi0 - gamma_phi * theta0;
-              }
-            }
-#ifdef BO_HOST_TRACE
-            printf("       soc %d a %.3e ok %d theta %.3e phi %.8e\n", soc, a_soc, (int)ok_soc, thetat, phit);
-#endif
-            if (ok_soc) {
-              ok = true;
-              BO_UNROLL
-              for (int i = 0; i < BO_MI; ++i) dz[i] = -z[i] + mu / s[i] - sigma[i] * ds[i];
-              break;
-            }
-            if (!(thetat <= kappa_soc * th_soc)) break;
-            th_soc = thetat;
-            (void)theta_old;
-            BO_UNROLL
-            for (int j = 0; j < BO_ME; ++j) rE[j] = a_soc * rE[j] + cEt[j];
-            BO_UNROLL
-            for (int i = 0; i < BO_MI; ++i) rI[i] = a_soc * rI[i] + (cIt[i] - st[i]);
-          }
-          if (!ok) {  // restore the uncorrected direction for the backtracking that follows
-            BO_UNROLL
-            for (int i = 0; i < BO_NX; ++i) dx[i] = dx0[i];
-            BO_UNROLL
-            for (int i = 0; i < BO_MI; ++i) ds[i] = ds0[i];
-          }
+    if (inertia != 0) {
+      // ---- inertia correction (IPOPT Algorithm IC); retried on the next trip ----
+      if (inertia < 0 && BO_ME > 0 && S.dc == 0.0) {
+        S.dc = 1e-8 * pow(S.mu, 0.25);  // singular: perturb the constraint block first
+      } else if (S.dw == 0.0) {
+        S.dw = (S.dw_last == 0.0) ? 1e-4 : fmax(1e-20, S.dw_last / 3.0);
+      } else {
+        S.dw *= (S.dw_last == 0.0) ? 100.0 : 8.0;
+      }
+      if (++S.attempt > BO_IC_MAX || S.dw > 1e40) return BO_ST_NUMERICAL;
+      return -1;
+    }
+    if (S.dw > 0.0 && S.heavy == 0) S.dw_last = S.dw;
+    BO_UNROLL
+    for (int j = 0; j < BO_ME; ++j) S.rE[j] = S.cE[j];
+    BO_UNROLL
+    for (int i = 0; i < BO_MI; ++i) S.rI[i] = S.cI[i] - S.s[i];
+    const double a_p = bo_ipm_step(S);
+    BO_UNROLL
+    for (int j = 0; j < BO_ME; ++j) S.y_step[j] = -S.sol[BO_NX + j];
+    double dphi = 0.0, dxn = 0.0;  // directional derivative of the barrier objective; step size
+    BO_UNROLL
+    for (int i = 0; i < BO_NX; ++i) {
+      dphi += S.g[i] * S.dx[i];
+      dxn = fmax(dxn, fabs(S.dx[i]));
+    }
+    BO_UNROLL
+    for (int i = 0; i < BO_MI; ++i) dphi -= S.mu * S.ds[i] / S.s[i];
+    S.dphi = dphi;
+    S.a = a_p;
+    // step-length cap (cf. SNOPT's "major step limit"): Newton steps of several radians through
+    // trigonometric kinematics are meaningless and wreck the multipliers
+    if (prm.max_step > 0.0 && S.a * dxn > prm.max_step) S.a = prm.max_step / dxn;
+    S.a_trial = S.a;
+    S.ls = 0;
+    S.soc = 0;
+    S.phase = BO_PH_TRIAL;
+  }
+
+  // =========================== PH_TRIAL ===========================
+  if (S.phase == BO_PH_TRIAL) {
+    double xt[BO_NX], st[BO_DIM(BO_MI)], cEt[BO_DIM(BO_ME)], cIt[BO_DIM(BO_MI)];
+    double ft, phit, thetat;
+    BO_UNROLL
+    for (int i = 0; i < BO_NX; ++i) xt[i] = S.x[i] + S.a_trial * S.dx[i];
+    BO_UNROLL
+    for (int i = 0; i < BO_MI; ++i) st[i] = S.s[i] + S.a_trial * S.ds[i];
+    bo_tape_fc(xt, S.p, &ft, cEt, cIt);
+    bo_measures(ft, cEt, cIt, st, S.mu, &phit, &thetat);
+    const bool finite = bo_isfinite(phit) && bo_isfinite(thetat);
+    const bool ftype = S.dphi < 0.0 && S.a * pow(-S.dphi, s_phi) > pow(S.theta0, s_theta) && S.theta0 <= S.theta_min;
+    const double slack = 10.0 * 2.2e-16 * fabs(S.phi0);
+    bool ok = false, armijo = false;
+    if (finite && thetat <= S.theta_max) {
+      bool in_filter = true;
+      for (int j = 0; j < S.nf; ++j)
+        if (!(thetat <= (1.0 - gamma_theta) * S.fth[j] || phit <= S.fph[j] - gamma_phi * S.fth[j])) in_filter = false;
+      if (in_filter) {
+        if (ftype) {
+          armijo = phit - S.phi0 - slack <= eta_phi * S.a * S.dphi;
+          ok = armijo;
+        } else {
+          ok = thetat <= (1.0 - gamma_theta) * S.theta0 || phit - slack <= S.phi0 - gamma_phi * S.theta0;
         }
-        if (ok) {
-          accepted = true;
-          a_used = a;
-          if (!(ftype && armijo) && nf < BO_NFILTER) {  // augment the filter (eq. 22)
-            fth[nf] = (1.0 - gamma_theta) * theta0;
-            fph[nf] = phi0 - gamma_phi * theta0;
-            ++nf;
-          } else if (!(ftype && armijo)) {
-            int worst = 0;  // filter full: overwrite the entry with the largest theta
-            for (int j = 1; j < BO_NFILTER; ++j)
-              if (fth[j] > fth[worst]) worst = j;
-            fth[worst] = (1.0 - gamma_theta) * theta0;
-            fph[worst] = phi0 - gamma_phi * theta0;
-          }
-          break;
-        }
-        a *= 0.5;
-        if (a < 1e-12) break;
       }
     }
-    if (!accepted) return BO_ST_LINE_SEARCH;
-
-    // ---- accept: primal, slack reset, duals with their own fraction-to-the-boundary step ----
-    double a_d = 1.0;
-    BO_UNROLL
-    for (int i = 0; i < BO_MI; ++i)
-      if (dz[i] < 0.0) a_d = fmin(a_d, -tau * z[i] / dz[i]);
-    BO_UNROLL
-    for (int i = 0; i < BO_NX; ++i) x[i] = xt[i];
-    BO_UNROLL
-    for (int i = 0; i < BO_MI; ++i) {
-      s[i] = fmax(st[i], cIt[i]);  // slack reset: lowers theta, never raises the barrier objective
-      z[i] += a_d * dz[i];
-      // keep z within a factor kappa_sigma of the central-path value mu/s (IPOPT eq. 16)
-      z[i] = fmax(fmin(z[i], kappa_sigma * mu / s[i]), mu / (kappa_sigma * s[i]));
+#ifdef BO_HOST_TRACE
+    printf("     heavy %d ls %d soc %d a %.3e ok %d ftype %d theta %.3e->%.3e phi %.8e->%.8e dphi %.3e dw %.2e\n", S.heavy, S.ls,
+           S.soc, S.a_trial, (int)ok, (int)ftype, S.theta0, thetat, S.phi0, phit, S.dphi, S.dw);
+#endif
+    if (ok) {
+      // ---- accept: primal, slack reset, duals with their own fraction-to-the-boundary step ----
+      if (!(ftype && armijo)) {  // augment the filter (eq. 22)
+        int slot = S.nf;
+        if (S.nf < BO_NFILTER) {
+          ++S.nf;
+        } else {  // full: overwrite the entry with the largest theta
+          slot = 0;
+          for (int j = 1; j < BO_NFILTER; ++j)
+            if (S.fth[j] > S.fth[slot]) slot = j;
+        }
+        S.fth[slot] = (1.0 - gamma_theta) * S.theta0;
+        S.fph[slot] = S.phi0 - gamma_phi * S.theta0;
+      }
+      double a_d = 1.0, dz[BO_DIM(BO_MI)];
+      BO_UNROLL
+      for (int i = 0; i < BO_MI; ++i) {
+        dz[i] = -S.z[i] + S.mu / S.s[i] - S.sigma[i] * S.ds[i];
+        if (dz[i] < 0.0) a_d = fmin(a_d, -S.tau * S.z[i] / dz[i]);
+      }
+      BO_UNROLL
+      for (int i = 0; i < BO_NX; ++i) S.x[i] = xt[i];
+      BO_UNROLL
+      for (int i = 0; i < BO_MI; ++i) {
+        S.s[i] = fmax(st[i], cIt[i]);  // slack reset: lowers theta, never raises the barrier objective
+        S.z[i] += a_d * dz[i];
+        // keep z within a factor kappa_sigma of the central-path value mu/s (IPOPT eq. 16)
+        S.z[i] = fmax(fmin(S.z[i], kappa_sigma * S.mu / S.s[i]), S.mu / (kappa_sigma * S.s[i]));
+      }
+      BO_UNROLL
+      for (int j = 0; j < BO_ME; ++j) S.y[j] += S.a * S.y_step[j];
+      S.recalc_y = S.dw > 0.0;
+      S.it += 1;
+      S.phase = BO_PH_EVAL;
+      return -1;
     }
-    BO_UNROLL
-    for (int j = 0; j < BO_ME; ++j) y[j] += a_used * y_step[j];
-    recalc_y = dw > 0.0;
+    // ---- not acceptable ----
+    bool try_soc = false;
+    if (S.soc == 0) {
+      // second-order correction (Waechter & Biegler section 2.4) for the first, full trial step only
+      if (S.ls == 0 && finite && thetat >= S.theta0 && (BO_ME + BO_MI) > 0) {
+        BO_UNROLL
+        for (int i = 0; i < BO_NX; ++i) S.dx0[i] = S.dx[i];
+        BO_UNROLL
+        for (int i = 0; i < BO_MI; ++i) S.ds0[i] = S.ds[i];
+        BO_UNROLL
+        for (int j = 0; j < BO_ME; ++j) S.rE[j] = S.a * S.cE[j] + cEt[j];
+        BO_UNROLL
+        for (int i = 0; i < BO_MI; ++i) S.rI[i] = S.a * (S.cI[i] - S.s[i]) + (cIt[i] - st[i]);
+        S.th_soc = thetat;
+        try_soc = true;
+      }
+    } else if (S.soc < 4 && finite && thetat <= kappa_soc * S.th_soc) {
+      BO_UNROLL
+      for (int j = 0; j < BO_ME; ++j) S.rE[j] = S.a_trial * S.rE[j] + cEt[j];
+      BO_UNROLL
+      for (int i = 0; i < BO_MI; ++i) S.rI[i] = S.a_trial * S.rI[i] + (cIt[i] - st[i]);
+      S.th_soc = thetat;
+      try_soc = true;
+    }
+    if (try_soc) {
+      S.a_trial = bo_ipm_step(S);  // corrected direction; tried on the next trip
+      S.soc += 1;
+      return -1;
+    }
+    if (S.soc > 0) {  // corrections did not help: back to the uncorrected direction
+      BO_UNROLL
+      for (int i = 0; i < BO_NX; ++i) S.dx[i] = S.dx0[i];
+      BO_UNROLL
+      for (int i = 0; i < BO_MI; ++i) S.ds[i] = S.ds0[i];
+      S.soc = 0;
+    }
+    S.a *= 0.5;
+    S.a_trial = S.a;
+    S.ls += 1;
+    if (S.ls >= BO_LS_MAX || S.a < 1e-12) {
+      // no acceptable step along this direction: convexify harder (dw large => minimum-norm
+      // feasibility step); this stands in for IPOPT's restoration phase on these small problems
+      if (++S.heavy >= BO_HEAVY_MAX) return BO_ST_LINE_SEARCH;
+      S.dw = fmax(S.dw * 100.0, 1.0);
+      S.phase = BO_PH_FACTOR;
+    }
   }
-  S.it = it + 1;
   return -1;
 }
 
@@ -578,7 +583,7 @@ BO_DEVICE int bo_ipm_solve(bo_ipm_state& S, const bo_solver_params prm) {
   bo_ipm_init(S, prm);
   int status;
   do {
-    status = bo_ipm_iterate(S, prm);
+    status = bo_ipm_trip(S, prm);
   } while (status < 0);
   return status;
 }
@@ -587,10 +592,10 @@ BO_DEVICE int bo_ipm_solve(bo_ipm_state& S, const bo_solver_params prm) {
 // Persistent lanes with per-lane work fetching.  Iteration counts differ widely between instances
 // (mean ~17, tail > 100 on the IK workload); a one-instance-per-thread launch would idle 31 lanes of
 // a warp while its slowest instance finishes.  Instead every lane runs a small state machine:
-// fetch an instance index from a global counter, initialise, then execute ONE interior-point
-// iteration per trip round the loop; all lanes of a warp reconverge at the top of the loop, so the
-// iteration body (the expensive, straight-line part) always runs warp-wide, and a lane whose
-// instance has finished picks up the next one instead of waiting.
+// fetch an instance index from a global counter, initialise, then execute one bo_ipm_trip() per
+// trip round the loop; all lanes of a warp reconverge at the top of the loop, so the three heavy
+// blocks of the trip (tape evaluation, factorisation, trial point) always run warp-wide, and a lane
+// whose instance has finished picks up the next one instead of waiting.
 // Global layout: row-major [B][n] (instance-major), see b200optas.h.
 extern "C" __global__ void __launch_bounds__(BO_TPB)
 bo_solve_kernel(long long B, const double* __restrict__ p_all, const double* __restrict__ x0_all,
@@ -616,7 +621,7 @@ bo_solve_kernel(long long B, const double* __restrict__ p_all, const double* __r
     }
     if (!__any_sync(0xffffffffu, active)) break;
     if (active) {
-      const int status = bo_ipm_iterate(S, prm);
+      const int status = bo_ipm_trip(S, prm);
       if (status >= 0) {
         BO_UNROLL
         for (int i = 0; i < BO_NX; ++i) x_all[b * BO_NX + i] = S.x[i];

@@ -76,10 +76,15 @@ def constraint_vectors(opt):
 
 
 def lower_problem(opt) -> LoweredProblem:
-    x, p = opt.x, opt.p
-    nx, np_ = opt.nx, opt.np
-    f = cs.SX(opt.f(x, p))
+    """Lower an ``Optimization`` (reference IR, optas/optimization.py:54-309)."""
     c_eq, c_ineq = constraint_vectors(opt)
+    return lower_nlp(opt.x, opt.p, cs.SX(opt.f(opt.x, opt.p)), c_eq, c_ineq)
+
+
+def lower_nlp(x, p, f, c_eq, c_ineq) -> LoweredProblem:
+    """Lower ``min f(x,p) s.t. c_eq(x,p) = 0, c_ineq(x,p) >= 0`` given as SX column vectors."""
+    x, p, f, c_eq, c_ineq = cs.SX(x), cs.SX(p), cs.SX(f), cs.SX(c_eq), cs.SX(c_ineq)
+    nx, np_ = x.numel(), p.numel()
     n_eq, n_ineq = c_eq.numel(), c_ineq.numel()
 
     y = cs.SX.sym("__y", n_eq)

@@ -319,6 +319,21 @@ class B200Solver(Solver):
         B = int(X.shape[0])
         self._handle.solve(B, P, X0, X, lam, f, status, iters, kkt, stream)
 
+    def solve_arrays(self, P: np.ndarray, X0: Optional[np.ndarray]) -> Dict[str, np.ndarray]:
+        """Batched solve on host arrays in ``vec()`` layout: ``P [B, np]``, ``X0 [B, nx]`` (None = zeros).
+        Returns ``x [B, nx]``, ``lam [B, n_eq + n_ineq]``, ``f``, ``status``, ``iters``, ``kkt`` ([B] each)."""
+        if self._handle is None:
+            raise RuntimeError("call setup() first")
+        lo = self._lowered
+        n = int(P.shape[0]) if lo.np_ else int(X0.shape[0])
+        P = np.ascontiguousarray(P, dtype=np.float64)
+        X0 = None if X0 is None else np.ascontiguousarray(X0, dtype=np.float64)
+        out = {"x": np.empty((n, lo.nx)), "lam": np.empty((n, lo.n_eq + lo.n_ineq)), "f": np.empty(n),
+               "status": np.empty(n, dtype=np.int32), "iters": np.empty(n, dtype=np.int32), "kkt": np.empty(n)}
+        self._handle.solve(n, P if lo.np_ else None, X0, out["x"], out["lam"], out["f"], out["status"], out["iters"],
+                           out["kkt"])
+        return out
+
     # -- solve --------------------------------------------------------------------------------
     def _run(self) -> np.ndarray:
         if self._handle is None:
@@ -331,13 +346,8 @@ class B200Solver(Solver):
         X0 = np.ascontiguousarray(np.broadcast_to(self._X0, (n, self.opt.nx)))
         P = np.ascontiguousarray(np.broadcast_to(self._P, (n, self.opt.np)))
         lo = self._lowered
-        X = np.empty((n, lo.nx))
-        lam = np.empty((n, lo.n_eq + lo.n_ineq))
-        f = np.empty(n)
-        status = np.empty(n, dtype=np.int32)
-        iters = np.empty(n, dtype=np.int32)
-        kkt = np.empty(n)
-        self._handle.solve(n, P if lo.np_ else None, X0, X, lam, f, status, iters, kkt)
+        r = self.solve_arrays(P, X0)
+        X, lam, f, status, iters, kkt = r["x"], r["lam"], r["f"], r["status"], r["iters"], r["kkt"]
         ok = status <= 1
         self._stats = {
             "success": bool(ok.all()),
