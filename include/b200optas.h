@@ -104,7 +104,7 @@ typedef struct bo_problem_desc {
 
 typedef struct bo_options {
   uint32_t flags;
-  int32_t max_iter;        /* <=0: default 200                                              */
+  int32_t max_iter;        /* <=0: default 100                                              */
   double tol;              /* <=0: default 1e-8  (scaled KKT error, as IPOPT's `tol`)      */
   double acceptable_tol;   /* <=0: default 1e-6                                             */
   double mu_init;          /* <=0: default 0.1   (as IPOPT's `mu_init`)                    */
@@ -112,7 +112,10 @@ typedef struct bo_options {
   const char* cache_dir;   /* NULL: <directory of libb200optas.so>/_jitcache               */
   const char* include_dir; /* NULL: <directory of libb200optas.so>/csrc/jit                */
   int32_t threads_per_block; /* <=0: tier default                                           */
-  int32_t reserved[7];
+  int32_t max_trips;       /* <=0: default 250.  Budget of solver trips per instance (one trip = at most
+                              one KKT evaluation + one factorisation + one trial point); an instance
+                              over budget ends with BO_MAX_ITER.  Bounds the tail latency of a batch. */
+  int32_t reserved[6];
 } bo_options;
 
 typedef struct bo_problem bo_problem;   /* opaque, owned by the library */

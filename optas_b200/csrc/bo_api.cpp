@@ -405,7 +405,8 @@ bo_options normalise(const bo_options* in) {
   bo_options o;
   memset(&o, 0, sizeof o);
   if (in) o = *in;
-  if (o.max_iter <= 0) o.max_iter = 200;
+  if (o.max_iter <= 0) o.max_iter = 100;
+  if (o.max_trips <= 0) o.max_trips = 250;
   if (!(o.tol > 0)) o.tol = 1e-8;
   if (!(o.acceptable_tol > 0)) o.acceptable_tol = 1e-6;
   if (!(o.mu_init > 0)) o.mu_init = 0.1;
@@ -419,6 +420,7 @@ struct SolverParams {  // must match bo_solver_params in csrc/jit/bo_common.cuh
   double acceptable_tol;
   double mu_init;
   double max_step;
+  int32_t max_trips;
 };
 
 }  // namespace
@@ -503,7 +505,7 @@ int bo_problem_create(const bo_problem_desc* desc, const bo_options* opts_in, bo
     return set_err(BO_ERR_UNSUPPORTED,
                    "bo_problem_create: nx+n_eq=%d, n_ineq=%d exceeds the register-resident tier (nx+n_eq<=40, n_ineq<=128)",
                    ps.nx + ps.n_eq, ps.n_ineq);
-  pr->tpb = pr->opts.threads_per_block > 0 ? pr->opts.threads_per_block : 64;
+  pr->tpb = pr->opts.threads_per_block > 0 ? pr->opts.threads_per_block : 128;
   if (getenv("BO_DEBUG")) fprintf(stderr, "[bo] emitting source\n");
   pr->source = bo::emit_problem_source(ps, pr->tpb);
   if (getenv("BO_DEBUG")) fprintf(stderr, "[bo] source %zu bytes\n", pr->source.size());
@@ -625,7 +627,7 @@ int bo_solve(bo_problem* pr, int64_t B, const double* p, const double* x0, doubl
   if ((rc = stage_out(kkt_res, sizeof(double), pr->d_kkt, &dkkt)) != BO_OK) return rc;
 
   long long Bll = B;
-  SolverParams prm{pr->opts.max_iter, pr->opts.tol, pr->opts.acceptable_tol, pr->opts.mu_init, pr->opts.max_step};
+  SolverParams prm{pr->opts.max_iter, pr->opts.tol, pr->opts.acceptable_tol, pr->opts.mu_init, pr->opts.max_step, pr->opts.max_trips};
   // persistent lanes: one wave of CTAs (multiple of the SM count), instances fetched from a counter
   CUdeviceptr dcounter = pr->d_counter.ptr;
   BO_CU(g_drv.cuMemsetD8Async(dcounter, 0, sizeof(unsigned long long), st));

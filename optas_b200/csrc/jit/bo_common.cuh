@@ -10,6 +10,7 @@
 #include <cstdint>
 #include <limits>
 #define BO_DEVICE static inline
+#define BO_NOINLINE static __attribute__((noinline))
 #define BO_RESTRICT __restrict__
 #define BO_UNROLL
 #define BO_INF (std::numeric_limits<double>::infinity())
@@ -21,6 +22,7 @@ using std::floor; using std::ceil; using std::exp; using std::atan2; using std::
 using std::asin; using std::acos; using std::atan; using std::sinh; using std::cosh; using std::tanh;
 #else
 #define BO_DEVICE __device__ __forceinline__
+#define BO_NOINLINE __device__ __noinline__
 #define BO_RESTRICT __restrict__
 #define BO_UNROLL _Pragma("unroll")
 #define BO_INF (__longlong_as_double(0x7ff0000000000000LL))
@@ -43,6 +45,7 @@ struct bo_solver_params {
   double acceptable_tol;
   double mu_init;
   double max_step;  // <= 0: unlimited
+  int32_t max_trips; // budget of solver trips per instance (bounds the tail of a batch)
 };
 
 // per-instance status codes (mirror bo_instance_status in include/b200optas.h)

@@ -32,7 +32,7 @@
 // dependent, so A lives in thread-local memory (L1-resident: 800 B for the 7-DoF IK problem).
 // Outputs the pivot record ipiv (LAPACK convention, 1-based, negative for 2x2 blocks) and the
 // inertia; returns false if a pivot block is numerically singular.
-BO_DEVICE bool bo_bk_factor(double* BO_RESTRICT A, int* BO_RESTRICT ipiv, int* n_neg_out) {
+BO_NOINLINE bool bo_bk_factor(double* BO_RESTRICT A, int* BO_RESTRICT ipiv, int* n_neg_out) {
   const double alpha = 0.6403882032022076;  // (1 + sqrt(17)) / 8
   // Like LAPACK, only an exactly (here: denormal-small) zero pivot is "singular"; near-singular
   // systems show up as a wrong inertia count and are handled by the caller's regularisation.
@@ -123,7 +123,7 @@ BO_DEVICE bool bo_bk_factor(double* BO_RESTRICT A, int* BO_RESTRICT ipiv, int* n
 }
 
 // Solve A x = b with the factorisation above (LAPACK dsytrs, lower variant), in place.
-BO_DEVICE void bo_bk_solve(const double* BO_RESTRICT A, const int* BO_RESTRICT ipiv, double* BO_RESTRICT b) {
+BO_NOINLINE void bo_bk_solve(const double* BO_RESTRICT A, const int* BO_RESTRICT ipiv, double* BO_RESTRICT b) {
   int k = 0;
   while (k < BO_NK) {  // forward: L D
     if (ipiv[k] > 0) {
@@ -186,7 +186,7 @@ BO_DEVICE int bo_kkt_factor(const double* BO_RESTRICT K, double dw, double dc, d
 }
 
 // Barrier objective and l1 constraint violation at (x, s) given the function values there.
-BO_DEVICE void bo_measures(double f, const double* cE, const double* cI, const double* s, double mu, double* phi,
+BO_NOINLINE void bo_measures(double f, const double* cE, const double* cI, const double* s, double mu, double* phi,
                            double* theta) {
   double viol = 0.0, bar = 0.0;
   BO_UNROLL
@@ -201,8 +201,12 @@ BO_DEVICE void bo_measures(double f, const double* cE, const double* cI, const d
 }
 
 #define BO_NFILTER 8
+#ifndef BO_LS_MAX
 #define BO_LS_MAX 16    /* backtracking halvings per direction (alpha >= 1.5e-5 alpha_max) */
+#endif
+#ifndef BO_HEAVY_MAX
 #define BO_HEAVY_MAX 5  /* re-solves with dw = 1, 1e2, 1e4, 1e6 when no step is acceptable */
+#endif
 #define BO_IC_MAX 60    /* inertia-correction attempts per iteration */
 
 #define BO_PH_EVAL 0    /* evaluate f, grad, c, J, H at x; test convergence; assemble K */
@@ -225,7 +229,7 @@ struct bo_ipm_state {
   double p[BO_DIM(BO_NP)], x[BO_NX], s[BO_DIM(BO_MI)], y[BO_DIM(BO_ME)], z[BO_DIM(BO_MI)];
   double fth[BO_NFILTER], fph[BO_NFILTER];
   double f, mu, tau, dw_last, err0, theta_max, theta_min;
-  int nf, it, n_acceptable, phase;
+  int nf, it, n_acceptable, phase, trips;
   bool recalc_y, ls_mode;
   // evaluation at x (valid from PH_EVAL to the end of the iteration)
   double g[BO_NX], cE[BO_DIM(BO_ME)], cI[BO_DIM(BO_MI)], rd[BO_NX], sigma[BO_DIM(BO_MI)];
@@ -241,6 +245,9 @@ struct bo_ipm_state {
   int ls, soc;  // soc: 0 = plain trial, k > 0 = k-th second-order-corrected trial
 };
 
+// The small tape is called from two places (start of an instance, every trial point): keep one copy.
+BO_NOINLINE void bo_eval_fc(const double* x, const double* p, double* f, double* cE, double* cI) { bo_tape_fc(x, p, f, cE, cI); }
+
 // Start an instance: S.p and S.x hold the parameters and the seed.
 BO_DEVICE void bo_ipm_init(bo_ipm_state& S, const bo_solver_params prm) {
   S.mu = prm.mu_init;
@@ -254,7 +261,8 @@ BO_DEVICE void bo_ipm_init(bo_ipm_state& S, const bo_solver_params prm) {
   S.recalc_y = false;
   S.ls_mode = false;
   S.phase = BO_PH_EVAL;
-  bo_tape_fc(S.x, S.p, &S.f, S.cE, S.cI);
+  S.trips = 0;
+  bo_eval_fc(S.x, S.p, &S.f, S.cE, S.cI);
   BO_UNROLL
   for (int i = 0; i < BO_MI; ++i) {
     S.s[i] = fmax(S.cI[i], 1e-2 * fmax(1.0, fabs(S.cI[i])));
@@ -266,7 +274,7 @@ BO_DEVICE void bo_ipm_init(bo_ipm_state& S, const bo_solver_params prm) {
 
 // Step for the constraint residuals (S.rE, S.rI) with the current factorisation: fills S.sol
 // (dx, -dy), S.dx, S.ds and returns the fraction-to-the-boundary primal step length.
-BO_DEVICE double bo_ipm_step(bo_ipm_state& S) {
+BO_NOINLINE double bo_ipm_step(bo_ipm_state& S) {
   double tvec[BO_DIM(BO_MI)];
   BO_UNROLL
   for (int i = 0; i < BO_MI; ++i) tvec[i] = -(S.z[i] - S.mu / S.s[i] + S.sigma[i] * S.rI[i]);
@@ -296,10 +304,11 @@ BO_DEVICE double bo_ipm_step(bo_ipm_state& S) {
 // IC).  IPOPT's restoration phase is replaced by re-solving the step with a heavily convexified
 // Hessian (dw -> large turns it into the minimum-norm feasibility step).
 BO_DEVICE int bo_ipm_trip(bo_ipm_state& S, const bo_solver_params prm) {
-  const double kappa_eps = 10.0, kappa_mu = 0.2, theta_mu = 1.5, tau_min = 0.99, s_max = 100.0;
+  const double kappa_eps = 10.0, kappa_mu = 0.2, tau_min = 0.99, s_max = 100.0;
   const double kappa_sigma = 1e10, gamma_theta = 1e-5, gamma_phi = 1e-5, eta_phi = 1e-8;
   const double s_phi = 2.3, s_theta = 1.1, kappa_soc = 0.99;
   const double mu_min = prm.tol * 0.1;
+  if (++S.trips > prm.max_trips) return BO_ST_MAX_ITER;
 
   // =========================== PH_EVAL ===========================
   if (S.phase == BO_PH_EVAL) {
@@ -368,7 +377,7 @@ BO_DEVICE int bo_ipm_trip(bo_ipm_state& S, const bo_solver_params prm) {
           for (int i = 0; i < BO_MI; ++i) e_comp = fmax(e_comp, fabs(S.s[i] * S.z[i] - S.mu));
           const double err_mu = fmax(fmax(e_dual / s_d, e_prim), e_comp / s_c);
           if (err_mu <= kappa_eps * S.mu && S.mu > mu_min) {
-            S.mu = fmax(mu_min, fmin(kappa_mu * S.mu, pow(S.mu, theta_mu)));
+            S.mu = fmax(mu_min, fmin(kappa_mu * S.mu, S.mu * sqrt(S.mu)));  // mu^theta_mu, theta_mu = 1.5
             S.nf = 0;
           } else {
             break;
@@ -425,7 +434,7 @@ BO_DEVICE int bo_ipm_trip(bo_ipm_state& S, const bo_solver_params prm) {
     if (inertia != 0) {
       // ---- inertia correction (IPOPT Algorithm IC); retried on the next trip ----
       if (inertia < 0 && BO_ME > 0 && S.dc == 0.0) {
-        S.dc = 1e-8 * pow(S.mu, 0.25);  // singular: perturb the constraint block first
+        S.dc = 1e-8 * sqrt(sqrt(S.mu));  // 1e-8 mu^(1/4)  // singular: perturb the constraint block first
       } else if (S.dw == 0.0) {
         S.dw = (S.dw_last == 0.0) ? 1e-4 : fmax(1e-20, S.dw_last / 3.0);
       } else {
@@ -469,10 +478,11 @@ BO_DEVICE int bo_ipm_trip(bo_ipm_state& S, const bo_solver_params prm) {
     for (int i = 0; i < BO_NX; ++i) xt[i] = S.x[i] + S.a_trial * S.dx[i];
     BO_UNROLL
     for (int i = 0; i < BO_MI; ++i) st[i] = S.s[i] + S.a_trial * S.ds[i];
-    bo_tape_fc(xt, S.p, &ft, cEt, cIt);
+    bo_eval_fc(xt, S.p, &ft, cEt, cIt);
     bo_measures(ft, cEt, cIt, st, S.mu, &phit, &thetat);
     const bool finite = bo_isfinite(phit) && bo_isfinite(thetat);
-    const bool ftype = S.dphi < 0.0 && S.a * pow(-S.dphi, s_phi) > pow(S.theta0, s_theta) && S.theta0 <= S.theta_min;
+    const bool ftype = S.dphi < 0.0 && S.theta0 <= S.theta_min &&
+                       (S.theta0 <= 0.0 || log(S.a) + s_phi * log(-S.dphi) > s_theta * log(S.theta0));
     const double slack = 10.0 * 2.2e-16 * fabs(S.phi0);
     bool ok = false, armijo = false;
     if (finite && thetat <= S.theta_max) {
@@ -619,7 +629,9 @@ bo_solve_kernel(long long B, const double* __restrict__ p_all, const double* __r
         exhausted = true;
       }
     }
-    if (!__any_sync(0xffffffffu, active)) break;
+    // CTA-wide barrier per trip: keeps the warps of a CTA in the same block of this (large) code at
+    // the same time, so instruction fetch is shared between them instead of thrashing the i-cache
+    if (!__syncthreads_or(active ? 1 : 0)) break;
     if (active) {
       const int status = bo_ipm_trip(S, prm);
       if (status >= 0) {

@@ -117,8 +117,8 @@ class NlpSolver:
         opts = {}
         for k, v in self.options.items():
             leaf = k.split(".")[-1]
-            if leaf in ("max_iter", "tol", "acceptable_tol", "mu_init", "max_step"):
-                opts[leaf] = int(v) if leaf == "max_iter" else float(v)
+            if leaf in ("max_iter", "max_trips", "tol", "acceptable_tol", "mu_init", "max_step"):
+                opts[leaf] = int(v) if leaf in ("max_iter", "max_trips") else float(v)
         flags = _capi.BO_FLAG_COMPILE_ONLY if self.compile_only else 0
         handle = _capi.ProblemHandle(lowered, flags=flags, **opts)
         self._compiled[key] = (handle, lowered, rows_eq, rows_ineq)

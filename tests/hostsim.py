@@ -26,10 +26,10 @@ _WRAPPER = r"""
 %(trace)s
 #include "%(gen)s"
 extern "C" void hostsim_solve(long long B, const double* p, const double* x0, double* x, double* lam, double* f,
-                              int* status, int* iters, double* kkt, int max_iter, double tol, double acc_tol,
-                              double mu_init, double max_step) {
+                              int* status, int* iters, double* kkt, int* trips, int max_iter, double tol, double acc_tol,
+                              double mu_init, double max_step, int max_trips) {
   bo_solver_params prm;
-  prm.max_iter = max_iter; prm.tol = tol; prm.acceptable_tol = acc_tol; prm.mu_init = mu_init; prm.max_step = max_step;
+  prm.max_iter = max_iter; prm.tol = tol; prm.acceptable_tol = acc_tol; prm.mu_init = mu_init; prm.max_step = max_step; prm.max_trips = max_trips;
   for (long long b = 0; b < B; ++b) {
     bo_ipm_state S;
     for (int i = 0; i < BO_NP; ++i) S.p[i] = p[b * BO_NP + i];
@@ -38,7 +38,7 @@ extern "C" void hostsim_solve(long long B, const double* p, const double* x0, do
     for (int i = 0; i < BO_NX; ++i) x[b * BO_NX + i] = S.x[i];
     for (int j = 0; j < BO_ME; ++j) lam[b * (BO_ME + BO_MI) + j] = S.y[j];
     for (int i = 0; i < BO_MI; ++i) lam[b * (BO_ME + BO_MI) + BO_ME + i] = S.z[i];
-    f[b] = S.f; iters[b] = S.it; kkt[b] = S.err0;
+    f[b] = S.f; iters[b] = S.it; kkt[b] = S.err0; if (trips) trips[b] = S.trips;
   }
 }
 """
@@ -63,14 +63,14 @@ class HostSim:
             os.replace(so + ".tmp", so)
         self.lib = C.CDLL(so)
         vp = C.c_void_p
-        self.lib.hostsim_solve.argtypes = [C.c_longlong] + [vp] * 8 + [C.c_int, C.c_double, C.c_double, C.c_double, C.c_double]
+        self.lib.hostsim_solve.argtypes = [C.c_longlong] + [vp] * 9 + [C.c_int, C.c_double, C.c_double, C.c_double, C.c_double, C.c_int]
 
-    def solve(self, P, X0, max_iter=200, tol=1e-8, acc_tol=1e-6, mu_init=0.1, max_step=0.5):
+    def solve(self, P, X0, max_iter=100, tol=1e-8, acc_tol=1e-6, mu_init=0.1, max_step=0.5, max_trips=250):
         B = X0.shape[0]
         P = np.ascontiguousarray(P, dtype=float)
         X0 = np.ascontiguousarray(X0, dtype=float)
         X = np.empty((B, self.nx)); lam = np.empty((B, max(self.nl, 1))); f = np.empty(B)
-        st = np.empty(B, dtype=np.int32); it = np.empty(B, dtype=np.int32); kkt = np.empty(B)
+        st = np.empty(B, dtype=np.int32); it = np.empty(B, dtype=np.int32); kkt = np.empty(B); trips = np.empty(B, dtype=np.int32)
         self.lib.hostsim_solve(B, P.ctypes.data, X0.ctypes.data, X.ctypes.data, lam.ctypes.data, f.ctypes.data,
-                               st.ctypes.data, it.ctypes.data, kkt.ctypes.data, max_iter, tol, acc_tol, mu_init, max_step)
-        return {"x": X, "lam": lam[:, :self.nl], "f": f, "status": st, "iters": it, "kkt": kkt}
+                               st.ctypes.data, it.ctypes.data, kkt.ctypes.data, trips.ctypes.data, max_iter, tol, acc_tol, mu_init, max_step, max_trips)
+        return {"x": X, "lam": lam[:, :self.nl], "f": f, "status": st, "iters": it, "kkt": kkt, "trips": trips}

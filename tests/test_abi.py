@@ -40,7 +40,7 @@ def test_opcode_header_matches_front_end():
 def test_options_struct_layout():
     from optas_b200 import _capi
 
-    # flags,max_iter (8) + 4 doubles (32) + 2 pointers (16) + tpb + 7 reserved (32)
+    # flags,max_iter (8) + 4 doubles (32) + 2 pointers (16) + tpb, max_trips, 6 reserved (32)
     assert C.sizeof(_capi.bo_options) == 88
     assert C.sizeof(_capi.bo_tape) == 64
     assert C.sizeof(_capi.bo_sparsity) == 24
