@@ -191,7 +191,7 @@ BO_NOINLINE void bo_measures(double f, const double* cE, const double* cI, const
   double viol = 0.0, bar = 0.0;
   BO_UNROLL
   for (int j = 0; j < BO_ME; ++j) viol += fabs(cE[j]);
-  BO_UNROLL
+  BO_NOUNROLL
   for (int i = 0; i < BO_MI; ++i) {
     viol += fabs(cI[i] - s[i]);
     bar += log(s[i]);
@@ -263,7 +263,7 @@ BO_DEVICE void bo_ipm_init(bo_ipm_state& S, const bo_solver_params prm) {
   S.phase = BO_PH_EVAL;
   S.trips = 0;
   bo_eval_fc(S.x, S.p, &S.f, S.cE, S.cI);
-  BO_UNROLL
+  BO_NOUNROLL
   for (int i = 0; i < BO_MI; ++i) {
     S.s[i] = fmax(S.cI[i], 1e-2 * fmax(1.0, fabs(S.cI[i])));
     S.z[i] = S.mu / S.s[i];
@@ -276,7 +276,7 @@ BO_DEVICE void bo_ipm_init(bo_ipm_state& S, const bo_solver_params prm) {
 // (dx, -dy), S.dx, S.ds and returns the fraction-to-the-boundary primal step length.
 BO_NOINLINE double bo_ipm_step(bo_ipm_state& S) {
   double tvec[BO_DIM(BO_MI)];
-  BO_UNROLL
+  BO_NOUNROLL
   for (int i = 0; i < BO_MI; ++i) tvec[i] = -(S.z[i] - S.mu / S.s[i] + S.sigma[i] * S.rI[i]);
   BO_UNROLL
   for (int i = 0; i < BO_NX; ++i) S.sol[i] = -S.rd[i];
@@ -288,7 +288,7 @@ BO_NOINLINE double bo_ipm_step(bo_ipm_state& S) {
   for (int i = 0; i < BO_NX; ++i) S.dx[i] = S.sol[i];
   bo_JI_mul(S.JI, S.dx, S.ds);
   double ap = 1.0;
-  BO_UNROLL
+  BO_NOUNROLL
   for (int i = 0; i < BO_MI; ++i) {
     S.ds[i] += S.rI[i];
     if (S.ds[i] < 0.0) ap = fmin(ap, -S.tau * S.s[i] / S.ds[i]);
@@ -296,17 +296,18 @@ BO_NOINLINE double bo_ipm_step(bo_ipm_state& S) {
   return ap;
 }
 
-// One trip of the solver state machine.  Returns -1 to continue, or the final BO_ST_* status.
+// One trip of the solver state machine = bo_trip_eval, bo_trip_factor, bo_trip_trial in that order.
+// Each returns -1 to continue, or the final BO_ST_* status.  They are separate functions so that the
+// GPU kernel can put a CTA barrier between them: the warps of a CTA then enter each (large,
+// straight-line) block together and share its instruction fetch.
 //
 // Algorithm: primal-dual interior point with IPOPT's filter line search (Waechter & Biegler 2006,
 // section 2.3, their default constants) on (theta = ||c||_1, phi = barrier objective), second-order
 // correction of the first trial step (section 2.4), inertia-correcting regularisation (Algorithm
 // IC).  IPOPT's restoration phase is replaced by re-solving the step with a heavily convexified
 // Hessian (dw -> large turns it into the minimum-norm feasibility step).
-BO_DEVICE int bo_ipm_trip(bo_ipm_state& S, const bo_solver_params prm) {
+BO_DEVICE int bo_trip_eval(bo_ipm_state& S, const bo_solver_params prm) {
   const double kappa_eps = 10.0, kappa_mu = 0.2, tau_min = 0.99, s_max = 100.0;
-  const double kappa_sigma = 1e10, gamma_theta = 1e-5, gamma_phi = 1e-5, eta_phi = 1e-8;
-  const double s_phi = 2.3, s_theta = 1.1, kappa_soc = 0.99;
   const double mu_min = prm.tol * 0.1;
   if (++S.trips > prm.max_trips) return BO_ST_MAX_ITER;
 
@@ -385,7 +386,7 @@ BO_DEVICE int bo_ipm_trip(bo_ipm_state& S, const bo_solver_params prm) {
         }
       }
       S.tau = fmax(tau_min, 1.0 - S.mu);
-      BO_UNROLL
+      BO_NOUNROLL
       for (int i = 0; i < BO_MI; ++i) S.sigma[i] = S.z[i] / S.s[i];
       bo_kkt_fill(S.H, S.JE, S.JI, S.sigma, S.K);
       bo_measures(S.f, S.cE, S.cI, S.s, S.mu, &S.phi0, &S.theta0);
@@ -402,6 +403,10 @@ BO_DEVICE int bo_ipm_trip(bo_ipm_state& S, const bo_solver_params prm) {
     }
   }
 
+  return -1;
+}
+
+BO_DEVICE int bo_trip_factor(bo_ipm_state& S, const bo_solver_params prm) {
   // =========================== PH_FACTOR ===========================
   if (S.phase == BO_PH_FACTOR) {
     const int inertia = bo_kkt_factor(S.K, S.dw, S.dc, S.LD, S.ipiv);
@@ -457,7 +462,7 @@ BO_DEVICE int bo_ipm_trip(bo_ipm_state& S, const bo_solver_params prm) {
       dphi += S.g[i] * S.dx[i];
       dxn = fmax(dxn, fabs(S.dx[i]));
     }
-    BO_UNROLL
+    BO_NOUNROLL
     for (int i = 0; i < BO_MI; ++i) dphi -= S.mu * S.ds[i] / S.s[i];
     S.dphi = dphi;
     S.a = a_p;
@@ -470,6 +475,12 @@ BO_DEVICE int bo_ipm_trip(bo_ipm_state& S, const bo_solver_params prm) {
     S.phase = BO_PH_TRIAL;
   }
 
+  return -1;
+}
+
+BO_DEVICE int bo_trip_trial(bo_ipm_state& S, const bo_solver_params prm) {
+  const double kappa_sigma = 1e10, gamma_theta = 1e-5, gamma_phi = 1e-5, eta_phi = 1e-8;
+  const double s_phi = 2.3, s_theta = 1.1, kappa_soc = 0.99;
   // =========================== PH_TRIAL ===========================
   if (S.phase == BO_PH_TRIAL) {
     double xt[BO_NX], st[BO_DIM(BO_MI)], cEt[BO_DIM(BO_ME)], cIt[BO_DIM(BO_MI)];
@@ -517,14 +528,14 @@ BO_DEVICE int bo_ipm_trip(bo_ipm_state& S, const bo_solver_params prm) {
         S.fph[slot] = S.phi0 - gamma_phi * S.theta0;
       }
       double a_d = 1.0, dz[BO_DIM(BO_MI)];
-      BO_UNROLL
+      BO_NOUNROLL
       for (int i = 0; i < BO_MI; ++i) {
         dz[i] = -S.z[i] + S.mu / S.s[i] - S.sigma[i] * S.ds[i];
         if (dz[i] < 0.0) a_d = fmin(a_d, -S.tau * S.z[i] / dz[i]);
       }
       BO_UNROLL
       for (int i = 0; i < BO_NX; ++i) S.x[i] = xt[i];
-      BO_UNROLL
+      BO_NOUNROLL
       for (int i = 0; i < BO_MI; ++i) {
         S.s[i] = fmax(st[i], cIt[i]);  // slack reset: lowers theta, never raises the barrier objective
         S.z[i] += a_d * dz[i];
@@ -588,6 +599,13 @@ BO_DEVICE int bo_ipm_trip(bo_ipm_state& S, const bo_solver_params prm) {
   return -1;
 }
 
+BO_DEVICE int bo_ipm_trip(bo_ipm_state& S, const bo_solver_params prm) {
+  int status = bo_trip_eval(S, prm);
+  if (status < 0) status = bo_trip_factor(S, prm);
+  if (status < 0) status = bo_trip_trial(S, prm);
+  return status;
+}
+
 // Convenience driver for one instance (used by the host-compiled test harness).
 BO_DEVICE int bo_ipm_solve(bo_ipm_state& S, const bo_solver_params prm) {
   bo_ipm_init(S, prm);
@@ -632,8 +650,13 @@ bo_solve_kernel(long long B, const double* __restrict__ p_all, const double* __r
     // CTA-wide barrier per trip: keeps the warps of a CTA in the same block of this (large) code at
     // the same time, so instruction fetch is shared between them instead of thrashing the i-cache
     if (!__syncthreads_or(active ? 1 : 0)) break;
+    int status = -1;
+    if (active) status = bo_trip_eval(S, prm);
+    __syncthreads();
+    if (active && status < 0) status = bo_trip_factor(S, prm);
+    __syncthreads();
+    if (active && status < 0) status = bo_trip_trial(S, prm);
     if (active) {
-      const int status = bo_ipm_trip(S, prm);
       if (status >= 0) {
         BO_UNROLL
         for (int i = 0; i < BO_NX; ++i) x_all[b * BO_NX + i] = S.x[i];
