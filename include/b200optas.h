@@ -115,7 +115,8 @@ typedef struct bo_options {
   int32_t max_trips;       /* <=0: default 250.  Budget of solver trips per instance (one trip = at most
                               one KKT evaluation + one factorisation + one trial point); an instance
                               over budget ends with BO_MAX_ITER.  Bounds the tail latency of a batch. */
-  int32_t reserved[6];
+  int32_t blocks_per_sm;   /* <=0: as many as fit (occupancy); else cap on resident CTAs per SM       */
+  int32_t reserved[5];
 } bo_options;
 
 typedef struct bo_problem bo_problem;   /* opaque, owned by the library */

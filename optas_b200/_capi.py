@@ -65,7 +65,7 @@ class bo_options(C.Structure):
         ("flags", C.c_uint32), ("max_iter", C.c_int32),
         ("tol", C.c_double), ("acceptable_tol", C.c_double), ("mu_init", C.c_double), ("max_step", C.c_double),
         ("cache_dir", C.c_char_p), ("include_dir", C.c_char_p),
-        ("threads_per_block", C.c_int32), ("max_trips", C.c_int32), ("reserved", C.c_int32 * 6),
+        ("threads_per_block", C.c_int32), ("max_trips", C.c_int32), ("blocks_per_sm", C.c_int32), ("reserved", C.c_int32 * 5),
     ]
 
 
@@ -143,12 +143,12 @@ def tape_struct(t: Tape, keep: _Keep) -> bo_tape:
 
 def options_struct(flags: int = 0, max_iter: int = 0, tol: float = 0.0, acceptable_tol: float = 0.0,
                    mu_init: float = 0.0, max_step: float = 0.0, cache_dir: Optional[str] = None, include_dir: Optional[str] = None,
-                   threads_per_block: int = 0, max_trips: int = 0) -> bo_options:
+                   threads_per_block: int = 0, max_trips: int = 0, blocks_per_sm: int = 0) -> bo_options:
     return bo_options(
         flags=flags, max_iter=max_iter, tol=tol, acceptable_tol=acceptable_tol, mu_init=mu_init, max_step=max_step,
         cache_dir=cache_dir.encode() if cache_dir else None,
         include_dir=include_dir.encode() if include_dir else None,
-        threads_per_block=threads_per_block, max_trips=max_trips,
+        threads_per_block=threads_per_block, max_trips=max_trips, blocks_per_sm=blocks_per_sm,
     )
 
 

@@ -525,6 +525,7 @@ int bo_problem_create(const bo_problem_desc* desc, const bo_options* opts_in, bo
     BO_CU(g_drv.cuDeviceGetAttribute(&pr->n_sm, CU_DEVICE_ATTRIBUTE_MULTIPROCESSOR_COUNT, dev));
     BO_CU(g_drv.cuOccupancyMaxActiveBlocksPerMultiprocessor(&pr->blocks_per_sm, pr->kernel.fn, pr->tpb, 0));
     if (pr->blocks_per_sm < 1) pr->blocks_per_sm = 1;
+    if (pr->opts.blocks_per_sm > 0 && pr->opts.blocks_per_sm < pr->blocks_per_sm) pr->blocks_per_sm = pr->opts.blocks_per_sm;
     if ((rc = pr->d_counter.reserve(sizeof(unsigned long long))) != BO_OK) return rc;
     pr->loaded = true;
     pr->timer.enabled = (pr->opts.flags & BO_FLAG_TIMING) != 0;

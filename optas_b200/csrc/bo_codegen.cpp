@@ -257,10 +257,10 @@ std::string emit_problem_source(const ProblemSource& ps, int tpb) {
   emit_sparse_helpers(o, "I", ps.jac_ineq, ps.n_ineq);
 
   const int nk = ps.nx + ps.n_eq;
-  auto kidx = [nk](int i, int j) { return i * nk + j; };  // full row-major storage, lower part used
+  auto kidx = [](int i, int j) { return i * (i + 1) / 2 + j; };  // packed lower triangle, i >= j
   o << "BO_DEVICE void bo_kkt_fill(const double* BO_RESTRICT H, const double* BO_RESTRICT JE, const double* BO_RESTRICT JI,\n"
        "                           const double* BO_RESTRICT sigma, double* BO_RESTRICT K) {\n";
-  o << "  BO_UNROLL\n  for (int i = 0; i < " << nk * nk << "; ++i) K[i] = 0.0;\n";
+  o << "  BO_UNROLL\n  for (int i = 0; i < " << nk * (nk + 1) / 2 << "; ++i) K[i] = 0.0;\n";
   for (int k = 0; k < ps.hess.nnz(); ++k) o << "  K[" << kidx(ps.hess.row[k], ps.hess.col[k]) << "] += H[" << k << "];\n";
   {
     std::vector<std::vector<int>> by_row(ps.n_ineq > 0 ? ps.n_ineq : 1);

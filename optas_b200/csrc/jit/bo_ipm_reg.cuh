@@ -23,8 +23,8 @@
 #include "bo_common.cuh"
 
 #define BO_NK (BO_NX + BO_ME)
-#define BO_KSZ (BO_NK * BO_NK)
-#define BO_KIDX(i, j) ((i) * BO_NK + (j)) /* row-major, lower triangle (i >= j) is the data */
+#define BO_KSZ ((BO_NK * (BO_NK + 1)) / 2)
+#define BO_KIDX(i, j) (((i) * ((i) + 1)) / 2 + (j)) /* packed lower triangle, i >= j */
 #define BO_DIM(n) ((n) > 0 ? (n) : 1)
 
 // Bunch-Kaufman LDL' (diagonal pivoting with 1x1 and 2x2 blocks; the unblocked LAPACK dsytf2
@@ -164,11 +164,10 @@ BO_NOINLINE void bo_bk_solve(const double* BO_RESTRICT A, const int* BO_RESTRICT
   }
 }
 
-// Factor K + diag(dw I, -dc I).  Returns 0 when the inertia is (BO_NX, BO_ME, 0), +1 when there
-// are too many negative eigenvalues (reduced Hessian not positive definite), -1 when singular.
-BO_DEVICE int bo_kkt_factor(const double* BO_RESTRICT K, double dw, double dc, double* BO_RESTRICT LD, int* BO_RESTRICT ipiv) {
-  for (int i = 0; i < BO_NK; ++i)
-    for (int j = 0; j <= i; ++j) LD[BO_KIDX(i, j)] = K[BO_KIDX(i, j)];
+// Factor A + diag(dw I, -dc I) in place (A = assembled KKT matrix, packed lower triangle).  Returns 0
+// when the inertia is (BO_NX, BO_ME, 0), +1 when there are too many negative eigenvalues (reduced
+// Hessian not positive definite), -1 when singular.
+BO_DEVICE int bo_kkt_factor(double dw, double dc, double* BO_RESTRICT LD, int* BO_RESTRICT ipiv) {
   for (int i = 0; i < BO_NX; ++i) LD[BO_KIDX(i, i)] += dw;
   for (int i = BO_NX; i < BO_NK; ++i) LD[BO_KIDX(i, i)] -= dc;
   int n_neg = 0;
@@ -234,7 +233,7 @@ struct bo_ipm_state {
   // evaluation at x (valid from PH_EVAL to the end of the iteration)
   double g[BO_NX], cE[BO_DIM(BO_ME)], cI[BO_DIM(BO_MI)], rd[BO_NX], sigma[BO_DIM(BO_MI)];
   double JE[BO_DIM(BO_NNZ_JE)], JI[BO_DIM(BO_NNZ_JI)], H[BO_DIM(BO_NNZ_H)];
-  double K[BO_KSZ], LD[BO_KSZ];
+  double LD[BO_KSZ];  // assembled KKT matrix, factored in place (re-assembled for every attempt)
   int ipiv[BO_NK];
   double phi0, theta0, dw, dc;
   int attempt, heavy;
@@ -325,7 +324,6 @@ BO_DEVICE int bo_trip_eval(bo_ipm_state& S, const bo_solver_params prm) {
       for (int i = 0; i < BO_DIM(BO_NNZ_H); ++i) S.H[i] = 0.0;
       BO_UNROLL
       for (int i = 0; i < BO_MI; ++i) S.sigma[i] = 0.0;
-      bo_kkt_fill(S.H, S.JE, S.JI, S.sigma, S.K);
       S.dw = 1.0;
       S.dc = 1e-10;
       S.phase = BO_PH_FACTOR;
@@ -388,7 +386,6 @@ BO_DEVICE int bo_trip_eval(bo_ipm_state& S, const bo_solver_params prm) {
       S.tau = fmax(tau_min, 1.0 - S.mu);
       BO_NOUNROLL
       for (int i = 0; i < BO_MI; ++i) S.sigma[i] = S.z[i] / S.s[i];
-      bo_kkt_fill(S.H, S.JE, S.JI, S.sigma, S.K);
       bo_measures(S.f, S.cE, S.cI, S.s, S.mu, &S.phi0, &S.theta0);
       if (S.it == 0) {
         S.theta_max = 1e4 * fmax(1.0, S.theta0);
@@ -409,7 +406,8 @@ BO_DEVICE int bo_trip_eval(bo_ipm_state& S, const bo_solver_params prm) {
 BO_DEVICE int bo_trip_factor(bo_ipm_state& S, const bo_solver_params prm) {
   // =========================== PH_FACTOR ===========================
   if (S.phase == BO_PH_FACTOR) {
-    const int inertia = bo_kkt_factor(S.K, S.dw, S.dc, S.LD, S.ipiv);
+    bo_kkt_fill(S.H, S.JE, S.JI, S.sigma, S.LD);
+    const int inertia = bo_kkt_factor(S.dw, S.dc, S.LD, S.ipiv);
     if (S.ls_mode) {
       if (inertia == 0) {
         double nz[BO_DIM(BO_MI)];

@@ -258,7 +258,8 @@ class B200Solver(Solver):
     # -- setup --------------------------------------------------------------------------------
     def setup(self, solver_name: Optional[str] = None, solver_options: Optional[Dict] = None, *,
               method: Optional[str] = None, tol: Optional[float] = None, options: Optional[Dict] = None,
-              compile_only: bool = False, timing: bool = False, threads_per_block: int = 0, max_trips: int = 0):
+              compile_only: bool = False, timing: bool = False, threads_per_block: int = 0, max_trips: int = 0,
+              blocks_per_sm: int = 0):
         from . import _capi
 
         name = solver_name if solver_name is not None else (method if method is not None else "ipopt")
@@ -298,7 +299,8 @@ class B200Solver(Solver):
         flags = (_capi.BO_FLAG_COMPILE_ONLY if compile_only else 0) | (_capi.BO_FLAG_TIMING if timing else 0)
         self._handle = _capi.ProblemHandle(self._lowered, flags=flags, max_iter=max_iter, tol=tol_use,
                                            acceptable_tol=acc_tol, mu_init=mu_init, max_step=max_step,
-                                           threads_per_block=threads_per_block, max_trips=max_trips)
+                                           threads_per_block=threads_per_block, max_trips=max_trips,
+                                           blocks_per_sm=blocks_per_sm)
         self._stats = None
         return self
 

@@ -4,19 +4,17 @@ import torch, optas_b200, numpy as np
 from optas_b200 import problems
 prob = problems.lwr_ik()
 dev = "cuda"
-def run(B, tpb, max_trips, reps=4):
+def run(B, tpb, max_trips, reps=4, bps=0):
     P, X0 = prob.sample(B, 0)
-    s = optas_b200.B200Solver(prob.opt).setup("ipopt", {"max_trips": max_trips}, timing=True, threads_per_block=tpb)
+    s = optas_b200.B200Solver(prob.opt).setup("ipopt", {"max_trips": max_trips}, timing=True, threads_per_block=tpb, blocks_per_sm=bps)
     Pd, X0d = torch.from_numpy(P).to(dev), torch.from_numpy(X0).to(dev); Xd = torch.empty_like(X0d)
     st = torch.empty(B, dtype=torch.int32, device=dev)
     for _ in range(2): s.solve_raw(Pd, X0d, Xd, None, None, st, None, None)
     torch.cuda.synchronize(); s._handle.kernel_time()
     for _ in range(reps): s.solve_raw(Pd, X0d, Xd, None, None, st, None, None)
     torch.cuda.synchronize(); ms, n = s._handle.kernel_time()
-    print(f"B {B:7d} tpb {tpb:3d} max_trips {max_trips:5d}: {ms/n:8.3f} ms  conv {float((st<=1).float().mean()):.4f}  -> {B/(ms/n)*1e3:.3e} inst/s", flush=True)
-for tpb in (64, 128, 256, 512):
-    run(65536, tpb, 250)
-for mt in (25, 100, 1000):
-    run(65536, 256, mt)
-for B in (1024, 262144, 1048576):
-    run(B, 256, 250)
+    print(f"B {B:7d} tpb {tpb:3d} bps {bps} max_trips {max_trips:5d}: {ms/n:8.3f} ms  conv {float((st<=1).float().mean()):.4f}  -> {B/(ms/n)*1e3:.3e} inst/s", flush=True)
+for tpb, bps in ((32, 1), (32, 2), (32, 4), (64, 1), (64, 2), (64, 4), (128, 1), (128, 2), (256, 1)):
+    run(262144, tpb, 250, bps=bps)
+run(65536, 128, 250)
+run(65536, 64, 250, bps=2)
