@@ -501,11 +501,14 @@ int bo_problem_create(const bo_problem_desc* desc, const bo_options* opts_in, bo
       !expect(ps.kkt, {ps.nx, ps.np, ps.n_eq, ps.n_ineq},
               {1, ps.nx, ps.n_eq, ps.n_ineq, ps.jac_eq.nnz(), ps.jac_ineq.nnz(), ps.hess.nnz()}, "kkt"))
     return set_err(BO_ERR_INVALID, "bo_problem_create: %s", err.c_str());
-  if (ps.nx + ps.n_eq > 40 || ps.n_ineq > 128)
+  // One instance per thread: the KKT matrix (packed lower triangle) and the iterate live in thread-local
+  // memory.  Up to ~40 rows that is L1-resident; up to 160 rows (C3: 122) it still works but runs out of
+  // L2 -- functional first, a shared-memory CTA-per-instance tier is the planned replacement.
+  if (ps.nx + ps.n_eq > 160 || ps.n_ineq > 512)
     return set_err(BO_ERR_UNSUPPORTED,
-                   "bo_problem_create: nx+n_eq=%d, n_ineq=%d exceeds the register-resident tier (nx+n_eq<=40, n_ineq<=128)",
+                   "bo_problem_create: nx+n_eq=%d, n_ineq=%d exceeds the thread-per-instance tier (nx+n_eq<=160, n_ineq<=512)",
                    ps.nx + ps.n_eq, ps.n_ineq);
-  pr->tpb = pr->opts.threads_per_block > 0 ? pr->opts.threads_per_block : 128;
+  pr->tpb = pr->opts.threads_per_block > 0 ? pr->opts.threads_per_block : (ps.nx + ps.n_eq > 40 ? 64 : 128);
   if (getenv("BO_DEBUG")) fprintf(stderr, "[bo] emitting source\n");
   pr->source = bo::emit_problem_source(ps, pr->tpb);
   if (getenv("BO_DEBUG")) fprintf(stderr, "[bo] source %zu bytes\n", pr->source.size());

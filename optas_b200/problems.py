@@ -121,4 +121,66 @@ def booth() -> Problem:
     return Problem("booth", opt, sample)
 
 
-ALL_BUILDERS = [lwr_ik, booth]
+
+
+# ----------------------------------------------------------------------------------------------
+# C3: point-mass MPC tick (reference: example/point_mass_mpc.py:88-154, class Controller)
+# ----------------------------------------------------------------------------------------------
+
+
+def point_mass_mpc(T: int = 20) -> Problem:
+    dt, obs_rad, pm_radius = 0.05, 0.2, 0.1
+    point_mass = TaskModel("point_mass", 2, time_derivs=[0, 1], dlim={0: [-1.5, 1.5], 1: [-1, 1]})
+    name = point_mass.get_name()
+    builder = OptimizationBuilder(T, tasks=point_mass, derivs_align=True)
+    curr = builder.add_parameter("curr", 2)
+    dcurr = builder.add_parameter("dcurr", 2)
+    goal = builder.add_parameter("goal", 2, T)
+    obs = builder.add_parameter("obs", 2, T)
+    builder.enforce_model_limits(name, time_deriv=0)
+    builder.enforce_model_limits(name, time_deriv=1)
+    builder.integrate_model_states(name, time_deriv=1, dt=dt)
+    builder.fix_configuration(name, config=curr)
+    builder.fix_configuration(name, config=dcurr, time_deriv=1)
+    X = builder.get_model_states(name)
+    safe_dist_sq = (obs_rad + pm_radius) ** 2
+    for i in range(T):
+        builder.add_geq_inequality_constraint(f"obs_avoid_{i}", cs.sumsqr(obs[:, i] - X[:, i]), safe_dist_sq)
+    builder.add_cost_term("optimal_path", cs.sumsqr(goal - X))
+    dX = builder.get_model_states(name, time_deriv=1)
+    w = 0.0025 / float(T)
+    ddX = (dX[:, 1:] - dX[:, :-1]) / dt
+    builder.add_cost_term("minimize_acceleration", w * cs.sumsqr(ddX))
+    opt = builder.build()
+
+    def sample(B: int, seed: int = 1):
+        """C3 inputs: random current state away from the obstacle, obstacle on the
+        script's circular path (point_mass_mpc.py:293-306), goal ramp toward (1, 1); seed = hold-position trajectory."""
+        rng = np.random.default_rng(seed)
+        t = rng.uniform(0.0, 4.4, size=B)
+        k = np.arange(T)
+        phase = np.pi * (t[:, None] + dt * k[None, :]) - np.pi
+        obs_path = 0.15 * np.stack([np.sin(phase), np.cos(phase) + 1.0], axis=1)  # [B, 2, T]
+        cur = np.empty((B, 2))
+        todo = np.ones(B, dtype=bool)
+        while todo.any():
+            cand = rng.uniform(-1.2, 1.2, size=(int(todo.sum()), 2))
+            far = np.linalg.norm(cand - obs_path[todo, :, 0], axis=1) >= 0.35
+            idx = np.where(todo)[0]
+            cur[idx[far]] = cand[far]
+            todo[idx[far]] = False
+        dcur = rng.uniform(-0.5, 0.5, size=(B, 2))
+        ramp = np.minimum(1.0, dt * k / 4.4)
+        goal_path = cur[:, :, None] + (1.0 - cur[:, :, None]) * ramp[None, None, :]
+        P = np.concatenate([cur, dcur, goal_path.transpose(0, 2, 1).reshape(B, -1), obs_path.transpose(0, 2, 1).reshape(B, -1)],
+                           axis=1)
+        # seed: hold the current position with zero velocity (layout: y/x 2 x T column-major, then dy/x).
+        # The all-zero seed of the script's first tick puts every knot at the origin, which lies ON the
+        # obstacle's path: the obstacle constraints start violated with (near-)zero gradient.
+        X0 = np.concatenate([np.tile(cur, (1, T)), np.zeros((B, 2 * T))], axis=1)
+        return np.ascontiguousarray(P), np.ascontiguousarray(X0)
+
+    return Problem("point_mass_mpc", opt, sample, {}, {"point_mass": point_mass})
+
+
+ALL_BUILDERS = [lwr_ik, booth, point_mass_mpc]

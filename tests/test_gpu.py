@@ -208,6 +208,57 @@ def test_batched_dict_api(ik):
     assert one[f"{name}/q"].shape == (7, 1)
 
 
+def test_nlpsol_factory_matches_solver(ik):
+    """The CasADi factory signature (optas/solver.py:346-398): problem = {x, p, f, g = v(x, p)},
+    lbg = 0, ubg = 1e10 -- the +- pairs are merged back into equalities and the result equals the
+    Solver-API result."""
+    import optas_b200 as optas
+    from optas_b200 import problems
+
+    prob, solver = ik
+    opt = prob.opt
+    x, p = opt.decision_variables.vec(), opt.parameters.vec()
+    nlp = optas.nlpsol("solver", "ipopt", {"x": x, "p": p, "f": opt.f(x, p), "g": opt.v(x, p)}, {})
+    pv, x0 = problems.lwr_ik_example_instance()
+    sol = nlp(x0=x0, p=pv, lbg=opt.lbv, ubg=opt.ubv)
+    assert nlp.stats()["success"] and nlp.stats()["iter_count"] >= 1
+    ref = _solve_host(solver, pv[None, :], x0[None, :])
+    assert np.array_equal(sol["x"].toarray().flatten(), ref["x"][0])
+    assert sol["lam_g"].shape == (20, 1) and sol["g"].shape == (20, 1)
+    # stationarity in CasADi's sign convention: grad f + J_g' lam_g = 0
+    import slsqp_driver
+
+    op = slsqp_driver.OracleProblem(opt)
+    xs = sol["x"].toarray().flatten()
+    resid = op.df(xs, pv) + op.dv(xs, pv).T @ sol["lam_g"].toarray().flatten()
+    assert np.abs(resid).max() < 1e-6
+
+
+def test_c3_point_mass_mpc_batch(torch_cuda):
+    """C3: MPC tick, 80 variables / 42 equalities / 180 inequalities, checked by the oracle."""
+    import kkt_check
+    import optas_b200
+    from optas_b200 import problems
+
+    prob = problems.point_mass_mpc()
+    solver = optas_b200.B200Solver(prob.opt).setup("ipopt")
+    B = 512
+    P, X0 = prob.sample(B, seed=1)
+    r = _solve_host(solver, P, X0)
+    ok = r["status"] <= 1
+    assert ok.mean() >= 0.97, ok.mean()
+    lo = solver._lowered
+    idx = np.where(ok)[0][:24]
+    res = kkt_check.kkt_residual(prob, r["x"][idx], P[idx], r["lam"][idx][:, :lo.n_eq], r["lam"][idx][:, lo.n_eq:])
+    assert res.max() < KKT_TOL, res.max()
+    # dynamics x_{t+1} = x_t + dt v_t and the initial state hold to round-off (linear equalities)
+    sol = prob.seed_dict(r["x"][ok])
+    Y, dY = sol["point_mass/y/x"], sol["point_mass/dy/x"]
+    assert np.abs(Y[:, :, 1:] - Y[:, :, :-1] - 0.05 * dY[:, :, :-1]).max() < 1e-9
+    assert np.abs(Y[:, :, 0] - P[ok, 0:2]).max() < 1e-9
+    assert (np.abs(Y) <= 1.5 + 1e-9).all() and (np.abs(dY) <= 1.0 + 1e-9).all()
+
+
 def test_error_on_fail(torch_cuda):
     import optas_b200
     from optas_b200 import problems

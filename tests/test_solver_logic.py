@@ -106,3 +106,24 @@ def test_pack_unpack_roundtrip():
     assert B2 == 5 and np.array_equal(M2[:, 7:], P[:, 7:]) and not M2[:, :7].any()
     M3, B3 = pack_batch(prob.opt.parameters, {"q_nominal": problems.LWR_Q_NOMINAL})
     assert B3 is None and M3.shape == (1, 10)
+
+
+def test_c3_point_mass_mpc_tick():
+    """C3 (example/point_mass_mpc.py Controller, T=20): nx=80, 42 linear equalities, 160 bounds, 20
+    obstacle inequalities.  Dimensions as in SURVEY.md 8a; solutions checked by the oracle."""
+    prob = problems.point_mass_mpc()
+    opt = prob.opt
+    assert (opt.nx, opt.np, opt.nk, opt.na, opt.ng, opt.nh, opt.nv) == (80, 84, 160, 42, 20, 0, 264)
+    assert type(opt).__name__ == "QuadraticCostNonlinearConstraints"
+    sim, lo = _sim(prob)
+    P, X0 = prob.sample(48, seed=1)
+    r = sim.solve(P, X0)
+    ok = r["status"] <= 1
+    assert ok.mean() >= 0.97
+    res = kkt_check.kkt_residual(prob, r["x"][ok][:16], P[ok][:16], r["lam"][ok][:16, :lo.n_eq], r["lam"][ok][:16, lo.n_eq:])
+    assert res.max() < 1e-6
+    # polish: the oracle seeded at the result stays there
+    op = slsqp_driver.OracleProblem(opt)
+    i = int(np.where(ok)[0][0])
+    pol = slsqp_driver.solve_slsqp(op, P[i], r["x"][i], form="split", options={"ftol": 1e-15, "maxiter": 100})
+    assert np.abs(pol.x - r["x"][i]).max() / max(1.0, np.abs(pol.x).max()) < 1e-6
