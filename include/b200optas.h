@@ -101,6 +101,8 @@ typedef struct bo_problem_desc {
 #define BO_FLAG_VERBOSE 2u      /* print ptxas info / cache hits to stderr                      */
 #define BO_FLAG_NO_CACHE 4u     /* ignore and do not write the on-disk cubin cache              */
 #define BO_FLAG_TIMING 8u       /* bracket every kernel launch with CUDA events (see *_kernel_time) */
+#define BO_FLAG_PIVOTED_LDL 16u  /* factor the KKT system with Bunch-Kaufman partial pivoting (data-dependent
+                                   control flow, slower) instead of the unpivoted rho-augmented LDL'  */
 
 typedef struct bo_options {
   uint32_t flags;

@@ -20,7 +20,7 @@ LIB_PATH = os.path.join(_HERE, "libb200optas.so")
 
 BO_ABI_VERSION = 1
 BO_OK, BO_ERR_INVALID, BO_ERR_COMPILE, BO_ERR_CUDA, BO_ERR_NO_DEVICE, BO_ERR_UNSUPPORTED = 0, -1, -2, -3, -4, -5
-BO_FLAG_COMPILE_ONLY, BO_FLAG_VERBOSE, BO_FLAG_NO_CACHE, BO_FLAG_TIMING = 1, 2, 4, 8
+BO_FLAG_COMPILE_ONLY, BO_FLAG_VERBOSE, BO_FLAG_NO_CACHE, BO_FLAG_TIMING, BO_FLAG_PIVOTED_LDL = 1, 2, 4, 8, 16
 STATUS_NAMES = {0: "converged", 1: "acceptable", 2: "max_iter", 3: "line_search", 4: "numerical"}
 
 EXPORTS = [

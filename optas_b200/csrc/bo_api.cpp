@@ -510,7 +510,7 @@ int bo_problem_create(const bo_problem_desc* desc, const bo_options* opts_in, bo
                    ps.nx + ps.n_eq, ps.n_ineq);
   pr->tpb = pr->opts.threads_per_block > 0 ? pr->opts.threads_per_block : (ps.nx + ps.n_eq > 40 ? 64 : 128);
   if (getenv("BO_DEBUG")) fprintf(stderr, "[bo] emitting source\n");
-  pr->source = bo::emit_problem_source(ps, pr->tpb);
+  pr->source = bo::emit_problem_source(ps, pr->tpb, (pr->opts.flags & BO_FLAG_PIVOTED_LDL) != 0);
   if (getenv("BO_DEBUG")) fprintf(stderr, "[bo] source %zu bytes\n", pr->source.size());
   int rc = jit_compile(pr->source, "bo_solve", "bo_solve_kernel", pr->opts, &pr->compiled);
   if (rc != BO_OK) return rc;

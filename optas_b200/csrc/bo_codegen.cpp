@@ -244,12 +244,13 @@ static void emit_sparse_helpers(std::ostringstream& o, const char* tag, const Sp
   o << "  (void)J; (void)x; (void)out;\n}\n";
 }
 
-std::string emit_problem_source(const ProblemSource& ps, int tpb) {
+std::string emit_problem_source(const ProblemSource& ps, int tpb, bool pivoted_ldl) {
   std::ostringstream o;
   o << "// generated by libb200optas (bo_codegen.cpp): tier-S solver, one instance per thread\n";
   o << "#define BO_NX " << ps.nx << "\n#define BO_NP " << ps.np << "\n#define BO_ME " << ps.n_eq << "\n#define BO_MI "
     << ps.n_ineq << "\n#define BO_NNZ_JE " << ps.jac_eq.nnz() << "\n#define BO_NNZ_JI " << ps.jac_ineq.nnz()
     << "\n#define BO_NNZ_H " << ps.hess.nnz() << "\n#define BO_TPB " << tpb << "\n";
+  if (pivoted_ldl) o << "#define BO_USE_BK 1\n";
   o << "#include \"bo_common.cuh\"\n\n";
   o << emit_tape_function(ps.fc, "bo_tape_fc") << "\n";
   o << emit_tape_function(ps.kkt, "bo_tape_kkt") << "\n";
@@ -280,6 +281,22 @@ std::string emit_problem_source(const ProblemSource& ps, int tpb) {
     o << "  K[" << kidx(ps.nx + ps.jac_eq.row[k], ps.jac_eq.col[k]) << "] += JE[" << k << "];\n";
   o << "  (void)H; (void)JE; (void)JI; (void)sigma;\n}\n";
 
+  // K[x,x] += rho * JE' JE (augmented-Lagrangian convexification of the (1,1) block, see bo_ipm_reg.cuh)
+  o << "BO_DEVICE void bo_JEtJE_acc(const double* BO_RESTRICT JE, double rho, double* BO_RESTRICT K) {\n";
+  {
+    std::vector<std::vector<int>> by_row(ps.n_eq > 0 ? ps.n_eq : 1);
+    for (int k = 0; k < ps.jac_eq.nnz(); ++k) by_row[ps.jac_eq.row[k]].push_back(k);
+    for (int r = 0; r < ps.n_eq; ++r) {
+      const auto& ks = by_row[r];
+      for (size_t u = 0; u < ks.size(); ++u)
+        for (size_t w = 0; w < ks.size(); ++w) {
+          const int cu = ps.jac_eq.col[ks[u]], cw = ps.jac_eq.col[ks[w]];
+          if (cu < cw || (cu == cw && u != w)) continue;
+          o << "  K[" << kidx(cu, cw) << "] += rho * JE[" << ks[u] << "] * JE[" << ks[w] << "];\n";
+        }
+    }
+  }
+  o << "  (void)JE; (void)rho; (void)K;\n}\n";
   o << "BO_DEVICE double bo_xHx(const double* BO_RESTRICT H, const double* BO_RESTRICT v) {\n  double acc = 0.0;\n";
   for (int k = 0; k < ps.hess.nnz(); ++k) {
     const int r = ps.hess.row[k], c = ps.hess.col[k];

@@ -27,6 +27,57 @@
 #define BO_KIDX(i, j) (((i) * ((i) + 1)) / 2 + (j)) /* packed lower triangle, i >= j */
 #define BO_DIM(n) ((n) > 0 ? (n) : 1)
 
+// ---- fast path: unpivoted LDL' with a fixed elimination order (x first, then y) ----
+// Every lane executes the same instruction sequence (no data-dependent pivoting), the loops have
+// compile-time bounds, and for small systems everything unrolls into straight-line FMAs.  It is only
+// valid when the (1,1) block is positive definite; the caller makes it so WITHOUT changing the
+// solution by adding rho*JE'JE to it and rho*JE'(rhs_y) to the right-hand side (adding rho*JE' times
+// the second block row to the first).  By Debreu's lemma H + rho JE'JE is positive definite for large
+// enough rho exactly when the reduced Hessian is, i.e. when the KKT inertia is correct.
+// With a constraint-block perturbation dc the same trick needs dc' = dc / (1 - rho dc) and
+// dy = dy'' / (1 - rho dc) (substitute dy'' = (1 - rho dc) dy to restore symmetry).
+// On exit LD holds D on the diagonal and the unit-lower L below it.  The pivot signs ARE the inertia:
+// a non-positive pivot in the x block means the reduced Hessian is not positive definite (or rho is
+// too small, which is handled the same way: more dw), a non-negative one in the y block means JE is
+// rank deficient (handled with dc) -- IPOPT's Algorithm IC, without a pivoting factorisation.
+// Define BO_USE_BK (BO_FLAG_PIVOTED_LDL) to factor with Bunch-Kaufman partial pivoting instead.
+#ifndef BO_STATIC_RHO
+#define BO_STATIC_RHO 1.0e6
+#endif
+BO_NOINLINE int bo_ldl_static(double* BO_RESTRICT A) {
+  int bad = 0;  // 0 ok, 1 = non-positive pivot in the x block, 2 = non-negative pivot in the y block
+  for (int j = 0; j < BO_NK; ++j) {
+    double d = A[BO_KIDX(j, j)];
+    const double scale = fmax(1.0, fabs(d));
+    for (int k = 0; k < j; ++k) {
+      const double l = A[BO_KIDX(j, k)];
+      d -= l * l * A[BO_KIDX(k, k)];
+    }
+    if (j < BO_NX) {
+      if (!(d > 1e-13 * scale) && bad == 0) bad = 1;
+    } else {
+      if (!(d < -1e-13) && bad == 0) bad = 2;
+    }
+    A[BO_KIDX(j, j)] = d;
+    const double dinv = 1.0 / d;
+    for (int i = j + 1; i < BO_NK; ++i) {
+      double v = A[BO_KIDX(i, j)];
+      for (int k = 0; k < j; ++k) v -= A[BO_KIDX(i, k)] * A[BO_KIDX(j, k)] * A[BO_KIDX(k, k)];
+      A[BO_KIDX(i, j)] = v * dinv;
+    }
+  }
+  return bad;
+}
+
+BO_NOINLINE void bo_ldl_static_solve(const double* BO_RESTRICT A, double* BO_RESTRICT b) {
+  for (int i = 1; i < BO_NK; ++i)
+    for (int k = 0; k < i; ++k) b[i] -= A[BO_KIDX(i, k)] * b[k];
+  for (int i = 0; i < BO_NK; ++i) b[i] /= A[BO_KIDX(i, i)];
+  for (int i = BO_NK - 2; i >= 0; --i)
+    for (int k = i + 1; k < BO_NK; ++k) b[i] -= A[BO_KIDX(k, i)] * b[k];
+}
+
+#ifdef BO_USE_BK
 // Bunch-Kaufman LDL' (diagonal pivoting with 1x1 and 2x2 blocks; the unblocked LAPACK dsytf2
 // algorithm, lower variant) of the symmetric indefinite KKT matrix, in place.  Pivoting is data
 // dependent, so A lives in thread-local memory (L1-resident: 800 B for the 7-DoF IK problem).
@@ -184,6 +235,11 @@ BO_DEVICE int bo_kkt_factor(double dw, double dc, double* BO_RESTRICT LD, int* B
   return n_neg > BO_ME ? 1 : -1;
 }
 
+#else
+// stubs so that the (never taken) pivoted branches compile away
+BO_DEVICE void bo_bk_solve(const double*, const int*, double*) {}
+#endif
+
 // Barrier objective and l1 constraint violation at (x, s) given the function values there.
 BO_NOINLINE void bo_measures(double f, const double* cE, const double* cI, const double* s, double mu, double* phi,
                            double* theta) {
@@ -229,13 +285,17 @@ struct bo_ipm_state {
   double fth[BO_NFILTER], fph[BO_NFILTER];
   double f, mu, tau, dw_last, err0, theta_max, theta_min;
   int nf, it, n_acceptable, phase, trips;
-  bool recalc_y, ls_mode;
+  bool recalc_y, ls_mode, static_fac;  // static_fac: LD holds the unpivoted factorisation (rho-augmented)
   // evaluation at x (valid from PH_EVAL to the end of the iteration)
   double g[BO_NX], cE[BO_DIM(BO_ME)], cI[BO_DIM(BO_MI)], rd[BO_NX], sigma[BO_DIM(BO_MI)];
   double JE[BO_DIM(BO_NNZ_JE)], JI[BO_DIM(BO_NNZ_JI)], H[BO_DIM(BO_NNZ_H)];
   double LD[BO_KSZ];  // assembled KKT matrix, factored in place (re-assembled for every attempt)
+#ifdef BO_USE_BK
   int ipiv[BO_NK];
-  double phi0, theta0, dw, dc;
+#else
+  int ipiv[1];
+#endif
+  double phi0, theta0, dw, dc, rho;
   int attempt, heavy;
   // step and line search
   double sol[BO_NK], dx[BO_NX], ds[BO_DIM(BO_MI)], y_step[BO_DIM(BO_ME)];
@@ -259,6 +319,7 @@ BO_DEVICE void bo_ipm_init(bo_ipm_state& S, const bo_solver_params prm) {
   S.n_acceptable = 0;
   S.recalc_y = false;
   S.ls_mode = false;
+  S.static_fac = false;
   S.phase = BO_PH_EVAL;
   S.trips = 0;
   bo_eval_fc(S.x, S.p, &S.f, S.cE, S.cI);
@@ -282,7 +343,18 @@ BO_NOINLINE double bo_ipm_step(bo_ipm_state& S) {
   bo_JIt_acc(S.JI, tvec, S.sol);
   BO_UNROLL
   for (int j = 0; j < BO_ME; ++j) S.sol[BO_NX + j] = -S.rE[j];
-  bo_bk_solve(S.LD, S.ipiv, S.sol);
+  if (S.static_fac) {
+    double t2[BO_DIM(BO_ME)];
+    BO_UNROLL
+    for (int j = 0; j < BO_ME; ++j) t2[j] = -S.rho * S.rE[j];
+    bo_JEt_acc(S.JE, t2, S.sol);  // first block row += rho * JE' * (second block rhs)
+    bo_ldl_static_solve(S.LD, S.sol);
+    const double undo = 1.0 / (1.0 - S.rho * S.dc);
+    BO_UNROLL
+    for (int j = 0; j < BO_ME; ++j) S.sol[BO_NX + j] *= undo;
+  } else {
+    bo_bk_solve(S.LD, S.ipiv, S.sol);
+  }
   BO_UNROLL
   for (int i = 0; i < BO_NX; ++i) S.dx[i] = S.sol[i];
   bo_JI_mul(S.JI, S.dx, S.ds);
@@ -407,7 +479,24 @@ BO_DEVICE int bo_trip_factor(bo_ipm_state& S, const bo_solver_params prm) {
   // =========================== PH_FACTOR ===========================
   if (S.phase == BO_PH_FACTOR) {
     bo_kkt_fill(S.H, S.JE, S.JI, S.sigma, S.LD);
-    const int inertia = bo_kkt_factor(S.dw, S.dc, S.LD, S.ipiv);
+    int inertia;
+#ifdef BO_USE_BK
+    S.static_fac = false;
+    inertia = bo_kkt_factor(S.dw, S.dc, S.LD, S.ipiv);
+#else
+    // unpivoted LDL' on the rho-augmented system (uniform control flow across the warp)
+    S.static_fac = true;
+    // rho relative to the scale of the Lagrangian Hessian (not of the barrier terms, which reach 1e10)
+    double hmax = 1.0;
+    for (int i = 0; i < BO_NNZ_H; ++i) hmax = fmax(hmax, fabs(S.H[i]));
+    const double rho = S.ls_mode ? 0.0 : BO_STATIC_RHO * hmax;
+    S.rho = rho;
+    if (!S.ls_mode) bo_JEtJE_acc(S.JE, rho, S.LD);
+    for (int i = 0; i < BO_NX; ++i) S.LD[BO_KIDX(i, i)] += S.dw;
+    for (int i = BO_NX; i < BO_NK; ++i) S.LD[BO_KIDX(i, i)] -= S.dc / (1.0 - rho * S.dc);
+    const int bad = bo_ldl_static(S.LD);
+    inertia = bad == 0 ? 0 : (bad == 1 ? 1 : -1);
+#endif
     if (S.ls_mode) {
       if (inertia == 0) {
         double nz[BO_DIM(BO_MI)];
@@ -418,7 +507,8 @@ BO_DEVICE int bo_trip_factor(bo_ipm_state& S, const bo_solver_params prm) {
         bo_JIt_acc(S.JI, nz, S.sol);
         BO_UNROLL
         for (int j = 0; j < BO_ME; ++j) S.sol[BO_NX + j] = 0.0;
-        bo_bk_solve(S.LD, S.ipiv, S.sol);
+        if (S.static_fac) bo_ldl_static_solve(S.LD, S.sol);
+        else bo_bk_solve(S.LD, S.ipiv, S.sol);
         bool fin = true;
         BO_UNROLL
         for (int j = 0; j < BO_ME; ++j) fin = fin && bo_isfinite(S.sol[BO_NX + j]);
