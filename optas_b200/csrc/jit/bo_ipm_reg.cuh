@@ -44,11 +44,19 @@
 #ifndef BO_STATIC_RHO
 #define BO_STATIC_RHO 1.0e6
 #endif
+// small systems: unroll completely (indices become compile-time, the matrix lives in registers)
+#if BO_NK <= 14
+#define BO_LDL_UNROLL BO_UNROLL
+#else
+#define BO_LDL_UNROLL BO_NOUNROLL
+#endif
 BO_NOINLINE int bo_ldl_static(double* BO_RESTRICT A) {
   int bad = 0;  // 0 ok, 1 = non-positive pivot in the x block, 2 = non-negative pivot in the y block
+  BO_LDL_UNROLL
   for (int j = 0; j < BO_NK; ++j) {
     double d = A[BO_KIDX(j, j)];
     const double scale = fmax(1.0, fabs(d));
+    BO_LDL_UNROLL
     for (int k = 0; k < j; ++k) {
       const double l = A[BO_KIDX(j, k)];
       d -= l * l * A[BO_KIDX(k, k)];
@@ -60,8 +68,10 @@ BO_NOINLINE int bo_ldl_static(double* BO_RESTRICT A) {
     }
     A[BO_KIDX(j, j)] = d;
     const double dinv = 1.0 / d;
+    BO_LDL_UNROLL
     for (int i = j + 1; i < BO_NK; ++i) {
       double v = A[BO_KIDX(i, j)];
+      BO_LDL_UNROLL
       for (int k = 0; k < j; ++k) v -= A[BO_KIDX(i, k)] * A[BO_KIDX(j, k)] * A[BO_KIDX(k, k)];
       A[BO_KIDX(i, j)] = v * dinv;
     }
@@ -70,11 +80,18 @@ BO_NOINLINE int bo_ldl_static(double* BO_RESTRICT A) {
 }
 
 BO_NOINLINE void bo_ldl_static_solve(const double* BO_RESTRICT A, double* BO_RESTRICT b) {
-  for (int i = 1; i < BO_NK; ++i)
+  BO_LDL_UNROLL
+  for (int i = 1; i < BO_NK; ++i) {
+    BO_LDL_UNROLL
     for (int k = 0; k < i; ++k) b[i] -= A[BO_KIDX(i, k)] * b[k];
+  }
+  BO_LDL_UNROLL
   for (int i = 0; i < BO_NK; ++i) b[i] /= A[BO_KIDX(i, i)];
-  for (int i = BO_NK - 2; i >= 0; --i)
+  BO_LDL_UNROLL
+  for (int i = BO_NK - 2; i >= 0; --i) {
+    BO_LDL_UNROLL
     for (int k = i + 1; k < BO_NK; ++k) b[i] -= A[BO_KIDX(k, i)] * b[k];
+  }
 }
 
 #ifdef BO_USE_BK
@@ -486,10 +503,7 @@ BO_DEVICE int bo_trip_factor(bo_ipm_state& S, const bo_solver_params prm) {
 #else
     // unpivoted LDL' on the rho-augmented system (uniform control flow across the warp)
     S.static_fac = true;
-    // rho relative to the scale of the Lagrangian Hessian (not of the barrier terms, which reach 1e10)
-    double hmax = 1.0;
-    for (int i = 0; i < BO_NNZ_H; ++i) hmax = fmax(hmax, fabs(S.H[i]));
-    const double rho = S.ls_mode ? 0.0 : BO_STATIC_RHO * hmax;
+    const double rho = S.ls_mode ? 0.0 : BO_STATIC_RHO;
     S.rho = rho;
     if (!S.ls_mode) bo_JEtJE_acc(S.JE, rho, S.LD);
     for (int i = 0; i < BO_NX; ++i) S.LD[BO_KIDX(i, i)] += S.dw;
