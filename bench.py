@@ -110,6 +110,14 @@ def cpu_baseline(sample: int, workers: int) -> dict:
             "seconds": dt}
 
 
+def workload_config(batch: int, world: int) -> dict:
+    """`config` of the JSON line -- identical for the B200 arm and the reference arm."""
+    return {"workload": "C2: KUKA LWR 7-DoF IK (example/example.py), random reachable p_goal, seed q_nominal",
+            "instances_per_gpu": batch, "global_instances": batch * world, "parallelism": f"batch-sharded x{world}",
+            "l2_flush_between_steps": True, "solver_tolerance": 1e-8,
+            "counted": "instances reported converged only"}
+
+
 def run_reference(args) -> None:
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -136,12 +144,11 @@ def run_reference(args) -> None:
         "impl": "reference", "metric": "IK problem-instances solved/sec", "value": value, "unit": "instances/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * total_t / max(1, args.steps),
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": "C2: KUKA LWR 7-DoF IK (example/example.py), random reachable p_goal, seed q_nominal",
-                   "instances_per_step": sample,
-                   "note": "reference's ScipyMinimizeSolver('SLSQP') formulation restated in oracle/ (CasADi+IPOPT is "
-                           "not installable in this image); bounded sample per step"},
+        "config": workload_config(args.batch, max(1, args.gpus)),
         "cpu_baseline": {"value": value, "unit": "instances/s", "cores": workers, "kind": "port",
-                         "sample": f"{sample} instances per step, {workers} worker processes"},
+                         "sample": f"{sample} instances of the workload per step (bounded sample of the {args.batch}-instance "
+                                   f"batch), {workers} worker processes; reference's ScipyMinimizeSolver('SLSQP') formulation "
+                                   "restated in oracle/ (CasADi+IPOPT is not installable in this image)"},
         "e2e": {"value": value, "unit": "instances/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -283,10 +290,7 @@ def main() -> None:
             "unit": "instances/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": dev_ms_max / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f64", "data": "synthetic",
-            "config": {"workload": "C2: KUKA LWR 7-DoF IK (example/example.py), random reachable p_goal, seed q_nominal",
-                       "instances_per_gpu": B, "global_instances": B * world, "parallelism": f"batch-sharded x{world}",
-                       "l2_flush_between_steps": True, "solver": "primal-dual interior point (filter line search), tol 1e-8",
-                       "counted": "instances with status converged/acceptable only"},
+            "config": workload_config(B, world),
             "converged_fraction": conv_total / (B * world),
             "mean_iterations": iters_total / B,
             "e2e": {"value": conv_e2e_total * args.steps / e2e_s_max, "unit": "instances/s",
