@@ -137,6 +137,10 @@ int bo_problem_destroy(bo_problem* prob);
 /* Generated CUDA source of the problem's kernels (for inspection, offline nvcc checks and
  * the host-compiled test harness).  Returns the length; copies at most cap-1 bytes + NUL.  */
 int64_t bo_problem_source(const bo_problem* prob, char* buf, int64_t cap);
+/* Tables of the sparse KKT factorisation (elimination order, fill pattern, update program) built by
+ * the symbolic analysis at create time; 0 entries for problems small enough for the dense path.
+ * Returns the number of int32 entries; copies them if cap is large enough.                    */
+int64_t bo_problem_ldl_table(const bo_problem* prob, int32_t* buf, int64_t cap);
 /* Resource usage of the compiled solver kernel: regs/thread, bytes local (spill), static smem. */
 int bo_problem_kernel_info(const bo_problem* prob, int32_t* regs, int32_t* local_bytes, int32_t* smem_bytes);
 

@@ -25,7 +25,7 @@ STATUS_NAMES = {0: "converged", 1: "acceptable", 2: "max_iter", 3: "line_search"
 
 EXPORTS = [
     "bo_abi_version", "bo_last_error", "bo_device_count",
-    "bo_problem_create", "bo_problem_destroy", "bo_problem_source", "bo_problem_kernel_info",
+    "bo_problem_create", "bo_problem_destroy", "bo_problem_source", "bo_problem_ldl_table", "bo_problem_kernel_info",
     "bo_solve", "bo_problem_kernel_time",
     "bo_function_create", "bo_function_destroy", "bo_function_eval", "bo_function_source",
     "bo_function_kernel_info", "bo_function_kernel_time",
@@ -89,6 +89,8 @@ def load() -> C.CDLL:
     lib.bo_problem_destroy.argtypes = [vp]
     lib.bo_problem_source.argtypes = [vp, C.c_char_p, C.c_int64]
     lib.bo_problem_source.restype = C.c_int64
+    lib.bo_problem_ldl_table.argtypes = [vp, i32p, C.c_int64]
+    lib.bo_problem_ldl_table.restype = C.c_int64
     lib.bo_problem_kernel_info.argtypes = [vp, i32p, i32p, i32p]
     lib.bo_solve.argtypes = [vp, C.c_int64] + [vp] * 8 + [vp]
     lib.bo_problem_kernel_time.argtypes = [vp, f64p, C.POINTER(C.c_int64)]
@@ -197,6 +199,13 @@ class ProblemHandle:
 
     def source(self) -> str:
         return _source(load().bo_problem_source, self._h)
+
+    def ldl_table(self) -> np.ndarray:
+        n = load().bo_problem_ldl_table(self._h, None, 0)
+        out = np.zeros(max(int(n), 1), dtype=np.int32)
+        if n > 0:
+            load().bo_problem_ldl_table(self._h, out.ctypes.data_as(C.POINTER(C.c_int32)), int(n))
+        return out[:int(n)]
 
     def kernel_info(self) -> dict:
         return _kernel_info(load().bo_problem_kernel_info, self._h)

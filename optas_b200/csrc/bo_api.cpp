@@ -23,6 +23,7 @@
 
 #include "b200optas.h"
 #include "bo_codegen.h"
+#include "bo_sparse.h"
 
 namespace {
 
@@ -421,6 +422,7 @@ struct SolverParams {  // must match bo_solver_params in csrc/jit/bo_common.cuh
   double mu_init;
   double max_step;
   int32_t max_trips;
+  CUdeviceptr ldl_tab;
 };
 
 }  // namespace
@@ -434,7 +436,9 @@ struct bo_problem {
   LoadedKernel kernel;
   bool loaded = false;
   int tpb = 64;
-  DevBuf d_p, d_x0, d_x, d_lam, d_f, d_status, d_iters, d_kkt, d_counter;
+  DevBuf d_p, d_x0, d_x, d_lam, d_f, d_status, d_iters, d_kkt, d_counter, d_ldl_tab;
+  bo::SparsePlan plan;
+  bool sparse = false;
   int blocks_per_sm = 1, n_sm = 1;
   Timer timer;
 };
@@ -510,7 +514,11 @@ int bo_problem_create(const bo_problem_desc* desc, const bo_options* opts_in, bo
                    ps.nx + ps.n_eq, ps.n_ineq);
   pr->tpb = pr->opts.threads_per_block > 0 ? pr->opts.threads_per_block : (ps.nx + ps.n_eq > 40 ? 64 : 128);
   if (getenv("BO_DEBUG")) fprintf(stderr, "[bo] emitting source\n");
-  pr->source = bo::emit_problem_source(ps, pr->tpb, (pr->opts.flags & BO_FLAG_PIVOTED_LDL) != 0);
+  // KKT systems beyond a dozen rows are factored sparsely: symbolic analysis here, once
+  const bool pivoted = (pr->opts.flags & BO_FLAG_PIVOTED_LDL) != 0;
+  pr->sparse = !pivoted && (ps.nx + ps.n_eq > 14);
+  if (pr->sparse) pr->plan = bo::make_sparse_plan(ps);
+  pr->source = bo::emit_problem_source(ps, pr->tpb, pivoted, pr->sparse ? &pr->plan : nullptr);
   if (getenv("BO_DEBUG")) fprintf(stderr, "[bo] source %zu bytes\n", pr->source.size());
   int rc = jit_compile(pr->source, "bo_solve", "bo_solve_kernel", pr->opts, &pr->compiled);
   if (rc != BO_OK) return rc;
@@ -530,6 +538,12 @@ int bo_problem_create(const bo_problem_desc* desc, const bo_options* opts_in, bo
     if (pr->blocks_per_sm < 1) pr->blocks_per_sm = 1;
     if (pr->opts.blocks_per_sm > 0 && pr->opts.blocks_per_sm < pr->blocks_per_sm) pr->blocks_per_sm = pr->opts.blocks_per_sm;
     if ((rc = pr->d_counter.reserve(sizeof(unsigned long long))) != BO_OK) return rc;
+    if (pr->sparse) {
+      const size_t bytes = pr->plan.table.size() * sizeof(int32_t);
+      if ((rc = pr->d_ldl_tab.reserve(bytes)) != BO_OK) return rc;
+      BO_CU(g_drv.cuMemcpyHtoDAsync_v2(pr->d_ldl_tab.ptr, pr->plan.table.data(), bytes, nullptr));
+      BO_CU(g_drv.cuStreamSynchronize(nullptr));
+    }
     pr->loaded = true;
     pr->timer.enabled = (pr->opts.flags & BO_FLAG_TIMING) != 0;
   }
@@ -540,7 +554,7 @@ int bo_problem_create(const bo_problem_desc* desc, const bo_options* opts_in, bo
 int bo_problem_destroy(bo_problem* pr) {
   if (!pr) return BO_OK;
   if (pr->loaded) {
-    for (DevBuf* b : {&pr->d_p, &pr->d_x0, &pr->d_x, &pr->d_lam, &pr->d_f, &pr->d_status, &pr->d_iters, &pr->d_kkt, &pr->d_counter})
+    for (DevBuf* b : {&pr->d_p, &pr->d_x0, &pr->d_x, &pr->d_lam, &pr->d_f, &pr->d_status, &pr->d_iters, &pr->d_kkt, &pr->d_counter, &pr->d_ldl_tab})
       b->release();
     pr->timer.release();
     if (pr->kernel.mod) g_drv.cuModuleUnload(pr->kernel.mod);
@@ -561,6 +575,13 @@ static int64_t copy_out(const std::string& s, char* buf, int64_t cap) {
 int64_t bo_problem_source(const bo_problem* pr, char* buf, int64_t cap) {
   if (!pr) return set_err(BO_ERR_INVALID, "null problem");
   return copy_out(pr->source, buf, cap);
+}
+
+int64_t bo_problem_ldl_table(const bo_problem* pr, int32_t* buf, int64_t cap) {
+  if (!pr) return set_err(BO_ERR_INVALID, "null problem");
+  const int64_t n = pr->sparse ? (int64_t)pr->plan.table.size() : 0;
+  if (buf && cap >= n && n > 0) memcpy(buf, pr->plan.table.data(), (size_t)n * sizeof(int32_t));
+  return n;
 }
 
 int bo_problem_kernel_info(const bo_problem* pr, int32_t* regs, int32_t* local_bytes, int32_t* smem_bytes) {
@@ -631,7 +652,7 @@ int bo_solve(bo_problem* pr, int64_t B, const double* p, const double* x0, doubl
   if ((rc = stage_out(kkt_res, sizeof(double), pr->d_kkt, &dkkt)) != BO_OK) return rc;
 
   long long Bll = B;
-  SolverParams prm{pr->opts.max_iter, pr->opts.tol, pr->opts.acceptable_tol, pr->opts.mu_init, pr->opts.max_step, pr->opts.max_trips};
+  SolverParams prm{pr->opts.max_iter, pr->opts.tol, pr->opts.acceptable_tol, pr->opts.mu_init, pr->opts.max_step, pr->opts.max_trips, pr->sparse ? pr->d_ldl_tab.ptr : 0};
   // persistent lanes: one wave of CTAs (multiple of the SM count), instances fetched from a counter
   CUdeviceptr dcounter = pr->d_counter.ptr;
   BO_CU(g_drv.cuMemsetD8Async(dcounter, 0, sizeof(unsigned long long), st));

@@ -13,6 +13,7 @@
 #include <sstream>
 
 #include "bo_opcodes.h"
+#include "bo_sparse.h"
 
 namespace bo {
 
@@ -244,13 +245,14 @@ static void emit_sparse_helpers(std::ostringstream& o, const char* tag, const Sp
   o << "  (void)J; (void)x; (void)out;\n}\n";
 }
 
-std::string emit_problem_source(const ProblemSource& ps, int tpb, bool pivoted_ldl) {
+std::string emit_problem_source(const ProblemSource& ps, int tpb, bool pivoted_ldl, const SparsePlan* sparse) {
   std::ostringstream o;
   o << "// generated by libb200optas (bo_codegen.cpp): tier-S solver, one instance per thread\n";
   o << "#define BO_NX " << ps.nx << "\n#define BO_NP " << ps.np << "\n#define BO_ME " << ps.n_eq << "\n#define BO_MI "
     << ps.n_ineq << "\n#define BO_NNZ_JE " << ps.jac_eq.nnz() << "\n#define BO_NNZ_JI " << ps.jac_ineq.nnz()
     << "\n#define BO_NNZ_H " << ps.hess.nnz() << "\n#define BO_TPB " << tpb << "\n";
   if (pivoted_ldl) o << "#define BO_USE_BK 1\n";
+  if (sparse) o << "#define BO_SPARSE_LDL 1\n#define BO_SPARSE_VALS " << sparse->vals_size() << "\n";
   o << "#include \"bo_common.cuh\"\n\n";
   o << emit_tape_function(ps.fc, "bo_tape_fc") << "\n";
   o << emit_tape_function(ps.kkt, "bo_tape_kkt") << "\n";
@@ -258,10 +260,13 @@ std::string emit_problem_source(const ProblemSource& ps, int tpb, bool pivoted_l
   emit_sparse_helpers(o, "I", ps.jac_ineq, ps.n_ineq);
 
   const int nk = ps.nx + ps.n_eq;
-  auto kidx = [](int i, int j) { return i * (i + 1) / 2 + j; };  // packed lower triangle, i >= j
+  // index of the (i, j) entry, i >= j, in the per-instance matrix storage: packed lower triangle, or the
+  // position in the sparse factor's value array
+  auto kidx = [sparse](int i, int j) { return sparse ? sparse->pos(i, j) : i * (i + 1) / 2 + j; };
+  const int ksize = sparse ? sparse->vals_size() : nk * (nk + 1) / 2;
   o << "BO_DEVICE void bo_kkt_fill(const double* BO_RESTRICT H, const double* BO_RESTRICT JE, const double* BO_RESTRICT JI,\n"
        "                           const double* BO_RESTRICT sigma, double* BO_RESTRICT K) {\n";
-  o << "  BO_UNROLL\n  for (int i = 0; i < " << nk * (nk + 1) / 2 << "; ++i) K[i] = 0.0;\n";
+  o << (sparse ? "  BO_NOUNROLL\n" : "  BO_UNROLL\n") << "  for (int i = 0; i < " << ksize << "; ++i) K[i] = 0.0;\n";
   for (int k = 0; k < ps.hess.nnz(); ++k) o << "  K[" << kidx(ps.hess.row[k], ps.hess.col[k]) << "] += H[" << k << "];\n";
   {
     std::vector<std::vector<int>> by_row(ps.n_ineq > 0 ? ps.n_ineq : 1);

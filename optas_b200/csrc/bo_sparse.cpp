@@ -1,0 +1,161 @@
+// bo_sparse.cpp -- ordering + symbolic LDL' + device tables for the static-order sparse factorisation.
+#include "bo_sparse.h"
+
+#include <algorithm>
+#include <set>
+
+namespace bo {
+
+int SparsePlan::pos(int i_old, int j_old) const {
+  int a = iperm[i_old], b = iperm[j_old];
+  if (a == b) return a;
+  if (a < b) std::swap(a, b);  // a > b: entry (row a, column b) of L
+  const auto lo = rowidx.begin() + colptr[b], hi = rowidx.begin() + colptr[b + 1];
+  const auto it = std::lower_bound(lo, hi, a);
+  if (it == hi || *it != a) return -1;
+  return n + (int)(it - rowidx.begin());
+}
+
+SparsePlan make_sparse_plan(const ProblemSource& ps) {
+  SparsePlan pl;
+  const int nx = ps.nx, n = ps.nx + ps.n_eq;
+  pl.n = n;
+  pl.nx = nx;
+
+  // ---- structural pattern of K (symmetric adjacency, no self loops) ----
+  std::vector<std::set<int>> adj(n);
+  auto link = [&](int a, int b) {
+    if (a != b) {
+      adj[a].insert(b);
+      adj[b].insert(a);
+    }
+  };
+  for (int k = 0; k < ps.hess.nnz(); ++k) link(ps.hess.row[k], ps.hess.col[k]);
+  auto rows_clique = [&](const Sparsity& sp, int n_rows) {  // J' D J couples the columns of every row
+    std::vector<std::vector<int>> by_row(n_rows > 0 ? n_rows : 1);
+    for (int k = 0; k < sp.nnz(); ++k) by_row[sp.row[k]].push_back(sp.col[k]);
+    for (const auto& cols : by_row)
+      for (size_t u = 0; u < cols.size(); ++u)
+        for (size_t w = u + 1; w < cols.size(); ++w) link(cols[u], cols[w]);
+  };
+  rows_clique(ps.jac_ineq, ps.n_ineq);
+  rows_clique(ps.jac_eq, ps.n_eq);
+  std::vector<std::vector<int>> x_of_y(ps.n_eq > 0 ? ps.n_eq : 1);
+  for (int k = 0; k < ps.jac_eq.nnz(); ++k) {
+    link(nx + ps.jac_eq.row[k], ps.jac_eq.col[k]);
+    x_of_y[ps.jac_eq.row[k]].push_back(ps.jac_eq.col[k]);
+  }
+
+  // ---- constrained greedy minimum-degree ordering on the elimination graph ----
+  std::vector<char> done(n, 0);
+  std::vector<int> pending_x(ps.n_eq > 0 ? ps.n_eq : 1, 0);  // variables of a constraint row not yet eliminated
+  for (int r = 0; r < ps.n_eq; ++r) {
+    std::set<int> uniq(x_of_y[r].begin(), x_of_y[r].end());
+    pending_x[r] = (int)uniq.size();
+    x_of_y[r].assign(uniq.begin(), uniq.end());
+  }
+  std::vector<std::vector<int>> y_of_x(nx);
+  for (int r = 0; r < ps.n_eq; ++r)
+    for (int c : x_of_y[r]) y_of_x[c].push_back(r);
+  std::vector<std::set<int>> g = adj;  // elimination graph (mutated)
+  pl.perm.reserve(n);
+  std::vector<std::vector<int>> col_struct;  // rows (old indices) below the diagonal of each eliminated column
+  col_struct.reserve(n);
+  for (int step = 0; step < n; ++step) {
+    int best = -1;
+    size_t best_deg = ~(size_t)0;
+    for (int v = 0; v < n; ++v) {
+      if (done[v]) continue;
+      if (v >= nx && pending_x[v - nx] > 0) continue;  // constraint row not yet eligible
+      if (g[v].size() < best_deg) {
+        best_deg = g[v].size();
+        best = v;
+      }
+    }
+    if (best < 0) {  // only ineligible rows left (cannot happen: all x are always eligible) -- take any
+      for (int v = 0; v < n; ++v)
+        if (!done[v]) { best = v; break; }
+    }
+    done[best] = 1;
+    pl.perm.push_back(best);
+    std::vector<int> nb(g[best].begin(), g[best].end());
+    col_struct.push_back(nb);
+    for (int a : nb) g[a].erase(best);
+    for (size_t u = 0; u < nb.size(); ++u)
+      for (size_t w = u + 1; w < nb.size(); ++w) {
+        g[nb[u]].insert(nb[w]);
+        g[nb[w]].insert(nb[u]);
+      }
+    g[best].clear();
+    if (best < nx)
+      for (int r : y_of_x[best]) pending_x[r] -= 1;
+  }
+  pl.iperm.assign(n, 0);
+  for (int k = 0; k < n; ++k) pl.iperm[pl.perm[k]] = k;
+
+  // ---- pattern of L in the permuted order ----
+  pl.colptr.assign(n + 1, 0);
+  for (int j = 0; j < n; ++j) {
+    std::vector<int> rows;
+    for (int old : col_struct[j]) rows.push_back(pl.iperm[old]);
+    std::sort(rows.begin(), rows.end());
+    pl.colptr[j + 1] = pl.colptr[j] + (int)rows.size();
+    pl.rowidx.insert(pl.rowidx.end(), rows.begin(), rows.end());
+  }
+
+  // ---- factor program (left-looking, column by column) ----
+  // row pattern of L: for each row j the (column k, entry index) pairs with k < j
+  std::vector<std::vector<std::pair<int, int>>> row_pat(n);
+  for (int k = 0; k < n; ++k)
+    for (int e = pl.colptr[k]; e < pl.colptr[k + 1]; ++e) row_pat[pl.rowidx[e]].push_back({k, e});
+  auto entry = [&](int row, int col) -> int {  // index into rowidx of L(row, col), row > col
+    const auto lo = pl.rowidx.begin() + pl.colptr[col], hi = pl.rowidx.begin() + pl.colptr[col + 1];
+    const auto it = std::lower_bound(lo, hi, row);
+    return (it == hi || *it != row) ? -1 : (int)(it - pl.rowidx.begin());
+  };
+  std::vector<int32_t> prog;
+  for (int j = 0; j < n; ++j) {
+    prog.push_back((int32_t)row_pat[j].size());
+    for (const auto& ke : row_pat[j]) {
+      const int k = ke.first, e_jk = ke.second;
+      prog.push_back(n + e_jk);  // position of L(j,k)
+      prog.push_back(k);         // position of D(k)
+      // rows i > j present in column k: they are updated in column j (fill guarantees they exist there)
+      const size_t count_at = prog.size();
+      prog.push_back(0);
+      int cnt = 0;
+      for (int e = pl.colptr[k]; e < pl.colptr[k + 1]; ++e) {
+        const int i = pl.rowidx[e];
+        if (i <= j) continue;
+        const int e_ij = entry(i, j);
+        if (e_ij < 0) continue;  // cannot happen for a correct symbolic factorisation
+        prog.push_back(n + e_ij);
+        prog.push_back(n + e);
+        ++cnt;
+        pl.flops += 1;
+      }
+      prog[count_at] = cnt;
+      pl.flops += 2;
+    }
+  }
+  // header + sections
+  // [0] n  [1] nnzL  [2] off_colptr  [3] off_rowidx  [4] off_perm  [5] off_sign  [6] off_prog  [7] total
+  std::vector<int32_t>& t = pl.table;
+  t.assign(8, 0);
+  t[0] = n;
+  t[1] = pl.nnzL();
+  t[2] = (int32_t)t.size();
+  t.insert(t.end(), pl.colptr.begin(), pl.colptr.end());
+  t[3] = (int32_t)t.size();
+  t.insert(t.end(), pl.rowidx.begin(), pl.rowidx.end());
+  t[4] = (int32_t)t.size();
+  t.insert(t.end(), pl.perm.begin(), pl.perm.end());
+  t[5] = (int32_t)t.size();
+  for (int j = 0; j < n; ++j) t.push_back(pl.perm[j] < nx ? 1 : -1);
+  t[6] = (int32_t)t.size();
+  t.insert(t.end(), prog.begin(), prog.end());
+  t[7] = (int32_t)t.size();
+  return pl;
+}
+
+}  // namespace bo

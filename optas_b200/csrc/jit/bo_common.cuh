@@ -48,6 +48,7 @@ struct bo_solver_params {
   double mu_init;
   double max_step;  // <= 0: unlimited
   int32_t max_trips; // budget of solver trips per instance (bounds the tail of a batch)
+  const int32_t* ldl_tab;  // sparse LDL' tables (bo_sparse.cpp) or null for the dense tiers
 };
 
 // per-instance status codes (mirror bo_instance_status in include/b200optas.h)

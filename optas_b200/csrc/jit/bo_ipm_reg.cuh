@@ -22,8 +22,20 @@
 #pragma once
 #include "bo_common.cuh"
 
+// Vector loops are unrolled (registers, compile-time indices) for small problems only; for larger
+// ones unrolling 100+ element loops everywhere explodes code size and compile time for no benefit
+// (the vectors live in local memory either way).
+#if (BO_NX + BO_ME + BO_MI) > 64 && !defined(BO_HOST_SIM)
+#undef BO_UNROLL
+#define BO_UNROLL _Pragma("unroll 1")
+#endif
+
 #define BO_NK (BO_NX + BO_ME)
+#ifdef BO_SPARSE_LDL
+#define BO_KSZ BO_SPARSE_VALS /* D (BO_NK) followed by the structural non-zeros of L */
+#else
 #define BO_KSZ ((BO_NK * (BO_NK + 1)) / 2)
+#endif
 #define BO_KIDX(i, j) (((i) * ((i) + 1)) / 2 + (j)) /* packed lower triangle, i >= j */
 #define BO_DIM(n) ((n) > 0 ? (n) : 1)
 
@@ -43,6 +55,11 @@
 // Define BO_USE_BK (BO_FLAG_PIVOTED_LDL) to factor with Bunch-Kaufman partial pivoting instead.
 #ifndef BO_STATIC_RHO
 #define BO_STATIC_RHO 1.0e6
+#endif
+#ifdef BO_SPARSE_LDL
+#define BO_LDL_SOLVE(LD, b) bo_ldl_sparse_solve(LD, prm.ldl_tab, b)
+#else
+#define BO_LDL_SOLVE(LD, b) bo_ldl_static_solve(LD, b)
 #endif
 // small systems: unroll completely (indices become compile-time, the matrix lives in registers)
 #if BO_NK <= 14
@@ -93,6 +110,63 @@ BO_NOINLINE void bo_ldl_static_solve(const double* BO_RESTRICT A, double* BO_RES
     for (int k = i + 1; k < BO_NK; ++k) b[i] -= A[BO_KIDX(k, i)] * b[k];
   }
 }
+
+#ifdef BO_SPARSE_LDL
+// ---- sparse variant of the unpivoted LDL': table-driven, identical control flow for every lane ----
+// Tables (int32, built by bo_sparse.cpp at bo_problem_create, uploaded once):
+//   [0] n  [1] nnzL  [2] off colptr[n+1]  [3] off rowidx[nnzL]  [4] off perm[n] (new -> old)
+//   [5] off sign[n] (+1 variable, -1 constraint row)  [6] off factor program  [7] total length
+// value array of one instance: vals[0..n) = D in elimination order, vals[n + e] = e-th non-zero of L.
+// Factor program, column by column (left-looking):
+//   n_k, then n_k records { pos L(j,k), pos D(k), cnt, cnt x { pos L(i,j), pos L(i,k) } }.
+BO_NOINLINE int bo_ldl_sparse(double* BO_RESTRICT vals, const int32_t* BO_RESTRICT tab) {
+  const int n = tab[0];
+  const int32_t* colptr = tab + tab[2];
+  const int32_t* sign = tab + tab[5];
+  const int32_t* prog = tab + tab[6];
+  int bad = 0, pc = 0;
+  for (int j = 0; j < n; ++j) {
+    double d = vals[j];
+    const double scale = fmax(1.0, fabs(d));
+    const int nk = prog[pc++];
+    for (int kk = 0; kk < nk; ++kk) {
+      const double ljk = vals[prog[pc]];
+      const double w = ljk * vals[prog[pc + 1]];
+      const int cnt = prog[pc + 2];
+      pc += 3;
+      d -= ljk * w;
+      for (int c = 0; c < cnt; ++c, pc += 2) vals[prog[pc]] -= vals[prog[pc + 1]] * w;
+    }
+    if (sign[j] > 0) {
+      if (!(d > 1e-13 * scale) && bad == 0) bad = 1;
+    } else {
+      if (!(d < -1e-13) && bad == 0) bad = 2;
+    }
+    vals[j] = d;
+    const double dinv = 1.0 / d;
+    for (int e = colptr[j]; e < colptr[j + 1]; ++e) vals[n + e] *= dinv;
+  }
+  return bad;
+}
+
+// b is indexed by ORIGINAL row (x then y); perm maps elimination position -> original row.
+BO_NOINLINE void bo_ldl_sparse_solve(const double* BO_RESTRICT vals, const int32_t* BO_RESTRICT tab, double* BO_RESTRICT b) {
+  const int n = tab[0];
+  const int32_t* colptr = tab + tab[2];
+  const int32_t* rowidx = tab + tab[3];
+  const int32_t* perm = tab + tab[4];
+  for (int j = 0; j < n; ++j) {
+    const double bj = b[perm[j]];
+    for (int e = colptr[j]; e < colptr[j + 1]; ++e) b[perm[rowidx[e]]] -= vals[n + e] * bj;
+  }
+  for (int j = 0; j < n; ++j) b[perm[j]] /= vals[j];
+  for (int j = n - 1; j >= 0; --j) {
+    double acc = b[perm[j]];
+    for (int e = colptr[j]; e < colptr[j + 1]; ++e) acc -= vals[n + e] * b[perm[rowidx[e]]];
+    b[perm[j]] = acc;
+  }
+}
+#endif
 
 #ifdef BO_USE_BK
 // Bunch-Kaufman LDL' (diagonal pivoting with 1x1 and 2x2 blocks; the unblocked LAPACK dsytf2
@@ -351,7 +425,7 @@ BO_DEVICE void bo_ipm_init(bo_ipm_state& S, const bo_solver_params prm) {
 
 // Step for the constraint residuals (S.rE, S.rI) with the current factorisation: fills S.sol
 // (dx, -dy), S.dx, S.ds and returns the fraction-to-the-boundary primal step length.
-BO_NOINLINE double bo_ipm_step(bo_ipm_state& S) {
+BO_NOINLINE double bo_ipm_step(bo_ipm_state& S, const bo_solver_params& prm) {
   double tvec[BO_DIM(BO_MI)];
   BO_NOUNROLL
   for (int i = 0; i < BO_MI; ++i) tvec[i] = -(S.z[i] - S.mu / S.s[i] + S.sigma[i] * S.rI[i]);
@@ -365,7 +439,7 @@ BO_NOINLINE double bo_ipm_step(bo_ipm_state& S) {
     BO_UNROLL
     for (int j = 0; j < BO_ME; ++j) t2[j] = -S.rho * S.rE[j];
     bo_JEt_acc(S.JE, t2, S.sol);  // first block row += rho * JE' * (second block rhs)
-    bo_ldl_static_solve(S.LD, S.sol);
+    BO_LDL_SOLVE(S.LD, S.sol);
     const double undo = 1.0 / (1.0 - S.rho * S.dc);
     BO_UNROLL
     for (int j = 0; j < BO_ME; ++j) S.sol[BO_NX + j] *= undo;
@@ -506,9 +580,18 @@ BO_DEVICE int bo_trip_factor(bo_ipm_state& S, const bo_solver_params prm) {
     const double rho = S.ls_mode ? 0.0 : BO_STATIC_RHO;
     S.rho = rho;
     if (!S.ls_mode) bo_JEtJE_acc(S.JE, rho, S.LD);
+#ifdef BO_SPARSE_LDL
+    {
+      const int32_t* sign = prm.ldl_tab + prm.ldl_tab[5];
+      const double dcp = S.dc / (1.0 - rho * S.dc);
+      for (int j = 0; j < BO_NK; ++j) S.LD[j] += sign[j] > 0 ? S.dw : -dcp;
+    }
+    const int bad = bo_ldl_sparse(S.LD, prm.ldl_tab);
+#else
     for (int i = 0; i < BO_NX; ++i) S.LD[BO_KIDX(i, i)] += S.dw;
     for (int i = BO_NX; i < BO_NK; ++i) S.LD[BO_KIDX(i, i)] -= S.dc / (1.0 - rho * S.dc);
     const int bad = bo_ldl_static(S.LD);
+#endif
     inertia = bad == 0 ? 0 : (bad == 1 ? 1 : -1);
 #endif
     if (S.ls_mode) {
@@ -521,7 +604,7 @@ BO_DEVICE int bo_trip_factor(bo_ipm_state& S, const bo_solver_params prm) {
         bo_JIt_acc(S.JI, nz, S.sol);
         BO_UNROLL
         for (int j = 0; j < BO_ME; ++j) S.sol[BO_NX + j] = 0.0;
-        if (S.static_fac) bo_ldl_static_solve(S.LD, S.sol);
+        if (S.static_fac) BO_LDL_SOLVE(S.LD, S.sol);
         else bo_bk_solve(S.LD, S.ipiv, S.sol);
         bool fin = true;
         BO_UNROLL
@@ -555,7 +638,7 @@ BO_DEVICE int bo_trip_factor(bo_ipm_state& S, const bo_solver_params prm) {
     for (int j = 0; j < BO_ME; ++j) S.rE[j] = S.cE[j];
     BO_UNROLL
     for (int i = 0; i < BO_MI; ++i) S.rI[i] = S.cI[i] - S.s[i];
-    const double a_p = bo_ipm_step(S);
+    const double a_p = bo_ipm_step(S, prm);
     BO_UNROLL
     for (int j = 0; j < BO_ME; ++j) S.y_step[j] = -S.sol[BO_NX + j];
     double dphi = 0.0, dxn = 0.0;  // directional derivative of the barrier objective; step size
@@ -676,7 +759,7 @@ BO_DEVICE int bo_trip_trial(bo_ipm_state& S, const bo_solver_params prm) {
       try_soc = true;
     }
     if (try_soc) {
-      S.a_trial = bo_ipm_step(S);  // corrected direction; tried on the next trip
+      S.a_trial = bo_ipm_step(S, prm);  // corrected direction; tried on the next trip
       S.soc += 1;
       return -1;
     }

@@ -417,6 +417,10 @@ class B200Solver(Solver):
     def kernel_source(self) -> str:
         return self._handle.source()
 
+    def ldl_table(self) -> np.ndarray:
+        """Tables of the sparse KKT factorisation (empty for the dense tiers)."""
+        return self._handle.ldl_table()
+
 
 class CasADiSolver(B200Solver):
     """Name-compatible drop-in for ``optas.CasADiSolver`` (ref :321-419): same constructor, same

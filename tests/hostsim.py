@@ -30,9 +30,9 @@ static long long bo_host_stats[4] = {0, 0, 0, 0};
 extern "C" void hostsim_stats(long long* out) { for (int i = 0; i < 4; ++i) { out[i] = bo_host_stats[i]; bo_host_stats[i] = 0; } }
 extern "C" void hostsim_solve(long long B, const double* p, const double* x0, double* x, double* lam, double* f,
                               int* status, int* iters, double* kkt, int* trips, int max_iter, double tol, double acc_tol,
-                              double mu_init, double max_step, int max_trips) {
+                              double mu_init, double max_step, int max_trips, const int* ldl_tab) {
   bo_solver_params prm;
-  prm.max_iter = max_iter; prm.tol = tol; prm.acceptable_tol = acc_tol; prm.mu_init = mu_init; prm.max_step = max_step; prm.max_trips = max_trips;
+  prm.max_iter = max_iter; prm.tol = tol; prm.acceptable_tol = acc_tol; prm.mu_init = mu_init; prm.max_step = max_step; prm.max_trips = max_trips; prm.ldl_tab = ldl_tab;
   for (long long b = 0; b < B; ++b) {
     bo_ipm_state S;
     for (int i = 0; i < BO_NP; ++i) S.p[i] = p[b * BO_NP + i];
@@ -48,7 +48,9 @@ extern "C" void hostsim_solve(long long B, const double* p, const double* x0, do
 
 
 class HostSim:
-    def __init__(self, generated_source: str, nx: int, np_: int, n_eq: int, n_ineq: int, trace: bool = False, defines: str = ""):
+    def __init__(self, generated_source: str, nx: int, np_: int, n_eq: int, n_ineq: int, trace: bool = False, defines: str = "",
+                 ldl_table=None):
+        self.ldl_table = None if ldl_table is None or len(ldl_table) == 0 else np.ascontiguousarray(ldl_table, dtype=np.int32)
         self.nx, self.np_, self.nl = nx, np_, n_eq + n_ineq
         key = hashlib.sha1(generated_source.encode()).hexdigest()[:16] + str(trace) + defines
         for name in ("bo_common.cuh", "bo_ipm_reg.cuh"):
@@ -67,7 +69,7 @@ class HostSim:
         self.lib = C.CDLL(so)
         vp = C.c_void_p
         self.lib.hostsim_stats.argtypes = [vp]
-        self.lib.hostsim_solve.argtypes = [C.c_longlong] + [vp] * 9 + [C.c_int, C.c_double, C.c_double, C.c_double, C.c_double, C.c_int]
+        self.lib.hostsim_solve.argtypes = [C.c_longlong] + [vp] * 9 + [C.c_int, C.c_double, C.c_double, C.c_double, C.c_double, C.c_int, vp]
 
     def solve(self, P, X0, max_iter=100, tol=1e-8, acc_tol=1e-6, mu_init=0.1, max_step=0.5, max_trips=250):
         B = X0.shape[0]
@@ -76,7 +78,8 @@ class HostSim:
         X = np.empty((B, self.nx)); lam = np.empty((B, max(self.nl, 1))); f = np.empty(B)
         st = np.empty(B, dtype=np.int32); it = np.empty(B, dtype=np.int32); kkt = np.empty(B); trips = np.empty(B, dtype=np.int32)
         self.lib.hostsim_solve(B, P.ctypes.data, X0.ctypes.data, X.ctypes.data, lam.ctypes.data, f.ctypes.data,
-                               st.ctypes.data, it.ctypes.data, kkt.ctypes.data, trips.ctypes.data, max_iter, tol, acc_tol, mu_init, max_step, max_trips)
+                               st.ctypes.data, it.ctypes.data, kkt.ctypes.data, trips.ctypes.data, max_iter, tol, acc_tol, mu_init, max_step, max_trips,
+                               None if self.ldl_table is None else self.ldl_table.ctypes.data)
         stats = np.zeros(4, dtype=np.int64)
         self.lib.hostsim_stats(stats.ctypes.data)
         self.last_stats = {"static": int(stats[0]), "bk_ok": int(stats[1]), "bk_retry": int(stats[2])}

@@ -40,7 +40,7 @@ def _worker(rank, world, port, out_dir):
     prob = problems.lwr_ik()
     solver = optas_b200.B200Solver(prob.opt).setup("ipopt", compile_only=True)
     lo = solver._lowered
-    sim = HostSim(solver.kernel_source(), lo.nx, lo.np_, lo.n_eq, lo.n_ineq)
+    sim = HostSim(solver.kernel_source(), lo.nx, lo.np_, lo.n_eq, lo.n_ineq, ldl_table=solver.ldl_table())
     P, X0 = prob.sample(101, seed=9)  # odd size: ragged shards
     res = solve_sharded(lambda p, x0: sim.solve(p, x0), P, X0)
     n_ok = reduce_counts(np.array([float((res["status"] <= 1).sum())]), "max")
@@ -65,7 +65,7 @@ def test_two_rank_gloo_matches_single_process(tmp_path):
     prob = problems.lwr_ik()
     solver = optas_b200.B200Solver(prob.opt).setup("ipopt", compile_only=True)
     lo = solver._lowered
-    sim = HostSim(solver.kernel_source(), lo.nx, lo.np_, lo.n_eq, lo.n_ineq)
+    sim = HostSim(solver.kernel_source(), lo.nx, lo.np_, lo.n_eq, lo.n_ineq, ldl_table=solver.ldl_table())
     P, X0 = prob.sample(101, seed=9)
     whole = sim.solve(P, X0)
     for key in ("x", "lam", "f", "status", "iters", "kkt"):

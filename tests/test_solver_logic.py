@@ -15,7 +15,7 @@ from optas_b200 import problems
 def _sim(prob):
     solver = optas_b200.B200Solver(prob.opt).setup("ipopt", compile_only=True)
     lo = solver._lowered
-    return HostSim(solver.kernel_source(), lo.nx, lo.np_, lo.n_eq, lo.n_ineq), lo
+    return HostSim(solver.kernel_source(), lo.nx, lo.np_, lo.n_eq, lo.n_ineq, ldl_table=solver.ldl_table()), lo
 
 
 def test_booth_known_answer():
