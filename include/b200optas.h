@@ -141,6 +141,8 @@ int64_t bo_problem_source(const bo_problem* prob, char* buf, int64_t cap);
  * the symbolic analysis at create time; 0 entries for problems small enough for the dense path.
  * Returns the number of int32 entries; copies them if cap is large enough.                    */
 int64_t bo_problem_ldl_table(const bo_problem* prob, int32_t* buf, int64_t cap);
+/* Constants of the interpreted tapes (table-driven tier for very large problems); 0 entries otherwise. */
+int64_t bo_problem_dtable(const bo_problem* prob, double* buf, int64_t cap);
 /* Resource usage of the compiled solver kernel: regs/thread, bytes local (spill), static smem. */
 int bo_problem_kernel_info(const bo_problem* prob, int32_t* regs, int32_t* local_bytes, int32_t* smem_bytes);
 

@@ -25,7 +25,7 @@ STATUS_NAMES = {0: "converged", 1: "acceptable", 2: "max_iter", 3: "line_search"
 
 EXPORTS = [
     "bo_abi_version", "bo_last_error", "bo_device_count",
-    "bo_problem_create", "bo_problem_destroy", "bo_problem_source", "bo_problem_ldl_table", "bo_problem_kernel_info",
+    "bo_problem_create", "bo_problem_destroy", "bo_problem_source", "bo_problem_ldl_table", "bo_problem_dtable", "bo_problem_kernel_info",
     "bo_solve", "bo_problem_kernel_time",
     "bo_function_create", "bo_function_destroy", "bo_function_eval", "bo_function_source",
     "bo_function_kernel_info", "bo_function_kernel_time",
@@ -91,6 +91,8 @@ def load() -> C.CDLL:
     lib.bo_problem_source.restype = C.c_int64
     lib.bo_problem_ldl_table.argtypes = [vp, i32p, C.c_int64]
     lib.bo_problem_ldl_table.restype = C.c_int64
+    lib.bo_problem_dtable.argtypes = [vp, f64p, C.c_int64]
+    lib.bo_problem_dtable.restype = C.c_int64
     lib.bo_problem_kernel_info.argtypes = [vp, i32p, i32p, i32p]
     lib.bo_solve.argtypes = [vp, C.c_int64] + [vp] * 8 + [vp]
     lib.bo_problem_kernel_time.argtypes = [vp, f64p, C.POINTER(C.c_int64)]
@@ -205,6 +207,13 @@ class ProblemHandle:
         out = np.zeros(max(int(n), 1), dtype=np.int32)
         if n > 0:
             load().bo_problem_ldl_table(self._h, out.ctypes.data_as(C.POINTER(C.c_int32)), int(n))
+        return out[:int(n)]
+
+    def dtable(self) -> np.ndarray:
+        n = load().bo_problem_dtable(self._h, None, 0)
+        out = np.zeros(max(int(n), 1))
+        if n > 0:
+            load().bo_problem_dtable(self._h, out.ctypes.data_as(C.POINTER(C.c_double)), int(n))
         return out[:int(n)]
 
     def kernel_info(self) -> dict:

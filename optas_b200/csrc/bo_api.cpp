@@ -11,6 +11,7 @@
 #include <sys/stat.h>
 #include <unistd.h>
 
+#include <algorithm>
 #include <cstdarg>
 #include <cstdio>
 #include <cstdlib>
@@ -269,7 +270,9 @@ int jit_compile(const std::string& source, const char* unit_name, const char* ke
   if (nvrtcCreateProgram(&prog, source.c_str(), file.c_str(), 0, nullptr, nullptr) != NVRTC_SUCCESS)
     return set_err(BO_ERR_COMPILE, "nvrtcCreateProgram failed");
   const std::string iflag = "-I" + inc;
-  const char* flags[] = {"--gpu-architecture=sm_100a", "--std=c++17", "-lineinfo", "--ptxas-options=-v", iflag.c_str()};
+  const std::string iflag2 = "-I" + (opts.include_dir ? std::string(opts.include_dir) : lib_dir() + "/../include");
+  const char* flags[] = {"--gpu-architecture=sm_100a", "--std=c++17", "-lineinfo", "--ptxas-options=-v", iflag.c_str(),
+                         iflag2.c_str()};
   const nvrtcResult res = nvrtcCompileProgram(prog, (int)(sizeof flags / sizeof flags[0]), flags);
   size_t log_size = 0;
   nvrtcGetProgramLogSize(prog, &log_size);
@@ -423,6 +426,9 @@ struct SolverParams {  // must match bo_solver_params in csrc/jit/bo_common.cuh
   double max_step;
   int32_t max_trips;
   CUdeviceptr ldl_tab;
+  CUdeviceptr dtab;
+  CUdeviceptr scratch;
+  long long scratch_stride;
 };
 
 }  // namespace
@@ -438,7 +444,8 @@ struct bo_problem {
   int tpb = 64;
   DevBuf d_p, d_x0, d_x, d_lam, d_f, d_status, d_iters, d_kkt, d_counter, d_ldl_tab;
   bo::SparsePlan plan;
-  bool sparse = false;
+  bool sparse = false, large = false;
+  DevBuf d_dtab, d_scratch;
   int blocks_per_sm = 1, n_sm = 1;
   Timer timer;
 };
@@ -505,20 +512,23 @@ int bo_problem_create(const bo_problem_desc* desc, const bo_options* opts_in, bo
       !expect(ps.kkt, {ps.nx, ps.np, ps.n_eq, ps.n_ineq},
               {1, ps.nx, ps.n_eq, ps.n_ineq, ps.jac_eq.nnz(), ps.jac_ineq.nnz(), ps.hess.nnz()}, "kkt"))
     return set_err(BO_ERR_INVALID, "bo_problem_create: %s", err.c_str());
-  // One instance per thread: the KKT matrix (packed lower triangle) and the iterate live in thread-local
-  // memory.  Up to ~40 rows that is L1-resident; up to 160 rows (C3: 122) it still works but runs out of
-  // L2 -- functional first, a shared-memory CTA-per-instance tier is the planned replacement.
-  if (ps.nx + ps.n_eq > 160 || ps.n_ineq > 512)
-    return set_err(BO_ERR_UNSUPPORTED,
-                   "bo_problem_create: nx+n_eq=%d, n_ineq=%d exceeds the thread-per-instance tier (nx+n_eq<=160, n_ineq<=512)",
-                   ps.nx + ps.n_eq, ps.n_ineq);
-  pr->tpb = pr->opts.threads_per_block > 0 ? pr->opts.threads_per_block : (ps.nx + ps.n_eq > 40 ? 64 : 128);
+  // Tiers (all one instance per thread, see csrc/jit/bo_ipm_reg.cuh):
+  //   dense   nx+n_eq <= 14            generated straight-line code, unrolled LDL' in registers
+  //   sparse  otherwise                generated tapes, table-driven sparse LDL' in thread-local memory
+  //   large   tapes > 30k instructions everything table-driven (interpreted tapes), factor in global scratch
+  if (ps.nx + ps.n_eq > 8192 || ps.n_ineq > 16384)
+    return set_err(BO_ERR_UNSUPPORTED, "bo_problem_create: nx+n_eq=%d, n_ineq=%d exceeds the built tiers", ps.nx + ps.n_eq,
+                   ps.n_ineq);
+  pr->tpb = pr->opts.threads_per_block > 0 ? pr->opts.threads_per_block : 64;
   if (getenv("BO_DEBUG")) fprintf(stderr, "[bo] emitting source\n");
   // KKT systems beyond a dozen rows are factored sparsely: symbolic analysis here, once
   const bool pivoted = (pr->opts.flags & BO_FLAG_PIVOTED_LDL) != 0;
   pr->sparse = !pivoted && (ps.nx + ps.n_eq > 14);
-  if (pr->sparse) pr->plan = bo::make_sparse_plan(ps);
-  pr->source = bo::emit_problem_source(ps, pr->tpb, pivoted, pr->sparse ? &pr->plan : nullptr);
+  pr->large = pr->sparse && (ps.kkt.n_instr() > 30000 || ps.nx + ps.n_eq > 400);
+  if (pivoted && ps.nx + ps.n_eq > 160)
+    return set_err(BO_ERR_UNSUPPORTED, "bo_problem_create: BO_FLAG_PIVOTED_LDL is limited to nx+n_eq <= 160");
+  if (pr->sparse) pr->plan = bo::make_sparse_plan(ps, pr->large);
+  pr->source = bo::emit_problem_source(ps, pr->tpb, pivoted, pr->sparse ? &pr->plan : nullptr, pr->large);
   if (getenv("BO_DEBUG")) fprintf(stderr, "[bo] source %zu bytes\n", pr->source.size());
   int rc = jit_compile(pr->source, "bo_solve", "bo_solve_kernel", pr->opts, &pr->compiled);
   if (rc != BO_OK) return rc;
@@ -542,6 +552,16 @@ int bo_problem_create(const bo_problem_desc* desc, const bo_options* opts_in, bo
       const size_t bytes = pr->plan.table.size() * sizeof(int32_t);
       if ((rc = pr->d_ldl_tab.reserve(bytes)) != BO_OK) return rc;
       BO_CU(g_drv.cuMemcpyHtoDAsync_v2(pr->d_ldl_tab.ptr, pr->plan.table.data(), bytes, nullptr));
+      if (pr->large) {
+        const size_t dbytes = std::max<size_t>(pr->plan.dtable.size(), 1) * sizeof(double);
+        if ((rc = pr->d_dtab.reserve(dbytes)) != BO_OK) return rc;
+        if (!pr->plan.dtable.empty())
+          BO_CU(g_drv.cuMemcpyHtoDAsync_v2(pr->d_dtab.ptr, pr->plan.dtable.data(), pr->plan.dtable.size() * sizeof(double), nullptr));
+        // large state per lane: fewer resident lanes (one CTA per SM) keeps the scratch within a few GB
+        pr->blocks_per_sm = 1;
+        const size_t lanes = (size_t)pr->n_sm * pr->blocks_per_sm * pr->tpb;
+        if ((rc = pr->d_scratch.reserve(lanes * (size_t)pr->plan.vals_size() * sizeof(double))) != BO_OK) return rc;
+      }
       BO_CU(g_drv.cuStreamSynchronize(nullptr));
     }
     pr->loaded = true;
@@ -554,7 +574,7 @@ int bo_problem_create(const bo_problem_desc* desc, const bo_options* opts_in, bo
 int bo_problem_destroy(bo_problem* pr) {
   if (!pr) return BO_OK;
   if (pr->loaded) {
-    for (DevBuf* b : {&pr->d_p, &pr->d_x0, &pr->d_x, &pr->d_lam, &pr->d_f, &pr->d_status, &pr->d_iters, &pr->d_kkt, &pr->d_counter, &pr->d_ldl_tab})
+    for (DevBuf* b : {&pr->d_p, &pr->d_x0, &pr->d_x, &pr->d_lam, &pr->d_f, &pr->d_status, &pr->d_iters, &pr->d_kkt, &pr->d_counter, &pr->d_ldl_tab, &pr->d_dtab, &pr->d_scratch})
       b->release();
     pr->timer.release();
     if (pr->kernel.mod) g_drv.cuModuleUnload(pr->kernel.mod);
@@ -581,6 +601,13 @@ int64_t bo_problem_ldl_table(const bo_problem* pr, int32_t* buf, int64_t cap) {
   if (!pr) return set_err(BO_ERR_INVALID, "null problem");
   const int64_t n = pr->sparse ? (int64_t)pr->plan.table.size() : 0;
   if (buf && cap >= n && n > 0) memcpy(buf, pr->plan.table.data(), (size_t)n * sizeof(int32_t));
+  return n;
+}
+
+int64_t bo_problem_dtable(const bo_problem* pr, double* buf, int64_t cap) {
+  if (!pr) return set_err(BO_ERR_INVALID, "null problem");
+  const int64_t n = pr->large ? (int64_t)pr->plan.dtable.size() : 0;
+  if (buf && cap >= n && n > 0) memcpy(buf, pr->plan.dtable.data(), (size_t)n * sizeof(double));
   return n;
 }
 
@@ -652,15 +679,17 @@ int bo_solve(bo_problem* pr, int64_t B, const double* p, const double* x0, doubl
   if ((rc = stage_out(kkt_res, sizeof(double), pr->d_kkt, &dkkt)) != BO_OK) return rc;
 
   long long Bll = B;
-  SolverParams prm{pr->opts.max_iter, pr->opts.tol, pr->opts.acceptable_tol, pr->opts.mu_init, pr->opts.max_step, pr->opts.max_trips, pr->sparse ? pr->d_ldl_tab.ptr : 0};
   // persistent lanes: one wave of CTAs (multiple of the SM count), instances fetched from a counter
   CUdeviceptr dcounter = pr->d_counter.ptr;
   BO_CU(g_drv.cuMemsetD8Async(dcounter, 0, sizeof(unsigned long long), st));
-  void* args[] = {&Bll, &dp, &dx0, &dx, &dlam, &df, &dstat, &dit, &dkkt, &dcounter, &prm};
   long long grid_ll = (long long)pr->n_sm * pr->blocks_per_sm;
   const long long need = (B + pr->tpb - 1) / pr->tpb;
   if (grid_ll > need) grid_ll = need;
   const unsigned grid = (unsigned)grid_ll;
+  SolverParams prm{pr->opts.max_iter, pr->opts.tol, pr->opts.acceptable_tol, pr->opts.mu_init, pr->opts.max_step,
+                   pr->opts.max_trips, pr->sparse ? pr->d_ldl_tab.ptr : 0, pr->large ? pr->d_dtab.ptr : 0,
+                   pr->large ? pr->d_scratch.ptr : 0, (long long)pr->n_sm * pr->blocks_per_sm * pr->tpb};
+  void* args[] = {&Bll, &dp, &dx0, &dx, &dlam, &df, &dstat, &dit, &dkkt, &dcounter, &prm};
   size_t slot = 0;
   if ((rc = pr->timer.begin(st, &slot)) != BO_OK) return rc;
   BO_CU(g_drv.cuLaunchKernel(pr->kernel.fn, grid, 1, 1, (unsigned)pr->tpb, 1, 1, 0, st, args, nullptr));

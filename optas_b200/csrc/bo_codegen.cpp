@@ -7,6 +7,7 @@
 // fold constants (structural +-1/0 entries of joint-limit Jacobians disappear entirely).
 #include "bo_codegen.h"
 
+#include <algorithm>
 #include <cmath>
 #include <cstdio>
 #include <map>
@@ -245,7 +246,7 @@ static void emit_sparse_helpers(std::ostringstream& o, const char* tag, const Sp
   o << "  (void)J; (void)x; (void)out;\n}\n";
 }
 
-std::string emit_problem_source(const ProblemSource& ps, int tpb, bool pivoted_ldl, const SparsePlan* sparse) {
+std::string emit_problem_source(const ProblemSource& ps, int tpb, bool pivoted_ldl, const SparsePlan* sparse, bool large) {
   std::ostringstream o;
   o << "// generated by libb200optas (bo_codegen.cpp): tier-S solver, one instance per thread\n";
   o << "#define BO_NX " << ps.nx << "\n#define BO_NP " << ps.np << "\n#define BO_ME " << ps.n_eq << "\n#define BO_MI "
@@ -253,6 +254,12 @@ std::string emit_problem_source(const ProblemSource& ps, int tpb, bool pivoted_l
     << "\n#define BO_NNZ_H " << ps.hess.nnz() << "\n#define BO_TPB " << tpb << "\n";
   if (pivoted_ldl) o << "#define BO_USE_BK 1\n";
   if (sparse) o << "#define BO_SPARSE_LDL 1\n#define BO_SPARSE_VALS " << sparse->vals_size() << "\n";
+  if (large) {
+    // table-driven tier: no generated code at all, only the sizes
+    o << "#define BO_LARGE 1\n#define BO_NWORK " << std::max(ps.fc.n_work, ps.kkt.n_work) << "\n";
+    o << "#include \"bo_common.cuh\"\n#include \"bo_ipm_reg.cuh\"\n";
+    return o.str();
+  }
   o << "#include \"bo_common.cuh\"\n\n";
   o << emit_tape_function(ps.fc, "bo_tape_fc") << "\n";
   o << emit_tape_function(ps.kkt, "bo_tape_kkt") << "\n";

@@ -45,7 +45,7 @@ struct ProblemSource {
 // Full translation unit of the tier-S (thread-per-instance) solver for this problem.
 struct SparsePlan;
 std::string emit_problem_source(const ProblemSource& ps, int threads_per_block, bool pivoted_ldl,
-                                const SparsePlan* sparse = nullptr);
+                                const SparsePlan* sparse = nullptr, bool large = false);
 // Full translation unit of the streaming evaluation kernel for one tape.
 std::string emit_function_source(const Tape& tape, int threads_per_block);
 

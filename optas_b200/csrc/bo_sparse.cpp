@@ -16,7 +16,7 @@ int SparsePlan::pos(int i_old, int j_old) const {
   return n + (int)(it - rowidx.begin());
 }
 
-SparsePlan make_sparse_plan(const ProblemSource& ps) {
+SparsePlan make_sparse_plan(const ProblemSource& ps, bool large) {
   SparsePlan pl;
   const int nx = ps.nx, n = ps.nx + ps.n_eq;
   pl.n = n;
@@ -138,23 +138,76 @@ SparsePlan make_sparse_plan(const ProblemSource& ps) {
       pl.flops += 2;
     }
   }
-  // header + sections
-  // [0] n  [1] nnzL  [2] off_colptr  [3] off_rowidx  [4] off_perm  [5] off_sign  [6] off_prog  [7] total
+  // header (32 entries) + sections
+  //  [0] n  [1] nnzL  [2] colptr  [3] rowidx  [4] perm  [5] sign  [6] factor program  [7] end of LDL part
+  //  large mode only:
+  //  [8]/[9] JE row/col  [10]/[11] JI row/col  [12] pos of every H nz  [13] pos of every JE nz
+  //  [14] JI'SJI program: count, then {pos, a, b, r}   [15] JE'JE program: count, then {pos, a, b}
+  //  [16] fc tape: n_instr, n_consts offset into dtable, then instr[4*n]   [17] kkt tape: same
   std::vector<int32_t>& t = pl.table;
-  t.assign(8, 0);
+  t.assign(32, 0);
+  auto section = [&](int slot) { t[slot] = (int32_t)t.size(); };
   t[0] = n;
   t[1] = pl.nnzL();
-  t[2] = (int32_t)t.size();
+  section(2);
   t.insert(t.end(), pl.colptr.begin(), pl.colptr.end());
-  t[3] = (int32_t)t.size();
+  section(3);
   t.insert(t.end(), pl.rowidx.begin(), pl.rowidx.end());
-  t[4] = (int32_t)t.size();
+  section(4);
   t.insert(t.end(), pl.perm.begin(), pl.perm.end());
-  t[5] = (int32_t)t.size();
+  section(5);
   for (int j = 0; j < n; ++j) t.push_back(pl.perm[j] < nx ? 1 : -1);
-  t[6] = (int32_t)t.size();
+  section(6);
   t.insert(t.end(), prog.begin(), prog.end());
-  t[7] = (int32_t)t.size();
+  section(7);
+  if (large) {
+    section(8);
+    t.insert(t.end(), ps.jac_eq.row.begin(), ps.jac_eq.row.end());
+    section(9);
+    t.insert(t.end(), ps.jac_eq.col.begin(), ps.jac_eq.col.end());
+    section(10);
+    t.insert(t.end(), ps.jac_ineq.row.begin(), ps.jac_ineq.row.end());
+    section(11);
+    t.insert(t.end(), ps.jac_ineq.col.begin(), ps.jac_ineq.col.end());
+    section(12);
+    for (int k = 0; k < ps.hess.nnz(); ++k) t.push_back(pl.pos(ps.hess.row[k], ps.hess.col[k]));
+    section(13);
+    for (int k = 0; k < ps.jac_eq.nnz(); ++k) t.push_back(pl.pos(nx + ps.jac_eq.row[k], ps.jac_eq.col[k]));
+    auto pair_program = [&](const Sparsity& sp, int n_rows, bool with_row) {
+      const size_t count_at = t.size();
+      t.push_back(0);
+      int cnt = 0;
+      std::vector<std::vector<int>> by_row(n_rows > 0 ? n_rows : 1);
+      for (int k = 0; k < sp.nnz(); ++k) by_row[sp.row[k]].push_back(k);
+      for (int r = 0; r < n_rows; ++r) {
+        const auto& ks = by_row[r];
+        for (size_t u = 0; u < ks.size(); ++u)
+          for (size_t w = 0; w < ks.size(); ++w) {
+            const int cu = sp.col[ks[u]], cw = sp.col[ks[w]];
+            if (cu < cw || (cu == cw && u != w)) continue;
+            t.push_back(pl.pos(cu, cw));
+            t.push_back(ks[u]);
+            t.push_back(ks[w]);
+            if (with_row) t.push_back(r);
+            ++cnt;
+          }
+      }
+      t[count_at] = cnt;
+    };
+    section(14);
+    pair_program(ps.jac_ineq, ps.n_ineq, true);
+    section(15);
+    pair_program(ps.jac_eq, ps.n_eq, false);
+    auto tape_section = [&](int slot, const Tape& tape) {
+      section(slot);
+      t.push_back((int32_t)tape.n_instr());
+      t.push_back((int32_t)pl.dtable.size());
+      t.insert(t.end(), tape.instr.begin(), tape.instr.end());
+      pl.dtable.insert(pl.dtable.end(), tape.consts.begin(), tape.consts.end());
+    };
+    tape_section(16, ps.fc);
+    tape_section(17, ps.kkt);
+  }
   return pl;
 }
 

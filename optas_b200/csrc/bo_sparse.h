@@ -28,6 +28,7 @@ struct SparsePlan {
   int pos(int i_old, int j_old) const;
   // flat table uploaded to the device (layout documented in bo_ipm_reg.cuh, "sparse LDL' tables")
   std::vector<int32_t> table;
+  std::vector<double> dtable;     // constants of the interpreted tapes (large mode only)
   int64_t flops = 0;              // multiply-adds of one numeric factorisation
 };
 
@@ -35,6 +36,8 @@ struct SparsePlan {
 // Ordering: greedy minimum degree, with a constraint row eligible only once every variable it touches
 // has been eliminated (keeps its pivot away from the bare -dc and the order time-interleaved for
 // horizon problems).
-SparsePlan make_sparse_plan(const ProblemSource& ps);
+// `large`: also append the structure tables, the KKT assembly program and the two tapes, so that the
+// kernel needs no problem-specific code at all (table-driven everything; see bo_ipm_reg.cuh BO_LARGE).
+SparsePlan make_sparse_plan(const ProblemSource& ps, bool large);
 
 }  // namespace bo

@@ -48,7 +48,10 @@ struct bo_solver_params {
   double mu_init;
   double max_step;  // <= 0: unlimited
   int32_t max_trips; // budget of solver trips per instance (bounds the tail of a batch)
-  const int32_t* ldl_tab;  // sparse LDL' tables (bo_sparse.cpp) or null for the dense tiers
+  const int32_t* ldl_tab;  // int tables (bo_sparse.cpp): sparse LDL' plan; in large mode also structure + tapes
+  const double* dtab;      // double table: constants of the interpreted tapes (large mode)
+  double* scratch;         // large mode: factor values of all lanes, [element][lane]
+  long long scratch_stride;  // = number of lanes of the launch
 };
 
 // per-instance status codes (mirror bo_instance_status in include/b200optas.h)

@@ -53,11 +53,14 @@
 // too small, which is handled the same way: more dw), a non-negative one in the y block means JE is
 // rank deficient (handled with dc) -- IPOPT's Algorithm IC, without a pivoting factorisation.
 // Define BO_USE_BK (BO_FLAG_PIVOTED_LDL) to factor with Bunch-Kaufman partial pivoting instead.
+#ifndef BO_DC_SCALE
+#define BO_DC_SCALE 1e-8
+#endif
 #ifndef BO_STATIC_RHO
 #define BO_STATIC_RHO 1.0e6
 #endif
 #ifdef BO_SPARSE_LDL
-#define BO_LDL_SOLVE(LD, b) bo_ldl_sparse_solve(LD, prm.ldl_tab, b)
+#define BO_LDL_SOLVE(LD, b) bo_ldl_sparse_solve(BO_LDP(S), BO_LDS(S), prm.ldl_tab, b)
 #else
 #define BO_LDL_SOLVE(LD, b) bo_ldl_static_solve(LD, b)
 #endif
@@ -119,53 +122,58 @@ BO_NOINLINE void bo_ldl_static_solve(const double* BO_RESTRICT A, double* BO_RES
 // value array of one instance: vals[0..n) = D in elimination order, vals[n + e] = e-th non-zero of L.
 // Factor program, column by column (left-looking):
 //   n_k, then n_k records { pos L(j,k), pos D(k), cnt, cnt x { pos L(i,j), pos L(i,k) } }.
-BO_NOINLINE int bo_ldl_sparse(double* BO_RESTRICT vals, const int32_t* BO_RESTRICT tab) {
+// `vals` is addressed with a stride so that the same code serves a thread-local array (stride 1) and
+// the [element][lane] global scratch of the large tier (stride = number of lanes: coalesced).
+#define BO_V(i) vals[(long long)(i) * stride]
+BO_NOINLINE int bo_ldl_sparse(double* BO_RESTRICT vals, long long stride, const int32_t* BO_RESTRICT tab) {
   const int n = tab[0];
   const int32_t* colptr = tab + tab[2];
   const int32_t* sign = tab + tab[5];
   const int32_t* prog = tab + tab[6];
   int bad = 0, pc = 0;
   for (int j = 0; j < n; ++j) {
-    double d = vals[j];
+    double d = BO_V(j);
     const double scale = fmax(1.0, fabs(d));
     const int nk = prog[pc++];
     for (int kk = 0; kk < nk; ++kk) {
-      const double ljk = vals[prog[pc]];
-      const double w = ljk * vals[prog[pc + 1]];
+      const double ljk = BO_V(prog[pc]);
+      const double w = ljk * BO_V(prog[pc + 1]);
       const int cnt = prog[pc + 2];
       pc += 3;
       d -= ljk * w;
-      for (int c = 0; c < cnt; ++c, pc += 2) vals[prog[pc]] -= vals[prog[pc + 1]] * w;
+      for (int c = 0; c < cnt; ++c, pc += 2) BO_V(prog[pc]) -= BO_V(prog[pc + 1]) * w;
     }
     if (sign[j] > 0) {
       if (!(d > 1e-13 * scale) && bad == 0) bad = 1;
     } else {
       if (!(d < -1e-13) && bad == 0) bad = 2;
     }
-    vals[j] = d;
+    BO_V(j) = d;
     const double dinv = 1.0 / d;
-    for (int e = colptr[j]; e < colptr[j + 1]; ++e) vals[n + e] *= dinv;
+    for (int e = colptr[j]; e < colptr[j + 1]; ++e) BO_V(n + e) *= dinv;
   }
   return bad;
 }
 
 // b is indexed by ORIGINAL row (x then y); perm maps elimination position -> original row.
-BO_NOINLINE void bo_ldl_sparse_solve(const double* BO_RESTRICT vals, const int32_t* BO_RESTRICT tab, double* BO_RESTRICT b) {
+BO_NOINLINE void bo_ldl_sparse_solve(const double* BO_RESTRICT vals, long long stride, const int32_t* BO_RESTRICT tab,
+                                     double* BO_RESTRICT b) {
   const int n = tab[0];
   const int32_t* colptr = tab + tab[2];
   const int32_t* rowidx = tab + tab[3];
   const int32_t* perm = tab + tab[4];
   for (int j = 0; j < n; ++j) {
     const double bj = b[perm[j]];
-    for (int e = colptr[j]; e < colptr[j + 1]; ++e) b[perm[rowidx[e]]] -= vals[n + e] * bj;
+    for (int e = colptr[j]; e < colptr[j + 1]; ++e) b[perm[rowidx[e]]] -= BO_V(n + e) * bj;
   }
-  for (int j = 0; j < n; ++j) b[perm[j]] /= vals[j];
+  for (int j = 0; j < n; ++j) b[perm[j]] /= BO_V(j);
   for (int j = n - 1; j >= 0; --j) {
     double acc = b[perm[j]];
-    for (int e = colptr[j]; e < colptr[j + 1]; ++e) acc -= vals[n + e] * b[perm[rowidx[e]]];
+    for (int e = colptr[j]; e < colptr[j + 1]; ++e) acc -= BO_V(n + e) * b[perm[rowidx[e]]];
     b[perm[j]] = acc;
   }
 }
+#undef BO_V
 #endif
 
 #ifdef BO_USE_BK
@@ -331,6 +339,129 @@ BO_DEVICE int bo_kkt_factor(double dw, double dc, double* BO_RESTRICT LD, int* B
 BO_DEVICE void bo_bk_solve(const double*, const int*, double*) {}
 #endif
 
+#ifdef BO_LARGE
+#define BO_LDP(S) ((S).ldp)
+#define BO_LDS(S) ((S).lds)
+#else
+#define BO_LDP(S) ((S).LD)
+#define BO_LDS(S) 1LL
+#endif
+
+#ifdef BO_LARGE
+// ===================== large tier: no problem-specific code, everything table-driven =====================
+// For horizon problems (C4, C5: 10^5-instruction tapes, KKT systems of 10^3 rows) generating
+// straight-line code is hopeless (megabytes of SASS, minutes of ptxas).  Instead the tapes are
+// INTERPRETED: the instruction stream is read from global memory at a warp-uniform address
+// (one broadcast transaction for 32 instances), operands live in a per-lane work array, and every lane
+// takes the same branch of the opcode switch -- there is no divergence, because all instances share the
+// tape.  Jacobian products and the KKT assembly run off coordinate tables the same way.
+#include "bo_opcodes.h"
+
+BO_NOINLINE void bo_tape_interp(const int32_t* BO_RESTRICT sec, const double* BO_RESTRICT dtab, double* BO_RESTRICT w,
+                                const double* const* in, double* const* out) {
+  const int n = sec[0];
+  const double* consts = dtab + sec[1];
+  const int32_t* ins = sec + 2;
+  for (int i = 0; i < n; ++i, ins += 4) {
+    const int op = ins[0] & 0xFF, dst = ins[1], a = ins[2], b = ins[3];
+    double r;
+    switch (op) {
+      case BO_OP_INPUT: r = in[b][a]; break;
+      case BO_OP_CONST: r = consts[a]; break;
+      case BO_OP_OUTPUT: out[b][a] = w[dst]; continue;
+      case BO_OP_ADD: r = w[a] + w[b]; break;
+      case BO_OP_SUB: r = w[a] - w[b]; break;
+      case BO_OP_MUL: r = w[a] * w[b]; break;
+      case BO_OP_DIV: r = w[a] / w[b]; break;
+      case BO_OP_NEG: r = -w[a]; break;
+      case BO_OP_SQ: r = w[a] * w[a]; break;
+      case BO_OP_SQRT: r = sqrt(w[a]); break;
+      case BO_OP_SIN: r = sin(w[a]); break;
+      case BO_OP_COS: r = cos(w[a]); break;
+      case BO_OP_TAN: r = tan(w[a]); break;
+      case BO_OP_ASIN: r = asin(w[a]); break;
+      case BO_OP_ACOS: r = acos(w[a]); break;
+      case BO_OP_ATAN: r = atan(w[a]); break;
+      case BO_OP_ATAN2: r = atan2(w[a], w[b]); break;
+      case BO_OP_FABS: r = fabs(w[a]); break;
+      case BO_OP_FMIN: r = fmin(w[a], w[b]); break;
+      case BO_OP_FMAX: r = fmax(w[a], w[b]); break;
+      case BO_OP_EXP: r = exp(w[a]); break;
+      case BO_OP_LOG: r = log(w[a]); break;
+      case BO_OP_POW: r = pow(w[a], w[b]); break;
+      case BO_OP_TANH: r = tanh(w[a]); break;
+      case BO_OP_SINH: r = sinh(w[a]); break;
+      case BO_OP_COSH: r = cosh(w[a]); break;
+      case BO_OP_FLOOR: r = floor(w[a]); break;
+      case BO_OP_CEIL: r = ceil(w[a]); break;
+      case BO_OP_SIGN: r = bo_sign(w[a]); break;
+      case BO_OP_NOT: r = (double)(w[a] == 0.0); break;
+      case BO_OP_LT: r = (double)(w[a] < w[b]); break;
+      case BO_OP_LE: r = (double)(w[a] <= w[b]); break;
+      case BO_OP_EQ: r = (double)(w[a] == w[b]); break;
+      case BO_OP_NE: r = (double)(w[a] != w[b]); break;
+      case BO_OP_AND: r = (double)((w[a] != 0.0) && (w[b] != 0.0)); break;
+      case BO_OP_OR: r = (double)((w[a] != 0.0) || (w[b] != 0.0)); break;
+      case BO_OP_IF_ELSE: r = w[(unsigned)ins[0] >> 8] != 0.0 ? w[a] : w[b]; break;
+      default: r = BO_NAN;
+    }
+    w[dst] = r;
+  }
+}
+
+BO_NOINLINE void bo_large_fc(const bo_solver_params& prm, const double* x, const double* p, double* f, double* cE, double* cI) {
+  double w[BO_NWORK];
+  const double* in[2] = {x, p};
+  double* out[3] = {f, cE, cI};
+  bo_tape_interp(prm.ldl_tab + prm.ldl_tab[16], prm.dtab, w, in, out);
+}
+
+BO_NOINLINE void bo_large_kkt(const bo_solver_params& prm, const double* x, const double* p, const double* y, const double* z,
+                              double* f, double* g, double* cE, double* cI, double* JE, double* JI, double* H) {
+  double w[BO_NWORK];
+  const double* in[4] = {x, p, y, z};
+  double* out[7] = {f, g, cE, cI, JE, JI, H};
+  bo_tape_interp(prm.ldl_tab + prm.ldl_tab[17], prm.dtab, w, in, out);
+}
+
+// out[col] += J[k] * v[row]   /   out[row] = sum J[k] * x[col]
+BO_NOINLINE void bo_coo_t_acc(const int32_t* BO_RESTRICT row, const int32_t* BO_RESTRICT col, int nnz, const double* J,
+                              const double* v, double* out) {
+  for (int k = 0; k < nnz; ++k) out[col[k]] += J[k] * v[row[k]];
+}
+BO_NOINLINE void bo_coo_mul(const int32_t* BO_RESTRICT row, const int32_t* BO_RESTRICT col, int nnz, int n_rows, const double* J,
+                            const double* x, double* out) {
+  for (int r = 0; r < n_rows; ++r) out[r] = 0.0;
+  for (int k = 0; k < nnz; ++k) out[row[k]] += J[k] * x[col[k]];
+}
+BO_NOINLINE void bo_large_fill(const bo_solver_params& prm, const double* H, const double* JE, const double* JI,
+                               const double* sigma, double* K, long long stride) {
+  const int32_t* t = prm.ldl_tab;
+  for (int i = 0; i < BO_KSZ; ++i) K[(long long)i * stride] = 0.0;
+  const int32_t* hp = t + t[12];
+  for (int k = 0; k < BO_NNZ_H; ++k) K[(long long)hp[k] * stride] += H[k];
+  const int32_t* ip = t + t[14];
+  const int ni = ip[0];
+  ip += 1;
+  for (int c = 0; c < ni; ++c, ip += 4) K[(long long)ip[0] * stride] += sigma[ip[3]] * JI[ip[1]] * JI[ip[2]];
+  const int32_t* ep = t + t[13];
+  for (int k = 0; k < BO_NNZ_JE; ++k) K[(long long)ep[k] * stride] += JE[k];
+}
+BO_NOINLINE void bo_large_jeje(const bo_solver_params& prm, const double* JE, double rho, double* K, long long stride) {
+  const int32_t* ep = prm.ldl_tab + prm.ldl_tab[15];
+  const int ne = ep[0];
+  ep += 1;
+  for (int c = 0; c < ne; ++c, ep += 3) K[(long long)ep[0] * stride] += rho * JE[ep[1]] * JE[ep[2]];
+}
+#define bo_eval_fc(x, p, f, cE, cI) bo_large_fc(prm, x, p, f, cE, cI)
+#define bo_tape_kkt(x, p, y, z, f, g, cE, cI, JE, JI, H) bo_large_kkt(prm, x, p, y, z, f, g, cE, cI, JE, JI, H)
+#define bo_JEt_acc(J, v, out) bo_coo_t_acc(prm.ldl_tab + prm.ldl_tab[8], prm.ldl_tab + prm.ldl_tab[9], BO_NNZ_JE, J, v, out)
+#define bo_JIt_acc(J, v, out) bo_coo_t_acc(prm.ldl_tab + prm.ldl_tab[10], prm.ldl_tab + prm.ldl_tab[11], BO_NNZ_JI, J, v, out)
+#define bo_JI_mul(J, x, out) bo_coo_mul(prm.ldl_tab + prm.ldl_tab[10], prm.ldl_tab + prm.ldl_tab[11], BO_NNZ_JI, BO_MI, J, x, out)
+#define bo_kkt_fill(H, JE, JI, sigma, K) bo_large_fill(prm, H, JE, JI, sigma, K, BO_LDS(S))
+#define bo_JEtJE_acc(JE, rho, K) bo_large_jeje(prm, JE, rho, K, BO_LDS(S))
+#endif  // BO_LARGE
+
 // Barrier objective and l1 constraint violation at (x, s) given the function values there.
 BO_NOINLINE void bo_measures(double f, const double* cE, const double* cI, const double* s, double mu, double* phi,
                            double* theta) {
@@ -380,7 +511,12 @@ struct bo_ipm_state {
   // evaluation at x (valid from PH_EVAL to the end of the iteration)
   double g[BO_NX], cE[BO_DIM(BO_ME)], cI[BO_DIM(BO_MI)], rd[BO_NX], sigma[BO_DIM(BO_MI)];
   double JE[BO_DIM(BO_NNZ_JE)], JI[BO_DIM(BO_NNZ_JI)], H[BO_DIM(BO_NNZ_H)];
+#ifdef BO_LARGE
+  double* ldp;        // this lane's slice of the global factor scratch ([element][lane])
+  long long lds;
+#else
   double LD[BO_KSZ];  // assembled KKT matrix, factored in place (re-assembled for every attempt)
+#endif
 #ifdef BO_USE_BK
   int ipiv[BO_NK];
 #else
@@ -396,7 +532,9 @@ struct bo_ipm_state {
 };
 
 // The small tape is called from two places (start of an instance, every trial point): keep one copy.
+#ifndef BO_LARGE
 BO_NOINLINE void bo_eval_fc(const double* x, const double* p, double* f, double* cE, double* cI) { bo_tape_fc(x, p, f, cE, cI); }
+#endif
 
 // Start an instance: S.p and S.x hold the parameters and the seed.
 BO_DEVICE void bo_ipm_init(bo_ipm_state& S, const bo_solver_params prm) {
@@ -444,7 +582,7 @@ BO_NOINLINE double bo_ipm_step(bo_ipm_state& S, const bo_solver_params& prm) {
     BO_UNROLL
     for (int j = 0; j < BO_ME; ++j) S.sol[BO_NX + j] *= undo;
   } else {
-    bo_bk_solve(S.LD, S.ipiv, S.sol);
+    bo_bk_solve(BO_LDP(S), S.ipiv, S.sol);
   }
   BO_UNROLL
   for (int i = 0; i < BO_NX; ++i) S.dx[i] = S.sol[i];
@@ -569,24 +707,24 @@ BO_DEVICE int bo_trip_eval(bo_ipm_state& S, const bo_solver_params prm) {
 BO_DEVICE int bo_trip_factor(bo_ipm_state& S, const bo_solver_params prm) {
   // =========================== PH_FACTOR ===========================
   if (S.phase == BO_PH_FACTOR) {
-    bo_kkt_fill(S.H, S.JE, S.JI, S.sigma, S.LD);
+    bo_kkt_fill(S.H, S.JE, S.JI, S.sigma, BO_LDP(S));
     int inertia;
 #ifdef BO_USE_BK
     S.static_fac = false;
-    inertia = bo_kkt_factor(S.dw, S.dc, S.LD, S.ipiv);
+    inertia = bo_kkt_factor(S.dw, S.dc, BO_LDP(S), S.ipiv);
 #else
     // unpivoted LDL' on the rho-augmented system (uniform control flow across the warp)
     S.static_fac = true;
     const double rho = S.ls_mode ? 0.0 : BO_STATIC_RHO;
     S.rho = rho;
-    if (!S.ls_mode) bo_JEtJE_acc(S.JE, rho, S.LD);
+    if (!S.ls_mode) bo_JEtJE_acc(S.JE, rho, BO_LDP(S));
 #ifdef BO_SPARSE_LDL
     {
       const int32_t* sign = prm.ldl_tab + prm.ldl_tab[5];
       const double dcp = S.dc / (1.0 - rho * S.dc);
-      for (int j = 0; j < BO_NK; ++j) S.LD[j] += sign[j] > 0 ? S.dw : -dcp;
+      for (int j = 0; j < BO_NK; ++j) BO_LDP(S)[(long long)j * BO_LDS(S)] += sign[j] > 0 ? S.dw : -dcp;
     }
-    const int bad = bo_ldl_sparse(S.LD, prm.ldl_tab);
+    const int bad = bo_ldl_sparse(BO_LDP(S), BO_LDS(S), prm.ldl_tab);
 #else
     for (int i = 0; i < BO_NX; ++i) S.LD[BO_KIDX(i, i)] += S.dw;
     for (int i = BO_NX; i < BO_NK; ++i) S.LD[BO_KIDX(i, i)] -= S.dc / (1.0 - rho * S.dc);
@@ -605,7 +743,7 @@ BO_DEVICE int bo_trip_factor(bo_ipm_state& S, const bo_solver_params prm) {
         BO_UNROLL
         for (int j = 0; j < BO_ME; ++j) S.sol[BO_NX + j] = 0.0;
         if (S.static_fac) BO_LDL_SOLVE(S.LD, S.sol);
-        else bo_bk_solve(S.LD, S.ipiv, S.sol);
+        else bo_bk_solve(BO_LDP(S), S.ipiv, S.sol);
         bool fin = true;
         BO_UNROLL
         for (int j = 0; j < BO_ME; ++j) fin = fin && bo_isfinite(S.sol[BO_NX + j]);
@@ -624,7 +762,7 @@ BO_DEVICE int bo_trip_factor(bo_ipm_state& S, const bo_solver_params prm) {
     if (inertia != 0) {
       // ---- inertia correction (IPOPT Algorithm IC); retried on the next trip ----
       if (inertia < 0 && BO_ME > 0 && S.dc == 0.0) {
-        S.dc = 1e-8 * sqrt(sqrt(S.mu));  // 1e-8 mu^(1/4)  // singular: perturb the constraint block first
+        S.dc = BO_DC_SCALE * sqrt(sqrt(S.mu));  // IPOPT: 1e-8 mu^(1/4)  // singular: perturb the constraint block first
       } else if (S.dw == 0.0) {
         S.dw = (S.dw_last == 0.0) ? 1e-4 : fmax(1e-20, S.dw_last / 3.0);
       } else {
@@ -729,7 +867,9 @@ BO_DEVICE int bo_trip_trial(bo_ipm_state& S, const bo_solver_params prm) {
       }
       BO_UNROLL
       for (int j = 0; j < BO_ME; ++j) S.y[j] += S.a * S.y_step[j];
-      S.recalc_y = S.dw > 0.0;
+      // regularised step (dw: nonconvex; dc: rank-deficient JE, whose multipliers are undetermined along
+      // null(JE') and would otherwise drift by residual/dc): re-estimate y by least squares next trip
+      S.recalc_y = S.dw > 0.0 || S.dc > 0.0;
       S.it += 1;
       S.phase = BO_PH_EVAL;
       return -1;
@@ -816,6 +956,10 @@ bo_solve_kernel(long long B, const double* __restrict__ p_all, const double* __r
                 int* __restrict__ status_all, int* __restrict__ iters_all, double* __restrict__ kkt_all,
                 unsigned long long* __restrict__ work_counter, const bo_solver_params prm) {
   bo_ipm_state S;
+#ifdef BO_LARGE
+  S.ldp = prm.scratch + ((long long)blockIdx.x * BO_TPB + threadIdx.x);
+  S.lds = prm.scratch_stride;
+#endif
   long long b = -1;
   bool active = false, exhausted = false;
   while (true) {

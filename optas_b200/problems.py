@@ -183,4 +183,126 @@ def point_mass_mpc(T: int = 20) -> Problem:
     return Problem("point_mass_mpc", opt, sample, {}, {"point_mass": point_mass})
 
 
-ALL_BUILDERS = [lwr_ik, booth, point_mass_mpc]
+
+
+# ----------------------------------------------------------------------------------------------
+# C5: dual-arm planner (reference: example/dual_arm.py:17-128 and :130-144)
+# ----------------------------------------------------------------------------------------------
+
+DUAL_ARM_Q0 = np.deg2rad([0.0, -30.0, 0.0, 90.0, 0.0, 30.0, 0.0])
+
+
+def dual_arm(T: int = 50) -> Problem:
+    Tmax, link_ee = 10.0, LWR_EE
+    dt = Tmax / float(T - 1)
+
+    def arm(name, base_position):
+        model = RobotModel(urdf_filename=LWR_URDF, name=name, time_derivs=[0, 1])
+        model.add_base_frame("global_world", xyz=base_position)
+        return model
+
+    kukal, kukar = arm("kukal", [0.0, -0.25, 0.0]), arm("kukar", [0.0, 0.25, 0.0])
+    builder = OptimizationBuilder(T=T, robots=[kukal, kukar])
+    qcl = builder.add_parameter("qcl", kukal.ndof)
+    qcr = builder.add_parameter("qcr", kukar.ndof)
+    builder.fix_configuration("kukal", qcl)
+    builder.fix_configuration("kukar", qcr)
+    builder.integrate_model_states("kukal", time_deriv=1, dt=dt)
+    builder.integrate_model_states("kukar", time_deriv=1, dt=dt)
+    posl_ee = kukal.get_global_link_position_function(link_ee, n=T)
+    posr_ee = kukar.get_global_link_position_function(link_ee, n=T)
+    Ql, Qr = builder.get_model_states("kukal"), builder.get_model_states("kukar")
+    ee_pos_pathl, ee_pos_pathr = posl_ee(Ql), posr_ee(Qr)
+    dQl, dQr = builder.get_model_states("kukal", time_deriv=1), builder.get_model_states("kukar", time_deriv=1)
+    w_dq = 0.01
+    builder.add_cost_term("kukal_min_join_vel", w_dq * cs.sumsqr(dQl))
+    builder.add_cost_term("kukar_min_join_vel", w_dq * cs.sumsqr(dQr))
+    pos0l = kukal.get_global_link_position(link_ee, qcl)
+    pos0r = kukar.get_global_link_position(link_ee, qcr)
+    pos1l, pos1r = pos0l + cs.DM([-0.1, 0.1, -0.2]), pos0r + cs.DM([-0.1, -0.1, -0.2])
+    pos2l, pos2r = pos1l + cs.DM([0.0, 0.0, 0.3]), pos1r + cs.DM([0.0, 0.0, 0.3])
+    path_eel, path_eer = cs.SX.zeros(3, T), cs.SX.zeros(3, T)
+    for i in range(T):
+        alpha_ = float(i) / float(T - 1)
+        if alpha_ < 0.4:
+            alpha = alpha_ / 0.4
+            path_eel[:, i] = alpha * pos1l + (1.0 - alpha) * pos0l
+            path_eer[:, i] = alpha * pos1r + (1.0 - alpha) * pos0r
+        elif alpha_ < 0.5:
+            path_eel[:, i], path_eer[:, i] = pos1l, pos1r
+        else:
+            alpha = (alpha_ - 0.5) / 0.5
+            path_eel[:, i] = alpha * pos2l + (1.0 - alpha) * pos1l
+            path_eer[:, i] = alpha * pos2r + (1.0 - alpha) * pos1r
+    builder.add_cost_term("ee_pos_pathl", cs.sumsqr(ee_pos_pathl - path_eel))
+    builder.add_cost_term("ee_pos_pathr", cs.sumsqr(ee_pos_pathr - path_eer))
+    opt = builder.build()
+
+    def sample(B: int, seed: int = 3):
+        """C5 inputs: qcl, qcr = deg2rad[0,-30,0,90,0,30,0] + N(0, 0.1^2) each; seed: both arms
+        hold their start configuration with zero velocity."""
+        rng = np.random.default_rng(seed)
+        qcl_ = DUAL_ARM_Q0 + 0.1 * rng.standard_normal((B, 7))
+        qcr_ = DUAL_ARM_Q0 + 0.1 * rng.standard_normal((B, 7))
+        P = np.concatenate([qcl_, qcr_], axis=1)
+        X0 = np.concatenate([np.tile(qcl_, (1, T)), np.zeros((B, 7 * (T - 1))), np.tile(qcr_, (1, T)),
+                             np.zeros((B, 7 * (T - 1)))], axis=1)
+        return np.ascontiguousarray(P), np.ascontiguousarray(X0)
+
+    return Problem("dual_arm", opt, sample, {}, {"kukal": kukal, "kukar": kukar})
+
+
+# ----------------------------------------------------------------------------------------------
+# C4: figure-of-eight trajectory optimisation (reference: example/figure_eight_plan.py:16-113)
+# ----------------------------------------------------------------------------------------------
+
+MED7_EE = "lbr_link_ee"
+FIG8_Q0 = np.deg2rad([0.0, 30.0, 0.0, -90.0, 0.0, -30.0, 0.0])
+
+
+def figure_eight(T: int = 50, joint_limits: bool = True) -> Problem:
+    """``joint_limits=True`` adds ``enforce_model_limits`` on q: BASELINE.json's C4 says "with joint-limit
+    ineq"; the reference script itself has none (SURVEY.md 0, 8a)."""
+    Tmax = 10.0
+    t = cs.linspace(0, Tmax, T)
+    dt = Tmax / float(T - 1)
+    kuka = RobotModel(urdf_filename=MED7_URDF, time_derivs=[0, 1])
+    name = kuka.get_name()
+    builder = OptimizationBuilder(T=T, robots=[kuka])
+    qc = builder.add_parameter("qc", kuka.ndof)
+    builder.fix_configuration(name, config=qc)
+    builder.fix_configuration(name, time_deriv=1)
+    builder.integrate_model_states(name, time_deriv=1, dt=dt)
+    Q = builder.get_model_states(name)
+    pos_ee = kuka.get_global_link_position_function(MED7_EE, n=T)(Q)
+    pc = kuka.get_global_link_position(MED7_EE, qc)
+    Rc = kuka.get_global_link_rotation(MED7_EE, qc)
+    quatc = kuka.get_global_link_quaternion(MED7_EE, qc)
+    path = cs.SX.zeros(3, T)
+    path[0, :] = 0.2 * cs.sin(t * cs.pi * 0.5).T
+    path[1, :] = 0.1 * cs.sin(t * cs.pi).T
+    for k in range(T):
+        path[:, k] = pc + Rc @ path[:, k]
+    builder.add_cost_term("ee_path", 1000.0 * cs.sumsqr(path - pos_ee))
+    dQ = builder.get_model_states(name, time_deriv=1)
+    builder.add_cost_term("min_join_vel", 0.01 * cs.sumsqr(dQ))
+    quat = kuka.get_global_link_quaternion_function(MED7_EE, n=T)
+    builder.add_equality_constraint("no_eff_rot", quat(Q), quatc)
+    if joint_limits:
+        builder.enforce_model_limits(name)
+    opt = builder.build()
+    lo = kuka.lower_actuated_joint_limits.toarray().flatten()
+    up = kuka.upper_actuated_joint_limits.toarray().flatten()
+
+    def sample(B: int, seed: int = 2):
+        """C4 inputs: qc = deg2rad[0,30,0,-90,0,-30,0] + N(0, 0.1^2) clipped to 0.95 limits;
+        seed q/x = qc tiled over the horizon, dq/x = 0 (figure_eight_plan.py:123-124)."""
+        rng = np.random.default_rng(seed)
+        qc_ = np.clip(FIG8_Q0 + 0.1 * rng.standard_normal((B, 7)), 0.95 * lo, 0.95 * up)
+        X0 = np.concatenate([np.tile(qc_, (1, T)), np.zeros((B, 7 * (T - 1)))], axis=1)
+        return np.ascontiguousarray(qc_), np.ascontiguousarray(X0)
+
+    return Problem("figure_eight", opt, sample, {}, {"robot": kuka})
+
+
+ALL_BUILDERS = [lwr_ik, booth, point_mass_mpc, figure_eight, dual_arm]

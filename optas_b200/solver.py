@@ -421,6 +421,9 @@ class B200Solver(Solver):
         """Tables of the sparse KKT factorisation (empty for the dense tiers)."""
         return self._handle.ldl_table()
 
+    def dtable(self) -> np.ndarray:
+        return self._handle.dtable()
+
 
 class CasADiSolver(B200Solver):
     """Name-compatible drop-in for ``optas.CasADiSolver`` (ref :321-419): same constructor, same

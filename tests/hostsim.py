@@ -30,11 +30,14 @@ static long long bo_host_stats[4] = {0, 0, 0, 0};
 extern "C" void hostsim_stats(long long* out) { for (int i = 0; i < 4; ++i) { out[i] = bo_host_stats[i]; bo_host_stats[i] = 0; } }
 extern "C" void hostsim_solve(long long B, const double* p, const double* x0, double* x, double* lam, double* f,
                               int* status, int* iters, double* kkt, int* trips, int max_iter, double tol, double acc_tol,
-                              double mu_init, double max_step, int max_trips, const int* ldl_tab) {
+                              double mu_init, double max_step, int max_trips, const int* ldl_tab, const double* dtab, double* scratch) {
   bo_solver_params prm;
-  prm.max_iter = max_iter; prm.tol = tol; prm.acceptable_tol = acc_tol; prm.mu_init = mu_init; prm.max_step = max_step; prm.max_trips = max_trips; prm.ldl_tab = ldl_tab;
+  prm.max_iter = max_iter; prm.tol = tol; prm.acceptable_tol = acc_tol; prm.mu_init = mu_init; prm.max_step = max_step; prm.max_trips = max_trips; prm.ldl_tab = ldl_tab; prm.dtab = dtab; prm.scratch = scratch; prm.scratch_stride = 1;
   for (long long b = 0; b < B; ++b) {
-    bo_ipm_state S;
+    static bo_ipm_state S;
+#ifdef BO_LARGE
+    S.ldp = scratch; S.lds = 1;
+#endif
     for (int i = 0; i < BO_NP; ++i) S.p[i] = p[b * BO_NP + i];
     for (int i = 0; i < BO_NX; ++i) S.x[i] = x0 ? x0[b * BO_NX + i] : 0.0;
     status[b] = bo_ipm_solve(S, prm);
@@ -49,7 +52,9 @@ extern "C" void hostsim_solve(long long B, const double* p, const double* x0, do
 
 class HostSim:
     def __init__(self, generated_source: str, nx: int, np_: int, n_eq: int, n_ineq: int, trace: bool = False, defines: str = "",
-                 ldl_table=None):
+                 ldl_table=None, dtable=None):
+        self.dtable = None if dtable is None or len(dtable) == 0 else np.ascontiguousarray(dtable, dtype=np.float64)
+        self.scratch = np.zeros(int(ldl_table[0] + ldl_table[1]) + 1) if ldl_table is not None and len(ldl_table) else None
         self.ldl_table = None if ldl_table is None or len(ldl_table) == 0 else np.ascontiguousarray(ldl_table, dtype=np.int32)
         self.nx, self.np_, self.nl = nx, np_, n_eq + n_ineq
         key = hashlib.sha1(generated_source.encode()).hexdigest()[:16] + str(trace) + defines
@@ -63,13 +68,13 @@ class HostSim:
             wrap = os.path.join(d, f"wrap_{os.getpid()}.cpp")
             open(gen, "w").write(generated_source)
             open(wrap, "w").write(_WRAPPER % {"gen": gen, "trace": ("#define BO_HOST_TRACE 1\n" if trace else "") + defines})
-            subprocess.run(["/usr/bin/g++", "-O1", "-shared", "-fPIC", "-std=c++17", "-I", _JIT_INC, wrap, "-o", so + ".tmp"],
+            subprocess.run(["/usr/bin/g++", "-O1", "-shared", "-fPIC", "-std=c++17", "-I", _JIT_INC, "-I", os.path.join(_HERE, "..", "include"), wrap, "-o", so + ".tmp"],
                            check=True)
             os.replace(so + ".tmp", so)
         self.lib = C.CDLL(so)
         vp = C.c_void_p
         self.lib.hostsim_stats.argtypes = [vp]
-        self.lib.hostsim_solve.argtypes = [C.c_longlong] + [vp] * 9 + [C.c_int, C.c_double, C.c_double, C.c_double, C.c_double, C.c_int, vp]
+        self.lib.hostsim_solve.argtypes = [C.c_longlong] + [vp] * 9 + [C.c_int, C.c_double, C.c_double, C.c_double, C.c_double, C.c_int, vp, vp, vp]
 
     def solve(self, P, X0, max_iter=100, tol=1e-8, acc_tol=1e-6, mu_init=0.1, max_step=0.5, max_trips=250):
         B = X0.shape[0]
@@ -79,7 +84,9 @@ class HostSim:
         st = np.empty(B, dtype=np.int32); it = np.empty(B, dtype=np.int32); kkt = np.empty(B); trips = np.empty(B, dtype=np.int32)
         self.lib.hostsim_solve(B, P.ctypes.data, X0.ctypes.data, X.ctypes.data, lam.ctypes.data, f.ctypes.data,
                                st.ctypes.data, it.ctypes.data, kkt.ctypes.data, trips.ctypes.data, max_iter, tol, acc_tol, mu_init, max_step, max_trips,
-                               None if self.ldl_table is None else self.ldl_table.ctypes.data)
+                               None if self.ldl_table is None else self.ldl_table.ctypes.data,
+                               None if self.dtable is None else self.dtable.ctypes.data,
+                               None if self.scratch is None else self.scratch.ctypes.data)
         stats = np.zeros(4, dtype=np.int64)
         self.lib.hostsim_stats(stats.ctypes.data)
         self.last_stats = {"static": int(stats[0]), "bk_ok": int(stats[1]), "bk_retry": int(stats[2])}
