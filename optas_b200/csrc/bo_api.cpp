@@ -557,8 +557,11 @@ int bo_problem_create(const bo_problem_desc* desc, const bo_options* opts_in, bo
         if ((rc = pr->d_dtab.reserve(dbytes)) != BO_OK) return rc;
         if (!pr->plan.dtable.empty())
           BO_CU(g_drv.cuMemcpyHtoDAsync_v2(pr->d_dtab.ptr, pr->plan.dtable.data(), pr->plan.dtable.size() * sizeof(double), nullptr));
-        // large state per lane: fewer resident lanes (one CTA per SM) keeps the scratch within a few GB
-        pr->blocks_per_sm = 1;
+        // large state per lane (hundreds of KB): cap the resident lanes so the scratch stays within a few GB
+        {
+          const int cap = pr->opts.blocks_per_sm > 0 ? pr->opts.blocks_per_sm : 2;
+          if (pr->blocks_per_sm > cap) pr->blocks_per_sm = cap;
+        }
         const size_t lanes = (size_t)pr->n_sm * pr->blocks_per_sm * pr->tpb;
         if ((rc = pr->d_scratch.reserve(lanes * (size_t)pr->plan.vals_size() * sizeof(double))) != BO_OK) return rc;
       }

@@ -128,38 +128,36 @@ class Tape:
         group_ptr = [0]
         n_work = 0
 
+        REMAT_GAP = 48  # a leaf (input / constant) whose next use is further away than this is re-loaded there
+
         for grp in groups:
             out_nodes = [outputs[s][e] for (s, e) in grp]
             order = _schedule(out_nodes, in_pos)
-            # last use (position in `order`) of every node, outputs live until stored
-            last_use: Dict[int, int] = {}
+            # positions (in `order`) at which every node is used as an operand
+            uses: Dict[int, List[int]] = {}
             for k, nd in enumerate(order):
                 for ch in (nd.a, nd.b, nd.c):
                     if ch is not None:
-                        last_use[ch.idx] = k
+                        lst = uses.setdefault(ch.idx, [])
+                        if not lst or lst[-1] != k:
+                            lst.append(k)
+            use_ptr: Dict[int, int] = {}
             stores: Dict[int, List[tuple]] = {}
             for (s, e), nd in zip(grp, out_nodes):
                 stores.setdefault(nd.idx, []).append((s, e))
             slot_of: Dict[int, int] = {}
             free: List[int] = []
             high = 0
-            for k, nd in enumerate(order):
-                # operands' slots (read before the destination is chosen)
-                ops = [slot_of[ch.idx] if ch is not None else 0 for ch in (nd.a, nd.b, nd.c)]
-                # release operand slots whose last use is this instruction
-                released = []
-                for ch in {c.idx: c for c in (nd.a, nd.b, nd.c) if c is not None}.values():
-                    if last_use.get(ch.idx) == k and ch.idx not in stores:
-                        released.append(slot_of[ch.idx])
-                    elif last_use.get(ch.idx) == k and ch.idx in stores:
-                        released.append(slot_of[ch.idx])  # already stored when it was produced
-                free.extend(released)
+
+            def take_slot() -> int:
+                nonlocal high
                 if free:
-                    dst = free.pop()
-                else:
-                    dst = high
-                    high += 1
-                slot_of[nd.idx] = dst
+                    return free.pop()
+                high += 1
+                return high - 1
+
+            def emit_leaf(nd) -> int:
+                dst = take_slot()
                 if nd.op == S.OP_CONST:
                     ci = const_index.get(nd.idx)
                     if ci is None:
@@ -167,20 +165,50 @@ class Tape:
                         consts.append(nd.val)
                         const_index[nd.idx] = ci
                     rows.append((S.OP_CONST, dst, ci, 0))
-                elif nd.op == S.OP_SYM:
+                else:
                     if nd.idx not in in_pos:
                         raise ValueError(f"free symbol '{nd.name}' is not an input of the tape")
                     s, e = in_pos[nd.idx]
                     rows.append((S.OP_INPUT, dst, e, s))
-                elif nd.op == S.OP_IF_ELSE:
-                    # node operands are (cond, then, else)
+                slot_of[nd.idx] = dst
+                return dst
+
+            for k, nd in enumerate(order):
+                leaf = nd.op in (S.OP_CONST, S.OP_SYM)
+                if leaf:
+                    # leaves are materialised on demand (below); a leaf that is itself an output is stored here
+                    if nd.idx in stores:
+                        dst = slot_of[nd.idx] if nd.idx in slot_of else emit_leaf(nd)
+                        for (s, e) in stores[nd.idx]:
+                            rows.append((S.OP_OUTPUT, dst, e, s))
+                        if not uses.get(nd.idx):
+                            free.append(slot_of.pop(nd.idx))
+                    continue
+                kids = [ch for ch in (nd.a, nd.b, nd.c) if ch is not None]
+                for ch in kids:
+                    if ch.idx not in slot_of:  # a leaf not (or no longer) resident
+                        emit_leaf(ch)
+                ops = [slot_of[ch.idx] if ch is not None else 0 for ch in (nd.a, nd.b, nd.c)]
+                # release operand slots: last use, or a leaf whose next use is far away
+                for ch in {c.idx: c for c in kids}.values():
+                    lst = uses[ch.idx]
+                    ptr = use_ptr.get(ch.idx, 0)
+                    while ptr < len(lst) and lst[ptr] <= k:
+                        ptr += 1
+                    use_ptr[ch.idx] = ptr
+                    is_leaf = ch.op in (S.OP_CONST, S.OP_SYM)
+                    if ptr >= len(lst) or (is_leaf and lst[ptr] - k > REMAT_GAP):
+                        free.append(slot_of.pop(ch.idx))
+                dst = take_slot()
+                slot_of[nd.idx] = dst
+                if nd.op == S.OP_IF_ELSE:
                     rows.append((S.OP_IF_ELSE | (ops[0] << 8), dst, ops[1], ops[2]))
                 else:
                     rows.append((nd.op, dst, ops[0], ops[1]))
                 for (s, e) in stores.get(nd.idx, ()):
                     rows.append((S.OP_OUTPUT, dst, e, s))
-                if nd.idx not in last_use:
-                    free.append(dst)  # value is never read again (pure output)
+                if not uses.get(nd.idx):
+                    free.append(slot_of.pop(nd.idx))  # value is never read again (pure output)
             n_work = max(n_work, high)
             group_ptr.append(len(rows))
 

@@ -259,6 +259,52 @@ def test_c3_point_mass_mpc_batch(torch_cuda):
     assert (np.abs(Y) <= 1.5 + 1e-9).all() and (np.abs(dY) <= 1.0 + 1e-9).all()
 
 
+def test_c5_dual_arm_batch(torch_cuda):
+    """C5 through the table-driven large tier, checked against the numpy closed form of the problem."""
+    import optas_b200
+    import problems_ref
+    from optas_b200 import problems
+
+    prob = problems.dual_arm()
+    solver = optas_b200.B200Solver(prob.opt).setup("ipopt")
+    B = 96
+    P, X0 = prob.sample(B, seed=3)
+    r = _solve_host(solver, P, X0)
+    assert (r["status"] <= 1).all(), np.bincount(r["status"])
+    lo = solver._lowered
+    for i in (0, 17, 95):
+        k = problems_ref.sparse_kkt_residual(lo, r["x"][i], P[i], r["lam"][i, :lo.n_eq], r["lam"][i, lo.n_eq:])
+        assert max(k["stationarity"], k["eq"]) < KKT_TOL
+        assert abs(r["f"][i] - problems_ref.dual_arm_cost(r["x"][i], P[i])) < 1e-10
+        assert np.abs(problems_ref.dual_arm_constraints(r["x"][i], P[i])).max() < 1e-8
+    # dict API: trajectories come back as [B, 7, T] and the first knot is the commanded configuration
+    solver.reset_parameters(prob.param_dict(P))
+    solver.reset_initial_seed(prob.seed_dict(X0))
+    sol = solver.solve()
+    assert sol["kukal/q"].shape == (B, 7, 50) and sol["kukar/dq"].shape == (B, 7, 49)
+    assert np.abs(sol["kukal/q"][:, :, 0] - P[:, :7]).max() < 1e-8
+
+
+def test_c4_figure_eight_short_horizon(torch_cuda):
+    """C4's problem class (nonlinear cost, quaternion equalities, joint-limit bounds) on a T = 10 horizon
+    (the T = 50 instance takes minutes in this first version of the large tier; tools/large_check.py)."""
+    import optas_b200
+    import problems_ref
+    from optas_b200 import problems
+
+    prob = problems.figure_eight(T=10)
+    solver = optas_b200.B200Solver(prob.opt).setup("ipopt", {"max_iter": 400, "max_trips": 2500})
+    B = 64
+    P, X0 = prob.sample(B, seed=2)
+    r = _solve_host(solver, P, X0)
+    ok = r["status"] <= 1
+    assert ok.mean() >= 0.9, np.bincount(r["status"])
+    lo = solver._lowered
+    i = int(np.where(ok)[0][0])
+    k = problems_ref.sparse_kkt_residual(lo, r["x"][i], P[i], r["lam"][i, :lo.n_eq], r["lam"][i, lo.n_eq:])
+    assert k["eq"] < 1e-6 and k["ineq"] < 1e-9
+
+
 def test_error_on_fail(torch_cuda):
     import optas_b200
     from optas_b200 import problems

@@ -15,7 +15,8 @@ from optas_b200 import problems
 def _sim(prob):
     solver = optas_b200.B200Solver(prob.opt).setup("ipopt", compile_only=True)
     lo = solver._lowered
-    return HostSim(solver.kernel_source(), lo.nx, lo.np_, lo.n_eq, lo.n_ineq, ldl_table=solver.ldl_table()), lo
+    return HostSim(solver.kernel_source(), lo.nx, lo.np_, lo.n_eq, lo.n_ineq, ldl_table=solver.ldl_table(),
+                   dtable=solver.dtable()), lo
 
 
 def test_booth_known_answer():
@@ -127,3 +128,49 @@ def test_c3_point_mass_mpc_tick():
     i = int(np.where(ok)[0][0])
     pol = slsqp_driver.solve_slsqp(op, P[i], r["x"][i], form="split", options={"ftol": 1e-15, "maxiter": 100})
     assert np.abs(pol.x - r["x"][i]).max() / max(1.0, np.abs(pol.x).max()) < 1e-6
+
+
+def test_c5_dual_arm_large_tier():
+    """C5 (example/dual_arm.py): 1386 variables, 700 linear equalities, T = 50 -- the table-driven tier
+    (interpreted tapes + sparse LDL').  Checked against the independent numpy closed form."""
+    import problems_ref
+
+    prob = problems.dual_arm()
+    opt = prob.opt
+    assert (opt.nx, opt.np, opt.nk, opt.na, opt.ng, opt.nh, opt.nv) == (1386, 14, 0, 700, 0, 0, 1400)
+    assert type(opt).__name__ == "NonlinearCostLinearConstraints"
+    sim, lo = _sim(prob)
+    P, X0 = prob.sample(3, seed=3)
+    # the tapes against the closed form at a random (infeasible) point
+    import tape_vm
+
+    rng = np.random.default_rng(0)
+    x = X0[0] + 0.05 * rng.standard_normal(opt.nx)
+    f, ce, _ = tape_vm.CTape(lo.fc)(x[None, :], P[:1])
+    assert abs(f[0, 0] - problems_ref.dual_arm_cost(x, P[0])) < 1e-12
+    assert np.abs(ce[0] - problems_ref.dual_arm_constraints(x, P[0])).max() < 1e-14
+    r = sim.solve(P, X0)
+    assert (r["status"] == 0).all()
+    for i in range(3):
+        k = problems_ref.sparse_kkt_residual(lo, r["x"][i], P[i], r["lam"][i, :lo.n_eq], r["lam"][i, lo.n_eq:])
+        assert max(k["stationarity"], k["eq"]) < 1e-7
+        assert abs(r["f"][i] - problems_ref.dual_arm_cost(r["x"][i], P[i])) < 1e-12
+        assert np.abs(problems_ref.dual_arm_constraints(r["x"][i], P[i])).max() < 1e-9
+
+
+def test_c4_figure_eight_large_tier():
+    """C4 (example/figure_eight_plan.py + joint limits): 693 variables, 357 linear + 200 quaternion
+    equalities (rank deficient by construction), 700 bounds."""
+    import problems_ref
+
+    prob = problems.figure_eight()
+    opt = prob.opt
+    assert (opt.nx, opt.np, opt.nk, opt.na, opt.ng, opt.nh) == (693, 7, 700, 357, 0, 200)
+    assert type(opt).__name__ == "NonlinearCostNonlinearConstraints"
+    sim, lo = _sim(prob)
+    P, X0 = prob.sample(2, seed=2)
+    r = sim.solve(P, X0, max_iter=400, max_trips=2500)
+    assert (r["status"] <= 1).all(), r["status"]
+    for i in range(2):
+        k = problems_ref.sparse_kkt_residual(lo, r["x"][i], P[i], r["lam"][i, :lo.n_eq], r["lam"][i, lo.n_eq:])
+        assert k["eq"] < 1e-6 and k["ineq"] < 1e-9 and k["stationarity"] < 1e-4 * max(1.0, np.abs(r["lam"][i]).max())
