@@ -216,17 +216,26 @@ struct Compiled {
 };
 
 void parse_ptxas(const std::string& log, const char* kernel, Compiled* c) {
-  // "ptxas info    : Compiling entry function 'bo_solve_kernel' for 'sm_100a'" ... "Used N registers"
-  const size_t at = log.find(std::string("'") + kernel + "'");
+  // "ptxas info    : Compiling entry function 'bo_solve_kernel' for 'sm_100a'" followed (after the
+  // lines of its non-inlined device functions) by "... Used N registers, ..." for the entry itself:
+  // take the LAST "Used" line after the entry marker, and the largest stack frame reported.
+  const size_t at = log.find(std::string("entry function '") + kernel + "'");
   if (at == std::string::npos) return;
-  const size_t used = log.find("Used ", at);
-  if (used != std::string::npos) c->regs = atoi(log.c_str() + used + 5);
-  const size_t fr = log.find("bytes stack frame", at);
-  if (fr != std::string::npos) {
-    size_t b = fr;
-    while (b > 0 && (isdigit((unsigned char)log[b - 1]) || log[b - 1] == ' ')) --b;
-    c->local_bytes = atoi(log.c_str() + b);
+  size_t pos = at, used = std::string::npos;
+  while ((pos = log.find("Used ", pos)) != std::string::npos) {
+    used = pos;
+    pos += 5;
   }
+  if (used != std::string::npos) c->regs = atoi(log.c_str() + used + 5);
+  pos = at;
+  int frame = 0;
+  while ((pos = log.find(" bytes stack frame", pos)) != std::string::npos) {
+    size_t b = pos;
+    while (b > 0 && isdigit((unsigned char)log[b - 1])) --b;
+    frame = std::max(frame, atoi(log.c_str() + b));
+    pos += 5;
+  }
+  c->local_bytes = frame;
   const size_t sm = log.find(" bytes smem", at);
   if (sm != std::string::npos) {
     size_t b = sm;
@@ -559,7 +568,7 @@ int bo_problem_create(const bo_problem_desc* desc, const bo_options* opts_in, bo
           BO_CU(g_drv.cuMemcpyHtoDAsync_v2(pr->d_dtab.ptr, pr->plan.dtable.data(), pr->plan.dtable.size() * sizeof(double), nullptr));
         // large state per lane (hundreds of KB): cap the resident lanes so the scratch stays within a few GB
         {
-          const int cap = pr->opts.blocks_per_sm > 0 ? pr->opts.blocks_per_sm : 2;
+          const int cap = pr->opts.blocks_per_sm > 0 ? pr->opts.blocks_per_sm : 4;  // latency-bound: lanes = throughput
           if (pr->blocks_per_sm > cap) pr->blocks_per_sm = cap;
         }
         const size_t lanes = (size_t)pr->n_sm * pr->blocks_per_sm * pr->tpb;

@@ -309,12 +309,7 @@ std::string emit_problem_source(const ProblemSource& ps, int tpb, bool pivoted_l
     }
   }
   o << "  (void)JE; (void)rho; (void)K;\n}\n";
-  o << "BO_DEVICE double bo_xHx(const double* BO_RESTRICT H, const double* BO_RESTRICT v) {\n  double acc = 0.0;\n";
-  for (int k = 0; k < ps.hess.nnz(); ++k) {
-    const int r = ps.hess.row[k], c = ps.hess.col[k];
-    o << "  acc += " << (r == c ? "" : "2.0 * ") << "H[" << k << "] * v[" << r << "] * v[" << c << "];\n";
-  }
-  o << "  (void)H; (void)v;\n  return acc;\n}\n\n";
+  o << "\n";
   o << "#include \"bo_ipm_reg.cuh\"\n";
   return o.str();
 }

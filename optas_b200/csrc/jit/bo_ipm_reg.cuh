@@ -1,18 +1,23 @@
-// bo_ipm_reg.cuh -- register-resident primal-dual interior-point / Newton-KKT solver,
-// ONE PROBLEM INSTANCE PER THREAD (tier "S": nx + n_eq up to a few tens).
+// bo_ipm_reg.cuh -- batched primal-dual interior-point / Newton-KKT solver, ONE PROBLEM INSTANCE PER
+// THREAD (lane), all iterations inside one launch.
 //
 // Replaces, for a whole batch at once, what the reference does per call inside
 // CasADiSolver._solve (optas/solver.py:386-398 -> casadi nlpsol("ipopt")): evaluate
-// f, grad f, c, Jacobians and the Hessian of the Lagrangian (here: straight-line code generated
-// from the problem's expression tapes, see bo_codegen.cpp), assemble the primal-dual KKT system,
-// factor it (dense LDL' with inertia-correcting regularisation), line-search, update the barrier.
+// f, grad f, c, Jacobians and the Hessian of the Lagrangian, assemble the primal-dual KKT system,
+// factor it (LDL' with inertia-correcting regularisation), filter line search, barrier update.
+//
+// Three tiers share this file (selected by bo_problem_create, see bo_api.cpp):
+//   dense   (nx+n_eq <= 14)      generated straight-line tapes; KKT matrix packed, LDL' fully unrolled
+//   sparse  (BO_SPARSE_LDL)      generated tapes; table-driven sparse LDL' from a host-side symbolic analysis
+//   large   (BO_LARGE)           nothing generated: tapes interpreted, Jacobian products / KKT assembly from
+//                                coordinate tables, factor values in a global [element][lane] scratch
 //
 // This header is included AFTER the generated prelude, which defines
 //   BO_NX, BO_NP, BO_ME, BO_MI, BO_NNZ_JE, BO_NNZ_JI, BO_NNZ_H, BO_TPB
 //   bo_tape_fc(x, p, f, cE, cI)
 //   bo_tape_kkt(x, p, y, z, f, g, cE, cI, JE, JI, H)
 //   bo_JEt_acc / bo_JIt_acc (out += J' v), bo_JE_mul / bo_JI_mul (out = J v),
-//   bo_kkt_fill(H, JE, JI, sigma, K), bo_xHx(H, v)
+//   bo_kkt_fill(H, JE, JI, sigma, K), bo_JEtJE_acc(JE, rho, K)
 //
 // Problem:  min f(x)  s.t.  cE(x) = 0,  cI(x) - s = 0,  s >= 0      (s: slacks)
 // Lagrangian L = f - y'cE - z'cI,  z >= 0.  Barrier sub-problem parameter mu.
