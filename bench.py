@@ -155,6 +155,87 @@ def run_reference(args) -> None:
     print(json.dumps(line))
 
 
+OTHER_CONFIGS = {
+    # name: (problem factory, total batch of BASELINE.json, scaling, solver options, label)
+    "c3": ("point_mass_mpc", 16384, "weak", {}, "C3: point_mass_mpc.py Controller tick, T=20 (nx 80, 42 eq, 180 ineq)"),
+    "c4": ("figure_eight", 4096, "weak", {"max_iter": 400, "max_trips": 2500},
+           "C4: figure_eight_plan.py T=50 + joint-limit bounds (nx 693, 557 eq, 700 ineq)"),
+    "c5": ("dual_arm", 32768, "strong", {}, "C5: dual_arm.py T=50 (nx 1386, 700 eq), 32768 instances sharded over the GPUs"),
+}
+
+
+def run_other_config(args) -> None:
+    """Extra bench lines for C3 / C4 / C5 (not read by the driver): device-resident `value` and `e2e`."""
+    import numpy as np
+    import torch
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+
+        dist.init_process_group("nccl", device_id=dev)
+    import optas_b200
+    from optas_b200 import problems
+    from optas_b200.distributed import shard_slice
+
+    factory, total, scaling, opts, label = OTHER_CONFIGS[args.config]
+    prob = getattr(problems, factory)()
+    if scaling == "strong":
+        lo_, hi_ = shard_slice(total, rank, world)
+        P, X0 = prob.sample(total)
+        P, X0 = np.ascontiguousarray(P[lo_:hi_]), np.ascontiguousarray(X0[lo_:hi_])
+    else:
+        P, X0 = prob.sample(total, seed=rank + 1)
+    B = X0.shape[0]
+    solver = optas_b200.B200Solver(prob.opt).setup("ipopt", opts, timing=True)
+    Pd, X0d = torch.from_numpy(P).to(dev), torch.from_numpy(X0).to(dev)
+    Xd = torch.empty_like(X0d)
+    std = torch.empty(B, dtype=torch.int32, device=dev)
+    itd = torch.empty(B, dtype=torch.int32, device=dev)
+    stream = torch.cuda.current_stream().cuda_stream
+    steps, warmup = max(1, min(args.steps, 3)), 1
+    for _ in range(warmup):
+        solver.solve_raw(Pd, X0d, Xd, None, None, std, itd, None, stream=stream)
+    torch.cuda.synchronize()
+    if dist is not None:
+        dist.barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        solver.solve_raw(Pd, X0d, Xd, None, None, std, itd, None, stream=stream)
+    e1.record()
+    torch.cuda.synchronize()
+    dev_ms = e0.elapsed_time(e1)
+    n_conv = int((std <= 1).sum().item())
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        r = solver.solve_arrays(P, X0)
+    e2e_s = time.perf_counter() - t0
+    t = torch.tensor([dev_ms, e2e_s], dtype=torch.float64, device=dev)
+    c = torch.tensor([float(n_conv), float(B)], dtype=torch.float64, device=dev)
+    if dist is not None:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dist.all_reduce(c, op=dist.ReduceOp.SUM)
+    if rank == 0:
+        print(json.dumps({
+            "metric": "problem-instances solved/sec", "value": float(c[0]) * steps / (float(t[0]) * 1e-3), "unit": "instances/s",
+            "n_gpus": world, "steps": steps, "warmup": warmup, "ms_per_step": float(t[0]) / steps, "higher_is_better": True,
+            "scaling": scaling, "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": label, "global_instances": int(c[1]), "parallelism": f"batch-sharded x{world}"},
+            "converged_fraction": float(c[0]) / float(c[1]), "mean_iterations": float(itd.float().mean().item()),
+            "e2e": {"value": float(c[0]) * steps / float(t[1]), "unit": "instances/s",
+                    "h2d_bytes_per_step": int(P.nbytes + X0.nbytes), "d2h_bytes_per_step": int(r["x"].nbytes + r["lam"].nbytes + 28 * B)},
+            "gpu_launches": steps, "solve_kernel": solver.kernel_info()}))
+    if dist is not None:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
 def main() -> None:
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -163,7 +244,13 @@ def main() -> None:
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--batch", type=int, default=BATCH_PER_GPU)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--config", default="c2", choices=["c2", "c3", "c4", "c5"],
+                    help="c2 (default) is the headline line the driver reads; c3/c4/c5 print an extra line for the other "
+                         "BASELINE.json configs (device-resident value + e2e only)")
     args = ap.parse_args()
+    if args.config != "c2":
+        run_other_config(args)
+        return
     if args.impl == "reference":
         run_reference(args)
         return

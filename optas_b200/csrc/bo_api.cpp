@@ -260,7 +260,10 @@ int jit_compile(const std::string& source, const char* unit_name, const char* ke
     if (!read_file(inc + "/" + hdr, &text)) return set_err(BO_ERR_INVALID, "JIT header %s/%s not found", inc.c_str(), hdr);
     h = fnv1a(text, h);
   }
-  h = fnv1a("nvrtc" + std::to_string(major) + "." + std::to_string(minor) + "sm_100a-lineinfo", h);
+  // experiment hook: extra -D options for the kernel templates (part of the cache key)
+  const char* extra_env = getenv("B200OPTAS_JIT_DEFINES");
+  const std::string extra = extra_env ? extra_env : "";
+  h = fnv1a("nvrtc" + std::to_string(major) + "." + std::to_string(minor) + "sm_100a-lineinfo" + extra, h);
   char hex[32];
   snprintf(hex, sizeof hex, "%016llx", (unsigned long long)h);
   const std::string stem = cache + "/" + unit_name + "_" + hex;
@@ -280,9 +283,16 @@ int jit_compile(const std::string& source, const char* unit_name, const char* ke
     return set_err(BO_ERR_COMPILE, "nvrtcCreateProgram failed");
   const std::string iflag = "-I" + inc;
   const std::string iflag2 = "-I" + (opts.include_dir ? std::string(opts.include_dir) : lib_dir() + "/../include");
-  const char* flags[] = {"--gpu-architecture=sm_100a", "--std=c++17", "-lineinfo", "--ptxas-options=-v", iflag.c_str(),
-                         iflag2.c_str()};
-  const nvrtcResult res = nvrtcCompileProgram(prog, (int)(sizeof flags / sizeof flags[0]), flags);
+  std::vector<std::string> extra_flags;
+  {
+    std::istringstream ss(extra);
+    std::string tok;
+    while (ss >> tok) extra_flags.push_back(tok);
+  }
+  std::vector<const char*> flags = {"--gpu-architecture=sm_100a", "--std=c++17", "-lineinfo", "--ptxas-options=-v",
+                                    iflag.c_str(), iflag2.c_str()};
+  for (const auto& f : extra_flags) flags.push_back(f.c_str());
+  const nvrtcResult res = nvrtcCompileProgram(prog, (int)flags.size(), flags.data());
   size_t log_size = 0;
   nvrtcGetProgramLogSize(prog, &log_size);
   out->log.assign(log_size, '\0');

@@ -986,9 +986,13 @@ bo_solve_kernel(long long B, const double* __restrict__ p_all, const double* __r
     if (!__syncthreads_or(active ? 1 : 0)) break;
     int status = -1;
     if (active) status = bo_trip_eval(S, prm);
+#ifndef BO_NO_PHASE_BARRIER
     __syncthreads();
+#endif
     if (active && status < 0) status = bo_trip_factor(S, prm);
+#ifndef BO_NO_PHASE_BARRIER
     __syncthreads();
+#endif
     if (active && status < 0) status = bo_trip_trial(S, prm);
     if (active) {
       if (status >= 0) {

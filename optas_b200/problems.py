@@ -73,7 +73,7 @@ def lwr_ik() -> Problem:
         construction), q_nominal fixed, seed x0 = q_nominal for every instance."""
         rng = np.random.default_rng(seed)
         q_rand = rng.uniform(0.8 * lo, 0.8 * up, size=(B, robot.ndof))
-        goals = fk._tape_eval_batch(q_rand) if hasattr(fk, "_tape_eval_batch") else _eval_rows(fk, q_rand)
+        goals = _eval_rows(fk, q_rand)
         P = np.concatenate([np.tile(LWR_Q_NOMINAL, (B, 1)), goals], axis=1)
         X0 = np.tile(LWR_Q_NOMINAL, (B, 1))
         return np.ascontiguousarray(P), np.ascontiguousarray(X0)

@@ -22,12 +22,9 @@ _JIT_INC = os.path.join(_HERE, "..", "optas_b200", "csrc", "jit")
 
 _WRAPPER = r"""
 #define BO_HOST_SIM 1
-#define BO_HOST_STATS 1
 #include <cstdio>
-static long long bo_host_stats[4] = {0, 0, 0, 0};
 %(trace)s
 #include "%(gen)s"
-extern "C" void hostsim_stats(long long* out) { for (int i = 0; i < 4; ++i) { out[i] = bo_host_stats[i]; bo_host_stats[i] = 0; } }
 extern "C" void hostsim_solve(long long B, const double* p, const double* x0, double* x, double* lam, double* f,
                               int* status, int* iters, double* kkt, int* trips, int max_iter, double tol, double acc_tol,
                               double mu_init, double max_step, int max_trips, const int* ldl_tab, const double* dtab, double* scratch) {
@@ -73,7 +70,6 @@ class HostSim:
             os.replace(so + ".tmp", so)
         self.lib = C.CDLL(so)
         vp = C.c_void_p
-        self.lib.hostsim_stats.argtypes = [vp]
         self.lib.hostsim_solve.argtypes = [C.c_longlong] + [vp] * 9 + [C.c_int, C.c_double, C.c_double, C.c_double, C.c_double, C.c_int, vp, vp, vp]
 
     def solve(self, P, X0, max_iter=100, tol=1e-8, acc_tol=1e-6, mu_init=0.1, max_step=0.5, max_trips=250):
@@ -87,7 +83,4 @@ class HostSim:
                                None if self.ldl_table is None else self.ldl_table.ctypes.data,
                                None if self.dtable is None else self.dtable.ctypes.data,
                                None if self.scratch is None else self.scratch.ctypes.data)
-        stats = np.zeros(4, dtype=np.int64)
-        self.lib.hostsim_stats(stats.ctypes.data)
-        self.last_stats = {"static": int(stats[0]), "bk_ok": int(stats[1]), "bk_retry": int(stats[2])}
         return {"x": X, "lam": lam[:, :self.nl], "f": f, "status": st, "iters": it, "kkt": kkt, "trips": trips}
