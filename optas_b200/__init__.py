@@ -20,7 +20,7 @@ from .spatialmath import ArrayType, arrayify_args
 from .models import RobotModel, TaskModel, Model
 from .builder import OptimizationBuilder
 from .optimization import Optimization
-from .solver import B200Solver, CasADiSolver, ScipyMinimizeSolver, Solver
+from .solver import B200Solver, CasADiSolver, CVXOPTSolver, OSQPSolver, ScipyMinimizeSolver, Solver
 from .nlpsol import nlpsol, qpsol
 
 __version__ = "0.1.0"

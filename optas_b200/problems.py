@@ -305,4 +305,38 @@ def figure_eight(T: int = 50, joint_limits: bool = True) -> Problem:
     return Problem("figure_eight", opt, sample, {}, {"robot": kuka})
 
 
-ALL_BUILDERS = [lwr_ik, booth, point_mass_mpc, figure_eight, dual_arm]
+# ----------------------------------------------------------------------------------------------
+# Differential IK as a QP (reference: example/planar_idk.py:12-70) -- the "next" row 8f-1
+# ----------------------------------------------------------------------------------------------
+
+PLANAR_URDF = os.path.join(ROBOTS, "planar_3dof.urdf")
+
+
+def planar_idk() -> Problem:
+    robot = RobotModel(urdf_filename=PLANAR_URDF, time_derivs=[1])
+    name, link_ee = robot.get_name(), "end"
+    builder = OptimizationBuilder(T=1, robots=[robot], derivs_align=True)
+    dq = builder.get_model_states(name, time_deriv=1)
+    q = builder.add_parameter("q", robot.ndof)
+    dx = builder.add_parameter("dx", 2)  # the script hard-codes dx = [0.01, 0]; a parameter here so it can be batched
+    J = robot.get_global_link_linear_jacobian_function(link_ee)
+    quat = robot.get_global_link_quaternion_function(link_ee)
+    phi = lambda q_: 2.0 * cs.atan2(quat(q_)[2], quat(q_)[3])
+    J_phi = robot.get_global_link_angular_geometric_jacobian_function(link=link_ee)
+    dt, lim = 0.01, 0.1
+    builder.add_cost_term("cost", cs.sumsqr(dq))
+    builder.add_equality_constraint("FDK", (J(q)[0:2, :]) @ dq, dx)
+    builder.add_bound_inequality_constraint("joint", [-lim] * 3, dq, [lim] * 3)
+    builder.add_bound_inequality_constraint("task", -70 * (cs.pi / 180.0), phi(q) + dt * (J_phi(q)[2, :]) @ dq, 0.0)
+    opt = builder.build()
+
+    def sample(B: int, seed: int = 5):
+        rng = np.random.default_rng(seed)
+        q_ = np.array([2.39, -2.55, -0.46]) + 0.05 * rng.standard_normal((B, 3))
+        dx_ = np.array([0.01, 0.0]) + 0.002 * rng.standard_normal((B, 2))
+        return np.ascontiguousarray(np.concatenate([q_, dx_], axis=1)), np.zeros((B, 3))
+
+    return Problem("planar_idk", opt, sample, {"J": J}, {"robot": robot})
+
+
+ALL_BUILDERS = [lwr_ik, booth, point_mass_mpc, figure_eight, dual_arm, planar_idk]

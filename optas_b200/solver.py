@@ -437,3 +437,29 @@ class ScipyMinimizeSolver(B200Solver):
 
     def setup(self, method: str = "SLSQP", tol: Optional[float] = None, options: Optional[Dict] = None, **kw):
         return super().setup(method=method, tol=tol, options=options, **kw)
+
+
+class OSQPSolver(B200Solver):
+    """Name-compatible drop-in for ``optas.OSQPSolver`` (ref :426-507): QP-only, ``setup(use_warm_start,
+    settings={})``; the QP is solved by the same GPU interior-point kernel (a convex QP takes a handful
+    of Newton iterations).  ``use_warm_start=False`` discards the seed like the reference does."""
+
+    def setup(self, use_warm_start: bool = False, settings: Optional[Dict] = None, **kw):
+        from .optimization import QP_COST
+
+        assert self.opt_type in QP_COST, "OSQP cannot solve this type of problem"
+        self.use_warm_start = use_warm_start
+        return super().setup("osqp", dict(settings or {}), **kw)
+
+    def reset_initial_seed(self, x0: Dict[str, ArrayType]) -> None:
+        super().reset_initial_seed(x0 if self.use_warm_start else {})
+
+
+class CVXOPTSolver(B200Solver):
+    """Name-compatible drop-in for ``optas.CVXOPTSolver`` (ref :514-580): QP-only, ``setup(solver_settings={})``."""
+
+    def setup(self, solver_settings: Optional[Dict] = None, **kw):
+        from .optimization import QP_COST
+
+        assert self.opt_type in QP_COST, "CVXOPT cannot solve this problem"
+        return super().setup("cvxopt", dict(solver_settings or {}), **kw)

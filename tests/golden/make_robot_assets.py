@@ -24,6 +24,7 @@ REF = "/root/reference/example/robots"
 SOURCES = {
     "kuka_lwr.urdf": os.path.join(REF, "kuka_lwr", "kuka_lwr.urdf"),
     "med7.urdf": os.path.join(REF, "kuka_lbr", "med7.urdf"),
+    "planar_3dof.urdf": os.path.join(REF, "planar_3dof.urdf"),
 }
 
 

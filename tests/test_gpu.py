@@ -305,6 +305,27 @@ def test_c4_figure_eight_short_horizon(torch_cuda):
     assert k["eq"] < 1e-6 and k["ineq"] < 1e-9
 
 
+def test_qp_drop_in_classes(torch_cuda):
+    """OSQPSolver / CVXOPTSolver spellings (optas/solver.py:426-580) on the differential-IK QP of
+    example/planar_idk.py; the reference asserts QP-only for both."""
+    import optas_b200 as optas
+    from optas_b200 import problems
+
+    prob = problems.planar_idk()
+    q_t, dx = np.array([2.39, -2.55, -0.46]), np.array([0.01, 0.0])
+    J = prob.functions["J"](q_t).toarray()[0:2, :]
+    for make in (lambda: optas.CVXOPTSolver(prob.opt).setup(), lambda: optas.OSQPSolver(prob.opt).setup(use_warm_start=True),
+                 lambda: optas.CasADiSolver(prob.opt).setup("qpoases")):
+        solver = make()
+        solver.reset_parameters({"q": q_t, "dx": dx})
+        sol = solver.solve()
+        assert solver.did_solve()
+        key = [k for k in sol if k.endswith("/dq")][0]
+        assert np.abs(sol[key].toarray().flatten() - np.linalg.pinv(J) @ dx).max() < 1e-7
+    with pytest.raises(AssertionError):
+        optas.OSQPSolver(problems.dual_arm().opt).setup(use_warm_start=False)
+
+
 def test_error_on_fail(torch_cuda):
     import optas_b200
     from optas_b200 import problems

@@ -174,3 +174,21 @@ def test_c4_figure_eight_large_tier():
     for i in range(2):
         k = problems_ref.sparse_kkt_residual(lo, r["x"][i], P[i], r["lam"][i, :lo.n_eq], r["lam"][i, lo.n_eq:])
         assert k["eq"] < 1e-6 and k["ineq"] < 1e-9 and k["stationarity"] < 1e-4 * max(1.0, np.abs(r["lam"][i]).max())
+
+
+def test_planar_differential_ik_qp():
+    """example/planar_idk.py: a QuadraticCostLinearConstraints problem; inside the bounds the QP solution
+    equals the pseudo-inverse solution (as the script itself prints for comparison)."""
+    prob = problems.planar_idk()
+    assert type(prob.opt).__name__ == "QuadraticCostLinearConstraints"
+    sim, lo = _sim(prob)
+    q_t, dx = np.array([2.39, -2.55, -0.46]), np.array([0.01, 0.0])
+    r = sim.solve(np.concatenate([q_t, dx])[None, :], np.zeros((1, 3)))
+    assert r["status"][0] == 0 and r["iters"][0] <= 10
+    J = prob.functions["J"](q_t).toarray()[0:2, :]
+    assert np.abs(r["x"][0] - np.linalg.pinv(J) @ dx).max() < 1e-7
+    P, X0 = prob.sample(128)
+    rb = sim.solve(P, X0)
+    assert (rb["status"] == 0).all()
+    res = kkt_check.kkt_residual(prob, rb["x"][:32], P[:32], rb["lam"][:32, :lo.n_eq], rb["lam"][:32, lo.n_eq:])
+    assert res.max() < 1e-7
