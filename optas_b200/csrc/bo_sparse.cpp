@@ -143,7 +143,8 @@ SparsePlan make_sparse_plan(const ProblemSource& ps, bool large) {
   //  large mode only:
   //  [8]/[9] JE row/col  [10]/[11] JI row/col  [12] pos of every H nz  [13] pos of every JE nz
   //  [14] JI'SJI program: count, then {pos, a, b, r}   [15] JE'JE program: count, then {pos, a, b}
-  //  [16] fc tape: n_instr, n_consts offset into dtable, then instr[4*n]   [17] kkt tape: same
+  //  [16] fc tape: n_instr, offset of its constants in dtable, 2 pad words, then instr[4*n] (16-byte aligned)
+  //  [17] kkt tape: same
   std::vector<int32_t>& t = pl.table;
   t.assign(32, 0);
   auto section = [&](int slot) { t[slot] = (int32_t)t.size(); };
@@ -199,9 +200,12 @@ SparsePlan make_sparse_plan(const ProblemSource& ps, bool large) {
     section(15);
     pair_program(ps.jac_eq, ps.n_eq, false);
     auto tape_section = [&](int slot, const Tape& tape) {
+      while (t.size() % 4 != 0) t.push_back(0);  // 16-byte alignment of the instruction rows (table base is 256-byte aligned)
       section(slot);
       t.push_back((int32_t)tape.n_instr());
       t.push_back((int32_t)pl.dtable.size());
+      t.push_back(0);
+      t.push_back(0);
       t.insert(t.end(), tape.instr.begin(), tape.instr.end());
       pl.dtable.insert(pl.dtable.end(), tape.consts.begin(), tape.consts.end());
     };

@@ -37,6 +37,8 @@ __device__ __forceinline__ void bo_sincos(double a, double* s, double* c) { sinc
 __device__ __forceinline__ bool bo_isfinite(double v) { return isfinite(v); }
 #endif
 
+struct alignas(16) bo_int4 { int x, y, z, w; };
+
 BO_DEVICE double bo_sign(double a) { return (double)((a > 0.0) - (a < 0.0)); }
 BO_DEVICE double bo_sq(double a) { return a * a; }
 

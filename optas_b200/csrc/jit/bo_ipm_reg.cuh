@@ -146,7 +146,20 @@ BO_NOINLINE int bo_ldl_sparse(double* BO_RESTRICT vals, long long stride, const 
       const int cnt = prog[pc + 2];
       pc += 3;
       d -= ljk * w;
-      for (int c = 0; c < cnt; ++c, pc += 2) BO_V(prog[pc]) -= BO_V(prog[pc + 1]) * w;
+      // targets (entries of column j) and sources (entries of column k) are disjoint and each target
+      // appears once: four independent load/FMA/store chains in flight instead of one
+      int c = 0;
+      for (; c + 4 <= cnt; c += 4, pc += 8) {
+        const int t0 = prog[pc], s0 = prog[pc + 1], t1 = prog[pc + 2], s1 = prog[pc + 3];
+        const int t2 = prog[pc + 4], s2 = prog[pc + 5], t3 = prog[pc + 6], s3 = prog[pc + 7];
+        const double a0 = BO_V(s0), a1 = BO_V(s1), a2 = BO_V(s2), a3 = BO_V(s3);
+        const double v0 = BO_V(t0), v1 = BO_V(t1), v2 = BO_V(t2), v3 = BO_V(t3);
+        BO_V(t0) = v0 - a0 * w;
+        BO_V(t1) = v1 - a1 * w;
+        BO_V(t2) = v2 - a2 * w;
+        BO_V(t3) = v3 - a3 * w;
+      }
+      for (; c < cnt; ++c, pc += 2) BO_V(prog[pc]) -= BO_V(prog[pc + 1]) * w;
     }
     if (sign[j] > 0) {
       if (!(d > 1e-13 * scale) && bad == 0) bad = 1;
@@ -366,9 +379,15 @@ BO_NOINLINE void bo_tape_interp(const int32_t* BO_RESTRICT sec, const double* BO
                                 const double* const* in, double* const* out) {
   const int n = sec[0];
   const double* consts = dtab + sec[1];
-  const int32_t* ins = sec + 2;
-  for (int i = 0; i < n; ++i, ins += 4) {
-    const int op = ins[0] & 0xFF, dst = ins[1], a = ins[2], b = ins[3];
+  // rows start 16-byte aligned (bo_sparse.cpp pads the section): one 128-bit load per instruction,
+  // and the next row is fetched while the current one executes
+  const bo_int4* rows = reinterpret_cast<const bo_int4*>(sec + 4);
+  bo_int4 nxt = n > 0 ? rows[0] : bo_int4{0, 0, 0, 0};
+  for (int i = 0; i < n; ++i) {
+    const bo_int4 cur = nxt;
+    if (i + 1 < n) nxt = rows[i + 1];
+    const int op = cur.x & 0xFF, dst = cur.y, a = cur.z, b = cur.w;
+    const int32_t ins0 = cur.x;
     double r;
     switch (op) {
       case BO_OP_INPUT: r = in[b][a]; break;
@@ -407,7 +426,7 @@ BO_NOINLINE void bo_tape_interp(const int32_t* BO_RESTRICT sec, const double* BO
       case BO_OP_NE: r = (double)(w[a] != w[b]); break;
       case BO_OP_AND: r = (double)((w[a] != 0.0) && (w[b] != 0.0)); break;
       case BO_OP_OR: r = (double)((w[a] != 0.0) || (w[b] != 0.0)); break;
-      case BO_OP_IF_ELSE: r = w[(unsigned)ins[0] >> 8] != 0.0 ? w[a] : w[b]; break;
+      case BO_OP_IF_ELSE: r = w[(unsigned)ins0 >> 8] != 0.0 ? w[a] : w[b]; break;
       default: r = BO_NAN;
     }
     w[dst] = r;
