@@ -509,6 +509,16 @@ BO_NOINLINE void bo_measures(double f, const double* cE, const double* cI, const
 #define BO_HEAVY_MAX 5  /* re-solves with dw = 1, 1e2, 1e4, 1e6 when no step is acceptable */
 #endif
 #define BO_IC_MAX 60    /* inertia-correction attempts per iteration */
+#ifndef BO_INNER_ROUNDS
+/* FACTOR/TRIAL repetitions per trip before the warp moves on to the next EVAL.  Pays when EVAL dominates
+ * (sparse / large tiers: C4 1.7x faster); for the dense tier the phases cost about the same and waiting
+ * for stragglers loses (measured on C2: 12.4 ms vs 8.9 ms), so there it is 1. */
+#if defined(BO_SPARSE_LDL)
+#define BO_INNER_ROUNDS 24
+#else
+#define BO_INNER_ROUNDS 1
+#endif
+#endif
 
 #define BO_PH_EVAL 0    /* evaluate f, grad, c, J, H at x; test convergence; assemble K */
 #define BO_PH_FACTOR 1  /* factor K + regularisation; on success compute the step */
@@ -1008,11 +1018,19 @@ bo_solve_kernel(long long B, const double* __restrict__ p_all, const double* __r
 #ifndef BO_NO_PHASE_BARRIER
     __syncthreads();
 #endif
-    if (active && status < 0) status = bo_trip_factor(S, prm);
-#ifndef BO_NO_PHASE_BARRIER
-    __syncthreads();
-#endif
-    if (active && status < 0) status = bo_trip_trial(S, prm);
+    // In the sparse / large tiers FACTOR and TRIAL are much cheaper than EVAL.  Lanes whose
+    // iteration needs several of them (inertia-correction retries, backtracking, second-order
+    // corrections, convexified re-solves) repeat them HERE, warp by warp, until every lane of the warp
+    // is ready for its next EVAL: the lanes of a warp then stay synchronised at iteration granularity
+    // and the expensive block is not re-executed for the sake of a few stragglers.
+    bool again = false;
+    for (int round = 0; round < BO_INNER_ROUNDS; ++round) {
+      if (round > 0 && again && ++S.trips > prm.max_trips) status = BO_ST_MAX_ITER;  // every extra round is a trip
+      if (active && status < 0 && S.phase == BO_PH_FACTOR) status = bo_trip_factor(S, prm);
+      if (active && status < 0 && S.phase == BO_PH_TRIAL) status = bo_trip_trial(S, prm);
+      again = active && status < 0 && S.phase != BO_PH_EVAL;
+      if (round + 1 >= BO_INNER_ROUNDS || !__any_sync(0xffffffffu, again)) break;
+    }
     if (active) {
       if (status >= 0) {
         BO_UNROLL

@@ -15,9 +15,8 @@ def run(B, tpb, max_trips, reps=4, bps=0):
     torch.cuda.synchronize(); ms, n = s._handle.kernel_time()
     print(f"B {B:7d} tpb {tpb:3d} bps {bps} max_trips {max_trips:5d}: {ms/n:8.3f} ms  conv {float((st<=1).float().mean()):.4f}  -> {B/(ms/n)*1e3:.3e} inst/s", flush=True)
 import os
-for defs in ("", "-DBO_NO_PHASE_BARRIER"):
+for defs in ("", "-DBO_INNER_ROUNDS=1"):
     os.environ["B200OPTAS_JIT_DEFINES"] = defs
     print("defines:", defs or "(none)", flush=True)
-    for tpb in (32, 64, 128):
-        run(65536, tpb, 250)
+    run(65536, 64, 250)
     run(1048576, 64, 250)
