@@ -89,6 +89,44 @@ def measured_peaks() -> dict:
     return {"hbm_gbs": 6650.0, "source": "fallback (B200_PROFILING.md)"}
 
 
+def fp64_peak_tflops(dev, stream) -> dict:
+    """Measured FP64 FMA throughput of this GPU: a tape of 16 independent Horner chains (128 multiply-adds
+    each, 4096 flop per evaluation, 256 B of I/O) pushed through the same streaming kernel as K1.
+    MEASURED_PEAKS.json has no FP64 figure; this is the denominator for the solver kernel's FP64 fraction."""
+    import torch
+    import optas_b200.sym as cs
+    from optas_b200.function import B200Function
+
+    x = cs.SX.sym("x", 16)
+    outs = []
+    for k in range(16):
+        v = x[k]
+        for j in range(128):
+            v = v * x[(k + 1) % 16] + (0.5 + 0.001 * j)
+        outs.append(v)
+    fn = B200Function(cs.Function("fma", [x], [cs.vertcat(*outs)]), timing=True)
+    Bf = 1 << 21
+    xin = torch.rand((Bf, 16), dtype=torch.float64, device=dev) * 0.5
+    out = torch.empty((Bf, 16), dtype=torch.float64, device=dev)
+    for _ in range(3):
+        fn.eval_raw(Bf, [xin], [out], stream=stream)
+    torch.cuda.synchronize()
+    fn.kernel_time()
+    for _ in range(5):
+        fn.eval_raw(Bf, [xin], [out], stream=stream)
+    torch.cuda.synchronize()
+    ms, n = fn.kernel_time()
+    flops = Bf * 16 * 128 * 2
+    return {"tflops": flops / (ms / n * 1e-3) / 1e12, "how": "16x128 FMA Horner chains per evaluation, 2 Mi evaluations, bo_eval_kernel",
+            "registers": fn.kernel_info()["registers"]}
+
+
+def tape_flops(tape) -> int:
+    """Arithmetic operations of one evaluation of a tape (each +,-,*,/,sqrt,sq,neg = 1; sin/cos = 1 each)."""
+    hist = tape.op_histogram()
+    return int(sum(v for k, v in hist.items() if k not in ("INPUT", "OUTPUT", "CONST")))
+
+
 def cpu_baseline(sample: int, workers: int) -> dict:
     """The CPU oracle (reference's SLSQP formulation, scipy defaults as the reference runs it) on
     `sample` instances of the same workload, one instance at a time per worker process."""
@@ -353,6 +391,7 @@ def main() -> None:
             fk.eval_raw(FK_BATCH, [q], [p_out, J_out], stream=stream)
         torch.cuda.synchronize()
         fk_ms_total, fk_n = fk.kernel_time()
+        fp64 = fp64_peak_tflops(dev, stream)
     fk_ms = fk_ms_total / fk_n
 
     # max over ranks of the device time, sum over ranks of the solved instances
@@ -395,7 +434,11 @@ def main() -> None:
                              "algorithmic_io_bytes_per_launch": B * 200,
                              "io_gbs": B * 200 / (kernel_ms / max(1, kernel_n) * 1e-3) / 1e9,
                              "registers": solver.kernel_info()["registers"],
-                             "local_bytes": solver.kernel_info()["local_bytes"]},
+                             "local_bytes": solver.kernel_info()["local_bytes"],
+                             "tape_flop_per_iteration": tape_flops(solver._lowered.kkt) + tape_flops(solver._lowered.fc),
+                             "achieved_tflops_tapes_only": iters_total * (tape_flops(solver._lowered.kkt) + tape_flops(solver._lowered.fc))
+                             / (kernel_ms / max(1, kernel_n) * 1e-3) / 1e12,
+                             "fp64_peak_measured": fp64},
             "clocks": clocks.summary(),
         }
         if not args.no_cpu_baseline and world == 1:
