@@ -103,6 +103,9 @@ typedef struct bo_problem_desc {
 #define BO_FLAG_TIMING 8u       /* bracket every kernel launch with CUDA events (see *_kernel_time) */
 #define BO_FLAG_PIVOTED_LDL 16u  /* factor the KKT system with Bunch-Kaufman partial pivoting (data-dependent
                                    control flow, slower) instead of the unpivoted rho-augmented LDL'  */
+#define BO_FLAG_COOP 32u         /* use the cooperative tier (one instance per CTA, factor in shared memory) even for
+                                   a problem small enough for the thread-per-instance sparse tier             */
+#define BO_FLAG_NO_COOP 64u      /* never use the cooperative tier (large problems then run thread-per-instance) */
 
 typedef struct bo_options {
   uint32_t flags;
@@ -145,6 +148,17 @@ int64_t bo_problem_ldl_table(const bo_problem* prob, int32_t* buf, int64_t cap);
 int64_t bo_problem_dtable(const bo_problem* prob, double* buf, int64_t cap);
 /* Resource usage of the compiled solver kernel: regs/thread, bytes local (spill), static smem. */
 int bo_problem_kernel_info(const bo_problem* prob, int32_t* regs, int32_t* local_bytes, int32_t* smem_bytes);
+/* Which tier the problem was lowered to and the sizes of its plan (diagnostics; copies min(cap, BO_TIER_INFO_LEN)):
+ *  [0] tier 0 dense / 1 sparse / 2 large (thread per instance)  3 cooperative (CTA per instance)
+ *  [1] threads per CTA  [2] dynamic shared memory bytes  [3] elimination-tree levels  [4]/[5] sub-tapes of fc / kkt
+ *  [6] parameter-only values of kkt  [7] partial-sum slots  [8] longest kkt sub-tape  [9] kkt instructions over all
+ *  sub-tapes  [10]/[11] lanes per factor target / solve row  [12] multiply-adds per factorisation  [13] work slots
+ *  [14] kkt components  [15] longest fc sub-tape  [16] fc instructions  [17] kkt once-per-instance instructions
+ *  [18] per-CTA global workspace (doubles)  [19] factor values (doubles)  [20] resident CTAs per SM  [21] SMs
+ *  [22] work slots of fc  [23] warps of the factor program  [24]/[25] steps of the longest factor / solve lane stream
+ *  [26]/[27] stride of the shared-memory work arrays of kkt / fc (0: thread-local)                                */
+#define BO_TIER_INFO_LEN 32
+int bo_problem_tier_info(const bo_problem* prob, int64_t* info, int32_t cap);
 
 /* Replaces optas/solver.py:395-396 (one nlpsol call + stats) for B instances at once.
  *   p   [B][np]        parameters                      (may be NULL iff np == 0)

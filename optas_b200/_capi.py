@@ -21,11 +21,14 @@ LIB_PATH = os.path.join(_HERE, "libb200optas.so")
 BO_ABI_VERSION = 1
 BO_OK, BO_ERR_INVALID, BO_ERR_COMPILE, BO_ERR_CUDA, BO_ERR_NO_DEVICE, BO_ERR_UNSUPPORTED = 0, -1, -2, -3, -4, -5
 BO_FLAG_COMPILE_ONLY, BO_FLAG_VERBOSE, BO_FLAG_NO_CACHE, BO_FLAG_TIMING, BO_FLAG_PIVOTED_LDL = 1, 2, 4, 8, 16
+BO_FLAG_COOP, BO_FLAG_NO_COOP = 32, 64
+TIER_NAMES = {0: "dense", 1: "sparse", 2: "large", 3: "coop"}
 STATUS_NAMES = {0: "converged", 1: "acceptable", 2: "max_iter", 3: "line_search", 4: "numerical"}
 
 EXPORTS = [
     "bo_abi_version", "bo_last_error", "bo_device_count",
     "bo_problem_create", "bo_problem_destroy", "bo_problem_source", "bo_problem_ldl_table", "bo_problem_dtable", "bo_problem_kernel_info",
+    "bo_problem_tier_info",
     "bo_solve", "bo_problem_kernel_time",
     "bo_function_create", "bo_function_destroy", "bo_function_eval", "bo_function_source",
     "bo_function_kernel_info", "bo_function_kernel_time",
@@ -94,6 +97,7 @@ def load() -> C.CDLL:
     lib.bo_problem_dtable.argtypes = [vp, f64p, C.c_int64]
     lib.bo_problem_dtable.restype = C.c_int64
     lib.bo_problem_kernel_info.argtypes = [vp, i32p, i32p, i32p]
+    lib.bo_problem_tier_info.argtypes = [vp, C.POINTER(C.c_int64), C.c_int32]
     lib.bo_solve.argtypes = [vp, C.c_int64] + [vp] * 8 + [vp]
     lib.bo_problem_kernel_time.argtypes = [vp, f64p, C.POINTER(C.c_int64)]
     lib.bo_function_create.argtypes = [C.POINTER(bo_tape), C.POINTER(bo_options), C.POINTER(vp)]
@@ -218,6 +222,17 @@ class ProblemHandle:
 
     def kernel_info(self) -> dict:
         return _kernel_info(load().bo_problem_kernel_info, self._h)
+
+    def tier_info(self) -> dict:
+        v = (C.c_int64 * 32)()
+        check(load().bo_problem_tier_info(self._h, v, 32))
+        keys = ["tier", "threads_per_block", "smem_dynamic", "levels", "nsub_fc", "nsub_kkt", "n_pe_kkt", "n_partial",
+                "kkt_max_len", "kkt_total_instr", "ldl_g", "solve_g", "factor_madds", "n_work", "kkt_components",
+                "fc_max_len", "fc_total_instr", "kkt_pre_len", "scratch_doubles", "factor_vals", "blocks_per_sm", "n_sm",
+                "n_work_fc", "ldl_warps", "factor_steps", "solve_steps", "kkt_wstride", "fc_wstride"]
+        d = {k: int(v[i]) for i, k in enumerate(keys)}
+        d["tier"] = TIER_NAMES[d["tier"]]
+        return d
 
     def solve(self, B: int, p, x0, x, lam=None, f=None, status=None, iters=None, kkt=None, stream: int = 0) -> None:
         check(load().bo_solve(self._h, B, _ptr(p), _ptr(x0), _ptr(x), _ptr(lam), _ptr(f), _ptr(status), _ptr(iters),

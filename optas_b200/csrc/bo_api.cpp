@@ -24,6 +24,7 @@
 
 #include "b200optas.h"
 #include "bo_codegen.h"
+#include "bo_coop.h"
 #include "bo_sparse.h"
 
 namespace {
@@ -255,7 +256,7 @@ int jit_compile(const std::string& source, const char* unit_name, const char* ke
 
   // hash = source + every header it may include + compiler version
   uint64_t h = fnv1a(source);
-  for (const char* hdr : {"bo_common.cuh", "bo_ipm_reg.cuh", "bo_stream_eval.cuh"}) {
+  for (const char* hdr : {"bo_common.cuh", "bo_ipm_reg.cuh", "bo_ipm_cta.cuh", "bo_stream_eval.cuh"}) {
     std::string text;
     if (!read_file(inc + "/" + hdr, &text)) return set_err(BO_ERR_INVALID, "JIT header %s/%s not found", inc.c_str(), hdr);
     h = fnv1a(text, h);
@@ -463,7 +464,9 @@ struct bo_problem {
   int tpb = 64;
   DevBuf d_p, d_x0, d_x, d_lam, d_f, d_status, d_iters, d_kkt, d_counter, d_ldl_tab;
   bo::SparsePlan plan;
-  bool sparse = false, large = false;
+  bo::CoopPlan coop_plan;
+  bool sparse = false, large = false, coop = false;
+  int smem_dynamic = 0;
   DevBuf d_dtab, d_scratch;
   int blocks_per_sm = 1, n_sm = 1;
   Timer timer;
@@ -546,8 +549,26 @@ int bo_problem_create(const bo_problem_desc* desc, const bo_options* opts_in, bo
   pr->large = pr->sparse && (ps.kkt.n_instr() > 30000 || ps.nx + ps.n_eq > 400);
   if (pivoted && ps.nx + ps.n_eq > 160)
     return set_err(BO_ERR_UNSUPPORTED, "bo_problem_create: BO_FLAG_PIVOTED_LDL is limited to nx+n_eq <= 160");
-  if (pr->sparse) pr->plan = bo::make_sparse_plan(ps, pr->large);
-  pr->source = bo::emit_problem_source(ps, pr->tpb, pivoted, pr->sparse ? &pr->plan : nullptr, pr->large);
+  // Cooperative tier (one instance per CTA, factor in shared memory; csrc/jit/bo_ipm_cta.cuh): the default for
+  // everything the large tier used to take, on request (BO_FLAG_COOP) for any sparse-tier problem.
+  if (pr->sparse && !(pr->opts.flags & BO_FLAG_NO_COOP) && (pr->large || (pr->opts.flags & BO_FLAG_COOP))) {
+    const int tpb = pr->opts.threads_per_block > 0 ? ((pr->opts.threads_per_block + 31) / 32) * 32 : (pr->large ? 256 : 64);
+    bo::CoopPlan cp = bo::make_coop_plan(ps, tpb);
+    const size_t smem = (size_t)cp.smem_doubles * sizeof(double);
+    if (cp.vals_size() + 1 < 32767 && ps.nx + ps.n_eq + 1 < 32767 && smem <= 227 * 1024) {
+      pr->coop = true;
+      pr->large = false;
+      pr->tpb = tpb;
+      pr->smem_dynamic = (int)smem;
+      pr->coop_plan = std::move(cp);
+    }
+  }
+  if (pr->coop) {
+    pr->source = bo::emit_coop_source(ps, pr->coop_plan, pr->tpb);
+  } else {
+    if (pr->sparse) pr->plan = bo::make_sparse_plan(ps, pr->large);
+    pr->source = bo::emit_problem_source(ps, pr->tpb, pivoted, pr->sparse ? &pr->plan : nullptr, pr->large);
+  }
   if (getenv("BO_DEBUG")) fprintf(stderr, "[bo] source %zu bytes\n", pr->source.size());
   int rc = jit_compile(pr->source, "bo_solve", "bo_solve_kernel", pr->opts, &pr->compiled);
   if (rc != BO_OK) return rc;
@@ -563,11 +584,24 @@ int bo_problem_create(const bo_problem_desc* desc, const bo_options* opts_in, bo
     rc = load_kernel(pr->compiled, "bo_solve_kernel", &pr->kernel);
     if (rc != BO_OK) return rc;
     BO_CU(g_drv.cuDeviceGetAttribute(&pr->n_sm, CU_DEVICE_ATTRIBUTE_MULTIPROCESSOR_COUNT, dev));
-    BO_CU(g_drv.cuOccupancyMaxActiveBlocksPerMultiprocessor(&pr->blocks_per_sm, pr->kernel.fn, pr->tpb, 0));
+    if (pr->smem_dynamic > 0)
+      BO_CU(g_drv.cuFuncSetAttribute(pr->kernel.fn, CU_FUNC_ATTRIBUTE_MAX_DYNAMIC_SHARED_SIZE_BYTES, pr->smem_dynamic));
+    BO_CU(g_drv.cuOccupancyMaxActiveBlocksPerMultiprocessor(&pr->blocks_per_sm, pr->kernel.fn, pr->tpb, (size_t)pr->smem_dynamic));
     if (pr->blocks_per_sm < 1) pr->blocks_per_sm = 1;
     if (pr->opts.blocks_per_sm > 0 && pr->opts.blocks_per_sm < pr->blocks_per_sm) pr->blocks_per_sm = pr->opts.blocks_per_sm;
     if ((rc = pr->d_counter.reserve(sizeof(unsigned long long))) != BO_OK) return rc;
-    if (pr->sparse) {
+    if (pr->coop) {
+      const bo::CoopPlan& cp = pr->coop_plan;
+      const size_t bytes = cp.itab.size() * sizeof(int32_t);
+      if ((rc = pr->d_ldl_tab.reserve(bytes)) != BO_OK) return rc;
+      BO_CU(g_drv.cuMemcpyHtoDAsync_v2(pr->d_ldl_tab.ptr, cp.itab.data(), bytes, nullptr));
+      const size_t dbytes = std::max<size_t>(cp.dtab.size(), 1) * sizeof(double);
+      if ((rc = pr->d_dtab.reserve(dbytes)) != BO_OK) return rc;
+      if (!cp.dtab.empty()) BO_CU(g_drv.cuMemcpyHtoDAsync_v2(pr->d_dtab.ptr, cp.dtab.data(), cp.dtab.size() * sizeof(double), nullptr));
+      const size_t ctas = (size_t)pr->n_sm * pr->blocks_per_sm;
+      if ((rc = pr->d_scratch.reserve(ctas * bo::coop_scratch_doubles(ps, cp) * sizeof(double))) != BO_OK) return rc;
+      BO_CU(g_drv.cuStreamSynchronize(nullptr));
+    } else if (pr->sparse) {
       const size_t bytes = pr->plan.table.size() * sizeof(int32_t);
       if ((rc = pr->d_ldl_tab.reserve(bytes)) != BO_OK) return rc;
       BO_CU(g_drv.cuMemcpyHtoDAsync_v2(pr->d_ldl_tab.ptr, pr->plan.table.data(), bytes, nullptr));
@@ -621,15 +655,17 @@ int64_t bo_problem_source(const bo_problem* pr, char* buf, int64_t cap) {
 
 int64_t bo_problem_ldl_table(const bo_problem* pr, int32_t* buf, int64_t cap) {
   if (!pr) return set_err(BO_ERR_INVALID, "null problem");
-  const int64_t n = pr->sparse ? (int64_t)pr->plan.table.size() : 0;
-  if (buf && cap >= n && n > 0) memcpy(buf, pr->plan.table.data(), (size_t)n * sizeof(int32_t));
+  const std::vector<int32_t>& tab = pr->coop ? pr->coop_plan.itab : pr->plan.table;
+  const int64_t n = (pr->sparse || pr->coop) ? (int64_t)tab.size() : 0;
+  if (buf && cap >= n && n > 0) memcpy(buf, tab.data(), (size_t)n * sizeof(int32_t));
   return n;
 }
 
 int64_t bo_problem_dtable(const bo_problem* pr, double* buf, int64_t cap) {
   if (!pr) return set_err(BO_ERR_INVALID, "null problem");
-  const int64_t n = pr->large ? (int64_t)pr->plan.dtable.size() : 0;
-  if (buf && cap >= n && n > 0) memcpy(buf, pr->plan.dtable.data(), (size_t)n * sizeof(double));
+  const std::vector<double>& tab = pr->coop ? pr->coop_plan.dtab : pr->plan.dtable;
+  const int64_t n = (pr->large || pr->coop) ? (int64_t)tab.size() : 0;
+  if (buf && cap >= n && n > 0) memcpy(buf, tab.data(), (size_t)n * sizeof(double));
   return n;
 }
 
@@ -638,6 +674,48 @@ int bo_problem_kernel_info(const bo_problem* pr, int32_t* regs, int32_t* local_b
   if (regs) *regs = pr->kernel.regs;
   if (local_bytes) *local_bytes = pr->kernel.local_bytes;
   if (smem_bytes) *smem_bytes = pr->kernel.smem_bytes;
+  return BO_OK;
+}
+
+int bo_problem_tier_info(const bo_problem* pr, int64_t* info, int32_t cap) {
+  if (!pr) return set_err(BO_ERR_INVALID, "null problem");
+  int64_t v[BO_TIER_INFO_LEN] = {0};
+  v[0] = pr->coop ? 3 : (pr->large ? 2 : (pr->sparse ? 1 : 0));
+  v[1] = pr->tpb;
+  v[2] = pr->smem_dynamic;
+  if (pr->coop) {
+    const bo::CoopPlan& cp = pr->coop_plan;
+    v[3] = cp.n_levels;
+    v[4] = cp.fc.nsub;
+    v[5] = cp.kkt.nsub;
+    v[6] = cp.kkt.n_pe;
+    v[7] = cp.kkt.n_part;
+    v[8] = cp.kkt.max_len;
+    v[9] = cp.kkt.total_instr;
+    v[10] = cp.ldl_g;
+    v[11] = cp.solve_g;
+    v[12] = cp.n_contrib;
+    v[13] = cp.n_work_kkt;
+    v[22] = cp.n_work_fc;
+    v[23] = cp.ldl_w;
+    v[24] = cp.fac_steps;
+    v[25] = cp.solve_steps;
+    v[26] = cp.kkt_wstride;
+    v[27] = cp.fc_wstride;
+    v[14] = cp.kkt.n_components;
+    v[15] = cp.fc.max_len;
+    v[16] = cp.fc.total_instr;
+    v[17] = cp.kkt.pre_len;
+    v[18] = (int64_t)bo::coop_scratch_doubles(pr->ps, cp);
+    v[19] = cp.vals_size();
+  } else if (pr->sparse) {
+    v[12] = pr->plan.flops;
+    v[19] = pr->plan.vals_size();
+  }
+  v[20] = pr->blocks_per_sm;
+  v[21] = pr->n_sm;
+  if (info)
+    for (int i = 0; i < cap && i < BO_TIER_INFO_LEN; ++i) info[i] = v[i];
   return BO_OK;
 }
 
@@ -705,16 +783,16 @@ int bo_solve(bo_problem* pr, int64_t B, const double* p, const double* x0, doubl
   CUdeviceptr dcounter = pr->d_counter.ptr;
   BO_CU(g_drv.cuMemsetD8Async(dcounter, 0, sizeof(unsigned long long), st));
   long long grid_ll = (long long)pr->n_sm * pr->blocks_per_sm;
-  const long long need = (B + pr->tpb - 1) / pr->tpb;
+  const long long need = pr->coop ? (long long)B : (B + pr->tpb - 1) / pr->tpb;  // coop: one instance per CTA
   if (grid_ll > need) grid_ll = need;
   const unsigned grid = (unsigned)grid_ll;
   SolverParams prm{pr->opts.max_iter, pr->opts.tol, pr->opts.acceptable_tol, pr->opts.mu_init, pr->opts.max_step,
-                   pr->opts.max_trips, pr->sparse ? pr->d_ldl_tab.ptr : 0, pr->large ? pr->d_dtab.ptr : 0,
-                   pr->large ? pr->d_scratch.ptr : 0, (long long)pr->n_sm * pr->blocks_per_sm * pr->tpb};
+                   pr->opts.max_trips, pr->sparse ? pr->d_ldl_tab.ptr : 0, (pr->large || pr->coop) ? pr->d_dtab.ptr : 0,
+                   (pr->large || pr->coop) ? pr->d_scratch.ptr : 0, (long long)pr->n_sm * pr->blocks_per_sm * pr->tpb};
   void* args[] = {&Bll, &dp, &dx0, &dx, &dlam, &df, &dstat, &dit, &dkkt, &dcounter, &prm};
   size_t slot = 0;
   if ((rc = pr->timer.begin(st, &slot)) != BO_OK) return rc;
-  BO_CU(g_drv.cuLaunchKernel(pr->kernel.fn, grid, 1, 1, (unsigned)pr->tpb, 1, 1, 0, st, args, nullptr));
+  BO_CU(g_drv.cuLaunchKernel(pr->kernel.fn, grid, 1, 1, (unsigned)pr->tpb, 1, 1, (unsigned)pr->smem_dynamic, st, args, nullptr));
   if ((rc = pr->timer.end(st, slot)) != BO_OK) return rc;
 
   for (const Out& o : outs) BO_CU(g_drv.cuMemcpyDtoHAsync_v2(o.host, o.dev, o.bytes, st));

@@ -1,0 +1,967 @@
+// bo_coop.cpp -- tables of the cooperative (instance-per-CTA) tier: tape partitioning, level-scheduled
+// sparse LDL' program, KKT assembly program, CSR/CSC views of the Jacobians.  See bo_coop.h.
+#include "bo_coop.h"
+
+#include <algorithm>
+#include <array>
+#include <functional>
+#include <map>
+#include <numeric>
+#include <queue>
+#include <sstream>
+
+#include "bo_opcodes.h"
+
+#define BO_OPX_NOP 5 /* padding rows of the lane-interleaved instruction streams (kernel: bo_ipm_cta.cuh) */
+
+namespace bo {
+namespace {
+
+// ======================================================================================
+// Tape -> DAG
+// ======================================================================================
+struct Node {
+  int op = 0;
+  int a = -1, b = -1, c = -1;  // interior: child node ids; INPUT: a = element, b = segment; CONST: a = index
+};
+struct OutRef {
+  int seg, elem, node;
+};
+struct Dag {
+  std::vector<Node> nodes;
+  std::vector<OutRef> outs;
+};
+
+bool is_leaf_op(int op) { return op == BO_OP_INPUT || op == BO_OP_CONST; }
+
+Dag build_dag(const Tape& t) {
+  Dag g;
+  std::vector<int> def(t.n_work, -1);
+  std::map<std::pair<int, std::pair<int, int>>, int> leaves;
+  for (int64_t i = 0; i < t.n_instr(); ++i) {
+    const int32_t* r = &t.instr[4 * i];
+    const int op = r[0] & 0xFF, c = (int)((uint32_t)r[0] >> 8), dst = r[1], a = r[2], b = r[3];
+    if (op == BO_OP_OUTPUT) {
+      g.outs.push_back({b, a, def[dst]});
+      continue;
+    }
+    Node nd;
+    nd.op = op;
+    if (is_leaf_op(op)) {
+      const auto key = std::make_pair(op, std::make_pair(a, op == BO_OP_INPUT ? b : 0));
+      auto it = leaves.find(key);
+      if (it == leaves.end()) {
+        nd.a = a;
+        nd.b = op == BO_OP_INPUT ? b : 0;
+        g.nodes.push_back(nd);
+        it = leaves.emplace(key, (int)g.nodes.size() - 1).first;
+      }
+      def[dst] = it->second;
+      continue;
+    }
+    if (op == BO_OP_IF_ELSE) {
+      nd.a = def[a];
+      nd.b = def[b];
+      nd.c = def[c];
+    } else if (op >= BO_OP_NEG && op <= BO_OP_COSH) {
+      nd.a = def[a];
+    } else {
+      nd.a = def[a];
+      nd.b = def[b];
+    }
+    g.nodes.push_back(nd);
+    def[dst] = (int)g.nodes.size() - 1;
+  }
+  return g;
+}
+
+struct UnionFind {
+  std::vector<int> p;
+  explicit UnionFind(int n) : p(n) { std::iota(p.begin(), p.end(), 0); }
+  int find(int x) {
+    while (p[x] != x) x = p[x] = p[p[x]];
+    return x;
+  }
+  void unite(int a, int b) {
+    a = find(a);
+    b = find(b);
+    if (a != b) p[std::max(a, b)] = std::min(a, b);
+  }
+};
+
+// ======================================================================================
+// Emission of one instruction stream (virtual code -> slots, leaves re-materialised on demand)
+// ======================================================================================
+struct VI {
+  int op;
+  int a = -1, b = -1, c = -1;  // value ids (DAG node id, or temp id >= n_nodes); OUTPUT: a = value, b = segment, c = element
+  int val = -1;                // value defined (-1 for OUTPUT)
+};
+
+struct Stream {
+  std::vector<int32_t> rows;
+  int n_work = 0;
+};
+
+// `leaf_row(node, dst)` returns the 4-int row loading a leaf-like value into slot dst.
+Stream assign_slots(const std::vector<VI>& code, const std::function<bool(int)>& leaflike,
+                    const std::function<void(int, int, int32_t*)>& leaf_row) {
+  const int GAP = 48;
+  std::map<int, std::vector<int>> uses;
+  for (int k = 0; k < (int)code.size(); ++k) {
+    const VI& v = code[k];
+    const int ops[3] = {v.a, v.op == BO_OP_OUTPUT ? -1 : v.b, v.op == BO_OP_OUTPUT ? -1 : v.c};
+    for (int o : ops)
+      if (o >= 0) {
+        auto& l = uses[o];
+        if (l.empty() || l.back() != k) l.push_back(k);
+      }
+  }
+  std::map<int, int> slot_of, use_ptr;
+  std::priority_queue<int, std::vector<int>, std::greater<int>> free_slots;
+  int high = 0;
+  auto take = [&]() {
+    if (!free_slots.empty()) {
+      const int s = free_slots.top();
+      free_slots.pop();
+      return s;
+    }
+    return high++;
+  };
+  Stream st;
+  auto push = [&](int32_t w0, int32_t w1, int32_t w2, int32_t w3) {
+    st.rows.push_back(w0);
+    st.rows.push_back(w1);
+    st.rows.push_back(w2);
+    st.rows.push_back(w3);
+  };
+  for (int k = 0; k < (int)code.size(); ++k) {
+    const VI& v = code[k];
+    const bool is_out = v.op == BO_OP_OUTPUT;
+    int ops[3] = {v.a, is_out ? -1 : v.b, is_out ? -1 : v.c};
+    for (int o : ops)
+      if (o >= 0 && !slot_of.count(o)) {  // only leaf-like values can be non-resident here
+        const int s = take();
+        int32_t row[4];
+        leaf_row(o, s, row);
+        push(row[0], row[1], row[2], row[3]);
+        slot_of[o] = s;
+      }
+    const int sa = ops[0] >= 0 ? slot_of[ops[0]] : 0, sb = ops[1] >= 0 ? slot_of[ops[1]] : 0,
+              sc = ops[2] >= 0 ? slot_of[ops[2]] : 0;
+    // release operands: last use, or a leaf whose next use is far away
+    for (int u = 0; u < 3; ++u) {
+      const int o = ops[u];
+      if (o < 0 || !slot_of.count(o)) continue;
+      bool dup = false;
+      for (int w = 0; w < u; ++w) dup = dup || ops[w] == o;
+      if (dup) continue;
+      const auto& l = uses[o];
+      int ptr = use_ptr[o];
+      while (ptr < (int)l.size() && l[ptr] <= k) ++ptr;
+      use_ptr[o] = ptr;
+      if (ptr >= (int)l.size() || (leaflike(o) && l[ptr] - k > GAP)) {
+        free_slots.push(slot_of[o]);
+        slot_of.erase(o);
+      }
+    }
+    if (is_out) {
+      push(BO_OP_OUTPUT, sa, v.c, v.b);
+      continue;
+    }
+    const int dst = take();
+    slot_of[v.val] = dst;
+    if (v.op == BO_OP_IF_ELSE)
+      push(BO_OP_IF_ELSE | (sc << 8), dst, sa, sb);
+    else
+      push(v.op, dst, sa, sb);
+    if (!uses.count(v.val)) {
+      free_slots.push(dst);
+      slot_of.erase(v.val);
+    }
+  }
+  st.n_work = std::max(high, 1);
+  return st;
+}
+
+// ======================================================================================
+// Tape partitioning
+// ======================================================================================
+struct Addend {
+  int node;
+  bool neg;
+  std::vector<int> coefs;
+};
+
+struct PartTape {
+  std::vector<Stream> subs;
+  Stream pre;
+  int n_pe = 0, n_part = 0;
+  int n_work = 1;            // work slots of the longest-lived sub-tape
+  std::vector<int32_t> red;  // seg, elem, start, count
+  CoopTapeInfo info;
+};
+
+PartTape partition_tape(const Tape& tape, int max_threads) {
+  const Dag g = build_dag(tape);
+  const int N = (int)g.nodes.size();
+  const int part_seg = (int)tape.out_sizes.size();  // extra output segment: per-thread partial sums
+  const int pe_seg = (int)tape.in_sizes.size();     // extra input segment: parameter-only sub-expressions
+
+  // x-dependence (anything but the parameter segment, which is input segment 1 of both solver tapes)
+  std::vector<char> xdep(N, 0);
+  std::vector<int> n_uses(N, 0);
+  for (int n = 0; n < N; ++n) {
+    const Node& nd = g.nodes[n];
+    if (nd.op == BO_OP_INPUT) {
+      xdep[n] = nd.b != 1;
+    } else if (nd.op != BO_OP_CONST) {
+      for (int ch : {nd.a, nd.b, nd.c})
+        if (ch >= 0) {
+          xdep[n] = xdep[n] || xdep[ch];
+          n_uses[ch] += 1;
+        }
+    }
+  }
+  for (const OutRef& o : g.outs) n_uses[o.node] += 1;
+  auto leaf = [&](int n) { return is_leaf_op(g.nodes[n].op); };
+  auto leaflike = [&](int n) { return n < N && (leaf(n) || !xdep[n]); };  // leaves + parameter-only sub-expressions
+
+  // linear trees at the roots: ADD / SUB / NEG / MUL-by-x-independent-factor nodes used exactly once
+  std::vector<signed char> trav(N, -1);
+  std::function<bool(int)> traversable = [&](int n) -> bool {
+    if (trav[n] >= 0) return trav[n] != 0;
+    const Node& nd = g.nodes[n];
+    bool t = false;
+    if (xdep[n] && n_uses[n] == 1) {
+      if (nd.op == BO_OP_ADD || nd.op == BO_OP_SUB || nd.op == BO_OP_NEG) {
+        t = true;
+      } else if (nd.op == BO_OP_MUL && xdep[nd.a] != xdep[nd.b]) {
+        const int d = xdep[nd.a] ? nd.a : nd.b;
+        t = !leaf(d) && traversable(d);
+      }
+    }
+    trav[n] = t ? 1 : 0;
+    return t;
+  };
+  std::vector<char> intree(N, 0);
+  std::vector<std::vector<Addend>> addends(g.outs.size());
+  for (size_t oi = 0; oi < g.outs.size(); ++oi) {
+    struct Item {
+      int node;
+      bool neg;
+      std::vector<int> coefs;
+    };
+    std::vector<Item> stack{{g.outs[oi].node, false, {}}};
+    while (!stack.empty()) {
+      Item it = stack.back();
+      stack.pop_back();
+      const Node& nd = g.nodes[it.node];
+      if (!leaf(it.node) && traversable(it.node)) {
+        intree[it.node] = 1;
+        if (nd.op == BO_OP_ADD || nd.op == BO_OP_SUB) {
+          stack.push_back({nd.b, nd.op == BO_OP_SUB ? !it.neg : it.neg, it.coefs});
+          stack.push_back({nd.a, it.neg, it.coefs});
+        } else if (nd.op == BO_OP_NEG) {
+          stack.push_back({nd.a, !it.neg, it.coefs});
+        } else {  // MUL by an x-independent factor
+          const int d = xdep[nd.a] ? nd.a : nd.b, k = xdep[nd.a] ? nd.b : nd.a;
+          it.coefs.push_back(k);
+          stack.push_back({d, it.neg, it.coefs});
+        }
+      } else {
+        addends[oi].push_back({it.node, it.neg, it.coefs});
+      }
+    }
+  }
+
+  // base components: x-dependent interior nodes outside the root trees, linked through shared operands
+  UnionFind uf(N);
+  auto interior = [&](int n) { return xdep[n] && !leaf(n); };
+  for (int n = 0; n < N; ++n) {
+    if (!interior(n) || intree[n]) continue;
+    const Node& nd = g.nodes[n];
+    for (int ch : {nd.a, nd.b, nd.c})
+      if (ch >= 0 && interior(ch)) uf.unite(n, ch);
+  }
+  std::vector<int> comp_size(N, 0);
+  for (int n = 0; n < N; ++n)
+    if (interior(n) && !intree[n]) comp_size[uf.find(n)] += 1;
+
+  // tasks: an unsplit output (whole root tree evaluated by one thread) or the addends of a split output
+  // that fall into one component
+  struct Task {
+    int out;                   // output index
+    std::vector<int> addends;  // indices into addends[out]; empty = unsplit (evaluate the root)
+  };
+  std::map<int, std::vector<Task>> comp_tasks;  // component root (or -1 - k for loose outputs) -> tasks
+  std::map<int, int64_t> comp_cost;
+  std::map<int, int> comp_first;
+  int n_loose = 0, n_split = 0;
+  std::vector<std::vector<int>> split_comps(g.outs.size());  // for split outputs: components in order of appearance
+  for (size_t oi = 0; oi < g.outs.size(); ++oi) {
+    std::vector<int> comps;
+    for (const Addend& ad : addends[oi])
+      if (interior(ad.node)) {
+        const int c = uf.find(ad.node);
+        if (std::find(comps.begin(), comps.end(), c) == comps.end()) comps.push_back(c);
+      }
+    int64_t tree_cost = (int64_t)addends[oi].size();
+    if (comps.size() <= 1) {
+      const int c = comps.empty() ? -1 - (n_loose++) : comps[0];
+      comp_tasks[c].push_back({(int)oi, {}});
+      comp_cost[c] += tree_cost + 1;
+      if (!comp_first.count(c)) comp_first[c] = (int)oi;
+    } else {
+      ++n_split;
+      split_comps[oi] = comps;
+      std::map<int, Task> per;
+      for (size_t k = 0; k < addends[oi].size(); ++k) {
+        const Addend& ad = addends[oi][k];
+        const int c = interior(ad.node) ? uf.find(ad.node) : comps[0];
+        Task& tk = per[c];
+        tk.out = (int)oi;
+        tk.addends.push_back((int)k);
+      }
+      for (auto& kv : per) {
+        comp_cost[kv.first] += (int64_t)kv.second.addends.size() * 2;
+        if (!comp_first.count(kv.first)) comp_first[kv.first] = (int)oi;
+        comp_tasks[kv.first].push_back(std::move(kv.second));
+      }
+    }
+  }
+  for (auto& kv : comp_cost)
+    if (kv.first >= 0) kv.second += comp_size[kv.first];
+
+  // components -> threads: longest first onto the least-loaded thread (ties: lowest id), so that the
+  // big isomorphic stage components end up one per lane in neighbouring lanes (lock-step in the interpreter)
+  std::vector<int> comps;
+  for (const auto& kv : comp_tasks) comps.push_back(kv.first);
+  std::sort(comps.begin(), comps.end(), [&](int a, int b) {
+    if (comp_cost[a] != comp_cost[b]) return comp_cost[a] > comp_cost[b];
+    return comp_first[a] < comp_first[b];
+  });
+  const int nsub = std::max(1, std::min<int>(max_threads, (int)comps.size()));
+  std::vector<int64_t> load(nsub, 0);
+  std::vector<std::vector<Task>> thread_tasks(nsub);
+  std::map<int, int> comp_thread;
+  for (int c : comps) {
+    int best = 0;
+    for (int t = 1; t < nsub; ++t)
+      if (load[t] < load[best]) best = t;
+    load[best] += comp_cost[c];
+    comp_thread[c] = best;
+    for (const Task& tk : comp_tasks[c]) thread_tasks[best].push_back(tk);
+  }
+
+  PartTape pt;
+  pt.info.nsub = nsub;
+  pt.info.n_components = (int)comps.size();
+  pt.info.n_split_outputs = n_split;
+
+  // partial slots of the split outputs: one per contributing THREAD, contiguous, in thread order
+  std::map<std::pair<int, int>, int> part_slot;  // (output, thread) -> slot
+  for (size_t oi = 0; oi < g.outs.size(); ++oi) {
+    if (split_comps[oi].empty()) continue;
+    std::vector<int> threads;
+    for (int c : split_comps[oi]) threads.push_back(comp_thread[c]);
+    std::sort(threads.begin(), threads.end());
+    threads.erase(std::unique(threads.begin(), threads.end()), threads.end());
+    const int start = pt.n_part;
+    for (int t : threads) part_slot[{(int)oi, t}] = pt.n_part++;
+    pt.red.push_back(g.outs[oi].seg);
+    pt.red.push_back(g.outs[oi].elem);
+    pt.red.push_back(start);
+    pt.red.push_back((int)threads.size());
+  }
+  pt.info.n_part = pt.n_part;
+  pt.info.n_red = (int)pt.red.size() / 4;
+
+  // parameter-only sub-expressions referenced from the x-dependent code: evaluated once per instance
+  std::map<int, int> pe_index;
+  auto pe_of = [&](int n) {
+    auto it = pe_index.find(n);
+    if (it == pe_index.end()) it = pe_index.emplace(n, (int)pe_index.size()).first;
+    return it->second;
+  };
+  auto leaf_row_main = [&](int n, int dst, int32_t* row) {
+    const Node& nd = g.nodes[n];
+    if (nd.op == BO_OP_CONST) {
+      row[0] = BO_OP_CONST; row[1] = dst; row[2] = nd.a; row[3] = 0;
+    } else if (nd.op == BO_OP_INPUT) {
+      row[0] = BO_OP_INPUT; row[1] = dst; row[2] = nd.a; row[3] = nd.b;
+    } else {
+      row[0] = BO_OP_INPUT; row[1] = dst; row[2] = pe_of(n); row[3] = pe_seg;
+    }
+  };
+
+  for (int t = 0; t < nsub; ++t) {
+    std::vector<Task>& tasks = thread_tasks[t];
+    std::stable_sort(tasks.begin(), tasks.end(), [](const Task& a, const Task& b) { return a.out < b.out; });
+    {  // several components of one split output on this thread share ONE partial slot: merge their addends
+      std::vector<Task> merged;
+      for (Task& tk : tasks) {
+        if (!merged.empty() && merged.back().out == tk.out && !tk.addends.empty() && !merged.back().addends.empty()) {
+          merged.back().addends.insert(merged.back().addends.end(), tk.addends.begin(), tk.addends.end());
+        } else {
+          merged.push_back(std::move(tk));
+        }
+      }
+      for (Task& tk : merged) std::sort(tk.addends.begin(), tk.addends.end());
+      tasks = std::move(merged);
+    }
+    std::vector<VI> code;
+    std::vector<char> done(N, 0);
+    int n_temp = 0;
+    auto emit_node = [&](int root) {
+      if (leaflike(root) || done[root]) return;
+      std::vector<std::pair<int, int>> stack{{root, 0}};
+      while (!stack.empty()) {
+        auto& top = stack.back();
+        const int n = top.first;
+        if (done[n]) {
+          stack.pop_back();
+          continue;
+        }
+        const Node& nd = g.nodes[n];
+        const int kids[3] = {nd.a, nd.b, nd.c};
+        bool pushed = false;
+        while (top.second < 3) {
+          const int ch = kids[top.second++];
+          if (ch >= 0 && !leaflike(ch) && !done[ch]) {
+            stack.push_back({ch, 0});
+            pushed = true;
+            break;
+          }
+        }
+        if (pushed) continue;
+        VI v;
+        v.op = nd.op;
+        v.a = nd.a;
+        v.b = nd.b;
+        v.c = nd.c;
+        v.val = n;
+        code.push_back(v);
+        done[n] = 1;
+        stack.pop_back();
+      }
+    };
+    auto temp_op = [&](int op, int a, int b) {
+      VI v;
+      v.op = op;
+      v.a = a;
+      v.b = b;
+      v.val = N + n_temp++;
+      code.push_back(v);
+      return v.val;
+    };
+    for (const Task& tk : tasks) {
+      const OutRef& o = g.outs[tk.out];
+      if (tk.addends.empty()) {
+        emit_node(o.node);
+        VI v;
+        v.op = BO_OP_OUTPUT;
+        v.a = o.node;
+        v.b = o.seg;
+        v.c = o.elem;
+        code.push_back(v);
+        continue;
+      }
+      int acc = -1;
+      for (int k : tk.addends) {
+        const Addend& ad = addends[tk.out][k];
+        emit_node(ad.node);
+        int val = ad.node;
+        for (int cf : ad.coefs) {
+          emit_node(cf);  // no-op: coefficients are leaf-like
+          val = temp_op(BO_OP_MUL, val, cf);
+        }
+        if (acc < 0)
+          acc = ad.neg ? temp_op(BO_OP_NEG, val, -1) : val;
+        else
+          acc = temp_op(ad.neg ? BO_OP_SUB : BO_OP_ADD, acc, val);
+      }
+      VI v;
+      v.op = BO_OP_OUTPUT;
+      v.a = acc;
+      v.b = part_seg;
+      v.c = part_slot.at({tk.out, t});
+      code.push_back(v);
+    }
+    Stream st = assign_slots(code, leaflike, leaf_row_main);
+    pt.info.total_instr += (int64_t)st.rows.size() / 4;
+    pt.info.max_len = std::max<int64_t>(pt.info.max_len, (int64_t)st.rows.size() / 4);
+    pt.n_work = std::max(pt.n_work, st.n_work);
+    pt.subs.push_back(std::move(st));
+  }
+
+  // the once-per-instance tape of the parameter-only sub-expressions (output segment 0 = the pe vector)
+  {
+    std::vector<std::pair<int, int>> order;  // (pe index, node)
+    for (const auto& kv : pe_index) order.push_back({kv.second, kv.first});
+    std::sort(order.begin(), order.end());
+    std::vector<VI> code;
+    std::vector<char> done(N, 0);
+    for (const auto& on : order) {
+      std::vector<std::pair<int, int>> stack{{on.second, 0}};
+      while (!stack.empty()) {
+        auto& top = stack.back();
+        const int n = top.first;
+        if (done[n] || leaf(n)) {
+          stack.pop_back();
+          continue;
+        }
+        const Node& nd = g.nodes[n];
+        const int kids[3] = {nd.a, nd.b, nd.c};
+        bool pushed = false;
+        while (top.second < 3) {
+          const int ch = kids[top.second++];
+          if (ch >= 0 && !leaf(ch) && !done[ch]) {
+            stack.push_back({ch, 0});
+            pushed = true;
+            break;
+          }
+        }
+        if (pushed) continue;
+        VI v;
+        v.op = nd.op;
+        v.a = nd.a;
+        v.b = nd.b;
+        v.c = nd.c;
+        v.val = n;
+        code.push_back(v);
+        done[n] = 1;
+        stack.pop_back();
+      }
+      VI v;
+      v.op = BO_OP_OUTPUT;
+      v.a = on.second;
+      v.b = 0;
+      v.c = on.first;
+      code.push_back(v);
+    }
+    auto leaf_row_pre = [&](int n, int dst, int32_t* row) {
+      const Node& nd = g.nodes[n];
+      row[0] = nd.op;
+      row[1] = dst;
+      row[2] = nd.a;
+      row[3] = nd.op == BO_OP_INPUT ? nd.b : 0;
+    };
+    pt.pre = assign_slots(code, [&](int n) { return n < N && leaf(n); }, leaf_row_pre);
+    pt.n_pe = (int)pe_index.size();
+    pt.info.n_pe = pt.n_pe;
+    pt.info.pre_len = (int64_t)pt.pre.rows.size() / 4;
+  }
+  return pt;
+}
+
+void append_tape_section(std::vector<int32_t>& t, int slot, const PartTape& pt, const Tape& tape, std::vector<double>& dtab) {
+  while (t.size() % 4 != 0) t.push_back(0);
+  const size_t s0 = t.size();
+  t[slot] = (int32_t)s0;
+  t.resize(s0 + TS_HEADER, 0);
+  const int nsub = (int)pt.subs.size();
+  t[s0 + TS_NSUB] = nsub;
+  t[s0 + TS_CONST0] = (int32_t)dtab.size();
+  dtab.insert(dtab.end(), tape.consts.begin(), tape.consts.end());
+  t[s0 + TS_NPE] = pt.n_pe;
+  t[s0 + TS_NPART] = pt.n_part;
+  t[s0 + TS_PART_SEG] = (int32_t)tape.out_sizes.size();
+  t[s0 + TS_PE_SEG] = (int32_t)tape.in_sizes.size();
+  // pre tape (sequential rows)
+  t[s0 + TS_PRE_N] = (int32_t)pt.pre.rows.size() / 4;
+  t[s0 + TS_PRE_OFF] = (int32_t)t.size();
+  t.insert(t.end(), pt.pre.rows.begin(), pt.pre.rows.end());
+  // lengths
+  t[s0 + TS_LEN_OFF] = (int32_t)t.size();
+  for (const Stream& s : pt.subs) t.push_back((int32_t)s.rows.size() / 4);
+  // reductions
+  t[s0 + TS_NRED] = (int32_t)pt.red.size() / 4;
+  t[s0 + TS_RED_OFF] = (int32_t)t.size();
+  t.insert(t.end(), pt.red.begin(), pt.red.end());
+  // lane-interleaved streams, one block per group of 32 sub-tapes: row i of lane l at wbase + i*32 + l
+  const int n_warps = (nsub + 31) / 32;
+  std::vector<int64_t> wbase(n_warps, 0);
+  int64_t rows_total = 0;
+  for (int w = 0; w < n_warps; ++w) {
+    wbase[w] = rows_total;
+    int64_t mx = 0;
+    for (int l = 0; l < 32 && w * 32 + l < nsub; ++l) mx = std::max<int64_t>(mx, (int64_t)pt.subs[w * 32 + l].rows.size() / 4);
+    rows_total += mx * 32;
+  }
+  t[s0 + TS_WBASE_OFF] = (int32_t)t.size();
+  for (int w = 0; w < n_warps; ++w) t.push_back((int32_t)wbase[w]);
+  while (t.size() % 4 != 0) t.push_back(0);
+  t[s0 + TS_STREAM_OFF] = (int32_t)t.size();
+  const size_t st0 = t.size();
+  t.resize(st0 + (size_t)rows_total * 4, 0);
+  for (size_t r = 0; r < (size_t)rows_total; ++r) t[st0 + 4 * r] = BO_OPX_NOP;
+  for (int s = 0; s < nsub; ++s) {
+    const int w = s / 32, l = s % 32;
+    const auto& rows = pt.subs[s].rows;
+    for (size_t i = 0; i < rows.size() / 4; ++i) {
+      const size_t at = st0 + 4 * ((size_t)wbase[w] + i * 32 + l);
+      for (int k = 0; k < 4; ++k) t[at + k] = rows[4 * i + k];
+    }
+  }
+}
+
+
+// ======================================================================================
+// Lane programs: a warp-wide, fully pre-scheduled instruction stream
+// ======================================================================================
+// One step = one 8-byte word per lane:  x = a | FINISH << 15 | b << 16 | LEVEL_END << 31,  y = c | tgt << 16.
+// Every lane does acc += vals[a] * (factor: vals[b] * vals[c] | solve: bp[b]).  On a FINISH step the G lanes of a
+// group add their accumulators up and lane 0 of the group finalises target `tgt` (0x7FFF: none); on a LEVEL_END
+// step the participating warps synchronise.  The flags are identical in all lanes of a warp.  Bit 15 of c marks a
+// diagonal factor target whose pivot must be positive (variable block).  Each (warp, level) segment is padded to a
+// multiple of BO_LP_CHUNK steps, so the executor can fetch the operands of a whole chunk before any of its finishes.
+struct LaneTarget {
+  int tgt;
+  std::vector<std::array<int, 3>> con;
+  bool positive = false;  // factor, diagonal target: pivot expected positive (variable block)
+};
+#define BO_LP_CHUNK 4 /* steps per chunk of the executor; a level boundary always ends a chunk */
+struct LaneProgram {
+  int W = 1, G = 1;
+  std::vector<std::vector<int32_t>> words;  // per warp: [step][32][2]
+  double cost = 0.0;
+  int64_t max_steps() const {
+    size_t m = 0;
+    for (const auto& w : words) m = std::max(m, w.size() / 64);
+    return (int64_t)m;
+  }
+};
+
+LaneProgram schedule_program(const std::vector<std::vector<LaneTarget>>& levels, int W, int G, int zero_a, int zero_b, int zero_c,
+                             bool emit) {
+  LaneProgram pr;
+  pr.W = W;
+  pr.G = G;
+  pr.words.resize(W);
+  const int ngrp = 32 / G, slots = W * ngrp;
+  int log2g = 0;
+  while ((1 << log2g) < G) ++log2g;
+  const double c_step = 25.0, c_finish = 80.0 + 30.0 * log2g, c_barrier = W > 1 ? 80.0 : 20.0;
+  for (const auto& lv : levels) {
+    std::vector<int> order(lv.size());
+    for (size_t k = 0; k < lv.size(); ++k) order[k] = (int)k;
+    std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return lv[a].con.size() > lv[b].con.size(); });
+    const int rounds = ((int)lv.size() + slots - 1) / slots;
+    double worst = 0.0;
+    for (int w = 0; w < W; ++w) {
+      double cost_w = 0.0;
+      int seg_steps = 0, cost_steps = 0;
+      for (int r = 0; r < rounds; ++r) {
+        // targets of this (warp, round): slot q = position within the round, warp = q % W, group = q / W
+        const LaneTarget* tg[32] = {nullptr};
+        int maxlen = -1;
+        for (int g = 0; g < ngrp; ++g) {
+          const int q = g * W + w, k = r * slots + q;
+          if (k < (int)lv.size()) {
+            tg[g] = &lv[order[k]];
+            maxlen = std::max(maxlen, (int)tg[g]->con.size());
+          }
+        }
+        if (maxlen < 0) continue;
+        const int steps = std::max(1, (maxlen + G - 1) / G);
+        cost_w += steps * c_step + c_finish;
+        cost_steps += steps;
+        if (!emit) continue;
+        for (int st = 0; st < steps; ++st) {
+          const bool fin = st + 1 == steps;
+          for (int lane = 0; lane < 32; ++lane) {
+            const int g = lane / G, sub = lane % G;
+            int a = zero_a, b = zero_b, c = zero_c, tgt = 0x7FFF;
+            if (tg[g]) {
+              const int ci = st * G + sub;
+              if (ci < (int)tg[g]->con.size()) {
+                a = tg[g]->con[ci][0];
+                b = tg[g]->con[ci][1];
+                c = tg[g]->con[ci][2];
+              }
+              if (fin && sub == 0) {
+                tgt = tg[g]->tgt;
+                if (tg[g]->positive) c |= 0x8000;
+              }
+            }
+            pr.words[w].push_back((int32_t)((uint32_t)a | (fin ? 0x8000u : 0u) | ((uint32_t)b << 16)));
+            pr.words[w].push_back((int32_t)((uint32_t)c | ((uint32_t)tgt << 16)));
+          }
+          ++seg_steps;
+        }
+      }
+      if (emit) {
+        // pad the segment to a whole number of chunks (at least one: every warp meets every level barrier)
+        while (seg_steps == 0 || seg_steps % BO_LP_CHUNK != 0) {
+          for (int lane = 0; lane < 32; ++lane) {
+            pr.words[w].push_back((int32_t)((uint32_t)zero_a | ((uint32_t)zero_b << 16)));
+            pr.words[w].push_back((int32_t)((uint32_t)zero_c | (0x7FFFu << 16)));
+          }
+          ++seg_steps;
+        }
+        const size_t last = pr.words[w].size() - 64;
+        for (int lane = 0; lane < 32; ++lane) pr.words[w][last + 2 * lane] |= (int32_t)0x80000000u;
+      }
+      cost_w += ((BO_LP_CHUNK - cost_steps % BO_LP_CHUNK) % BO_LP_CHUNK) * c_step;
+      worst = std::max(worst, cost_w);
+    }
+    pr.cost += worst + c_barrier;
+  }
+  return pr;
+}
+
+LaneProgram best_program(const std::vector<std::vector<LaneTarget>>& levels, int max_warps, int zero_a, int zero_b, int zero_c) {
+  int bw = 1, bg = 1;
+  double best = -1.0;
+  for (int W = 1; W <= max_warps; W *= 2)
+    for (int G = 1; G <= 32; G *= 2) {
+      const LaneProgram p = schedule_program(levels, W, G, zero_a, zero_b, zero_c, false);
+      if (best < 0.0 || p.cost < best) {
+        best = p.cost;
+        bw = W;
+        bg = G;
+      }
+    }
+  return schedule_program(levels, bw, bg, zero_a, zero_b, zero_c, true);
+}
+
+// table section: [0] W  [1] G  [2] stream offset (absolute, 16-byte aligned)  [3] total steps, then per warp
+// { first step, number of steps }
+void append_program(std::vector<int32_t>& t, int slot, const LaneProgram& pr) {
+  t[slot] = (int32_t)t.size();
+  const size_t h = t.size();
+  t.resize(h + 4 + 2 * (size_t)pr.W, 0);
+  t[h] = pr.W;
+  t[h + 1] = pr.G;
+  int64_t first = 0;
+  for (int w = 0; w < pr.W; ++w) {
+    t[h + 4 + 2 * w] = (int32_t)first;
+    t[h + 5 + 2 * w] = (int32_t)(pr.words[w].size() / 64);
+    first += (int64_t)pr.words[w].size() / 64;
+  }
+  t[h + 3] = (int32_t)first;
+  while (t.size() % 4 != 0) t.push_back(0);
+  t[h + 2] = (int32_t)t.size();
+  for (int w = 0; w < pr.W; ++w) t.insert(t.end(), pr.words[w].begin(), pr.words[w].end());
+}
+
+}  // namespace
+
+CoopPlan make_coop_plan(const ProblemSource& ps, int tpb) {
+  CoopPlan pl;
+  pl.sp = make_sparse_plan(ps, false);
+  const SparsePlan& sp = pl.sp;
+  const int n = sp.n, nx = ps.nx, nnzL = sp.nnzL();
+  std::vector<int32_t>& t = pl.itab;
+  t.assign(CT_HEADER, 0);
+  t[CT_N] = n;
+  t[CT_NNZL] = nnzL;
+  auto section = [&](int slot) { t[slot] = (int32_t)t.size(); };
+  section(CT_PERM);
+  t.insert(t.end(), sp.perm.begin(), sp.perm.end());
+  section(CT_SIGN);
+  for (int j = 0; j < n; ++j) t.push_back(sp.perm[j] < nx ? 1 : -1);
+
+  // ---- levels of the elimination tree: column j can be computed once every column k with L(j,k) != 0 is done ----
+  std::vector<int> lev(n, 0);
+  for (int j = 0; j < n; ++j)
+    for (int e = sp.colptr[j]; e < sp.colptr[j + 1]; ++e) lev[sp.rowidx[e]] = std::max(lev[sp.rowidx[e]], lev[j] + 1);
+  const int nlev = n ? *std::max_element(lev.begin(), lev.end()) + 1 : 0;
+  pl.n_levels = nlev;
+  t[CT_NLEV] = nlev;
+  std::vector<std::vector<int>> cols_of(nlev);
+  for (int j = 0; j < n; ++j) cols_of[lev[j]].push_back(j);
+  // row pattern: (column k, entry index e) with k < row
+  std::vector<std::vector<std::pair<int, int>>> row_pat(n);
+  for (int k = 0; k < n; ++k)
+    for (int e = sp.colptr[k]; e < sp.colptr[k + 1]; ++e) row_pat[sp.rowidx[e]].push_back({k, e});
+  auto entry = [&](int row, int col) -> int {
+    const auto lo = sp.rowidx.begin() + sp.colptr[col], hi = sp.rowidx.begin() + sp.colptr[col + 1];
+    const auto it = std::lower_bound(lo, hi, row);
+    return (it == hi || *it != row) ? -1 : (int)(it - sp.rowidx.begin());
+  };
+
+  // ---- lane programs: the factorisation and the two triangular solves, fully pre-scheduled ----
+  const int zero_v = sp.vals_size();  // index of a cell of `vals` that always holds 0.0 (padding operand)
+  const int zero_b = n;               // same in the permuted right-hand side
+  {
+    std::vector<std::vector<LaneTarget>> fac(nlev), fwd(nlev), bwd(nlev);
+    for (int L = 0; L < nlev; ++L) {
+      for (int j : cols_of[L]) {
+        LaneTarget d;
+        d.tgt = j;
+        d.positive = sp.perm[j] < nx;
+        for (const auto& ke : row_pat[j]) d.con.push_back({n + ke.second, n + ke.second, ke.first});
+        pl.n_contrib += (int64_t)d.con.size();
+        fac[L].push_back(std::move(d));
+        for (int e = sp.colptr[j]; e < sp.colptr[j + 1]; ++e) {
+          const int i = sp.rowidx[e];
+          LaneTarget o;
+          o.tgt = n + e;
+          for (const auto& ke : row_pat[j]) {
+            const int e_ik = entry(i, ke.first);
+            if (e_ik >= 0) o.con.push_back({n + e_ik, n + ke.second, ke.first});
+          }
+          pl.n_contrib += (int64_t)o.con.size();
+          fac[L].push_back(std::move(o));
+        }
+        LaneTarget f;  // forward: z(j) = b(j) - sum_k C(j,k) u(k)
+        f.tgt = j;
+        for (const auto& ke : row_pat[j]) f.con.push_back({n + ke.second, ke.first, zero_v});
+        fwd[L].push_back(std::move(f));
+        LaneTarget w;  // backward: x(j) = u(j) - (1/D(j)) sum_i C(i,j) x(i)
+        w.tgt = j;
+        for (int e = sp.colptr[j]; e < sp.colptr[j + 1]; ++e) w.con.push_back({n + e, sp.rowidx[e], zero_v});
+        bwd[nlev - 1 - L].push_back(std::move(w));
+      }
+    }
+    const int max_warps = std::max(1, tpb / 32);
+    LaneProgram pf = best_program(fac, max_warps, zero_v, zero_v, zero_v);
+    LaneProgram pw = best_program(fwd, 1, zero_v, zero_b, zero_v);
+    LaneProgram pb = best_program(bwd, 1, zero_v, zero_b, zero_v);
+    pl.ldl_g = pf.G;
+    pl.ldl_w = pf.W;
+    pl.solve_g = pw.G;
+    pl.fac_steps = pf.max_steps();
+    pl.solve_steps = pw.max_steps() + pb.max_steps();
+    append_program(t, CT_PROG_FAC, pf);
+    append_program(t, CT_PROG_FWD, pw);
+    append_program(t, CT_PROG_BWD, pb);
+  }
+
+  // ---- KKT assembly, target-owned: every diagonal position plus every position that receives a term ----
+  // term = { kind, a, b, r }: 0: H[a]   1: JE[a]   2: sigma[r] JI[a] JI[b]   3: rho JE[a] JE[b]
+  {
+    std::map<int, std::vector<int32_t>> terms;
+    for (int j = 0; j < n; ++j) terms[j];
+    for (int k = 0; k < ps.hess.nnz(); ++k) {
+      auto& v = terms[sp.pos(ps.hess.row[k], ps.hess.col[k])];
+      v.insert(v.end(), {0, k, 0, 0});
+    }
+    for (int k = 0; k < ps.jac_eq.nnz(); ++k) {
+      auto& v = terms[sp.pos(nx + ps.jac_eq.row[k], ps.jac_eq.col[k])];
+      v.insert(v.end(), {1, k, 0, 0});
+    }
+    auto pairs = [&](const Sparsity& s, int n_rows, int kind) {
+      std::vector<std::vector<int>> by_row(n_rows > 0 ? n_rows : 1);
+      for (int k = 0; k < s.nnz(); ++k) by_row[s.row[k]].push_back(k);
+      for (int r = 0; r < n_rows; ++r) {
+        const auto& ks = by_row[r];
+        for (size_t u = 0; u < ks.size(); ++u)
+          for (size_t w = 0; w < ks.size(); ++w) {
+            const int cu = s.col[ks[u]], cw = s.col[ks[w]];
+            if (cu < cw || (cu == cw && u != w)) continue;
+            auto& v = terms[sp.pos(cu, cw)];
+            v.insert(v.end(), {kind, ks[u], ks[w], r});
+          }
+      }
+    };
+    pairs(ps.jac_ineq, ps.n_ineq, 2);
+    pairs(ps.jac_eq, ps.n_eq, 3);
+    t[CT_ANT] = (int32_t)terms.size();
+    std::vector<int32_t> apos, aptr{0}, aterm;
+    for (const auto& kv : terms) {
+      apos.push_back(kv.first);
+      aterm.insert(aterm.end(), kv.second.begin(), kv.second.end());
+      aptr.push_back((int32_t)aterm.size() / 4);
+    }
+    section(CT_APOS);
+    t.insert(t.end(), apos.begin(), apos.end());
+    section(CT_APTR);
+    t.insert(t.end(), aptr.begin(), aptr.end());
+    while (t.size() % 4 != 0) t.push_back(0);
+    section(CT_ATERM);
+    t.insert(t.end(), aterm.begin(), aterm.end());
+  }
+
+  // ---- CSR / CSC views of the Jacobians: entries { nz index, other coordinate } ----
+  auto views = [&](const Sparsity& s, int n_rows, int slot_rptr) {
+    std::vector<std::vector<std::pair<int, int>>> by_row(n_rows > 0 ? n_rows : 1), by_col(nx);
+    for (int k = 0; k < s.nnz(); ++k) {
+      by_row[s.row[k]].push_back({k, s.col[k]});
+      by_col[s.col[k]].push_back({k, s.row[k]});
+    }
+    auto dump = [&](const std::vector<std::vector<std::pair<int, int>>>& lists, int count, int slot) {
+      section(slot);
+      int32_t acc = 0;
+      t.push_back(0);
+      for (int r = 0; r < count; ++r) {
+        acc += (int32_t)lists[r].size();
+        t.push_back(acc);
+      }
+      while (t.size() % 2 != 0) t.push_back(0);
+      section(slot + 1);
+      for (int r = 0; r < count; ++r)
+        for (const auto& e : lists[r]) {
+          t.push_back(e.first);
+          t.push_back(e.second);
+        }
+    };
+    dump(by_row, n_rows, slot_rptr);
+    dump(by_col, nx, slot_rptr + 2);
+  };
+  views(ps.jac_eq, ps.n_eq, CT_JE_RPTR);
+  views(ps.jac_ineq, ps.n_ineq, CT_JI_RPTR);
+
+  // ---- tapes: partitioned so that the interpreter's work arrays fit in shared memory ----
+  // Shared memory of a CTA (doubles): [ red | ints | vals + 1 | bp + 1 | free ].  While the KKT tape runs the factor is
+  // dead, so its work arrays w[slot][thread] may use everything after the ints; the f/c tape runs at trial points with
+  // the factor alive and gets the free tail only.
+  {
+    const int total = 227 * 1024 / 8;
+    const int fixed = 5 * (tpb / 32) + 4 + (sp.vals_size() + 1) + (n + 1);
+    const int kkt_cap = total - (5 * (tpb / 32) + 4);
+    const int fc_cap = total - fixed;
+    auto fit = [&](const Tape& tape, int cap, int* wstride) {
+      int nsub = tpb;
+      for (;;) {
+        PartTape pt = partition_tape(tape, nsub);
+        const int stride = ((pt.info.nsub + 31) / 32) * 32;
+        if ((int64_t)pt.n_work * stride <= cap) {
+          *wstride = stride;
+          return pt;
+        }
+        if (nsub <= 32) {
+          *wstride = 0;  // does not fit even with one warp of sub-tapes: thread-local work array
+          return partition_tape(tape, tpb);
+        }
+        nsub = std::max(32, std::min(nsub - 32, (cap / std::max(pt.n_work, 1)) / 32 * 32));
+      }
+    };
+    PartTape fc = fit(ps.fc, fc_cap, &pl.fc_wstride);
+    PartTape kkt = fit(ps.kkt, kkt_cap, &pl.kkt_wstride);
+    pl.fc = fc.info;
+    pl.kkt = kkt.info;
+    pl.n_work_fc = fc.n_work;
+    pl.n_work_kkt = kkt.n_work;
+    pl.n_work_pre = std::max(fc.pre.n_work, kkt.pre.n_work);
+    append_tape_section(t, CT_TAPE_FC, fc, ps.fc, pl.dtab);
+    append_tape_section(t, CT_TAPE_KKT, kkt, ps.kkt, pl.dtab);
+    const int fc_w = pl.fc_wstride * pl.n_work_fc, kkt_w = pl.kkt_wstride * pl.n_work_kkt;
+    pl.smem_doubles = std::max(fixed + fc_w, 5 * (tpb / 32) + 4 + kkt_w);
+  }
+  return pl;
+}
+
+size_t coop_scratch_doubles(const ProblemSource& ps, const CoopPlan& pl) {
+  const size_t nx = ps.nx, me = ps.n_eq, mi = ps.n_ineq;
+  return ps.np + 6 * nx + 6 * me + 10 * mi + ps.jac_eq.nnz() + ps.jac_ineq.nnz() + ps.hess.nnz() + (nx + me) + pl.fc.n_pe +
+         pl.kkt.n_pe + std::max(pl.fc.n_part, pl.kkt.n_part) + 8;
+}
+
+std::string emit_coop_source(const ProblemSource& ps, const CoopPlan& pl, int tpb) {
+  std::ostringstream o;
+  o << "// generated by libb200optas (bo_coop.cpp): cooperative tier, one instance per CTA, fully table-driven\n";
+  o << "#define BO_NX " << ps.nx << "\n#define BO_NP " << ps.np << "\n#define BO_ME " << ps.n_eq << "\n#define BO_MI "
+    << ps.n_ineq << "\n#define BO_NNZ_JE " << ps.jac_eq.nnz() << "\n#define BO_NNZ_JI " << ps.jac_ineq.nnz()
+    << "\n#define BO_NNZ_H " << ps.hess.nnz() << "\n#define BO_TPB " << tpb << "\n";
+  o << "#define BO_COOP 1\n#define BO_VALS " << pl.vals_size() << "\n#define BO_NWORK_FC " << pl.n_work_fc << "\n#define BO_NWORK_KKT "
+    << pl.n_work_kkt << "\n#define BO_NWORK_PRE " << pl.n_work_pre << "\n#define BO_FC_WSTRIDE " << pl.fc_wstride
+    << "\n#define BO_KKT_WSTRIDE " << pl.kkt_wstride << "\n#define BO_SMEM_DOUBLES " << pl.smem_doubles << "\n#define BO_NPE_FC "
+    << pl.fc.n_pe << "\n#define BO_NPE_KKT " << pl.kkt.n_pe << "\n#define BO_NPART " << std::max(pl.fc.n_part, pl.kkt.n_part) << "\n";
+  o << "#include \"bo_common.cuh\"\n#include \"bo_ipm_cta.cuh\"\n";
+  return o.str();
+}
+
+}  // namespace bo

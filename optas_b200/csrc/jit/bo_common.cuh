@@ -38,6 +38,7 @@ __device__ __forceinline__ bool bo_isfinite(double v) { return isfinite(v); }
 #endif
 
 struct alignas(16) bo_int4 { int x, y, z, w; };
+struct alignas(8) bo_int2 { int x, y; };
 
 BO_DEVICE double bo_sign(double a) { return (double)((a > 0.0) - (a < 0.0)); }
 BO_DEVICE double bo_sq(double a) { return a * a; }

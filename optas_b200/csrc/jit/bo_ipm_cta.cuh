@@ -1,0 +1,1002 @@
+// bo_ipm_cta.cuh -- batched primal-dual interior-point solver, ONE PROBLEM INSTANCE PER CTA
+// (cooperative tier; the algorithm and its constants are those of bo_ipm_reg.cuh, which documents them).
+//
+// Replaces CasADiSolver._solve (optas/solver.py:386-398 -> casadi nlpsol("ipopt")) for horizon problems
+// (MPC / trajectory optimisation: example/point_mass_mpc.py, figure_eight_plan.py, dual_arm.py), whose
+// per-instance state does not fit a thread:
+//   * the sparse LDL' factor of the KKT system lives in SHARED memory and is computed by all threads of
+//     the CTA with a level-scheduled left-looking program in which every entry has exactly one owner
+//     (a group of BO_LDL_G lanes) -- deterministic, no atomics; one barrier per elimination-tree level;
+//   * the tapes are partitioned into independent sub-tapes (one per horizon stage), thread t interprets
+//     sub-tape t; the instruction streams of the 32 lanes of a warp are interleaved so that a warp reads
+//     512 contiguous bytes per step, and isomorphic stages run in lock step;
+//   * parameter-only sub-expressions (e.g. the FK of the current configuration that anchors a path) are
+//     evaluated once per instance;
+//   * triangular solves run on warp 0 with warp-level barriers only; everything else is thread-parallel
+//     gathers + block reductions with fixed summation order (bitwise reproducible for any batch split).
+// All tables come from bo_coop.cpp; this file has no problem-specific code (only the BO_* sizes).
+//
+// The same text compiles for the host (BO_HOST_SIM: one "thread", barriers and reductions are no-ops);
+// that build is the CPU test harness of the solver logic, never part of libb200optas.so.
+#pragma once
+#include "bo_common.cuh"
+#include "bo_opcodes.h"
+#define BO_OPX_NOP 5
+
+#define BO_NK (BO_NX + BO_ME)
+#define BO_DIM(n) ((n) > 0 ? (n) : 1)
+
+#ifndef BO_DC_SCALE
+#define BO_DC_SCALE 1e-8
+#endif
+#ifndef BO_STATIC_RHO
+#define BO_STATIC_RHO 1.0e6
+#endif
+#define BO_NFILTER 8
+#ifndef BO_LS_MAX
+#define BO_LS_MAX 16
+#endif
+#ifndef BO_HEAVY_MAX
+#define BO_HEAVY_MAX 5
+#endif
+#define BO_IC_MAX 60
+#define BO_PH_EVAL 0
+#define BO_PH_FACTOR 1
+#define BO_PH_TRIAL 2
+
+// header slots of the integer table (bo_coop.h)
+#define CT_N 0
+#define CT_NNZL 1
+#define CT_PERM 2
+#define CT_SIGN 3
+#define CT_NLEV 4
+#define CT_PROG_FAC 5
+#define CT_PROG_FWD 6
+#define CT_PROG_BWD 7
+#define CT_ANT 8
+#define CT_APOS 9
+#define CT_APTR 10
+#define CT_ATERM 11
+#define CT_JE_RPTR 12
+#define CT_JE_RENT 13
+#define CT_JE_CPTR 14
+#define CT_JE_CENT 15
+#define CT_JI_RPTR 16
+#define CT_JI_RENT 17
+#define CT_JI_CPTR 18
+#define CT_JI_CENT 19
+#define CT_TAPE_FC 20
+#define CT_TAPE_KKT 21
+#define TS_NSUB 0
+#define TS_CONST0 1
+#define TS_NPE 2
+#define TS_NPART 3
+#define TS_PRE_N 4
+#define TS_PRE_OFF 5
+#define TS_LEN_OFF 6
+#define TS_WBASE_OFF 7
+#define TS_STREAM_OFF 8
+#define TS_NRED 9
+#define TS_RED_OFF 10
+#define TS_PART_SEG 11
+#define TS_PE_SEG 12
+
+// ---------------------------------------------------------------------------------------------------
+// thread / barrier / reduction primitives
+// ---------------------------------------------------------------------------------------------------
+#ifdef BO_HOST_SIM
+#define BO_TID 0
+#define BO_NT 1
+static inline void bo_sync() {}
+static inline void bo_syncwarp() {}
+static inline double bo_shfl_xor(double v, int) { return v; }
+#else
+#define BO_TID ((int)threadIdx.x)
+#define BO_NT BO_TPB
+__device__ __forceinline__ void bo_sync() { __syncthreads(); }
+__device__ __forceinline__ void bo_bar_warps(int n_warps) {  // barrier among warps 0..n_warps-1 (named barrier 1)
+  if (n_warps > 1) asm volatile("bar.sync 1, %0;" ::"r"(n_warps * 32) : "memory");
+  else __syncwarp();
+}
+__device__ __forceinline__ void bo_syncwarp() { __syncwarp(); }
+__device__ __forceinline__ double bo_shfl_xor(double v, int m) { return __shfl_xor_sync(0xffffffffu, v, m); }
+#endif
+#define BO_PAR(i, n) for (int i = BO_TID; i < (n); i += BO_NT)
+
+// Shared memory of a CTA (doubles): [ red | 4 (ints) | vals + 1 | bp + 1 | free ]  -- BO_SMEM_DOUBLES in all, sized by
+// bo_coop.cpp.  On the device the arrays are addressed off the __shared__ symbol so that the compiler emits
+// LDS/STS with folded offsets instead of generic loads through a pointer kept in a struct.
+#define BO_SM_RED 0
+#define BO_SM_INTS (5 * (BO_TPB / 32))
+#define BO_SM_VALS (BO_SM_INTS + 4)
+#define BO_SM_BP (BO_SM_VALS + BO_VALS + 1)
+#define BO_SM_FREE (BO_SM_BP + BO_NK + 1)
+#ifdef BO_HOST_SIM
+#define BO_VALS_P(C) ((C).vals)
+#define BO_BP_P(C) ((C).bp)
+#define BO_RED_P(C) ((C).red)
+#define BO_WKKT_P(C) ((C).wkkt)
+#define BO_WFC_P(C) ((C).wfc)
+#else
+extern __shared__ double bo_smem[];
+#define BO_VALS_P(C) (bo_smem + BO_SM_VALS)
+#define BO_BP_P(C) (bo_smem + BO_SM_BP)
+#define BO_RED_P(C) (bo_smem + BO_SM_RED)
+#define BO_WKKT_P(C) (bo_smem + BO_SM_VALS)
+#define BO_WFC_P(C) (bo_smem + BO_SM_FREE)
+#endif
+
+#define BO_RED_SUM 0
+#define BO_RED_MAX 1
+#define BO_RED_MIN 2
+BO_DEVICE double bo_red_op(int op, double a, double b) { return op == BO_RED_SUM ? a + b : (op == BO_RED_MAX ? fmax(a, b) : fmin(a, b)); }
+
+// Reduce K values at once over the CTA; every thread receives all results.  Fixed tree: lanes by
+// xor-shuffle, then the warps in index order -- the same bits for any launch geometry with this BO_TPB.
+template <int K>
+BO_DEVICE void bo_reduce(double (&v)[K], const int (&op)[K], double* red) {
+#ifndef BO_HOST_SIM
+  for (int off = 16; off > 0; off >>= 1)
+    for (int k = 0; k < K; ++k) v[k] = bo_red_op(op[k], v[k], bo_shfl_xor(v[k], off));
+  if (BO_NT > 32) {
+    const int warp = BO_TID >> 5, lane = BO_TID & 31;
+    if (lane == 0)
+      for (int k = 0; k < K; ++k) red[warp * K + k] = v[k];
+    __syncthreads();
+    for (int k = 0; k < K; ++k) {
+      double r = red[k];
+      for (int w = 1; w < BO_NT / 32; ++w) r = bo_red_op(op[k], r, red[w * K + k]);
+      v[k] = r;
+    }
+    __syncthreads();
+  }
+#else
+  (void)v; (void)op; (void)red;
+#endif
+}
+
+// ---------------------------------------------------------------------------------------------------
+// per-CTA workspace
+// ---------------------------------------------------------------------------------------------------
+// vectors of one instance, in a per-CTA slice of global scratch (L1/L2 resident: <= 150 KB per CTA)
+#define BO_OFF_P 0
+#define BO_OFF_X (BO_OFF_P + BO_NP)
+#define BO_OFF_S (BO_OFF_X + BO_NX)
+#define BO_OFF_Y (BO_OFF_S + BO_MI)
+#define BO_OFF_Z (BO_OFF_Y + BO_ME)
+#define BO_OFF_G (BO_OFF_Z + BO_MI)
+#define BO_OFF_CE (BO_OFF_G + BO_NX)
+#define BO_OFF_CI (BO_OFF_CE + BO_ME)
+#define BO_OFF_RD (BO_OFF_CI + BO_MI)
+#define BO_OFF_SIG (BO_OFF_RD + BO_NX)
+#define BO_OFF_JE (BO_OFF_SIG + BO_MI)
+#define BO_OFF_JI (BO_OFF_JE + BO_NNZ_JE)
+#define BO_OFF_H (BO_OFF_JI + BO_NNZ_JI)
+#define BO_OFF_SOL (BO_OFF_H + BO_NNZ_H)
+#define BO_OFF_DX (BO_OFF_SOL + BO_NK)
+#define BO_OFF_DS (BO_OFF_DX + BO_NX)
+#define BO_OFF_YST (BO_OFF_DS + BO_MI)
+#define BO_OFF_DX0 (BO_OFF_YST + BO_ME)
+#define BO_OFF_DS0 (BO_OFF_DX0 + BO_NX)
+#define BO_OFF_RE (BO_OFF_DS0 + BO_MI)
+#define BO_OFF_RI (BO_OFF_RE + BO_ME)
+#define BO_OFF_XT (BO_OFF_RI + BO_MI)
+#define BO_OFF_ST (BO_OFF_XT + BO_NX)
+#define BO_OFF_CET (BO_OFF_ST + BO_MI)
+#define BO_OFF_CIT (BO_OFF_CET + BO_ME)
+#define BO_OFF_TV (BO_OFF_CIT + BO_MI)
+#define BO_OFF_T2 (BO_OFF_TV + BO_MI)
+#define BO_OFF_PEF (BO_OFF_T2 + BO_ME)
+#define BO_OFF_PEK (BO_OFF_PEF + BO_NPE_FC)
+#define BO_OFF_PART (BO_OFF_PEK + BO_NPE_KKT)
+#define BO_OFF_F (BO_OFF_PART + BO_NPART)
+#define BO_SCRATCH_DOUBLES (BO_OFF_F + 8)
+
+#if defined(BO_PROFILE) && !defined(BO_HOST_SIM)
+#define BO_PROF_BEGIN() const long long bo_prof_t0 = clock64()
+#define BO_PROF_END(k) do { if (BO_TID == 0) C.prof[k] += clock64() - bo_prof_t0; } while (0)
+#else
+#define BO_PROF_BEGIN() do { } while (0)
+#define BO_PROF_END(k) do { } while (0)
+#endif
+
+struct bo_cta {
+  long long* prof;  // shared: cycle counters per phase (BO_PROFILE builds)
+  double* wkkt;     // shared: work arrays of the KKT tape, w[slot][thread] (aliases vals/bp: the factor is dead then)
+  double* wfc;      // shared: work arrays of the f/c tape (free tail)
+  double* W;        // global scratch slice of this CTA
+  double* vals;     // shared: 1/D (elimination order) then the unscaled factor entries C = L D
+  double* bp;       // shared: right-hand side / solution in elimination order
+  double* red;      // shared: reduction scratch
+  int* ibuf;        // shared: small integers
+  const int32_t* tab;
+  const double* dtab;
+};
+
+// scalar state of the iteration: every thread of the CTA holds an identical copy (all control flow is CTA-uniform)
+struct bo_cta_state {
+  double fth[BO_NFILTER], fph[BO_NFILTER];
+  double f, mu, tau, dw_last, err0, theta_max, theta_min;
+  int nf, it, n_acceptable, phase, trips;
+  bool recalc_y, ls_mode;
+  double phi0, theta0, dw, dc, rho;
+  int attempt, heavy;
+  double a, a_trial, dphi, th_soc;
+  int ls, soc;
+};
+
+// ---------------------------------------------------------------------------------------------------
+// tape interpreter: thread t runs sub-tape t
+// ---------------------------------------------------------------------------------------------------
+// w[slot * wstride]: the work array is either thread-local (wstride 1) or a column of the shared-memory array
+// w[slot][thread] (wstride = a multiple of 32: conflict-free whatever slots the lanes of a warp touch).
+// The rows of a lane are `stride` int4 apart; they are fetched BO_ROW_CHUNK at a time, one chunk ahead
+// (independent loads in flight; the stream is sequential and L2 resident).
+#define BO_ROW_CHUNK 8
+BO_DEVICE void bo_interp_rows(const bo_int4* BO_RESTRICT rows, int n, int stride, const double* BO_RESTRICT consts,
+                              double* BO_RESTRICT w, int wstride, const double* const* in, double* const* out) {
+#define BO_W(i) w[(i) * wstride]
+  bo_int4 nxt[BO_ROW_CHUNK];
+  BO_UNROLL
+  for (int u = 0; u < BO_ROW_CHUNK; ++u) nxt[u] = u < n ? rows[(long long)u * stride] : bo_int4{BO_OPX_NOP, 0, 0, 0};
+  for (int base = 0; base < n; base += BO_ROW_CHUNK) {
+    bo_int4 cur[BO_ROW_CHUNK];
+    BO_UNROLL
+    for (int u = 0; u < BO_ROW_CHUNK; ++u) cur[u] = nxt[u];
+    BO_UNROLL
+    for (int u = 0; u < BO_ROW_CHUNK; ++u) {
+      const int i = base + BO_ROW_CHUNK + u;
+      nxt[u] = i < n ? rows[(long long)i * stride] : bo_int4{BO_OPX_NOP, 0, 0, 0};
+    }
+    BO_UNROLL
+    for (int u = 0; u < BO_ROW_CHUNK; ++u) {
+      const int op = cur[u].x & 0xFF, dst = cur[u].y, a = cur[u].z, b = cur[u].w;
+      double r;
+      switch (op) {
+        case BO_OPX_NOP: continue;
+        case BO_OP_INPUT: r = in[b][a]; break;
+        case BO_OP_CONST: r = consts[a]; break;
+        case BO_OP_OUTPUT: out[b][a] = BO_W(dst); continue;
+        case BO_OP_ADD: r = BO_W(a) + BO_W(b); break;
+        case BO_OP_SUB: r = BO_W(a) - BO_W(b); break;
+        case BO_OP_MUL: r = BO_W(a) * BO_W(b); break;
+        case BO_OP_DIV: r = BO_W(a) / BO_W(b); break;
+        case BO_OP_NEG: r = -BO_W(a); break;
+        case BO_OP_SQ: r = BO_W(a) * BO_W(a); break;
+        case BO_OP_SQRT: r = sqrt(BO_W(a)); break;
+        case BO_OP_SIN: r = sin(BO_W(a)); break;
+        case BO_OP_COS: r = cos(BO_W(a)); break;
+        case BO_OP_TAN: r = tan(BO_W(a)); break;
+        case BO_OP_ASIN: r = asin(BO_W(a)); break;
+        case BO_OP_ACOS: r = acos(BO_W(a)); break;
+        case BO_OP_ATAN: r = atan(BO_W(a)); break;
+        case BO_OP_ATAN2: r = atan2(BO_W(a), BO_W(b)); break;
+        case BO_OP_FABS: r = fabs(BO_W(a)); break;
+        case BO_OP_FMIN: r = fmin(BO_W(a), BO_W(b)); break;
+        case BO_OP_FMAX: r = fmax(BO_W(a), BO_W(b)); break;
+        case BO_OP_EXP: r = exp(BO_W(a)); break;
+        case BO_OP_LOG: r = log(BO_W(a)); break;
+        case BO_OP_POW: r = pow(BO_W(a), BO_W(b)); break;
+        case BO_OP_TANH: r = tanh(BO_W(a)); break;
+        case BO_OP_SINH: r = sinh(BO_W(a)); break;
+        case BO_OP_COSH: r = cosh(BO_W(a)); break;
+        case BO_OP_FLOOR: r = floor(BO_W(a)); break;
+        case BO_OP_CEIL: r = ceil(BO_W(a)); break;
+        case BO_OP_SIGN: r = bo_sign(BO_W(a)); break;
+        case BO_OP_NOT: r = (double)(BO_W(a) == 0.0); break;
+        case BO_OP_LT: r = (double)(BO_W(a) < BO_W(b)); break;
+        case BO_OP_LE: r = (double)(BO_W(a) <= BO_W(b)); break;
+        case BO_OP_EQ: r = (double)(BO_W(a) == BO_W(b)); break;
+        case BO_OP_NE: r = (double)(BO_W(a) != BO_W(b)); break;
+        case BO_OP_AND: r = (double)((BO_W(a) != 0.0) && (BO_W(b) != 0.0)); break;
+        case BO_OP_OR: r = (double)((BO_W(a) != 0.0) || (BO_W(b) != 0.0)); break;
+        case BO_OP_IF_ELSE: r = BO_W((unsigned)cur[u].x >> 8) != 0.0 ? BO_W(a) : BO_W(b); break;
+        default: r = BO_NAN;
+      }
+      BO_W(dst) = r;
+    }
+  }
+#undef BO_W
+}
+
+// Run a partitioned tape: in/out are the segment pointers with room for the extra segments (in[pe_seg] =
+// parameter-only values, out[part_seg] = partial sums).  ws/wstride: shared-memory work arrays (wstride 0: use a
+// thread-local array of NW doubles).  Ends with a barrier.
+template <int NW>
+BO_DEVICE void bo_cta_tape_run(const bo_cta& C, int slot, const double** in, double** out, double* pe, double* part, double* ws,
+                               int wstride) {
+  const int32_t* sec = C.tab + C.tab[slot];
+  const double* consts = C.dtab + sec[TS_CONST0];
+  in[sec[TS_PE_SEG]] = pe;
+  out[sec[TS_PART_SEG]] = part;
+  const int nsub = sec[TS_NSUB];
+  const int32_t* len = C.tab + sec[TS_LEN_OFF];
+  const int32_t* wbase = C.tab + sec[TS_WBASE_OFF];
+  const bo_int4* stream = reinterpret_cast<const bo_int4*>(C.tab + sec[TS_STREAM_OFF]);
+#ifdef BO_HOST_SIM
+  double wl[NW];
+  for (int t = 0; t < nsub; ++t) bo_interp_rows(stream + wbase[t >> 5] + (t & 31), len[t], 32, consts, wl, 1, in, out);
+  (void)ws; (void)wstride;
+#else
+  if (wstride > 0) {
+    if (BO_TID < nsub) bo_interp_rows(stream + wbase[BO_TID >> 5] + (BO_TID & 31), len[BO_TID], 32, consts, ws + BO_TID, wstride, in, out);
+  } else {
+    double wl[NW];
+    for (int t = BO_TID; t < nsub; t += BO_NT) bo_interp_rows(stream + wbase[t >> 5] + (t & 31), len[t], 32, consts, wl, 1, in, out);
+  }
+#endif
+  bo_sync();
+  const int nred = sec[TS_NRED];
+  const int32_t* red = C.tab + sec[TS_RED_OFF];
+  BO_PAR(r, nred) {
+    const int32_t* e = red + 4 * r;
+    double acc = part[e[2]];
+    for (int k = 1; k < e[3]; ++k) acc += part[e[2] + k];
+    out[e[0]][e[1]] = acc;
+  }
+  bo_sync();
+}
+BO_NOINLINE void bo_cta_tape_fc(const bo_cta& C, const double** in, double** out) {
+  BO_PROF_BEGIN();
+  bo_cta_tape_run<BO_NWORK_FC>(C, CT_TAPE_FC, in, out, C.W + BO_OFF_PEF, C.W + BO_OFF_PART, BO_WFC_P(C), BO_FC_WSTRIDE);
+  BO_PROF_END(1);
+}
+BO_NOINLINE void bo_cta_tape_kkt(const bo_cta& C, const double** in, double** out) {
+  BO_PROF_BEGIN();
+  bo_cta_tape_run<BO_NWORK_KKT>(C, CT_TAPE_KKT, in, out, C.W + BO_OFF_PEK, C.W + BO_OFF_PART, BO_WKKT_P(C), BO_KKT_WSTRIDE);
+  BO_PROF_END(0);
+}
+
+// once per instance: the parameter-only sub-expressions of both tapes
+BO_NOINLINE void bo_cta_pre(const bo_cta& C) {
+  double w[BO_NWORK_PRE];
+  for (int which = 0; which < 2; ++which) {
+    // one thread each (different warps when there are several), sequential rows
+    const int owner = (which == 0 || BO_NT <= 32) ? 0 : 32;
+    if (BO_TID != owner % BO_NT) continue;
+    const int32_t* sec = C.tab + C.tab[which == 0 ? CT_TAPE_FC : CT_TAPE_KKT];
+    const double* in[2] = {nullptr, C.W + BO_OFF_P};
+    double* out[1] = {C.W + (which == 0 ? BO_OFF_PEF : BO_OFF_PEK)};
+    bo_interp_rows(reinterpret_cast<const bo_int4*>(C.tab + sec[TS_PRE_OFF]), sec[TS_PRE_N], 1, C.dtab + sec[TS_CONST0], w, 1, in, out);
+  }
+  bo_sync();
+}
+
+BO_DEVICE double bo_cta_eval_fc(const bo_cta& C, const double* x, double* cE, double* cI) {
+  const double* in[3] = {x, C.W + BO_OFF_P, nullptr};
+  double* out[4] = {C.W + BO_OFF_F, cE, cI, nullptr};
+  bo_cta_tape_fc(C, in, out);
+  return C.W[BO_OFF_F];
+}
+
+BO_DEVICE double bo_cta_eval_kkt(const bo_cta& C) {
+  double* W = C.W;
+  const double* in[5] = {W + BO_OFF_X, W + BO_OFF_P, W + BO_OFF_Y, W + BO_OFF_Z, nullptr};
+  double* out[8] = {W + BO_OFF_F, W + BO_OFF_G, W + BO_OFF_CE, W + BO_OFF_CI, W + BO_OFF_JE, W + BO_OFF_JI, W + BO_OFF_H, nullptr};
+  bo_cta_tape_kkt(C, in, out);
+  return W[BO_OFF_F];
+}
+
+// ---------------------------------------------------------------------------------------------------
+// Jacobian products as gathers (one owner per output element)
+// ---------------------------------------------------------------------------------------------------
+// sum over the entries of list `r` of J[nz] * v[other]
+BO_DEVICE double bo_gather(const int32_t* BO_RESTRICT ptr, const int32_t* BO_RESTRICT ent, int r, const double* BO_RESTRICT J,
+                           const double* BO_RESTRICT v) {
+  double acc = 0.0;
+  for (int e = ptr[r]; e < ptr[r + 1]; ++e) acc += J[ent[2 * e]] * v[ent[2 * e + 1]];
+  return acc;
+}
+#define BO_JE_T(c, v) bo_gather(C.tab + C.tab[CT_JE_CPTR], C.tab + C.tab[CT_JE_CENT], c, C.W + BO_OFF_JE, v)
+#define BO_JI_T(c, v) bo_gather(C.tab + C.tab[CT_JI_CPTR], C.tab + C.tab[CT_JI_CENT], c, C.W + BO_OFF_JI, v)
+#define BO_JI_ROW(r, v) bo_gather(C.tab + C.tab[CT_JI_RPTR], C.tab + C.tab[CT_JI_RENT], r, C.W + BO_OFF_JI, v)
+
+// ---------------------------------------------------------------------------------------------------
+// KKT assembly + level-scheduled sparse LDL' in shared memory
+// ---------------------------------------------------------------------------------------------------
+// vals <- K + diag(dw I, -dcp I): every position has one owner thread.  Ends with a barrier.
+BO_NOINLINE void bo_cta_assemble(const bo_cta& C, double rho, double dw, double dcp) {
+  BO_PROF_BEGIN();
+  double* vals = BO_VALS_P(C);
+  BO_PAR(i, BO_VALS) vals[i] = 0.0;
+  bo_sync();
+  const int32_t* t = C.tab;
+  const int nt = t[CT_ANT];
+  const int32_t* apos = t + t[CT_APOS];
+  const int32_t* aptr = t + t[CT_APTR];
+  const bo_int4* term = reinterpret_cast<const bo_int4*>(t + t[CT_ATERM]);
+  const int32_t* sign = t + t[CT_SIGN];
+  const double *H = C.W + BO_OFF_H, *JE = C.W + BO_OFF_JE, *JI = C.W + BO_OFF_JI, *sigma = C.W + BO_OFF_SIG;
+  BO_PAR(k, nt) {
+    const int pos = apos[k];
+    double acc = 0.0;
+    for (int e = aptr[k]; e < aptr[k + 1]; ++e) {
+      const bo_int4 q = term[e];
+      if (q.x == 0) acc += H[q.y];
+      else if (q.x == 1) acc += JE[q.y];
+      else if (q.x == 2) acc += sigma[q.w] * JI[q.y] * JI[q.z];
+      else acc += rho * JE[q.y] * JE[q.z];
+    }
+    if (pos < BO_NK) acc += sign[pos] > 0 ? dw : -dcp;
+    vals[pos] = acc;
+  }
+  if (BO_TID == 0) {  // padding operands of the lane programs
+    vals[BO_VALS] = 0.0;
+    BO_BP_P(C)[BO_NK] = 0.0;
+  }
+  bo_sync();
+  BO_PROF_END(2);
+}
+
+// Lane programs (bo_coop.cpp): warp-wide pre-scheduled streams, one 8-byte word per lane and step,
+//   x = a | FINISH << 15 | b << 16 | LEVEL_END << 31,   y = c | POSITIVE << 15 | tgt << 16
+// MODE 0 factor:   acc += vals[a] vals[b] vals[c];   finish: d = vals[tgt] - acc, diagonal: vals[tgt] = 1/d (+ pivot test)
+// MODE 1 forward:  acc += vals[a] bp[b];             finish: bp[tgt] = (bp[tgt] - acc) vals[tgt]
+// MODE 2 backward: acc += vals[a] bp[b];             finish: bp[tgt] -= acc vals[tgt]
+// Streams come in chunks of BO_LP_CHUNK steps; a level boundary always ends a chunk, and nothing written inside
+// a level is read inside it, so the operands of a whole chunk are fetched up front (independent shared-memory
+// loads) before its finishes run.  The words do not depend on the data: they are fetched BO_LP_AHEAD steps ahead.
+#define BO_LP_CHUNK 4
+#define BO_LP_AHEAD 16
+template <int MODE>
+BO_DEVICE void bo_lane_finish(const bo_cta& C, double* BO_RESTRICT vals, double* BO_RESTRICT bp, int tgt, bool positive, double acc) {
+  if (MODE == 0) {
+    const double a0 = vals[tgt];
+    const double d = a0 - acc;
+    if (tgt < BO_NK) {
+      const double scale = fmax(1.0, fabs(a0));
+      const bool bad = positive ? !(d > 1e-13 * scale) : !(d < -1e-13);
+#ifdef BO_HOST_SIM
+      if (bad && tgt < C.ibuf[0]) C.ibuf[0] = tgt;
+#else
+      if (bad) atomicMin(&C.ibuf[0], tgt);
+#endif
+      vals[tgt] = 1.0 / d;
+    } else {
+      vals[tgt] = d;
+    }
+  } else if (MODE == 1) {
+    bp[tgt] = (bp[tgt] - acc) * vals[tgt];
+  } else {
+    bp[tgt] -= acc * vals[tgt];
+  }
+}
+
+template <int MODE>
+BO_DEVICE void bo_lane_program(const bo_cta& C, int slot) {
+  const int32_t* h = C.tab + C.tab[slot];
+  const int W = h[0], G = h[1];
+  double* vals = BO_VALS_P(C);
+  double* bp = BO_BP_P(C);
+#ifdef BO_HOST_SIM
+  // faithful emulation: warps advance level by level, lanes in lock step, the same xor-tree for the group sums
+  int pc[32] = {0};
+  double acc[32][32];
+  for (int w = 0; w < W; ++w)
+    for (int l = 0; l < 32; ++l) acc[w][l] = 0.0;
+  bool more = true;
+  while (more) {
+    more = false;
+    for (int w = 0; w < W; ++w) {
+      const int32_t* s = C.tab + h[2] + 64LL * h[4 + 2 * w];
+      const int n = h[5 + 2 * w];
+      while (pc[w] < n) {
+        const int32_t* row = s + 64LL * pc[w];
+        for (int l = 0; l < 32; ++l) {
+          const unsigned x = (unsigned)row[2 * l], y = (unsigned)row[2 * l + 1];
+          const int a = x & 0x7FFFu, b = (x >> 16) & 0x7FFFu, c = y & 0x7FFFu;
+          acc[w][l] += MODE == 0 ? vals[a] * vals[b] * vals[c] : vals[a] * bp[b];
+        }
+        const unsigned x0 = (unsigned)row[0];
+        if (x0 & 0x8000u) {
+          for (int off = G >> 1; off > 0; off >>= 1) {
+            double t[32];
+            for (int l = 0; l < 32; ++l) t[l] = acc[w][l] + acc[w][l ^ off];
+            for (int l = 0; l < 32; ++l) acc[w][l] = t[l];
+          }
+          for (int l = 0; l < 32; ++l) {
+            const unsigned y = (unsigned)row[2 * l + 1];
+            const int tgt = (y >> 16) & 0x7FFFu;
+            if (tgt != 0x7FFF) bo_lane_finish<MODE>(C, vals, bp, tgt, (y & 0x8000u) != 0, acc[w][l]);
+            acc[w][l] = 0.0;
+          }
+        }
+        ++pc[w];
+        if (x0 & 0x80000000u) break;
+      }
+      more = more || pc[w] < n;
+    }
+  }
+#else
+  const int warp = BO_TID >> 5, lane = BO_TID & 31;
+  if (warp < W) {
+    const bo_int2* s = reinterpret_cast<const bo_int2*>(C.tab + h[2]) + 32LL * h[4 + 2 * warp] + lane;
+    const int n = h[5 + 2 * warp];  // a multiple of BO_LP_CHUNK
+    const bo_int2 pad = bo_int2{BO_VALS | (BO_VALS << 16), BO_VALS | (0x7FFF << 16)};
+    bo_int2 nxt[BO_LP_AHEAD];
+    BO_UNROLL
+    for (int u = 0; u < BO_LP_AHEAD; ++u) nxt[u] = u < n ? s[32 * u] : pad;
+    double acc = 0.0;
+    for (int base = 0; base < n; base += BO_LP_AHEAD) {
+      bo_int2 cur[BO_LP_AHEAD];
+      BO_UNROLL
+      for (int u = 0; u < BO_LP_AHEAD; ++u) cur[u] = nxt[u];
+      BO_UNROLL
+      for (int u = 0; u < BO_LP_AHEAD; ++u) {
+        const int i = base + BO_LP_AHEAD + u;
+        nxt[u] = i < n ? s[32 * i] : pad;
+      }
+      BO_UNROLL
+      for (int ch = 0; ch < BO_LP_AHEAD / BO_LP_CHUNK; ++ch) {
+        if (base + ch * BO_LP_CHUNK >= n) break;
+        double prod[BO_LP_CHUNK];
+        BO_UNROLL
+        for (int u = 0; u < BO_LP_CHUNK; ++u) {
+          const unsigned x = (unsigned)cur[ch * BO_LP_CHUNK + u].x, y = (unsigned)cur[ch * BO_LP_CHUNK + u].y;
+          const int a = x & 0x7FFFu, b = (x >> 16) & 0x7FFFu;
+          if (MODE == 0) prod[u] = vals[a] * vals[b] * vals[y & 0x7FFFu];
+          else prod[u] = vals[a] * bp[b];
+        }
+        BO_UNROLL
+        for (int u = 0; u < BO_LP_CHUNK; ++u) {
+          const unsigned x = (unsigned)cur[ch * BO_LP_CHUNK + u].x, y = (unsigned)cur[ch * BO_LP_CHUNK + u].y;
+          acc += prod[u];
+          if (x & 0x8000u) {
+            for (int off = G >> 1; off > 0; off >>= 1) acc += bo_shfl_xor(acc, off);
+            const int tgt = (y >> 16) & 0x7FFFu;
+            if (tgt != 0x7FFF) bo_lane_finish<MODE>(C, vals, bp, tgt, (y & 0x8000u) != 0, acc);
+            acc = 0.0;
+          }
+        }
+        if ((unsigned)cur[ch * BO_LP_CHUNK + BO_LP_CHUNK - 1].x & 0x80000000u) bo_bar_warps(W);
+      }
+    }
+  }
+#endif
+}
+
+// In-place factorisation.  On exit vals[j] = 1/D(j), vals[n+e] = C(i,j) = L(i,j) D(j).
+// Returns 0 ok, 1 = first bad pivot is in the x block (non-positive), 2 = in the y block (non-negative).
+BO_NOINLINE int bo_cta_factor(const bo_cta& C) {
+  BO_PROF_BEGIN();
+  if (BO_TID == 0) C.ibuf[0] = BO_NK;  // first bad pivot column (elimination order); BO_NK = none
+  bo_sync();
+  bo_lane_program<0>(C, CT_PROG_FAC);
+  bo_sync();
+  const int badcol = C.ibuf[0];
+  bo_sync();
+  BO_PROF_END(3);
+  if (badcol >= BO_NK) return 0;
+  return (C.tab + C.tab[CT_SIGN])[badcol] > 0 ? 1 : 2;
+}
+
+// Solve K b = b (b indexed by original row: x then y) with the factorisation in vals.  The substitutions run
+// on warp 0 (a level holds a couple of rows); ends with a CTA barrier.
+BO_NOINLINE void bo_cta_ldl_solve(const bo_cta& C, double* b) {
+  BO_PROF_BEGIN();
+  const int32_t* perm = C.tab + C.tab[CT_PERM];
+  double* bp = BO_BP_P(C);
+  BO_PAR(j, BO_NK) bp[j] = b[perm[j]];
+  bo_sync();
+  bo_lane_program<1>(C, CT_PROG_FWD);
+  bo_lane_program<2>(C, CT_PROG_BWD);
+  bo_sync();
+  BO_PAR(j, BO_NK) b[perm[j]] = bp[j];
+  bo_sync();
+  BO_PROF_END(4);
+}
+
+// ---------------------------------------------------------------------------------------------------
+// the iteration (transcription of bo_ipm_reg.cuh's trip functions with CTA-parallel vector work)
+// ---------------------------------------------------------------------------------------------------
+BO_DEVICE void bo_cta_measures(const bo_cta& C, double f, const double* cE, const double* cI, const double* s, double mu,
+                               double* phi, double* theta) {
+  double v[2] = {0.0, 0.0};
+  BO_PAR(j, BO_ME) v[0] += fabs(cE[j]);
+  BO_PAR(i, BO_MI) {
+    v[0] += fabs(cI[i] - s[i]);
+    v[1] += log(s[i]);
+  }
+  const int op[2] = {BO_RED_SUM, BO_RED_SUM};
+  bo_reduce<2>(v, op, BO_RED_P(C));
+  *theta = v[0];
+  *phi = f - mu * v[1];
+}
+
+BO_DEVICE void bo_cta_init(bo_cta_state& S, const bo_cta& C, const bo_solver_params& prm) {
+  double* W = C.W;
+  S.mu = prm.mu_init;
+  S.dw_last = 0.0;
+  S.err0 = BO_INF;
+  S.theta_max = BO_INF;
+  S.theta_min = 0.0;
+  S.nf = 0;
+  S.it = 0;
+  S.n_acceptable = 0;
+  S.recalc_y = false;
+  S.ls_mode = false;
+  S.phase = BO_PH_EVAL;
+  S.trips = 0;
+  bo_cta_pre(C);
+  S.f = bo_cta_eval_fc(C, W + BO_OFF_X, W + BO_OFF_CE, W + BO_OFF_CI);
+  BO_PAR(i, BO_MI) {
+    const double ci = W[BO_OFF_CI + i];
+    const double s = fmax(ci, 1e-2 * fmax(1.0, fabs(ci)));
+    W[BO_OFF_S + i] = s;
+    W[BO_OFF_Z + i] = S.mu / s;
+  }
+  BO_PAR(j, BO_ME) W[BO_OFF_Y + j] = 0.0;
+  bo_sync();
+}
+
+// Step for the residuals (rE, rI) with the current factorisation: fills sol (dx, -dy), dx, ds; returns the
+// fraction-to-the-boundary primal step length.
+BO_NOINLINE double bo_cta_step(bo_cta_state& S, const bo_cta& C) {
+  double* W = C.W;
+  BO_PAR(i, BO_MI) W[BO_OFF_TV + i] = -(W[BO_OFF_Z + i] - S.mu / W[BO_OFF_S + i] + W[BO_OFF_SIG + i] * W[BO_OFF_RI + i]);
+  BO_PAR(j, BO_ME) {
+    W[BO_OFF_SOL + BO_NX + j] = -W[BO_OFF_RE + j];
+    W[BO_OFF_T2 + j] = -S.rho * W[BO_OFF_RE + j];
+  }
+  bo_sync();
+  BO_PAR(c, BO_NX) W[BO_OFF_SOL + c] = -W[BO_OFF_RD + c] + BO_JI_T(c, W + BO_OFF_TV) + BO_JE_T(c, W + BO_OFF_T2);
+  bo_sync();
+  bo_cta_ldl_solve(C, W + BO_OFF_SOL);
+  const double undo = 1.0 / (1.0 - S.rho * S.dc);
+  BO_PAR(j, BO_ME) W[BO_OFF_SOL + BO_NX + j] *= undo;
+  BO_PAR(i, BO_NX) W[BO_OFF_DX + i] = W[BO_OFF_SOL + i];
+  bo_sync();
+  double v[1] = {1.0};
+  BO_PAR(i, BO_MI) {
+    const double ds = BO_JI_ROW(i, W + BO_OFF_DX) + W[BO_OFF_RI + i];
+    W[BO_OFF_DS + i] = ds;
+    if (ds < 0.0) v[0] = fmin(v[0], -S.tau * W[BO_OFF_S + i] / ds);
+  }
+  const int op[1] = {BO_RED_MIN};
+  bo_reduce<1>(v, op, BO_RED_P(C));
+  bo_sync();
+  return v[0];
+}
+
+BO_DEVICE int bo_cta_trip_eval(bo_cta_state& S, const bo_cta& C, const bo_solver_params& prm) {
+  const double kappa_eps = 10.0, kappa_mu = 0.2, tau_min = 0.99, s_max = 100.0;
+  const double mu_min = prm.tol * 0.1;
+  double* W = C.W;
+  if (++S.trips > prm.max_trips) return BO_ST_MAX_ITER;
+  if (S.phase != BO_PH_EVAL) return -1;
+  S.f = bo_cta_eval_kkt(C);
+  if (S.recalc_y && BO_ME > 0) {
+    // least-squares multiplier estimate after a regularised step (see bo_ipm_reg.cuh)
+    S.recalc_y = false;
+    S.ls_mode = true;
+    BO_PAR(i, BO_NNZ_H) W[BO_OFF_H + i] = 0.0;
+    BO_PAR(i, BO_MI) W[BO_OFF_SIG + i] = 0.0;
+    bo_sync();
+    S.dw = 1.0;
+    S.dc = 1e-10;
+    S.phase = BO_PH_FACTOR;
+    return -1;
+  }
+  // residuals and the scaled optimality error
+  double v[5] = {0.0, 0.0, 0.0, 0.0, 0.0};  // e_dual, e_prim, e_comp0 (max) ; sum |y|, sum |z|
+  BO_PAR(c, BO_NX) {
+    const double rd = W[BO_OFF_G + c] - BO_JE_T(c, W + BO_OFF_Y) - BO_JI_T(c, W + BO_OFF_Z);
+    W[BO_OFF_RD + c] = rd;
+    v[0] = fmax(v[0], fabs(rd));
+  }
+  BO_PAR(j, BO_ME) {
+    v[1] = fmax(v[1], fabs(W[BO_OFF_CE + j]));
+    v[3] += fabs(W[BO_OFF_Y + j]);
+  }
+  BO_PAR(i, BO_MI) {
+    v[1] = fmax(v[1], fabs(W[BO_OFF_CI + i] - W[BO_OFF_S + i]));
+    v[2] = fmax(v[2], W[BO_OFF_S + i] * W[BO_OFF_Z + i]);
+    v[4] += fabs(W[BO_OFF_Z + i]);
+  }
+  {
+    const int op[5] = {BO_RED_MAX, BO_RED_MAX, BO_RED_MAX, BO_RED_SUM, BO_RED_SUM};
+    bo_reduce<5>(v, op, BO_RED_P(C));
+  }
+  const double e_dual = v[0], e_prim = v[1], e_comp0 = v[2], sum_z = v[4], sum_mult = v[3] + v[4];
+  const double s_d = (BO_ME + BO_MI) > 0 ? fmax(s_max, sum_mult / (double)BO_DIM(BO_ME + BO_MI)) / s_max : 1.0;
+  const double s_c = BO_MI > 0 ? fmax(s_max, sum_z / (double)BO_DIM(BO_MI)) / s_max : 1.0;
+  S.err0 = fmax(fmax(e_dual / s_d, e_prim), e_comp0 / s_c);
+#ifdef BO_HOST_TRACE
+  printf("it %3d f %.6e err0 %.3e (dual %.3e prim %.3e comp %.3e) mu %.2e nf %d dw_last %.2e\n", S.it, S.f, S.err0,
+         e_dual / s_d, e_prim, e_comp0 / s_c, S.mu, S.nf, S.dw_last);
+#endif
+  if (!bo_isfinite(S.err0) || !bo_isfinite(S.f)) return BO_ST_NUMERICAL;
+  if (S.err0 <= prm.tol) return BO_ST_CONVERGED;
+  S.n_acceptable = (S.err0 <= prm.acceptable_tol) ? S.n_acceptable + 1 : 0;
+  if (S.n_acceptable >= 15) return BO_ST_ACCEPTABLE;
+  if (S.it >= prm.max_iter) return BO_ST_MAX_ITER;
+  // barrier parameter update (monotone Fiacco-McCormick); resets the filter
+  if (BO_MI > 0) {
+    for (int rep = 0; rep < 8; ++rep) {
+      double w1[1] = {0.0};
+      BO_PAR(i, BO_MI) w1[0] = fmax(w1[0], fabs(W[BO_OFF_S + i] * W[BO_OFF_Z + i] - S.mu));
+      const int op[1] = {BO_RED_MAX};
+      bo_reduce<1>(w1, op, BO_RED_P(C));
+      const double err_mu = fmax(fmax(e_dual / s_d, e_prim), w1[0] / s_c);
+      if (err_mu <= kappa_eps * S.mu && S.mu > mu_min) {
+        S.mu = fmax(mu_min, fmin(kappa_mu * S.mu, S.mu * sqrt(S.mu)));
+        S.nf = 0;
+      } else {
+        break;
+      }
+    }
+  }
+  S.tau = fmax(tau_min, 1.0 - S.mu);
+  BO_PAR(i, BO_MI) W[BO_OFF_SIG + i] = W[BO_OFF_Z + i] / W[BO_OFF_S + i];
+  bo_cta_measures(C, S.f, W + BO_OFF_CE, W + BO_OFF_CI, W + BO_OFF_S, S.mu, &S.phi0, &S.theta0);
+  if (S.it == 0) {
+    S.theta_max = 1e4 * fmax(1.0, S.theta0);
+    S.theta_min = 1e-4 * fmax(1.0, S.theta0);
+  }
+  S.dw = 0.0;
+  S.dc = 0.0;
+  S.attempt = 0;
+  S.heavy = 0;
+  S.ls_mode = false;
+  S.phase = BO_PH_FACTOR;
+  bo_sync();
+  return -1;
+}
+
+BO_DEVICE int bo_cta_trip_factor(bo_cta_state& S, const bo_cta& C, const bo_solver_params& prm) {
+  double* W = C.W;
+  if (S.phase != BO_PH_FACTOR) return -1;
+  const double rho = S.ls_mode ? 0.0 : BO_STATIC_RHO;
+  S.rho = rho;
+  bo_cta_assemble(C, rho, S.dw, S.dc / (1.0 - rho * S.dc));
+  const int bad = bo_cta_factor(C);
+  const int inertia = bad == 0 ? 0 : (bad == 1 ? 1 : -1);
+  if (S.ls_mode) {
+    if (inertia == 0) {
+      BO_PAR(c, BO_NX) W[BO_OFF_SOL + c] = W[BO_OFF_G + c] - BO_JI_T(c, W + BO_OFF_Z);
+      BO_PAR(j, BO_ME) W[BO_OFF_SOL + BO_NX + j] = 0.0;
+      bo_sync();
+      bo_cta_ldl_solve(C, W + BO_OFF_SOL);
+      double v[1] = {0.0};
+      BO_PAR(j, BO_ME) v[0] = fmax(v[0], bo_isfinite(W[BO_OFF_SOL + BO_NX + j]) ? 0.0 : 1.0);
+      const int op[1] = {BO_RED_MAX};
+      bo_reduce<1>(v, op, BO_RED_P(C));
+      if (v[0] == 0.0) {
+        BO_PAR(j, BO_ME) W[BO_OFF_Y + j] = W[BO_OFF_SOL + BO_NX + j];
+      }
+      bo_sync();
+    }
+    S.ls_mode = false;
+    S.phase = BO_PH_EVAL;
+    return -1;
+  }
+#ifdef BO_HOST_TRACE
+  if (inertia != 0) printf("     inertia %d at dw %.3e dc %.3e\n", inertia, S.dw, S.dc);
+#endif
+  if (inertia != 0) {
+    if (inertia < 0 && BO_ME > 0 && S.dc == 0.0) {
+      S.dc = BO_DC_SCALE * sqrt(sqrt(S.mu));
+    } else if (S.dw == 0.0) {
+      S.dw = (S.dw_last == 0.0) ? 1e-4 : fmax(1e-20, S.dw_last / 3.0);
+    } else {
+      S.dw *= (S.dw_last == 0.0) ? 100.0 : 8.0;
+    }
+    if (++S.attempt > BO_IC_MAX || S.dw > 1e40) return S.err0 <= prm.acceptable_tol ? BO_ST_ACCEPTABLE : BO_ST_NUMERICAL;
+    return -1;
+  }
+  if (S.dw > 0.0 && S.heavy == 0) S.dw_last = S.dw;
+  BO_PAR(j, BO_ME) W[BO_OFF_RE + j] = W[BO_OFF_CE + j];
+  BO_PAR(i, BO_MI) W[BO_OFF_RI + i] = W[BO_OFF_CI + i] - W[BO_OFF_S + i];
+  bo_sync();
+  const double a_p = bo_cta_step(S, C);
+  BO_PAR(j, BO_ME) W[BO_OFF_YST + j] = -W[BO_OFF_SOL + BO_NX + j];
+  double v[3] = {0.0, 0.0, 0.0};  // g'dx, sum ds/s, max |dx|
+  BO_PAR(i, BO_NX) {
+    v[0] += W[BO_OFF_G + i] * W[BO_OFF_DX + i];
+    v[2] = fmax(v[2], fabs(W[BO_OFF_DX + i]));
+  }
+  BO_PAR(i, BO_MI) v[1] += W[BO_OFF_DS + i] / W[BO_OFF_S + i];
+  {
+    const int op[3] = {BO_RED_SUM, BO_RED_SUM, BO_RED_MAX};
+    bo_reduce<3>(v, op, BO_RED_P(C));
+  }
+  S.dphi = v[0] - S.mu * v[1];
+  const double dxn = v[2];
+  S.a = a_p;
+  if (prm.max_step > 0.0 && S.a * dxn > prm.max_step) S.a = prm.max_step / dxn;
+  S.a_trial = S.a;
+  S.ls = 0;
+  S.soc = 0;
+  S.phase = BO_PH_TRIAL;
+  bo_sync();
+  return -1;
+}
+
+BO_DEVICE int bo_cta_trip_trial(bo_cta_state& S, const bo_cta& C, const bo_solver_params& prm) {
+  const double kappa_sigma = 1e10, gamma_theta = 1e-5, gamma_phi = 1e-5, eta_phi = 1e-8;
+  const double s_phi = 2.3, s_theta = 1.1, kappa_soc = 0.99;
+  double* W = C.W;
+  if (S.phase != BO_PH_TRIAL) return -1;
+  BO_PAR(i, BO_NX) W[BO_OFF_XT + i] = W[BO_OFF_X + i] + S.a_trial * W[BO_OFF_DX + i];
+  BO_PAR(i, BO_MI) W[BO_OFF_ST + i] = W[BO_OFF_S + i] + S.a_trial * W[BO_OFF_DS + i];
+  bo_sync();
+  const double ft = bo_cta_eval_fc(C, W + BO_OFF_XT, W + BO_OFF_CET, W + BO_OFF_CIT);
+  double phit, thetat;
+  bo_cta_measures(C, ft, W + BO_OFF_CET, W + BO_OFF_CIT, W + BO_OFF_ST, S.mu, &phit, &thetat);
+  const bool finite = bo_isfinite(phit) && bo_isfinite(thetat);
+  const bool ftype = S.dphi < 0.0 && S.theta0 <= S.theta_min &&
+                     (S.theta0 <= 0.0 || log(S.a) + s_phi * log(-S.dphi) > s_theta * log(S.theta0));
+  const double slack = 10.0 * 2.2e-16 * fabs(S.phi0);
+  bool ok = false, armijo = false;
+  if (finite && thetat <= S.theta_max) {
+    bool in_filter = true;
+    for (int j = 0; j < S.nf; ++j)
+      if (!(thetat <= (1.0 - gamma_theta) * S.fth[j] || phit <= S.fph[j] - gamma_phi * S.fth[j])) in_filter = false;
+    if (in_filter) {
+      if (ftype) {
+        armijo = phit - S.phi0 - slack <= eta_phi * S.a * S.dphi;
+        ok = armijo;
+      } else {
+        ok = thetat <= (1.0 - gamma_theta) * S.theta0 || phit - slack <= S.phi0 - gamma_phi * S.theta0;
+      }
+    }
+  }
+#ifdef BO_HOST_TRACE
+  printf("     heavy %d ls %d soc %d a %.3e ok %d ftype %d theta %.3e->%.3e phi %.8e->%.8e dphi %.3e dw %.2e\n", S.heavy, S.ls,
+         S.soc, S.a_trial, (int)ok, (int)ftype, S.theta0, thetat, S.phi0, phit, S.dphi, S.dw);
+#endif
+  if (ok) {
+    if (!(ftype && armijo)) {
+      int slot = S.nf;
+      if (S.nf < BO_NFILTER) {
+        ++S.nf;
+      } else {
+        slot = 0;
+        for (int j = 1; j < BO_NFILTER; ++j)
+          if (S.fth[j] > S.fth[slot]) slot = j;
+      }
+      S.fth[slot] = (1.0 - gamma_theta) * S.theta0;
+      S.fph[slot] = S.phi0 - gamma_phi * S.theta0;
+    }
+    // dual step with its own fraction-to-the-boundary rule (dz kept in TV)
+    double v[1] = {1.0};
+    BO_PAR(i, BO_MI) {
+      const double dz = -W[BO_OFF_Z + i] + S.mu / W[BO_OFF_S + i] - W[BO_OFF_SIG + i] * W[BO_OFF_DS + i];
+      W[BO_OFF_TV + i] = dz;
+      if (dz < 0.0) v[0] = fmin(v[0], -S.tau * W[BO_OFF_Z + i] / dz);
+    }
+    const int op[1] = {BO_RED_MIN};
+    bo_reduce<1>(v, op, BO_RED_P(C));
+    const double a_d = v[0];
+    BO_PAR(i, BO_NX) W[BO_OFF_X + i] = W[BO_OFF_XT + i];
+    BO_PAR(i, BO_MI) {
+      const double s = fmax(W[BO_OFF_ST + i], W[BO_OFF_CIT + i]);
+      W[BO_OFF_S + i] = s;
+      double z = W[BO_OFF_Z + i] + a_d * W[BO_OFF_TV + i];
+      z = fmax(fmin(z, kappa_sigma * S.mu / s), S.mu / (kappa_sigma * s));
+      W[BO_OFF_Z + i] = z;
+    }
+    BO_PAR(j, BO_ME) W[BO_OFF_Y + j] += S.a * W[BO_OFF_YST + j];
+    S.recalc_y = S.dw > 0.0 || S.dc > 0.0;
+    S.it += 1;
+    S.phase = BO_PH_EVAL;
+    bo_sync();
+    return -1;
+  }
+  bool try_soc = false;
+  if (S.soc == 0) {
+    if (S.ls == 0 && finite && thetat >= S.theta0 && (BO_ME + BO_MI) > 0) {
+      BO_PAR(i, BO_NX) W[BO_OFF_DX0 + i] = W[BO_OFF_DX + i];
+      BO_PAR(i, BO_MI) W[BO_OFF_DS0 + i] = W[BO_OFF_DS + i];
+      BO_PAR(j, BO_ME) W[BO_OFF_RE + j] = S.a * W[BO_OFF_CE + j] + W[BO_OFF_CET + j];
+      BO_PAR(i, BO_MI) W[BO_OFF_RI + i] = S.a * (W[BO_OFF_CI + i] - W[BO_OFF_S + i]) + (W[BO_OFF_CIT + i] - W[BO_OFF_ST + i]);
+      S.th_soc = thetat;
+      try_soc = true;
+    }
+  } else if (S.soc < 4 && finite && thetat <= kappa_soc * S.th_soc) {
+    BO_PAR(j, BO_ME) W[BO_OFF_RE + j] = S.a_trial * W[BO_OFF_RE + j] + W[BO_OFF_CET + j];
+    BO_PAR(i, BO_MI) W[BO_OFF_RI + i] = S.a_trial * W[BO_OFF_RI + i] + (W[BO_OFF_CIT + i] - W[BO_OFF_ST + i]);
+    S.th_soc = thetat;
+    try_soc = true;
+  }
+  if (try_soc) {
+    bo_sync();
+    S.a_trial = bo_cta_step(S, C);
+    S.soc += 1;
+    return -1;
+  }
+  if (S.soc > 0) {
+    BO_PAR(i, BO_NX) W[BO_OFF_DX + i] = W[BO_OFF_DX0 + i];
+    BO_PAR(i, BO_MI) W[BO_OFF_DS + i] = W[BO_OFF_DS0 + i];
+    bo_sync();
+    S.soc = 0;
+  }
+  S.a *= 0.5;
+  S.a_trial = S.a;
+  S.ls += 1;
+  if (S.ls >= BO_LS_MAX || S.a < 1e-12) {
+    if (++S.heavy >= BO_HEAVY_MAX) return S.err0 <= prm.acceptable_tol ? BO_ST_ACCEPTABLE : BO_ST_LINE_SEARCH;  // IPOPT: a failed step at an acceptable point ends "solved to acceptable level"
+    S.dw = fmax(S.dw * 100.0, 1.0);
+    S.phase = BO_PH_FACTOR;
+  }
+  return -1;
+}
+
+// One instance, start to finish.  W[P], W[X] hold the parameters and the seed on entry.
+BO_DEVICE int bo_cta_solve(bo_cta_state& S, const bo_cta& C, const bo_solver_params& prm) {
+  bo_cta_init(S, C, prm);
+  int status;
+  do {
+    status = bo_cta_trip_eval(S, C, prm);
+    if (status < 0) status = bo_cta_trip_factor(S, C, prm);
+    if (status < 0) status = bo_cta_trip_trial(S, C, prm);
+  } while (status < 0);
+  return status;
+}
+
+#ifndef BO_HOST_SIM
+// Persistent CTAs, instances fetched from a global counter.  Same signature as the thread-per-instance
+// kernel; prm.scratch = per-CTA vector workspace ([gridDim.x][BO_SCRATCH_DOUBLES]).
+extern "C" __global__ void __launch_bounds__(BO_TPB)
+bo_solve_kernel(long long B, const double* __restrict__ p_all, const double* __restrict__ x0_all,
+                double* __restrict__ x_all, double* __restrict__ lam_all, double* __restrict__ f_all,
+                int* __restrict__ status_all, int* __restrict__ iters_all, double* __restrict__ kkt_all,
+                unsigned long long* __restrict__ work_counter, const bo_solver_params prm) {
+  bo_cta C;
+  C.red = bo_smem + BO_SM_RED;
+  C.ibuf = reinterpret_cast<int*>(bo_smem + BO_SM_INTS);
+  C.prof = nullptr;
+  C.vals = bo_smem + BO_SM_VALS;
+  C.bp = bo_smem + BO_SM_BP;
+  C.wkkt = bo_smem + BO_SM_VALS;
+  C.wfc = bo_smem + BO_SM_FREE;
+#ifdef BO_PROFILE
+  __shared__ long long bo_prof[8];
+  C.prof = bo_prof;
+#endif
+  C.W = prm.scratch + (long long)blockIdx.x * BO_SCRATCH_DOUBLES;
+  C.tab = prm.ldl_tab;
+  C.dtab = prm.dtab;
+  bo_cta_state S;
+  while (true) {
+    if (threadIdx.x == 0) {
+      const unsigned long long b = atomicAdd(work_counter, 1ULL);
+      C.ibuf[1] = b < (unsigned long long)B ? (int)b : -1;
+    }
+    __syncthreads();
+    const long long b = C.ibuf[1];
+    __syncthreads();
+    if (b < 0) break;
+    BO_PAR(i, BO_NP) C.W[BO_OFF_P + i] = p_all[b * BO_NP + i];
+    BO_PAR(i, BO_NX) C.W[BO_OFF_X + i] = x0_all ? x0_all[b * BO_NX + i] : 0.0;
+    __syncthreads();
+#ifdef BO_PROFILE
+    if (threadIdx.x < 8) C.prof[threadIdx.x] = 0;
+    const long long bo_t_start = clock64();
+#endif
+    const int status = bo_cta_solve(S, C, prm);
+    __syncthreads();
+    BO_PAR(i, BO_NX) x_all[b * BO_NX + i] = C.W[BO_OFF_X + i];
+#ifdef BO_PROFILE
+    // profiling build: the first 8 doubles of x are replaced by the cycle counters
+    // (0 kkt tape, 1 f/c tape, 2 assembly, 3 factorisation, 4 solves, 7 whole instance)
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      C.prof[7] = clock64() - bo_t_start;
+      for (int k = 0; k < 8 && k < BO_NX; ++k) x_all[b * BO_NX + k] = (double)C.prof[k];
+    }
+#endif
+    if (lam_all) {
+      BO_PAR(j, BO_ME) lam_all[b * (BO_ME + BO_MI) + j] = C.W[BO_OFF_Y + j];
+      BO_PAR(i, BO_MI) lam_all[b * (BO_ME + BO_MI) + BO_ME + i] = C.W[BO_OFF_Z + i];
+    }
+    if (threadIdx.x == 0) {
+      if (f_all) f_all[b] = S.f;
+      if (status_all) status_all[b] = status;
+      if (iters_all) iters_all[b] = S.it;
+      if (kkt_all) kkt_all[b] = S.err0;
+    }
+    __syncthreads();
+  }
+}
+#endif

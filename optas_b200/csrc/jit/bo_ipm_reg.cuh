@@ -802,7 +802,7 @@ BO_DEVICE int bo_trip_factor(bo_ipm_state& S, const bo_solver_params prm) {
       } else {
         S.dw *= (S.dw_last == 0.0) ? 100.0 : 8.0;
       }
-      if (++S.attempt > BO_IC_MAX || S.dw > 1e40) return BO_ST_NUMERICAL;
+      if (++S.attempt > BO_IC_MAX || S.dw > 1e40) return S.err0 <= prm.acceptable_tol ? BO_ST_ACCEPTABLE : BO_ST_NUMERICAL;
       return -1;
     }
     if (S.dw > 0.0 && S.heavy == 0) S.dw_last = S.dw;
@@ -950,7 +950,7 @@ BO_DEVICE int bo_trip_trial(bo_ipm_state& S, const bo_solver_params prm) {
     if (S.ls >= BO_LS_MAX || S.a < 1e-12) {
       // no acceptable step along this direction: convexify harder (dw large => minimum-norm
       // feasibility step); this stands in for IPOPT's restoration phase on these small problems
-      if (++S.heavy >= BO_HEAVY_MAX) return BO_ST_LINE_SEARCH;
+      if (++S.heavy >= BO_HEAVY_MAX) return S.err0 <= prm.acceptable_tol ? BO_ST_ACCEPTABLE : BO_ST_LINE_SEARCH;  // IPOPT: a failed step at an acceptable point ends "solved to acceptable level"
       S.dw = fmax(S.dw * 100.0, 1.0);
       S.phase = BO_PH_FACTOR;
     }

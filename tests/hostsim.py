@@ -46,6 +46,70 @@ extern "C" void hostsim_solve(long long B, const double* p, const double* x0, do
 }
 """
 
+_WRAPPER_COOP = r"""
+#define BO_HOST_SIM 1
+#include <cstdio>
+#include <vector>
+%(trace)s
+#include "%(gen)s"
+extern "C" void hostsim_solve(long long B, const double* p, const double* x0, double* x, double* lam, double* f,
+                              int* status, int* iters, double* kkt, int* trips, int max_iter, double tol, double acc_tol,
+                              double mu_init, double max_step, int max_trips, const int* ldl_tab, const double* dtab, double* scratch) {
+  bo_solver_params prm;
+  prm.max_iter = max_iter; prm.tol = tol; prm.acceptable_tol = acc_tol; prm.mu_init = mu_init; prm.max_step = max_step; prm.max_trips = max_trips; prm.ldl_tab = ldl_tab; prm.dtab = dtab; prm.scratch = scratch; prm.scratch_stride = 1;
+  std::vector<double> W(BO_SCRATCH_DOUBLES), vals(BO_VALS + 1), bp(BO_NK + 1), red(64);
+  int ibuf[4];
+  bo_cta C;
+  C.W = W.data(); C.vals = vals.data(); C.bp = bp.data(); C.red = red.data(); C.ibuf = ibuf; C.tab = ldl_tab; C.dtab = dtab; C.prof = nullptr; C.wkkt = nullptr; C.wfc = nullptr;
+  for (long long b = 0; b < B; ++b) {
+    bo_cta_state S;
+    for (int i = 0; i < BO_NP; ++i) W[BO_OFF_P + i] = p[b * BO_NP + i];
+    for (int i = 0; i < BO_NX; ++i) W[BO_OFF_X + i] = x0 ? x0[b * BO_NX + i] : 0.0;
+    status[b] = bo_cta_solve(S, C, prm);
+    for (int i = 0; i < BO_NX; ++i) x[b * BO_NX + i] = W[BO_OFF_X + i];
+    for (int j = 0; j < BO_ME; ++j) lam[b * (BO_ME + BO_MI) + j] = W[BO_OFF_Y + j];
+    for (int i = 0; i < BO_MI; ++i) lam[b * (BO_ME + BO_MI) + BO_ME + i] = W[BO_OFF_Z + i];
+    f[b] = S.f; iters[b] = S.it; kkt[b] = S.err0; if (trips) trips[b] = S.trips;
+  }
+}
+// component probes for tests/test_coop_logic.py
+struct Probe {
+  std::vector<double> W, vals, bp, red; int ibuf[4]; bo_cta C;
+  Probe(const int* tab, const double* dtab) : W(BO_SCRATCH_DOUBLES), vals(BO_VALS + 1), bp(BO_NK + 1), red(64) {
+    C.W = W.data(); C.vals = vals.data(); C.bp = bp.data(); C.red = red.data(); C.ibuf = ibuf; C.tab = tab; C.dtab = dtab; C.prof = nullptr; C.wkkt = nullptr; C.wfc = nullptr;
+  }
+};
+static void cp(double* dst, const double* src, int n) { for (int i = 0; i < n; ++i) dst[i] = src[i]; }
+extern "C" void hostsim_coop_kkt(const int* tab, const double* dtab, const double* p, const double* x, const double* y, const double* z,
+                                 double* f, double* g, double* cE, double* cI, double* JE, double* JI, double* H) {
+  Probe P(tab, dtab); double* W = P.W.data();
+  cp(W + BO_OFF_P, p, BO_NP); cp(W + BO_OFF_X, x, BO_NX); cp(W + BO_OFF_Y, y, BO_ME); cp(W + BO_OFF_Z, z, BO_MI);
+  bo_cta_pre(P.C);
+  *f = bo_cta_eval_kkt(P.C);
+  cp(g, W + BO_OFF_G, BO_NX); cp(cE, W + BO_OFF_CE, BO_ME); cp(cI, W + BO_OFF_CI, BO_MI);
+  cp(JE, W + BO_OFF_JE, BO_NNZ_JE); cp(JI, W + BO_OFF_JI, BO_NNZ_JI); cp(H, W + BO_OFF_H, BO_NNZ_H);
+}
+extern "C" void hostsim_coop_fc(const int* tab, const double* dtab, const double* p, const double* x, double* f, double* cE, double* cI) {
+  Probe P(tab, dtab); double* W = P.W.data();
+  cp(W + BO_OFF_P, p, BO_NP); cp(W + BO_OFF_XT, x, BO_NX);
+  bo_cta_pre(P.C);
+  *f = bo_cta_eval_fc(P.C, W + BO_OFF_XT, W + BO_OFF_CET, W + BO_OFF_CIT);
+  cp(cE, W + BO_OFF_CET, BO_ME); cp(cI, W + BO_OFF_CIT, BO_MI);
+}
+// assemble K(H, JE, JI, sigma, rho) + diag(dw, -dcp), factor, solve K sol = rhs (in place).  Returns the factor's verdict.
+extern "C" int hostsim_coop_linsolve(const int* tab, const double* dtab, const double* H, const double* JE, const double* JI,
+                                     const double* sigma, double rho, double dw, double dcp, double* rhs) {
+  Probe P(tab, dtab); double* W = P.W.data();
+  cp(W + BO_OFF_H, H, BO_NNZ_H); cp(W + BO_OFF_JE, JE, BO_NNZ_JE); cp(W + BO_OFF_JI, JI, BO_NNZ_JI); cp(W + BO_OFF_SIG, sigma, BO_MI);
+  bo_cta_assemble(P.C, rho, dw, dcp);
+  const int bad = bo_cta_factor(P.C);
+  cp(W + BO_OFF_SOL, rhs, BO_NK);
+  bo_cta_ldl_solve(P.C, W + BO_OFF_SOL);
+  cp(rhs, W + BO_OFF_SOL, BO_NK);
+  return bad;
+}
+"""
+
 
 class HostSim:
     def __init__(self, generated_source: str, nx: int, np_: int, n_eq: int, n_ineq: int, trace: bool = False, defines: str = "",
@@ -55,7 +119,9 @@ class HostSim:
         self.ldl_table = None if ldl_table is None or len(ldl_table) == 0 else np.ascontiguousarray(ldl_table, dtype=np.int32)
         self.nx, self.np_, self.nl = nx, np_, n_eq + n_ineq
         key = hashlib.sha1(generated_source.encode()).hexdigest()[:16] + str(trace) + defines
-        for name in ("bo_common.cuh", "bo_ipm_reg.cuh"):
+        coop = "#define BO_COOP 1" in generated_source
+        key += hashlib.sha1((_WRAPPER_COOP if coop else _WRAPPER).encode()).hexdigest()[:8]
+        for name in ("bo_common.cuh", "bo_ipm_reg.cuh", "bo_ipm_cta.cuh"):
             key += hashlib.sha1(open(os.path.join(_JIT_INC, name), "rb").read()).hexdigest()[:8]
         d = os.path.join(tempfile.gettempdir(), "b200optas_hostsim")
         os.makedirs(d, exist_ok=True)
@@ -64,7 +130,7 @@ class HostSim:
             gen = os.path.join(d, f"gen_{os.getpid()}.cu")
             wrap = os.path.join(d, f"wrap_{os.getpid()}.cpp")
             open(gen, "w").write(generated_source)
-            open(wrap, "w").write(_WRAPPER % {"gen": gen, "trace": ("#define BO_HOST_TRACE 1\n" if trace else "") + defines})
+            open(wrap, "w").write((_WRAPPER_COOP if coop else _WRAPPER) % {"gen": gen, "trace": ("#define BO_HOST_TRACE 1\n" if trace else "") + defines})
             subprocess.run(["/usr/bin/g++", "-O1", "-shared", "-fPIC", "-std=c++17", "-I", _JIT_INC, "-I", os.path.join(_HERE, "..", "include"), wrap, "-o", so + ".tmp"],
                            check=True)
             os.replace(so + ".tmp", so)
