@@ -268,7 +268,11 @@ def run_other_config(args) -> None:
             "converged_fraction": float(c[0]) / float(c[1]), "mean_iterations": float(itd.float().mean().item()),
             "e2e": {"value": float(c[0]) * steps / float(t[1]), "unit": "instances/s",
                     "h2d_bytes_per_step": int(P.nbytes + X0.nbytes), "d2h_bytes_per_step": int(r["x"].nbytes + r["lam"].nbytes + 28 * B)},
-            "gpu_launches": steps, "solve_kernel": solver.kernel_info()}))
+            "gpu_launches": steps, "solve_kernel": solver.kernel_info(),
+            "tier": {k: v for k, v in solver.tier_info().items() if k in (
+                "tier", "threads_per_block", "smem_dynamic", "blocks_per_sm", "levels", "segments", "factor_vals",
+                "factor_madds", "factor_steps", "solve_steps", "ldl_warps", "ldl_g", "solve_g", "generated_tapes",
+                "kkt_components", "kkt_classes", "kkt_code_rows", "kkt_total_instr")}}))
     if dist is not None:
         dist.barrier()
         dist.destroy_process_group()

@@ -156,7 +156,8 @@ int bo_problem_kernel_info(const bo_problem* prob, int32_t* regs, int32_t* local
  *  [14] kkt components  [15] longest fc sub-tape  [16] fc instructions  [17] kkt once-per-instance instructions
  *  [18] per-CTA global workspace (doubles)  [19] factor values (doubles)  [20] resident CTAs per SM  [21] SMs
  *  [22] work slots of fc  [23] warps of the factor program  [24]/[25] steps of the longest factor / solve lane stream
- *  [26]/[27] stride of the shared-memory work arrays of kkt / fc (0: thread-local)                                */
+ *  [26]/[27] stride of the shared-memory work arrays of kkt / fc (0: thread-local)  [28] elimination segments
+ *  [29] tapes compiled per component class (1) or interpreted (0)  [30]/[31] classes / generated rows of kkt         */
 #define BO_TIER_INFO_LEN 32
 int bo_problem_tier_info(const bo_problem* prob, int64_t* info, int32_t cap);
 

@@ -229,7 +229,8 @@ class ProblemHandle:
         keys = ["tier", "threads_per_block", "smem_dynamic", "levels", "nsub_fc", "nsub_kkt", "n_pe_kkt", "n_partial",
                 "kkt_max_len", "kkt_total_instr", "ldl_g", "solve_g", "factor_madds", "n_work", "kkt_components",
                 "fc_max_len", "fc_total_instr", "kkt_pre_len", "scratch_doubles", "factor_vals", "blocks_per_sm", "n_sm",
-                "n_work_fc", "ldl_warps", "factor_steps", "solve_steps", "kkt_wstride", "fc_wstride"]
+                "n_work_fc", "ldl_warps", "factor_steps", "solve_steps", "kkt_wstride", "fc_wstride", "segments",
+                "generated_tapes", "kkt_classes", "kkt_code_rows"]
         d = {k: int(v[i]) for i, k in enumerate(keys)}
         d["tier"] = TIER_NAMES[d["tier"]]
         return d

@@ -551,11 +551,14 @@ int bo_problem_create(const bo_problem_desc* desc, const bo_options* opts_in, bo
     return set_err(BO_ERR_UNSUPPORTED, "bo_problem_create: BO_FLAG_PIVOTED_LDL is limited to nx+n_eq <= 160");
   // Cooperative tier (one instance per CTA, factor in shared memory; csrc/jit/bo_ipm_cta.cuh): the default for
   // everything the large tier used to take, on request (BO_FLAG_COOP) for any sparse-tier problem.
-  if (pr->sparse && !(pr->opts.flags & BO_FLAG_NO_COOP) && (pr->large || (pr->opts.flags & BO_FLAG_COOP))) {
+  if (pr->sparse && !(pr->opts.flags & BO_FLAG_NO_COOP)) {
     const int tpb = pr->opts.threads_per_block > 0 ? ((pr->opts.threads_per_block + 31) / 32) * 32 : (pr->large ? 256 : 64);
     bo::CoopPlan cp = bo::make_coop_plan(ps, tpb);
     const size_t smem = (size_t)cp.smem_doubles * sizeof(double);
-    if (cp.vals_size() + 1 < 32767 && ps.nx + ps.n_eq + 1 < 32767 && smem <= 227 * 1024) {
+    // worth it when the tapes split into enough independent pieces to occupy the CTA (horizon problems do: one
+    // piece per stage), or when the problem is too large for a thread anyway
+    const bool wanted = pr->large || (pr->opts.flags & BO_FLAG_COOP) || cp.kkt.n_components >= 16;
+    if (wanted && cp.vals_size() + 1 < 32767 && ps.nx + ps.n_eq + 1 < 32767 && smem <= 227 * 1024) {
       pr->coop = true;
       pr->large = false;
       pr->tpb = tpb;
@@ -702,6 +705,10 @@ int bo_problem_tier_info(const bo_problem* pr, int64_t* info, int32_t cap) {
     v[25] = cp.solve_steps;
     v[26] = cp.kkt_wstride;
     v[27] = cp.fc_wstride;
+    v[28] = cp.n_segments;
+    v[29] = cp.gen_tapes ? 1 : 0;
+    v[30] = cp.kkt.n_classes;
+    v[31] = cp.kkt.code_rows;
     v[14] = cp.kkt.n_components;
     v[15] = cp.fc.max_len;
     v[16] = cp.fc.total_instr;

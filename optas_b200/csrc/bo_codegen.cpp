@@ -116,7 +116,9 @@ TapeStats tape_stats(const Tape& tape) {
   return st;
 }
 
-std::string emit_tape_function(const Tape& tape, const std::string& name) {
+std::string emit_tape_function(const Tape& tape, const std::string& name) { return emit_tape_function(tape, name, nullptr); }
+
+std::string emit_tape_function(const Tape& tape, const std::string& name, const TapeEmitHooks* hooks) {
   const int64_t n = tape.n_instr();
   // pass 1: SSA operands (value ids = defining instruction index)
   std::vector<int64_t> cur(tape.n_work, -1), sa(n, -1), sb(n, -1), sc(n, -1);
@@ -151,17 +153,21 @@ std::string emit_tape_function(const Tape& tape, const std::string& name) {
   std::vector<char> emitted(n, 0);
 
   std::ostringstream o;
-  o << "BO_DEVICE void " << name << "(";
-  bool first = true;
-  for (size_t k = 0; k < tape.in_sizes.size(); ++k) {
-    o << (first ? "" : ", ") << "const double* BO_RESTRICT i" << k;
-    first = false;
+  if (hooks) {
+    o << hooks->signature << " {\n" << hooks->prologue;
+  } else {
+    o << "BO_DEVICE void " << name << "(";
+    bool first = true;
+    for (size_t k = 0; k < tape.in_sizes.size(); ++k) {
+      o << (first ? "" : ", ") << "const double* BO_RESTRICT i" << k;
+      first = false;
+    }
+    for (size_t k = 0; k < tape.out_sizes.size(); ++k) {
+      o << (first ? "" : ", ") << "double* BO_RESTRICT o" << k;
+      first = false;
+    }
+    o << ") {\n";
   }
-  for (size_t k = 0; k < tape.out_sizes.size(); ++k) {
-    o << (first ? "" : ", ") << "double* BO_RESTRICT o" << k;
-    first = false;
-  }
-  o << ") {\n";
   auto V = [](int64_t id) { return "v" + std::to_string(id); };
   for (int64_t i = 0; i < n; ++i) {
     const int32_t* r = &tape.instr[4 * i];
@@ -169,7 +175,8 @@ std::string emit_tape_function(const Tape& tape, const std::string& name) {
     if (emitted[i]) continue;
     const std::string a = sa[i] >= 0 ? V(sa[i]) : "", b = sb[i] >= 0 ? V(sb[i]) : "", c = sc[i] >= 0 ? V(sc[i]) : "";
     if (op == BO_OP_OUTPUT) {
-      o << "  o" << r[3] << "[" << r[2] << "] = " << a << ";\n";
+      if (hooks) o << "  " << hooks->output_stmt(i, r, a) << "\n";
+      else o << "  o" << r[3] << "[" << r[2] << "] = " << a << ";\n";
       continue;
     }
     if (op == BO_OP_SIN || op == BO_OP_COS) {
@@ -185,8 +192,14 @@ std::string emit_tape_function(const Tape& tape, const std::string& name) {
     }
     o << "  const double " << V(i) << " = ";
     switch (op) {
-      case BO_OP_INPUT: o << "i" << r[3] << "[" << r[2] << "]"; break;
-      case BO_OP_CONST: o << fmt_const(tape.consts[r[2]]); break;
+      case BO_OP_INPUT:
+        if (hooks) o << hooks->input_expr(i, r);
+        else o << "i" << r[3] << "[" << r[2] << "]";
+        break;
+      case BO_OP_CONST:
+        if (hooks && !hooks->const_expr(i, r).empty()) o << hooks->const_expr(i, r);
+        else o << fmt_const(tape.consts[r[2]]);
+        break;
       case BO_OP_ADD: o << a << " + " << b; break;
       case BO_OP_SUB: o << a << " - " << b; break;
       case BO_OP_MUL: o << a << " * " << b; break;

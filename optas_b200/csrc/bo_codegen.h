@@ -1,5 +1,6 @@
 // bo_codegen.h -- expression tape -> straight-line CUDA C++ (host side of libb200optas).
 #pragma once
+#include <functional>
 #include <string>
 #include <vector>
 
@@ -29,6 +30,14 @@ bool copy_sparsity(const bo_sparsity& in, int32_t n_rows, int32_t n_cols, bool l
 // Emit `BO_DEVICE void <name>(const double* i0, ..., double* o0, ...)` evaluating the tape.
 // sin/cos of the same operand are fused into one sincos.
 std::string emit_tape_function(const Tape& tape, const std::string& name);
+// Same with the function head and the leaf / store statements supplied by the caller (row = the 4-int instruction;
+// const_expr may return "" to get the literal).
+struct TapeEmitHooks {
+  std::string signature, prologue;
+  std::function<std::string(int64_t, const int32_t*)> input_expr, const_expr;
+  std::function<std::string(int64_t, const int32_t*, const std::string&)> output_stmt;
+};
+std::string emit_tape_function(const Tape& tape, const std::string& name, const TapeEmitHooks* hooks);
 
 // Count of floating-point operations (adds, muls, ... 1 each; sincos counted as 2 calls).
 struct TapeStats {

@@ -4,6 +4,8 @@
 
 #include <algorithm>
 #include <array>
+#include <cstdio>
+#include <cstdlib>
 #include <functional>
 #include <map>
 #include <numeric>
@@ -555,6 +557,180 @@ PartTape partition_tape(const Tape& tape, int max_threads) {
   return pt;
 }
 
+// ======================================================================================
+// Component classes: isomorphic components (same instruction rows up to which input / constant / output element
+// they touch -- all stages of a horizon problem) share ONE generated straight-line function
+// ======================================================================================
+struct TapeClass {
+  std::vector<int32_t> rows;           // representative rows
+  std::vector<int> members;            // component (sub-tape) indices
+  std::vector<int> var_rows;           // rows whose element index differs per member (INPUT / OUTPUT / non-uniform CONST)
+};
+
+std::vector<TapeClass> classify(const PartTape& pt, const Tape& tape) {
+  std::map<std::vector<int32_t>, int> ids;
+  std::vector<TapeClass> classes;
+  for (size_t k = 0; k < pt.subs.size(); ++k) {
+    const std::vector<int32_t>& rows = pt.subs[k].rows;
+    std::vector<int32_t> key(rows);
+    for (size_t i = 0; i < rows.size() / 4; ++i) {
+      const int op = rows[4 * i] & 0xFF;
+      if (op == BO_OP_INPUT || op == BO_OP_OUTPUT || op == BO_OP_CONST) key[4 * i + 2] = 0;
+    }
+    auto it = ids.find(key);
+    if (it == ids.end()) {
+      it = ids.emplace(std::move(key), (int)classes.size()).first;
+      classes.emplace_back();
+      classes.back().rows = rows;
+    }
+    classes[it->second].members.push_back((int)k);
+  }
+  for (TapeClass& c : classes) {
+    for (size_t i = 0; i < c.rows.size() / 4; ++i) {
+      const int op = c.rows[4 * i] & 0xFF;
+      if (op == BO_OP_INPUT || op == BO_OP_OUTPUT) {
+        bool same = true;
+        for (int m : c.members) same = same && pt.subs[m].rows[4 * i + 2] == c.rows[4 * i + 2];
+        if (!same) c.var_rows.push_back((int)i);
+      } else if (op == BO_OP_CONST) {
+        bool same = true;
+        const double v0 = tape.consts[c.rows[4 * i + 2]];
+        for (int m : c.members) {
+          const double v = tape.consts[pt.subs[m].rows[4 * i + 2]];
+          same = same && (v == v0 || (v != v && v0 != v0));
+        }
+        if (!same) c.var_rows.push_back((int)i);
+      }
+    }
+  }
+  return classes;
+}
+
+// Table section + CUDA source of a tape compiled per component class.  `pt` must hold ONE component per sub-tape
+// (partition_tape with an unlimited thread count).  Work lists: entries { class, index-table offset, stride, count }
+// = up to 32 members of one class, run by the 32 lanes of a warp in lock step; entries are spread over the warps
+// longest first.
+std::string append_gen_tape(std::vector<int32_t>& t, int slot, const PartTape& pt, const std::vector<TapeClass>& classes,
+                            const Tape& tape, std::vector<double>& dtab, int n_warps, const std::string& tag, CoopTapeInfo* info) {
+  while (t.size() % 4 != 0) t.push_back(0);
+  const size_t s0 = t.size();
+  t[slot] = (int32_t)s0;
+  t.resize(s0 + TS_HEADER, 0);
+  t[s0 + TS_NSUB] = 0;
+  t[s0 + TS_CONST0] = (int32_t)dtab.size();
+  dtab.insert(dtab.end(), tape.consts.begin(), tape.consts.end());
+  t[s0 + TS_NPE] = pt.n_pe;
+  t[s0 + TS_NPART] = pt.n_part;
+  t[s0 + TS_PART_SEG] = (int32_t)tape.out_sizes.size();
+  t[s0 + TS_PE_SEG] = (int32_t)tape.in_sizes.size();
+  t[s0 + TS_PRE_N] = (int32_t)pt.pre.rows.size() / 4;
+  t[s0 + TS_PRE_OFF] = (int32_t)t.size();
+  t.insert(t.end(), pt.pre.rows.begin(), pt.pre.rows.end());
+  t[s0 + TS_NRED] = (int32_t)pt.red.size() / 4;
+  t[s0 + TS_RED_OFF] = (int32_t)t.size();
+  t.insert(t.end(), pt.red.begin(), pt.red.end());
+  // index tables: per class [var][member]
+  std::vector<int32_t> ix_off(classes.size(), 0);
+  for (size_t c = 0; c < classes.size(); ++c) {
+    const TapeClass& cl = classes[c];
+    ix_off[c] = (int32_t)t.size();
+    for (int row : cl.var_rows)
+      for (int m : cl.members) t.push_back(pt.subs[m].rows[4 * row + 2]);
+  }
+  // work lists
+  struct Entry {
+    int cls, first, count;
+    int64_t cost;
+  };
+  std::vector<Entry> entries;
+  for (size_t c = 0; c < classes.size(); ++c)
+    for (int first = 0; first < (int)classes[c].members.size(); first += 32)
+      entries.push_back({(int)c, first, std::min(32, (int)classes[c].members.size() - first), (int64_t)classes[c].rows.size() / 4});
+  std::stable_sort(entries.begin(), entries.end(), [](const Entry& a, const Entry& b) { return a.cost > b.cost; });
+  std::vector<std::vector<Entry>> per_warp(n_warps);
+  std::vector<int64_t> load(n_warps, 0);
+  for (const Entry& e : entries) {
+    int best = 0;
+    for (int w = 1; w < n_warps; ++w)
+      if (load[w] < load[best]) best = w;
+    load[best] += e.cost + 4;
+    per_warp[best].push_back(e);
+  }
+  t[s0 + TS_GEN_NWARP] = n_warps;
+  t[s0 + TS_GEN_WL_OFF] = (int32_t)t.size();
+  const size_t wl0 = t.size();
+  t.resize(wl0 + 2 * (size_t)n_warps, 0);
+  for (int w = 0; w < n_warps; ++w) {
+    t[wl0 + 2 * w] = (int32_t)t.size();
+    t[wl0 + 2 * w + 1] = (int32_t)per_warp[w].size();
+    for (const Entry& e : per_warp[w]) {
+      t.push_back(e.cls);
+      t.push_back(ix_off[e.cls] + e.first);
+      t.push_back((int32_t)classes[e.cls].members.size());
+      t.push_back(e.count);
+    }
+  }
+  info->n_classes = (int)classes.size();
+  info->warp_rows = *std::max_element(load.begin(), load.end());
+
+  // code
+  std::ostringstream o;
+  const int n_in = (int)tape.in_sizes.size() + 1, n_out = (int)tape.out_sizes.size() + 1;
+  for (size_t c = 0; c < classes.size(); ++c) {
+    const TapeClass& cl = classes[c];
+    Tape ct;
+    ct.instr = cl.rows;
+    ct.consts = tape.consts;
+    ct.n_work = 1;
+    for (size_t i = 0; i < cl.rows.size() / 4; ++i) ct.n_work = std::max(ct.n_work, cl.rows[4 * i + 1] + 1);
+    std::map<int, int> var_of;
+    for (size_t v = 0; v < cl.var_rows.size(); ++v) var_of[cl.var_rows[v]] = (int)v;
+    info->code_rows += (int64_t)cl.rows.size() / 4;
+    TapeEmitHooks hk;
+    const std::string fname = "bo_" + tag + "_c" + std::to_string(c);
+    hk.signature = std::string(cl.rows.size() / 4 > 48 ? "BO_NOINLINE" : "BO_DEVICE") + " void " + fname +
+                   "(const int32_t* BO_RESTRICT ix, int stride, const double* const* BO_RESTRICT in, double* const* BO_RESTRICT out, "
+                   "const double* BO_RESTRICT consts)";
+    std::ostringstream pro;
+    for (int k = 0; k < n_in; ++k) pro << "  const double* const BO_RESTRICT i" << k << " = in[" << k << "];\n";
+    for (int k = 0; k < n_out; ++k) pro << "  double* const BO_RESTRICT o" << k << " = out[" << k << "];\n";
+    pro << "  (void)ix; (void)stride; (void)consts;";
+    for (int k = 0; k < n_in; ++k) pro << " (void)i" << k << ";";
+    for (int k = 0; k < n_out; ++k) pro << " (void)o" << k << ";";
+    pro << "\n";
+    hk.prologue = pro.str();
+    auto elem = [var_of](int64_t i, const int32_t* r) {
+      auto it = var_of.find((int)i);
+      if (it == var_of.end()) return std::to_string(r[2]);
+      return "ix[" + std::to_string(it->second) + " * stride]";
+    };
+    hk.input_expr = [elem](int64_t i, const int32_t* r) { return "i" + std::to_string(r[3]) + "[" + elem(i, r) + "]"; };
+    hk.const_expr = [elem, var_of](int64_t i, const int32_t* r) {
+      if (!var_of.count((int)i)) return std::string();
+      return "consts[" + elem(i, r) + "]";
+    };
+    hk.output_stmt = [elem](int64_t i, const int32_t* r, const std::string& v) {
+      return "o" + std::to_string(r[3]) + "[" + elem(i, r) + "] = " + v + ";";
+    };
+    o << emit_tape_function(ct, fname, &hk) << "\n";
+  }
+  o << "BO_DEVICE void bo_gen_" << tag
+    << "(const int32_t* BO_RESTRICT tab, const int32_t* BO_RESTRICT sec, int warp, int lane, const double* const* in, double* const* out, "
+       "const double* consts) {\n"
+       "  if (warp >= sec[" << (int)TS_GEN_NWARP << "]) return;\n"
+       "  const int32_t* wl = tab + sec[" << (int)TS_GEN_WL_OFF << "] + 2 * warp;\n"
+       "  const int32_t* e = tab + wl[0];\n"
+       "  const int ne = wl[1];\n"
+       "  for (int k = 0; k < ne; ++k, e += 4) {\n"
+       "    if (lane >= e[3]) continue;\n"
+       "    const int32_t* ix = tab + e[1] + lane;\n"
+       "    switch (e[0]) {\n";
+  for (size_t c = 0; c < classes.size(); ++c)
+    o << "      case " << c << ": bo_" << tag << "_c" << c << "(ix, e[2], in, out, consts); break;\n";
+  o << "      default: break;\n    }\n  }\n}\n\n";
+  return o.str();
+}
+
 void append_tape_section(std::vector<int32_t>& t, int slot, const PartTape& pt, const Tape& tape, std::vector<double>& dtab) {
   while (t.size() % 4 != 0) t.push_back(0);
   const size_t s0 = t.size();
@@ -610,18 +786,20 @@ void append_tape_section(std::vector<int32_t>& t, int slot, const PartTape& pt, 
 // ======================================================================================
 // Lane programs: a warp-wide, fully pre-scheduled instruction stream
 // ======================================================================================
-// One step = one 8-byte word per lane:  x = a | FINISH << 15 | b << 16 | LEVEL_END << 31,  y = c | tgt << 16.
-// Every lane does acc += vals[a] * (factor: vals[b] * vals[c] | solve: bp[b]).  On a FINISH step the G lanes of a
-// group add their accumulators up and lane 0 of the group finalises target `tgt` (0x7FFF: none); on a LEVEL_END
-// step the participating warps synchronise.  The flags are identical in all lanes of a warp.  Bit 15 of c marks a
-// diagonal factor target whose pivot must be positive (variable block).  Each (warp, level) segment is padded to a
-// multiple of BO_LP_CHUNK steps, so the executor can fetch the operands of a whole chunk before any of its finishes.
+// A stream is a sequence of ROUNDS; a round is one header word per lane followed by K operand words per lane
+// (8 bytes each, lane-interleaved: word i of lane l at [i][l]):
+//   header:  x = K | LEVEL_END << 31,  y = tgt | POSITIVE << 15      (tgt = 0x7FFF: this lane finalises nothing)
+//   operand: x = a | b << 16,          y = c
+// In a round every lane does K times acc += vals[a] * (factor: vals[b] * vals[c] | solve: bp[b]); then the G lanes of
+// a group add their accumulators up and lane 0 of the group finalises `tgt`; after a LEVEL_END round the
+// participating warps synchronise.  K and LEVEL_END are the same in all lanes of a warp.  POSITIVE marks a diagonal
+// factor target whose pivot must be positive (variable block).  Every warp stream ends with one padding word so the
+// executor may always fetch one word ahead.
 struct LaneTarget {
   int tgt;
   std::vector<std::array<int, 3>> con;
   bool positive = false;  // factor, diagonal target: pivot expected positive (variable block)
 };
-#define BO_LP_CHUNK 4 /* steps per chunk of the executor; a level boundary always ends a chunk */
 struct LaneProgram {
   int W = 1, G = 1;
   std::vector<std::vector<int32_t>> words;  // per warp: [step][32][2]
@@ -642,7 +820,20 @@ LaneProgram schedule_program(const std::vector<std::vector<LaneTarget>>& levels,
   const int ngrp = 32 / G, slots = W * ngrp;
   int log2g = 0;
   while ((1 << log2g) < G) ++log2g;
-  const double c_step = 25.0, c_finish = 80.0 + 30.0 * log2g, c_barrier = W > 1 ? 80.0 : 20.0;
+  // latency model of one warp (cycles): an operand step, a round (header, group sum, finalisation), a level barrier
+  const double c_step = 100.0, c_round = 250.0 + 40.0 * log2g, c_barrier = W > 1 ? 200.0 : 20.0;
+  auto header = [&](std::vector<int32_t>& out, int K, bool level_end, const LaneTarget* const* tg) {
+    for (int lane = 0; lane < 32; ++lane) {
+      const int g = lane / G, sub = lane % G;
+      int tgt = 0x7FFF, pos = 0;
+      if (tg && tg[g] && sub == 0) {
+        tgt = tg[g]->tgt;
+        pos = tg[g]->positive ? 0x8000 : 0;
+      }
+      out.push_back((int32_t)((uint32_t)K | (level_end ? 0x80000000u : 0u)));
+      out.push_back((int32_t)((uint32_t)tgt | (uint32_t)pos));
+    }
+  };
   for (const auto& lv : levels) {
     std::vector<int> order(lv.size());
     for (size_t k = 0; k < lv.size(); ++k) order[k] = (int)k;
@@ -651,71 +842,67 @@ LaneProgram schedule_program(const std::vector<std::vector<LaneTarget>>& levels,
     double worst = 0.0;
     for (int w = 0; w < W; ++w) {
       double cost_w = 0.0;
-      int seg_steps = 0, cost_steps = 0;
+      // rounds of this warp in this level
+      std::vector<std::array<const LaneTarget*, 32>> mine;
       for (int r = 0; r < rounds; ++r) {
-        // targets of this (warp, round): slot q = position within the round, warp = q % W, group = q / W
-        const LaneTarget* tg[32] = {nullptr};
-        int maxlen = -1;
+        std::array<const LaneTarget*, 32> tg;
+        tg.fill(nullptr);
+        bool any = false;
         for (int g = 0; g < ngrp; ++g) {
-          const int q = g * W + w, k = r * slots + q;
+          const int q = g * W + w, k = r * slots + q;  // slot q of the round: warp = q % W, group = q / W
           if (k < (int)lv.size()) {
             tg[g] = &lv[order[k]];
-            maxlen = std::max(maxlen, (int)tg[g]->con.size());
+            any = true;
           }
         }
-        if (maxlen < 0) continue;
-        const int steps = std::max(1, (maxlen + G - 1) / G);
-        cost_w += steps * c_step + c_finish;
-        cost_steps += steps;
+        if (any) mine.push_back(tg);
+      }
+      if (mine.empty()) {
+        if (emit) header(pr.words[w], 0, true, nullptr);  // nothing to do in this level: only meet the barrier
+        cost_w += 30.0;
+      }
+      for (size_t r = 0; r < mine.size(); ++r) {
+        int maxlen = 0;
+        for (int g = 0; g < ngrp; ++g)
+          if (mine[r][g]) maxlen = std::max(maxlen, (int)mine[r][g]->con.size());
+        const int K = (maxlen + G - 1) / G;
+        cost_w += K * c_step + c_round;
         if (!emit) continue;
-        for (int st = 0; st < steps; ++st) {
-          const bool fin = st + 1 == steps;
+        header(pr.words[w], K, r + 1 == mine.size(), mine[r].data());
+        for (int st = 0; st < K; ++st)
           for (int lane = 0; lane < 32; ++lane) {
             const int g = lane / G, sub = lane % G;
-            int a = zero_a, b = zero_b, c = zero_c, tgt = 0x7FFF;
-            if (tg[g]) {
-              const int ci = st * G + sub;
-              if (ci < (int)tg[g]->con.size()) {
-                a = tg[g]->con[ci][0];
-                b = tg[g]->con[ci][1];
-                c = tg[g]->con[ci][2];
-              }
-              if (fin && sub == 0) {
-                tgt = tg[g]->tgt;
-                if (tg[g]->positive) c |= 0x8000;
-              }
+            int a = zero_a, b = zero_b, c = zero_c;
+            const LaneTarget* tg = mine[r][g];
+            const int ci = st * G + sub;
+            if (tg && ci < (int)tg->con.size()) {
+              a = tg->con[ci][0];
+              b = tg->con[ci][1];
+              c = tg->con[ci][2];
             }
-            pr.words[w].push_back((int32_t)((uint32_t)a | (fin ? 0x8000u : 0u) | ((uint32_t)b << 16)));
-            pr.words[w].push_back((int32_t)((uint32_t)c | ((uint32_t)tgt << 16)));
+            pr.words[w].push_back((int32_t)((uint32_t)a | ((uint32_t)b << 16)));
+            pr.words[w].push_back((int32_t)c);
           }
-          ++seg_steps;
-        }
       }
-      if (emit) {
-        // pad the segment to a whole number of chunks (at least one: every warp meets every level barrier)
-        while (seg_steps == 0 || seg_steps % BO_LP_CHUNK != 0) {
-          for (int lane = 0; lane < 32; ++lane) {
-            pr.words[w].push_back((int32_t)((uint32_t)zero_a | ((uint32_t)zero_b << 16)));
-            pr.words[w].push_back((int32_t)((uint32_t)zero_c | (0x7FFFu << 16)));
-          }
-          ++seg_steps;
-        }
-        const size_t last = pr.words[w].size() - 64;
-        for (int lane = 0; lane < 32; ++lane) pr.words[w][last + 2 * lane] |= (int32_t)0x80000000u;
-      }
-      cost_w += ((BO_LP_CHUNK - cost_steps % BO_LP_CHUNK) % BO_LP_CHUNK) * c_step;
       worst = std::max(worst, cost_w);
     }
     pr.cost += worst + c_barrier;
   }
+  if (emit)
+    for (int w = 0; w < W; ++w) header(pr.words[w], 0, false, nullptr);  // trailing padding word (never executed)
   return pr;
 }
 
-LaneProgram best_program(const std::vector<std::vector<LaneTarget>>& levels, int max_warps, int zero_a, int zero_b, int zero_c) {
+LaneProgram best_program(const std::vector<std::vector<LaneTarget>>& levels, int max_warps, int zero_a, int zero_b, int zero_c,
+                         const char* env_w, const char* env_g) {
   int bw = 1, bg = 1;
   double best = -1.0;
+  // experiment hooks: force the number of warps / lanes per target of the factor program
+  const int force_w = getenv(env_w) ? atoi(getenv(env_w)) : 0;
+  const int force_g = getenv(env_g) ? atoi(getenv(env_g)) : 0;
   for (int W = 1; W <= max_warps; W *= 2)
     for (int G = 1; G <= 32; G *= 2) {
+      if ((force_w && W != force_w) || (force_g && G != force_g)) continue;
       const LaneProgram p = schedule_program(levels, W, G, zero_a, zero_b, zero_c, false);
       if (best < 0.0 || p.cost < best) {
         best = p.cost;
@@ -737,7 +924,7 @@ void append_program(std::vector<int32_t>& t, int slot, const LaneProgram& pr) {
   int64_t first = 0;
   for (int w = 0; w < pr.W; ++w) {
     t[h + 4 + 2 * w] = (int32_t)first;
-    t[h + 5 + 2 * w] = (int32_t)(pr.words[w].size() / 64);
+    t[h + 5 + 2 * w] = (int32_t)(pr.words[w].size() / 64) - 1;  // words to execute (the trailing padding word excluded)
     first += (int64_t)pr.words[w].size() / 64;
   }
   t[h + 3] = (int32_t)first;
@@ -748,9 +935,37 @@ void append_program(std::vector<int32_t>& t, int slot, const LaneProgram& pr) {
 
 }  // namespace
 
+static CoopPlan make_coop_plan_segments(const ProblemSource& ps, int tpb, int n_segments, bool ldl_only);
+
+// The elimination order is chosen by trial: cutting every chain of the KKT graph into 2 (3) pieces that factor
+// independently roughly halves the elimination-tree height for a little extra fill; whichever variant gives the
+// shortest lane programs (factorisation + both substitutions, longest warp) and still fits shared memory wins.
 CoopPlan make_coop_plan(const ProblemSource& ps, int tpb) {
+  int best_seg = 1;
+  if (getenv("BO_SEGMENTS")) {
+    best_seg = atoi(getenv("BO_SEGMENTS"));
+  } else {
+    int64_t best_steps = -1;
+    for (int seg = 1; seg <= 3; ++seg) {
+      const CoopPlan c = make_coop_plan_segments(ps, tpb, seg, true);
+      const size_t smem = ((size_t)c.vals_size() + ps.nx + ps.n_eq + 5 * (tpb / 32) + 8) * sizeof(double);
+      if (seg > 1 && smem > 227 * 1024) break;
+      const int64_t steps = c.fac_steps + c.solve_steps;
+      if (best_steps < 0 || steps < best_steps - best_steps / 32) {  // > 3 % shorter
+        best_steps = steps;
+        best_seg = seg;
+      } else {
+        break;
+      }
+    }
+  }
+  return make_coop_plan_segments(ps, tpb, best_seg, false);
+}
+
+static CoopPlan make_coop_plan_segments(const ProblemSource& ps, int tpb, int n_segments, bool ldl_only) {
   CoopPlan pl;
-  pl.sp = make_sparse_plan(ps, false);
+  pl.n_segments = n_segments;
+  pl.sp = make_sparse_plan(ps, false, n_segments);
   const SparsePlan& sp = pl.sp;
   const int n = sp.n, nx = ps.nx, nnzL = sp.nnzL();
   std::vector<int32_t>& t = pl.itab;
@@ -817,18 +1032,22 @@ CoopPlan make_coop_plan(const ProblemSource& ps, int tpb) {
       }
     }
     const int max_warps = std::max(1, tpb / 32);
-    LaneProgram pf = best_program(fac, max_warps, zero_v, zero_v, zero_v);
-    LaneProgram pw = best_program(fwd, 1, zero_v, zero_b, zero_v);
-    LaneProgram pb = best_program(bwd, 1, zero_v, zero_b, zero_v);
+    LaneProgram pf = best_program(fac, max_warps, zero_v, zero_v, zero_v, "BO_FAC_WARPS", "BO_FAC_G");
+    const int solve_warps = getenv("BO_SOLVE_MAX_WARPS") ? atoi(getenv("BO_SOLVE_MAX_WARPS")) : max_warps;
+    LaneProgram pw = best_program(fwd, std::min(solve_warps, max_warps), zero_v, zero_b, zero_v, "BO_SOLVE_WARPS", "BO_SOLVE_G");
+    LaneProgram pb = best_program(bwd, std::min(solve_warps, max_warps), zero_v, zero_b, zero_v, "BO_SOLVE_WARPS", "BO_SOLVE_G");
     pl.ldl_g = pf.G;
     pl.ldl_w = pf.W;
     pl.solve_g = pw.G;
+    pl.solve_bwd_g = pb.G;
     pl.fac_steps = pf.max_steps();
     pl.solve_steps = pw.max_steps() + pb.max_steps();
     append_program(t, CT_PROG_FAC, pf);
     append_program(t, CT_PROG_FWD, pw);
     append_program(t, CT_PROG_BWD, pb);
   }
+
+  if (ldl_only) return pl;
 
   // ---- KKT assembly, target-owned: every diagonal position plus every position that receives a term ----
   // term = { kind, a, b, r }: 0: H[a]   1: JE[a]   2: sigma[r] JI[a] JI[b]   3: rho JE[a] JE[b]
@@ -929,6 +1148,44 @@ CoopPlan make_coop_plan(const ProblemSource& ps, int tpb) {
         nsub = std::max(32, std::min(nsub - 32, (cap / std::max(pt.n_work, 1)) / 32 * 32));
       }
     };
+    if (getenv("BO_DEBUG_CLASSES")) {
+      for (const Tape* tp : {&ps.fc, &ps.kkt}) {
+        PartTape all = partition_tape(*tp, 1 << 30);
+        std::vector<TapeClass> cl = classify(all, *tp);
+        int64_t code = 0, work = 0;
+        for (const TapeClass& c : cl) {
+          code += (int64_t)c.rows.size() / 4;
+          work += (int64_t)c.rows.size() / 4 * (((int64_t)c.members.size() + 31) / 32);
+        }
+        fprintf(stderr, "[classes] %zu components, %zu classes, %lld code rows, %lld warp-rows, %d partial slots\n", all.subs.size(), cl.size(),
+                (long long)code, (long long)work, all.n_part);
+        std::vector<const TapeClass*> order;
+        for (const TapeClass& c : cl) order.push_back(&c);
+        std::sort(order.begin(), order.end(), [](const TapeClass* a, const TapeClass* b) { return a->rows.size() * a->members.size() > b->rows.size() * b->members.size(); });
+        for (size_t k = 0; k < order.size() && k < 12; ++k)
+          fprintf(stderr, "    class rows %zu members %zu var_rows %zu\n", order[k]->rows.size() / 4, order[k]->members.size(), order[k]->var_rows.size());
+      }
+    }
+    bool gen = getenv("BO_NO_GEN_TAPES") == nullptr;
+    if (gen) {
+      PartTape fca = partition_tape(ps.fc, 1 << 30), kka = partition_tape(ps.kkt, 1 << 30);
+      std::vector<TapeClass> fcc = classify(fca, ps.fc), kkc = classify(kka, ps.kkt);
+      int64_t code = 0;
+      for (const TapeClass& c : fcc) code += (int64_t)c.rows.size() / 4;
+      for (const TapeClass& c : kkc) code += (int64_t)c.rows.size() / 4;
+      if (code <= 40000 && fcc.size() + kkc.size() <= 400) {
+        pl.gen_tapes = true;
+        pl.fc = fca.info;
+        pl.kkt = kka.info;
+        pl.gen_code = append_gen_tape(t, CT_TAPE_FC, fca, fcc, ps.fc, pl.dtab, tpb / 32, "fc", &pl.fc);
+        pl.gen_code += append_gen_tape(t, CT_TAPE_KKT, kka, kkc, ps.kkt, pl.dtab, tpb / 32, "kkt", &pl.kkt);
+        pl.n_work_pre = std::max(fca.pre.n_work, kka.pre.n_work);
+        pl.smem_doubles = fixed;
+      } else {
+        gen = false;
+      }
+    }
+    if (!gen) {
     PartTape fc = fit(ps.fc, fc_cap, &pl.fc_wstride);
     PartTape kkt = fit(ps.kkt, kkt_cap, &pl.kkt_wstride);
     pl.fc = fc.info;
@@ -940,6 +1197,7 @@ CoopPlan make_coop_plan(const ProblemSource& ps, int tpb) {
     append_tape_section(t, CT_TAPE_KKT, kkt, ps.kkt, pl.dtab);
     const int fc_w = pl.fc_wstride * pl.n_work_fc, kkt_w = pl.kkt_wstride * pl.n_work_kkt;
     pl.smem_doubles = std::max(fixed + fc_w, 5 * (tpb / 32) + 4 + kkt_w);
+    }
   }
   return pl;
 }
@@ -960,7 +1218,18 @@ std::string emit_coop_source(const ProblemSource& ps, const CoopPlan& pl, int tp
     << pl.n_work_kkt << "\n#define BO_NWORK_PRE " << pl.n_work_pre << "\n#define BO_FC_WSTRIDE " << pl.fc_wstride
     << "\n#define BO_KKT_WSTRIDE " << pl.kkt_wstride << "\n#define BO_SMEM_DOUBLES " << pl.smem_doubles << "\n#define BO_NPE_FC "
     << pl.fc.n_pe << "\n#define BO_NPE_KKT " << pl.kkt.n_pe << "\n#define BO_NPART " << std::max(pl.fc.n_part, pl.kkt.n_part) << "\n";
-  o << "#include \"bo_common.cuh\"\n#include \"bo_ipm_cta.cuh\"\n";
+  {
+    // resident CTAs per SM the kernel is compiled for (register cap): as many as the shared memory allows, at least
+    // 64 registers per thread
+    const int by_smem = (int)(227 * 1024 / std::max<size_t>(1, (size_t)pl.smem_doubles * 8 + 1024));
+    const int by_regs = 65536 / (tpb * 64);
+    const int min_ctas = std::max(1, std::min(std::min(by_smem, by_regs), 32));
+    o << "#define BO_MIN_CTAS " << min_ctas << "\n#define BO_FAC_G " << pl.ldl_g << "\n#define BO_FWD_G " << pl.solve_g
+      << "\n#define BO_BWD_G " << pl.solve_bwd_g << "\n";
+  }
+  o << "#include \"bo_common.cuh\"\n";
+  if (pl.gen_tapes) o << "#define BO_GEN_TAPES 1\n" << pl.gen_code;
+  o << "#include \"bo_ipm_cta.cuh\"\n";
   return o.str();
 }
 

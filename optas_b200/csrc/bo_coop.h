@@ -35,12 +35,15 @@ enum CoopSlot {
 // slots of a tape section (relative to the section start; offsets inside are absolute)
 enum CoopTapeSlot {
   TS_NSUB = 0, TS_CONST0, TS_NPE, TS_NPART, TS_PRE_N, TS_PRE_OFF, TS_LEN_OFF, TS_WBASE_OFF, TS_STREAM_OFF,
-  TS_NRED, TS_RED_OFF, TS_PART_SEG, TS_PE_SEG, TS_HEADER = 16
+  TS_NRED, TS_RED_OFF, TS_PART_SEG, TS_PE_SEG, TS_GEN_NWARP, TS_GEN_WL_OFF, TS_HEADER = 16
 };
 
 struct CoopTapeInfo {
   int nsub = 0, n_pe = 0, n_part = 0, n_red = 0, n_components = 0, n_split_outputs = 0;
   int64_t total_instr = 0, max_len = 0, pre_len = 0;
+  int n_classes = 0;              // generated tapes: component classes (one straight-line function each)
+  int64_t code_rows = 0;          // generated tapes: instructions over all class functions
+  int64_t warp_rows = 0;          // generated tapes: longest per-warp work list (instructions executed in lock step)
 };
 
 struct CoopPlan {
@@ -50,9 +53,12 @@ struct CoopPlan {
   int n_work_fc = 1, n_work_kkt = 1, n_work_pre = 1;  // interpreter work slots per sub-tape
   int fc_wstride = 0, kkt_wstride = 0;  // stride of the shared-memory work arrays w[slot][thread]; 0 = thread-local
   int smem_doubles = 0;        // dynamic shared memory of the kernel
+  bool gen_tapes = false;      // tapes compiled to straight-line code per component class (else interpreted)
+  std::string gen_code;        // the generated class functions + dispatchers
   int n_levels = 0;            // elimination-tree height (= barriers per factorisation)
+  int n_segments = 1;          // pieces every chain of the KKT graph was cut into for the elimination order
   int ldl_g = 1, ldl_w = 1;    // factor program: lanes per target, participating warps
-  int solve_g = 1;             // lanes cooperating on one row/column of a triangular solve
+  int solve_g = 1, solve_bwd_g = 1;  // lanes cooperating on one row (forward) / column (backward) of a triangular solve
   int64_t fac_steps = 0, solve_steps = 0;  // longest warp stream of the factor / both triangular solves
   int64_t n_contrib = 0;       // multiply-adds of one numeric factorisation
   CoopTapeInfo fc, kkt;

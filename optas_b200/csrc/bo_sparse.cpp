@@ -16,7 +16,7 @@ int SparsePlan::pos(int i_old, int j_old) const {
   return n + (int)(it - rowidx.begin());
 }
 
-SparsePlan make_sparse_plan(const ProblemSource& ps, bool large) {
+SparsePlan make_sparse_plan(const ProblemSource& ps, bool large, int n_segments) {
   SparsePlan pl;
   const int nx = ps.nx, n = ps.nx + ps.n_eq;
   pl.n = n;
@@ -57,20 +57,61 @@ SparsePlan make_sparse_plan(const ProblemSource& ps, bool large) {
   std::vector<std::vector<int>> y_of_x(nx);
   for (int r = 0; r < ps.n_eq; ++r)
     for (int c : x_of_y[r]) y_of_x[c].push_back(r);
+  // Segmented variant (n_segments > 1), for chain-like structures (horizon problems): every connected component is
+  // cut into n_segments pieces along its longest axis (BFS layers from a pseudo-peripheral vertex); the layer of
+  // vertices at each cut is a separator that is eliminated last.  The pieces factor independently, so the
+  // elimination tree is ~n_segments times lower; the price is the fill of the separator blocks.
+  std::vector<char> is_sep(n, 0);
+  if (n_segments > 1) {
+    auto bfs = [&](int src, std::vector<int>& dist) {
+      dist.assign(n, -1);
+      std::vector<int> q{src};
+      dist[src] = 0;
+      for (size_t h = 0; h < q.size(); ++h)
+        for (int w : adj[q[h]])
+          if (dist[w] < 0) {
+            dist[w] = dist[q[h]] + 1;
+            q.push_back(w);
+          }
+      return q;
+    };
+    std::vector<char> seen(n, 0);
+    std::vector<int> d0, du;
+    std::vector<int> seg(n, 0);
+    for (int s0 = 0; s0 < n; ++s0) {
+      if (seen[s0]) continue;
+      const std::vector<int> comp = bfs(s0, d0);
+      for (int v : comp) seen[v] = 1;
+      const int u = comp.back();  // farthest from s0: one end of the component
+      const std::vector<int> cu = bfs(u, du);
+      const int depth = du[cu.back()] + 1;
+      if (depth < 4 * n_segments) continue;  // too short to be worth cutting
+      for (int x : comp) seg[x] = (int)((int64_t)du[x] * n_segments / depth);
+      for (int x : comp)
+        for (int w : adj[x])
+          if (seg[w] < seg[x]) is_sep[x] = 1;
+    }
+  }
   std::vector<std::set<int>> g = adj;  // elimination graph (mutated)
   pl.perm.reserve(n);
   std::vector<std::vector<int>> col_struct;  // rows (old indices) below the diagonal of each eliminated column
   col_struct.reserve(n);
+  bool interior_phase = n_segments > 1;
   for (int step = 0; step < n; ++step) {
     int best = -1;
     size_t best_deg = ~(size_t)0;
-    for (int v = 0; v < n; ++v) {
-      if (done[v]) continue;
-      if (v >= nx && pending_x[v - nx] > 0) continue;  // constraint row not yet eligible
-      if (g[v].size() < best_deg) {
-        best_deg = g[v].size();
-        best = v;
+    for (int pass = 0; pass < 2 && best < 0; ++pass) {
+      for (int v = 0; v < n; ++v) {
+        if (done[v]) continue;
+        if (v >= nx && pending_x[v - nx] > 0) continue;  // constraint row not yet eligible
+        if (interior_phase && is_sep[v]) continue;        // separators wait until the pieces are done
+        if (g[v].size() < best_deg) {
+          best_deg = g[v].size();
+          best = v;
+        }
       }
+      if (best < 0 && interior_phase) interior_phase = false;  // pieces exhausted: now the separators
+      else break;
     }
     if (best < 0) {  // only ineligible rows left (cannot happen: all x are always eligible) -- take any
       for (int v = 0; v < n; ++v)

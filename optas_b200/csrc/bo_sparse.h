@@ -38,6 +38,6 @@ struct SparsePlan {
 // horizon problems).
 // `large`: also append the structure tables, the KKT assembly program and the two tapes, so that the
 // kernel needs no problem-specific code at all (table-driven everything; see bo_ipm_reg.cuh BO_LARGE).
-SparsePlan make_sparse_plan(const ProblemSource& ps, bool large);
+SparsePlan make_sparse_plan(const ProblemSource& ps, bool large, int n_segments = 1);
 
 }  // namespace bo

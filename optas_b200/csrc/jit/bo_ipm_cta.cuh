@@ -80,6 +80,8 @@
 #define TS_RED_OFF 10
 #define TS_PART_SEG 11
 #define TS_PE_SEG 12
+#define TS_GEN_NWARP 13
+#define TS_GEN_WL_OFF 14
 
 // ---------------------------------------------------------------------------------------------------
 // thread / barrier / reduction primitives
@@ -112,6 +114,8 @@ __device__ __forceinline__ double bo_shfl_xor(double v, int m) { return __shfl_x
 #define BO_SM_BP (BO_SM_VALS + BO_VALS + 1)
 #define BO_SM_FREE (BO_SM_BP + BO_NK + 1)
 #ifdef BO_HOST_SIM
+#define BO_VALS_AT(C, i) ((C).vals[i])
+#define BO_BP_AT(C, i) ((C).bp[i])
 #define BO_VALS_P(C) ((C).vals)
 #define BO_BP_P(C) ((C).bp)
 #define BO_RED_P(C) ((C).red)
@@ -119,6 +123,9 @@ __device__ __forceinline__ double bo_shfl_xor(double v, int m) { return __shfl_x
 #define BO_WFC_P(C) ((C).wfc)
 #else
 extern __shared__ double bo_smem[];
+// index the __shared__ array itself (never through a generic pointer: that costs an S2UR + address rebuild per access)
+#define BO_VALS_AT(C, i) (bo_smem[BO_SM_VALS + (i)])
+#define BO_BP_AT(C, i) (bo_smem[BO_SM_BP + (i)])
 #define BO_VALS_P(C) (bo_smem + BO_SM_VALS)
 #define BO_BP_P(C) (bo_smem + BO_SM_BP)
 #define BO_RED_P(C) (bo_smem + BO_SM_RED)
@@ -195,7 +202,9 @@ BO_DEVICE void bo_reduce(double (&v)[K], const int (&op)[K], double* red) {
 #if defined(BO_PROFILE) && !defined(BO_HOST_SIM)
 #define BO_PROF_BEGIN() const long long bo_prof_t0 = clock64()
 #define BO_PROF_END(k) do { if (BO_TID == 0) C.prof[k] += clock64() - bo_prof_t0; } while (0)
+#define BO_PROF_COUNT(k) do { if (BO_TID == 0) C.prof[k] += 1; } while (0)
 #else
+#define BO_PROF_COUNT(k) do { } while (0)
 #define BO_PROF_BEGIN() do { } while (0)
 #define BO_PROF_END(k) do { } while (0)
 #endif
@@ -313,6 +322,21 @@ BO_DEVICE void bo_cta_tape_run(const bo_cta& C, int slot, const double** in, dou
   const int32_t* len = C.tab + sec[TS_LEN_OFF];
   const int32_t* wbase = C.tab + sec[TS_WBASE_OFF];
   const bo_int4* stream = reinterpret_cast<const bo_int4*>(C.tab + sec[TS_STREAM_OFF]);
+#ifdef BO_GEN_TAPES
+  // tapes compiled to straight-line code per component class (bo_coop.cpp): warp w runs its work list, lane l the l-th
+  // member of each entry -- isomorphic components (the stages of the horizon) in lock step, values in registers
+  (void)nsub; (void)len; (void)wbase; (void)stream; (void)ws; (void)wstride;
+#ifdef BO_HOST_SIM
+  for (int w = 0; w < sec[TS_GEN_NWARP]; ++w)
+    for (int l = 0; l < 32; ++l) {
+      if (slot == CT_TAPE_FC) bo_gen_fc(C.tab, sec, w, l, in, out, consts);
+      else bo_gen_kkt(C.tab, sec, w, l, in, out, consts);
+    }
+#else
+  if (slot == CT_TAPE_FC) bo_gen_fc(C.tab, sec, BO_TID >> 5, BO_TID & 31, in, out, consts);
+  else bo_gen_kkt(C.tab, sec, BO_TID >> 5, BO_TID & 31, in, out, consts);
+#endif
+#else
 #ifdef BO_HOST_SIM
   double wl[NW];
   for (int t = 0; t < nsub; ++t) bo_interp_rows(stream + wbase[t >> 5] + (t & 31), len[t], 32, consts, wl, 1, in, out);
@@ -324,6 +348,7 @@ BO_DEVICE void bo_cta_tape_run(const bo_cta& C, int slot, const double** in, dou
     double wl[NW];
     for (int t = BO_TID; t < nsub; t += BO_NT) bo_interp_rows(stream + wbase[t >> 5] + (t & 31), len[t], 32, consts, wl, 1, in, out);
   }
+#endif
 #endif
   bo_sync();
   const int nred = sec[TS_NRED];
@@ -428,20 +453,23 @@ BO_NOINLINE void bo_cta_assemble(const bo_cta& C, double rho, double dw, double 
   BO_PROF_END(2);
 }
 
-// Lane programs (bo_coop.cpp): warp-wide pre-scheduled streams, one 8-byte word per lane and step,
-//   x = a | FINISH << 15 | b << 16 | LEVEL_END << 31,   y = c | POSITIVE << 15 | tgt << 16
+// Lane programs (bo_coop.cpp): warp-wide pre-scheduled streams of ROUNDS, 8 bytes per lane and word, word i of
+// lane l at [i][l].  A round = one header word + K operand words:
+//   header:  x = K | LEVEL_END << 31,  y = tgt | POSITIVE << 15      (tgt = 0x7FFF: this lane finalises nothing)
+//   operand: x = a | b << 16,          y = c
 // MODE 0 factor:   acc += vals[a] vals[b] vals[c];   finish: d = vals[tgt] - acc, diagonal: vals[tgt] = 1/d (+ pivot test)
 // MODE 1 forward:  acc += vals[a] bp[b];             finish: bp[tgt] = (bp[tgt] - acc) vals[tgt]
 // MODE 2 backward: acc += vals[a] bp[b];             finish: bp[tgt] -= acc vals[tgt]
-// Streams come in chunks of BO_LP_CHUNK steps; a level boundary always ends a chunk, and nothing written inside
-// a level is read inside it, so the operands of a whole chunk are fetched up front (independent shared-memory
-// loads) before its finishes run.  The words do not depend on the data: they are fetched BO_LP_AHEAD steps ahead.
-#define BO_LP_CHUNK 4
-#define BO_LP_AHEAD 16
+// After the K steps the G lanes of a group add up their accumulators (xor-shuffles) and lane 0 of the group
+// finalises; after a LEVEL_END round the participating warps synchronise.  The words do not depend on the data:
+// they are fetched a block (BO_LP_BLOCK words) ahead.
+#ifndef BO_LP_BLOCK
+#define BO_LP_BLOCK 8
+#endif
 template <int MODE>
-BO_DEVICE void bo_lane_finish(const bo_cta& C, double* BO_RESTRICT vals, double* BO_RESTRICT bp, int tgt, bool positive, double acc) {
+BO_DEVICE void bo_lane_finish(const bo_cta& C, int tgt, bool positive, double acc) {
   if (MODE == 0) {
-    const double a0 = vals[tgt];
+    const double a0 = BO_VALS_AT(C, tgt);
     const double d = a0 - acc;
     if (tgt < BO_NK) {
       const double scale = fmax(1.0, fabs(a0));
@@ -449,31 +477,26 @@ BO_DEVICE void bo_lane_finish(const bo_cta& C, double* BO_RESTRICT vals, double*
 #ifdef BO_HOST_SIM
       if (bad && tgt < C.ibuf[0]) C.ibuf[0] = tgt;
 #else
-      if (bad) atomicMin(&C.ibuf[0], tgt);
+      if (bad) atomicMin(reinterpret_cast<int*>(&bo_smem[BO_SM_INTS]), tgt);
 #endif
-      vals[tgt] = 1.0 / d;
+      BO_VALS_AT(C, tgt) = 1.0 / d;
     } else {
-      vals[tgt] = d;
+      BO_VALS_AT(C, tgt) = d;
     }
   } else if (MODE == 1) {
-    bp[tgt] = (bp[tgt] - acc) * vals[tgt];
+    BO_BP_AT(C, tgt) = (BO_BP_AT(C, tgt) - acc) * BO_VALS_AT(C, tgt);
   } else {
-    bp[tgt] -= acc * vals[tgt];
+    BO_BP_AT(C, tgt) -= acc * BO_VALS_AT(C, tgt);
   }
 }
 
-template <int MODE>
+template <int MODE, int G>
 BO_DEVICE void bo_lane_program(const bo_cta& C, int slot) {
   const int32_t* h = C.tab + C.tab[slot];
-  const int W = h[0], G = h[1];
-  double* vals = BO_VALS_P(C);
-  double* bp = BO_BP_P(C);
+  const int W = h[0];
 #ifdef BO_HOST_SIM
   // faithful emulation: warps advance level by level, lanes in lock step, the same xor-tree for the group sums
   int pc[32] = {0};
-  double acc[32][32];
-  for (int w = 0; w < W; ++w)
-    for (int l = 0; l < 32; ++l) acc[w][l] = 0.0;
   bool more = true;
   while (more) {
     more = false;
@@ -481,28 +504,31 @@ BO_DEVICE void bo_lane_program(const bo_cta& C, int slot) {
       const int32_t* s = C.tab + h[2] + 64LL * h[4 + 2 * w];
       const int n = h[5 + 2 * w];
       while (pc[w] < n) {
-        const int32_t* row = s + 64LL * pc[w];
-        for (int l = 0; l < 32; ++l) {
-          const unsigned x = (unsigned)row[2 * l], y = (unsigned)row[2 * l + 1];
-          const int a = x & 0x7FFFu, b = (x >> 16) & 0x7FFFu, c = y & 0x7FFFu;
-          acc[w][l] += MODE == 0 ? vals[a] * vals[b] * vals[c] : vals[a] * bp[b];
-        }
-        const unsigned x0 = (unsigned)row[0];
-        if (x0 & 0x8000u) {
-          for (int off = G >> 1; off > 0; off >>= 1) {
-            double t[32];
-            for (int l = 0; l < 32; ++l) t[l] = acc[w][l] + acc[w][l ^ off];
-            for (int l = 0; l < 32; ++l) acc[w][l] = t[l];
-          }
+        const int32_t* hdr = s + 64LL * pc[w];
+        const unsigned hx = (unsigned)hdr[0];
+        const int K = hx & 0xFFFFu;
+        double acc[32];
+        for (int l = 0; l < 32; ++l) acc[l] = 0.0;
+        for (int k = 0; k < K; ++k) {
+          const int32_t* row = s + 64LL * (pc[w] + 1 + k);
           for (int l = 0; l < 32; ++l) {
-            const unsigned y = (unsigned)row[2 * l + 1];
-            const int tgt = (y >> 16) & 0x7FFFu;
-            if (tgt != 0x7FFF) bo_lane_finish<MODE>(C, vals, bp, tgt, (y & 0x8000u) != 0, acc[w][l]);
-            acc[w][l] = 0.0;
+            const unsigned x = (unsigned)row[2 * l], y = (unsigned)row[2 * l + 1];
+            const int a = x & 0xFFFFu, b = x >> 16, c = y & 0xFFFFu;
+            acc[l] += MODE == 0 ? BO_VALS_AT(C, a) * BO_VALS_AT(C, b) * BO_VALS_AT(C, c) : BO_VALS_AT(C, a) * BO_BP_AT(C, b);
           }
         }
-        ++pc[w];
-        if (x0 & 0x80000000u) break;
+        for (int off = G >> 1; off > 0; off >>= 1) {
+          double t[32];
+          for (int l = 0; l < 32; ++l) t[l] = acc[l] + acc[l ^ off];
+          for (int l = 0; l < 32; ++l) acc[l] = t[l];
+        }
+        for (int l = 0; l < 32; ++l) {
+          const unsigned y = (unsigned)hdr[2 * l + 1];
+          const int tgt = y & 0x7FFFu;
+          if (tgt != 0x7FFF) bo_lane_finish<MODE>(C, tgt, (y & 0x8000u) != 0, acc[l]);
+        }
+        pc[w] += K + 1;
+        if (hx & 0x80000000u) break;
       }
       more = more || pc[w] < n;
     }
@@ -510,45 +536,50 @@ BO_DEVICE void bo_lane_program(const bo_cta& C, int slot) {
 #else
   const int warp = BO_TID >> 5, lane = BO_TID & 31;
   if (warp < W) {
+    // The stream is consumed as a flat sequence of words, BO_LP_BLOCK at a time, one block ahead (independent
+    // loads in flight); a header word closes the round before it (group sum, finalisation, level barrier) and opens
+    // the next one.  The trailing padding header closes the last round.
     const bo_int2* s = reinterpret_cast<const bo_int2*>(C.tab + h[2]) + 32LL * h[4 + 2 * warp] + lane;
-    const int n = h[5 + 2 * warp];  // a multiple of BO_LP_CHUNK
-    const bo_int2 pad = bo_int2{BO_VALS | (BO_VALS << 16), BO_VALS | (0x7FFF << 16)};
-    bo_int2 nxt[BO_LP_AHEAD];
+    const int n = h[5 + 2 * warp] + 1;
+    const bo_int2 pad = bo_int2{0, 0x7FFF};
+    bo_int2 nxt[BO_LP_BLOCK];
     BO_UNROLL
-    for (int u = 0; u < BO_LP_AHEAD; ++u) nxt[u] = u < n ? s[32 * u] : pad;
+    for (int u = 0; u < BO_LP_BLOCK; ++u) nxt[u] = u < n ? s[32 * u] : pad;
     double acc = 0.0;
-    for (int base = 0; base < n; base += BO_LP_AHEAD) {
-      bo_int2 cur[BO_LP_AHEAD];
+    int rem = 0;
+    unsigned open_y = 0x7FFFu;
+    bool open = false, level_end = false;
+    for (int base = 0; base < n; base += BO_LP_BLOCK) {
+      bo_int2 cur[BO_LP_BLOCK];
       BO_UNROLL
-      for (int u = 0; u < BO_LP_AHEAD; ++u) cur[u] = nxt[u];
+      for (int u = 0; u < BO_LP_BLOCK; ++u) cur[u] = nxt[u];
       BO_UNROLL
-      for (int u = 0; u < BO_LP_AHEAD; ++u) {
-        const int i = base + BO_LP_AHEAD + u;
+      for (int u = 0; u < BO_LP_BLOCK; ++u) {
+        const int i = base + BO_LP_BLOCK + u;
         nxt[u] = i < n ? s[32 * i] : pad;
       }
       BO_UNROLL
-      for (int ch = 0; ch < BO_LP_AHEAD / BO_LP_CHUNK; ++ch) {
-        if (base + ch * BO_LP_CHUNK >= n) break;
-        double prod[BO_LP_CHUNK];
-        BO_UNROLL
-        for (int u = 0; u < BO_LP_CHUNK; ++u) {
-          const unsigned x = (unsigned)cur[ch * BO_LP_CHUNK + u].x, y = (unsigned)cur[ch * BO_LP_CHUNK + u].y;
-          const int a = x & 0x7FFFu, b = (x >> 16) & 0x7FFFu;
-          if (MODE == 0) prod[u] = vals[a] * vals[b] * vals[y & 0x7FFFu];
-          else prod[u] = vals[a] * bp[b];
-        }
-        BO_UNROLL
-        for (int u = 0; u < BO_LP_CHUNK; ++u) {
-          const unsigned x = (unsigned)cur[ch * BO_LP_CHUNK + u].x, y = (unsigned)cur[ch * BO_LP_CHUNK + u].y;
-          acc += prod[u];
-          if (x & 0x8000u) {
+      for (int u = 0; u < BO_LP_BLOCK; ++u) {
+        if (base + u >= n) break;
+        const unsigned x = (unsigned)cur[u].x, y = (unsigned)cur[u].y;
+        if (rem == 0) {
+          if (open) {
+            BO_UNROLL
             for (int off = G >> 1; off > 0; off >>= 1) acc += bo_shfl_xor(acc, off);
-            const int tgt = (y >> 16) & 0x7FFFu;
-            if (tgt != 0x7FFF) bo_lane_finish<MODE>(C, vals, bp, tgt, (y & 0x8000u) != 0, acc);
+            const int tgt = open_y & 0x7FFFu;
+            if (tgt != 0x7FFF) bo_lane_finish<MODE>(C, tgt, (open_y & 0x8000u) != 0, acc);
             acc = 0.0;
+            if (level_end) bo_bar_warps(W);
           }
+          rem = x & 0xFFFFu;
+          level_end = (x >> 31) != 0;
+          open_y = y;
+          open = true;
+        } else {
+          if (MODE == 0) acc += BO_VALS_AT(C, x & 0xFFFFu) * BO_VALS_AT(C, x >> 16) * BO_VALS_AT(C, y);
+          else acc += BO_VALS_AT(C, x & 0xFFFFu) * BO_BP_AT(C, x >> 16);
+          --rem;
         }
-        if ((unsigned)cur[ch * BO_LP_CHUNK + BO_LP_CHUNK - 1].x & 0x80000000u) bo_bar_warps(W);
       }
     }
   }
@@ -561,11 +592,12 @@ BO_NOINLINE int bo_cta_factor(const bo_cta& C) {
   BO_PROF_BEGIN();
   if (BO_TID == 0) C.ibuf[0] = BO_NK;  // first bad pivot column (elimination order); BO_NK = none
   bo_sync();
-  bo_lane_program<0>(C, CT_PROG_FAC);
+  bo_lane_program<0, BO_FAC_G>(C, CT_PROG_FAC);
   bo_sync();
   const int badcol = C.ibuf[0];
   bo_sync();
   BO_PROF_END(3);
+  BO_PROF_COUNT(5);
   if (badcol >= BO_NK) return 0;
   return (C.tab + C.tab[CT_SIGN])[badcol] > 0 ? 1 : 2;
 }
@@ -578,12 +610,13 @@ BO_NOINLINE void bo_cta_ldl_solve(const bo_cta& C, double* b) {
   double* bp = BO_BP_P(C);
   BO_PAR(j, BO_NK) bp[j] = b[perm[j]];
   bo_sync();
-  bo_lane_program<1>(C, CT_PROG_FWD);
-  bo_lane_program<2>(C, CT_PROG_BWD);
+  bo_lane_program<1, BO_FWD_G>(C, CT_PROG_FWD);
+  bo_lane_program<2, BO_BWD_G>(C, CT_PROG_BWD);
   bo_sync();
   BO_PAR(j, BO_NK) b[perm[j]] = bp[j];
   bo_sync();
   BO_PROF_END(4);
+  BO_PROF_COUNT(6);
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -937,7 +970,7 @@ BO_DEVICE int bo_cta_solve(bo_cta_state& S, const bo_cta& C, const bo_solver_par
 #ifndef BO_HOST_SIM
 // Persistent CTAs, instances fetched from a global counter.  Same signature as the thread-per-instance
 // kernel; prm.scratch = per-CTA vector workspace ([gridDim.x][BO_SCRATCH_DOUBLES]).
-extern "C" __global__ void __launch_bounds__(BO_TPB)
+extern "C" __global__ void __launch_bounds__(BO_TPB, BO_MIN_CTAS)
 bo_solve_kernel(long long B, const double* __restrict__ p_all, const double* __restrict__ x0_all,
                 double* __restrict__ x_all, double* __restrict__ lam_all, double* __restrict__ f_all,
                 int* __restrict__ status_all, int* __restrict__ iters_all, double* __restrict__ kkt_all,
@@ -979,7 +1012,7 @@ bo_solve_kernel(long long B, const double* __restrict__ p_all, const double* __r
     BO_PAR(i, BO_NX) x_all[b * BO_NX + i] = C.W[BO_OFF_X + i];
 #ifdef BO_PROFILE
     // profiling build: the first 8 doubles of x are replaced by the cycle counters
-    // (0 kkt tape, 1 f/c tape, 2 assembly, 3 factorisation, 4 solves, 7 whole instance)
+    // (0 kkt tape, 1 f/c tape, 2 assembly, 3 factorisation, 4 solves, 5 #factorisations, 6 #solves, 7 whole instance)
     __syncthreads();
     if (threadIdx.x == 0) {
       C.prof[7] = clock64() - bo_t_start;

@@ -1,0 +1,154 @@
+"""Cooperative tier (one instance per CTA; csrc/bo_coop.cpp + csrc/jit/bo_ipm_cta.cuh) on a GPU-less machine.
+
+The generated kernel source compiles for the host (tests/hostsim.py: one "thread", the warp-wide lane
+programs emulated lane by lane with the same reduction tree), so the pieces the tier adds -- tape
+partitioning + per-class code generation, target-owned KKT assembly, the level-scheduled LDL' lane programs,
+the CTA-parallel iteration -- are checked here against numpy and against the thread-per-instance tier.
+A test harness, not a product path."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+from hostsim import HostSim
+
+import optas_b200
+from optas_b200 import problems
+
+
+def _vp(a):
+    return a.ctypes.data_as(C.c_void_p)
+
+
+def _coop(prob, **kw):
+    solver = optas_b200.B200Solver(prob.opt).setup("ipopt", compile_only=True, coop=True, **kw)
+    lo = solver._lowered
+    tab, dtab = np.ascontiguousarray(solver.ldl_table()), np.ascontiguousarray(solver.dtable())
+    sim = HostSim(solver.kernel_source(), lo.nx, lo.np_, lo.n_eq, lo.n_ineq, ldl_table=tab, dtable=dtab)
+    return solver, sim, lo, tab, dtab
+
+
+def _eval_tapes(sim, lo, tab, dtab, p, x, y, z):
+    kkt = [np.zeros(max(n, 1)) for n in lo.kkt.out_sizes]
+    sim.lib.hostsim_coop_kkt(_vp(tab), _vp(dtab), _vp(p), _vp(x), _vp(y), _vp(z), *[_vp(o) for o in kkt])
+    fc = [np.zeros(max(n, 1)) for n in lo.fc.out_sizes]
+    sim.lib.hostsim_coop_fc(_vp(tab), _vp(dtab), _vp(p), _vp(x), *[_vp(o) for o in fc])
+    return [o[:n] for o, n in zip(kkt, lo.kkt.out_sizes)], [o[:n] for o, n in zip(fc, lo.fc.out_sizes)]
+
+
+@pytest.mark.parametrize("generated", [True, False])
+@pytest.mark.parametrize("name", ["point_mass_mpc", "dual_arm"])
+def test_partitioned_tapes_equal_the_reference_interpreter(name, generated, monkeypatch):
+    """Partitioning (independent sub-tapes, parameter-only prefix, partial sums reduced in fixed order) and the
+    per-class code generation must not change what the tapes compute: compare with Tape.eval_numpy."""
+    if not generated:
+        monkeypatch.setenv("BO_NO_GEN_TAPES", "1")
+    prob = getattr(problems, name)()
+    solver, sim, lo, tab, dtab = _coop(prob)
+    info = solver.tier_info()
+    assert info["tier"] == "coop" and info["generated_tapes"] == int(generated)
+    assert info["kkt_components"] >= 16
+    rng = np.random.default_rng(5)
+    P, X0 = prob.sample(1, seed=4)
+    p = np.ascontiguousarray(P[0])
+    x = X0[0] + 0.1 * rng.standard_normal(lo.nx)
+    y, z = rng.standard_normal(max(lo.n_eq, 1))[:lo.n_eq], rng.random(max(lo.n_ineq, 1))[:lo.n_ineq] + 0.1
+    y, z = np.ascontiguousarray(y), np.ascontiguousarray(z)
+    kkt, fc = _eval_tapes(sim, lo, tab, dtab, p, x, y, z)
+    for got, ref in zip(kkt, lo.kkt.eval_numpy([x, p, y, z])):
+        if ref.size:
+            assert np.abs(got - ref).max() <= 1e-12 * max(1.0, np.abs(ref).max())
+    for got, ref in zip(fc, lo.fc.eval_numpy([x, p])):
+        if ref.size:
+            assert np.abs(got - ref).max() <= 1e-12 * max(1.0, np.abs(ref).max())
+
+
+def test_horizon_problems_compile_to_a_few_classes():
+    """All stages of a horizon problem are isomorphic: thousands of components, a handful of functions."""
+    s = optas_b200.B200Solver(problems.dual_arm().opt).setup("ipopt", compile_only=True)
+    info = s.tier_info()
+    assert info["tier"] == "coop" and info["generated_tapes"] == 1
+    assert info["kkt_components"] > 1000 and info["kkt_classes"] <= 32
+    assert info["kkt_code_rows"] < info["kkt_total_instr"] / 10
+    assert info["smem_dynamic"] <= 227 * 1024
+    # the IK problem (one kinematic chain, 10 x 10 KKT system) stays on the thread-per-instance dense tier
+    assert optas_b200.B200Solver(problems.lwr_ik().opt).setup("ipopt", compile_only=True).tier_info()["tier"] == "dense"
+
+
+@pytest.mark.parametrize("segments", ["1", "2", "3"])
+def test_lane_program_factorisation_and_solve(segments, monkeypatch):
+    """Assembly + level-scheduled LDL' + both substitutions, as executed by the lane programs, against a dense
+    numpy solve; the pivot signs must report the inertia (Debreu: positive definite (1,1) block <=> correct)."""
+    monkeypatch.setenv("BO_SEGMENTS", segments)
+    prob = problems.point_mass_mpc()
+    solver, sim, lo, tab, dtab = _coop(prob)
+    assert solver.tier_info()["segments"] == int(segments)
+    rng = np.random.default_rng(0)
+    P, X0 = prob.sample(1, seed=0)
+    x = X0[0] + 0.1 * rng.standard_normal(lo.nx)
+    y, z = rng.standard_normal(lo.n_eq), rng.random(lo.n_ineq) + 0.1
+    _, _, _, _, JE, JI, H = lo.kkt.eval_numpy([x, P[0], y, z])
+    sigma = rng.random(lo.n_ineq) + 0.5
+    nx, me = lo.nx, lo.n_eq
+    Hd = lo.hess.dense(H, (nx, nx), symmetric=True)
+    JEd, JId = lo.jac_eq.dense(JE, (me, nx)), lo.jac_ineq.dense(JI, (lo.n_ineq, nx))
+    sim.lib.hostsim_coop_linsolve.argtypes = [C.c_void_p] * 6 + [C.c_double] * 3 + [C.c_void_p]
+    for rho, dw, dcp, hscale in ((1e3, 0.5, 1e-3, 1.0), (1e6, 0.0, 0.0, 1.0), (10.0, 0.0, 0.0, -50.0)):
+        K = np.zeros((nx + me, nx + me))
+        K[:nx, :nx] = hscale * Hd + JId.T @ np.diag(sigma) @ JId + rho * JEd.T @ JEd + dw * np.eye(nx)
+        K[nx:, :nx], K[:nx, nx:] = JEd, JEd.T
+        K[nx:, nx:] = -dcp * np.eye(me)
+        rhs = rng.standard_normal(nx + me)
+        sol = rhs.copy()
+        Hs = np.ascontiguousarray(hscale * H)
+        bad = sim.lib.hostsim_coop_linsolve(_vp(tab), _vp(dtab), _vp(Hs), _vp(np.ascontiguousarray(JE)),
+                                            _vp(np.ascontiguousarray(JI)), _vp(sigma), rho, dw, dcp, _vp(sol))
+        pd = np.linalg.eigvalsh(K[:nx, :nx]).min() > 0
+        if dcp == 0.0 and pd:
+            # -dc = 0: the y pivots are -JE (..)^-1 JE' < 0 for full-rank JE
+            pass
+        assert (bad == 0) == bool(pd), (rho, dw, dcp, hscale, bad)
+        if bad == 0:
+            ref = np.linalg.solve(K, rhs)
+            assert np.abs(sol - ref).max() <= 1e-9 * max(1.0, np.abs(ref).max())
+
+
+def test_coop_tier_agrees_with_the_thread_per_instance_tier():
+    """Same algorithm, same constants: on C3 both tiers must land on the same solutions (round-off apart)."""
+    prob = problems.point_mass_mpc()
+    P, X0 = prob.sample(24, seed=1)
+    _, sim, lo, _, _ = _coop(prob)
+    r = sim.solve(P, X0)
+    ref_solver = optas_b200.B200Solver(prob.opt).setup("ipopt", compile_only=True, coop=False)
+    assert ref_solver.tier_info()["tier"] == "sparse"
+    ref = HostSim(ref_solver.kernel_source(), lo.nx, lo.np_, lo.n_eq, lo.n_ineq, ldl_table=ref_solver.ldl_table(),
+                  dtable=ref_solver.dtable()).solve(P, X0)
+    assert (r["status"] == ref["status"]).all() and (r["status"] == 0).all()
+    assert (r["iters"] == ref["iters"]).all()
+    assert np.abs(r["x"] - ref["x"]).max() < 1e-9
+    assert np.abs(r["f"] - ref["f"]).max() < 1e-12
+
+
+def test_coop_tier_table_indices_are_in_bounds():
+    """Every operand of the lane programs addresses the factor / right-hand side (or their zero padding cell)."""
+    prob = problems.point_mass_mpc()
+    solver, _, lo, tab, _ = _coop(prob)
+    info = solver.tier_info()
+    nvals, nk = info["factor_vals"], lo.nx + lo.n_eq
+    for slot, solve in ((5, False), (6, True), (7, True)):  # CT_PROG_FAC / FWD / BWD
+        h = tab[tab[slot]:]
+        W, stream = int(h[0]), int(h[2])
+        for w in range(W):
+            first, n = int(h[4 + 2 * w]), int(h[5 + 2 * w])
+            words = tab[stream + 64 * first: stream + 64 * (first + n + 1)].reshape(-1, 32, 2).astype(np.int64) & 0xFFFFFFFF
+            i = 0
+            while i < n:
+                K = int(words[i, 0, 0] & 0xFFFF)
+                assert ((words[i, :, 0] & 0xFFFF) == K).all()  # warp-uniform
+                tg = words[i, :, 1] & 0x7FFF
+                assert ((tg == 0x7FFF) | (tg < (nk if solve else nvals))).all()
+                ops = words[i + 1: i + 1 + K]
+                a, b, c = ops[:, :, 0] & 0xFFFF, ops[:, :, 0] >> 16, ops[:, :, 1]
+                assert (a <= nvals).all() and (b <= (nk if solve else nvals)).all() and (c <= nvals).all()
+                i += K + 1
+            assert i == n

@@ -234,14 +234,17 @@ def test_nlpsol_factory_matches_solver(ik):
     assert np.abs(resid).max() < 1e-6
 
 
-def test_c3_point_mass_mpc_batch(torch_cuda):
-    """C3: MPC tick, 80 variables / 42 equalities / 180 inequalities, checked by the oracle."""
+@pytest.mark.parametrize("coop", [True, False])
+def test_c3_point_mass_mpc_batch(torch_cuda, coop):
+    """C3: MPC tick, 80 variables / 42 equalities / 180 inequalities, checked by the oracle -- on the cooperative
+    tier (one instance per CTA, the default for horizon problems) and the thread-per-instance sparse tier."""
     import kkt_check
     import optas_b200
     from optas_b200 import problems
 
     prob = problems.point_mass_mpc()
-    solver = optas_b200.B200Solver(prob.opt).setup("ipopt")
+    solver = optas_b200.B200Solver(prob.opt).setup("ipopt", coop=coop)
+    assert solver.tier_info()["tier"] == ("coop" if coop else "sparse")
     B = 512
     P, X0 = prob.sample(B, seed=1)
     r = _solve_host(solver, P, X0)
@@ -259,14 +262,17 @@ def test_c3_point_mass_mpc_batch(torch_cuda):
     assert (np.abs(Y) <= 1.5 + 1e-9).all() and (np.abs(dY) <= 1.0 + 1e-9).all()
 
 
-def test_c5_dual_arm_batch(torch_cuda):
-    """C5 through the table-driven large tier, checked against the numpy closed form of the problem."""
+@pytest.mark.parametrize("coop", [True, False])
+def test_c5_dual_arm_batch(torch_cuda, coop):
+    """C5 through the cooperative tier (default) and the table-driven thread-per-instance tier, checked against the
+    numpy closed form of the problem."""
     import optas_b200
     import problems_ref
     from optas_b200 import problems
 
     prob = problems.dual_arm()
-    solver = optas_b200.B200Solver(prob.opt).setup("ipopt")
+    solver = optas_b200.B200Solver(prob.opt).setup("ipopt", coop=coop)
+    assert solver.tier_info()["tier"] == ("coop" if coop else "large")
     B = 96
     P, X0 = prob.sample(B, seed=3)
     r = _solve_host(solver, P, X0)
@@ -285,15 +291,17 @@ def test_c5_dual_arm_batch(torch_cuda):
     assert np.abs(sol["kukal/q"][:, :, 0] - P[:, :7]).max() < 1e-8
 
 
-def test_c4_figure_eight_short_horizon(torch_cuda):
-    """C4's problem class (nonlinear cost, quaternion equalities, joint-limit bounds) on a T = 10 horizon
-    (the T = 50 instance takes minutes in this first version of the large tier; tools/large_check.py)."""
+@pytest.mark.parametrize("T", [10, 50])
+def test_c4_figure_eight(torch_cuda, T):
+    """C4 (nonlinear cost, quaternion equalities, joint-limit bounds): a short horizon and the full T = 50 instance
+    of BASELINE.json (1250-row KKT system, factor in shared memory, one instance per CTA)."""
     import optas_b200
     import problems_ref
     from optas_b200 import problems
 
-    prob = problems.figure_eight(T=10)
+    prob = problems.figure_eight(T=T)
     solver = optas_b200.B200Solver(prob.opt).setup("ipopt", {"max_iter": 400, "max_trips": 2500})
+    assert solver.tier_info()["tier"] == "coop"
     B = 64
     P, X0 = prob.sample(B, seed=2)
     r = _solve_host(solver, P, X0)
@@ -303,6 +311,29 @@ def test_c4_figure_eight_short_horizon(torch_cuda):
     i = int(np.where(ok)[0][0])
     k = problems_ref.sparse_kkt_residual(lo, r["x"][i], P[i], r["lam"][i, :lo.n_eq], r["lam"][i, lo.n_eq:])
     assert k["eq"] < 1e-6 and k["ineq"] < 1e-9
+
+
+def test_coop_tier_is_bitwise_reproducible_across_batch_splits(torch_cuda):
+    """No cross-instance arithmetic and fixed reduction trees inside a CTA: any split of the batch (= any number of
+    GPUs) returns the same bits, also with device-resident buffers."""
+    import optas_b200
+    from optas_b200 import problems
+
+    torch = torch_cuda
+    prob = problems.point_mass_mpc()
+    solver = optas_b200.B200Solver(prob.opt).setup("ipopt")
+    assert solver.tier_info()["tier"] == "coop"
+    B = 1000
+    P, X0 = prob.sample(B, seed=7)
+    full = _solve_host(solver, P, X0)
+    parts = [_solve_host(solver, P[a:b], X0[a:b]) for a, b in ((0, 333), (333, 1000))]
+    for key in ("x", "lam", "f", "status", "iters"):
+        assert np.array_equal(full[key], np.concatenate([p[key] for p in parts])), key
+    Pd, Xd = torch.from_numpy(P).cuda(), torch.from_numpy(X0).cuda()
+    out = torch.empty((B, prob.opt.nx), dtype=torch.float64, device="cuda")
+    solver.solve_raw(Pd, Xd, out, stream=torch.cuda.current_stream().cuda_stream)
+    torch.cuda.synchronize()
+    assert np.array_equal(out.cpu().numpy(), full["x"])
 
 
 def test_mpc_warm_start_device_resident(torch_cuda):

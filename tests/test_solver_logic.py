@@ -12,8 +12,8 @@ import optas_b200
 from optas_b200 import problems
 
 
-def _sim(prob):
-    solver = optas_b200.B200Solver(prob.opt).setup("ipopt", compile_only=True)
+def _sim(prob, **kw):
+    solver = optas_b200.B200Solver(prob.opt).setup("ipopt", compile_only=True, **kw)
     lo = solver._lowered
     return HostSim(solver.kernel_source(), lo.nx, lo.np_, lo.n_eq, lo.n_ineq, ldl_table=solver.ldl_table(),
                    dtable=solver.dtable()), lo
@@ -109,14 +109,15 @@ def test_pack_unpack_roundtrip():
     assert B3 is None and M3.shape == (1, 10)
 
 
-def test_c3_point_mass_mpc_tick():
+@pytest.mark.parametrize("coop", [True, False])
+def test_c3_point_mass_mpc_tick(coop):
     """C3 (example/point_mass_mpc.py Controller, T=20): nx=80, 42 linear equalities, 160 bounds, 20
     obstacle inequalities.  Dimensions as in SURVEY.md 8a; solutions checked by the oracle."""
     prob = problems.point_mass_mpc()
     opt = prob.opt
     assert (opt.nx, opt.np, opt.nk, opt.na, opt.ng, opt.nh, opt.nv) == (80, 84, 160, 42, 20, 0, 264)
     assert type(opt).__name__ == "QuadraticCostNonlinearConstraints"
-    sim, lo = _sim(prob)
+    sim, lo = _sim(prob, coop=coop)
     P, X0 = prob.sample(48, seed=1)
     r = sim.solve(P, X0)
     ok = r["status"] <= 1
@@ -130,16 +131,18 @@ def test_c3_point_mass_mpc_tick():
     assert np.abs(pol.x - r["x"][i]).max() / max(1.0, np.abs(pol.x).max()) < 1e-6
 
 
-def test_c5_dual_arm_large_tier():
-    """C5 (example/dual_arm.py): 1386 variables, 700 linear equalities, T = 50 -- the table-driven tier
-    (interpreted tapes + sparse LDL').  Checked against the independent numpy closed form."""
+@pytest.mark.parametrize("coop", [True, False])
+def test_c5_dual_arm_large_tier(coop):
+    """C5 (example/dual_arm.py): 1386 variables, 700 linear equalities, T = 50 -- the cooperative tier (one
+    instance per CTA; default) and the table-driven thread-per-instance tier (interpreted tapes + sparse LDL').
+    Checked against the independent numpy closed form."""
     import problems_ref
 
     prob = problems.dual_arm()
     opt = prob.opt
     assert (opt.nx, opt.np, opt.nk, opt.na, opt.ng, opt.nh, opt.nv) == (1386, 14, 0, 700, 0, 0, 1400)
     assert type(opt).__name__ == "NonlinearCostLinearConstraints"
-    sim, lo = _sim(prob)
+    sim, lo = _sim(prob, coop=coop)
     P, X0 = prob.sample(3, seed=3)
     # the tapes against the closed form at a random (infeasible) point
     import tape_vm

@@ -27,5 +27,7 @@ tot = c[:, 7].mean()
 print(f"{name}: {B} instances (one per CTA), mean iterations {r['iters'].mean():.1f}, status {np.bincount(r['status'], minlength=5)}")
 for k in (0, 1, 2, 3, 4, 7):
     print(f"  {names[k]:10s} {c[:, k].mean()/1e3:10.1f} kcycles per instance ({100*c[:, k].mean()/tot:5.1f} %)  {(c[:, k:k+1]/it).mean()/1e3:8.2f} kcycles per iteration")
+print(f"  factorisations per iteration {(c[:, 5:6]/it).mean():.2f}, solves per iteration {(c[:, 6:7]/it).mean():.2f}, "
+      f"kcycles per factorisation {c[:, 3].sum()/max(c[:, 5].sum(), 1)/1e3:.1f}, per solve {c[:, 4].sum()/max(c[:, 6].sum(), 1)/1e3:.1f}")
 rest = tot - c[:, :5].sum(axis=1).mean()
 print(f"  {'other':10s} {rest/1e3:10.1f} kcycles per instance ({100*rest/tot:5.1f} %)")
