@@ -412,6 +412,106 @@ class B200Solver(Solver):
     def number_of_iterations(self) -> int:
         return int(self._stats["iter_count"])
 
+    # -- batched diagnostics on the GPU (ref :167-314 evaluates them one instance at a time) ----------
+    def _diagnostic_function(self, key: str, exprs: List):
+        """Streaming kernel (K1) evaluating ``exprs(x, p)``; built and compiled on first use."""
+        from .function import B200Function
+
+        cache = self.__dict__.setdefault("_diag_functions", {})
+        if key not in cache:
+            # one output segment holding every expression (column-major flattening each), split again on the host
+            sizes = [cs.SX(e).numel() for e in exprs]
+            fun = B200Function(cs.Function(key, [self.opt.x, self.opt.p], [cs.vertcat(*[cs.vec(cs.SX(e)) for e in exprs])]))
+            cache[key] = (fun, np.cumsum([0] + sizes))
+
+        fun, offs = cache[key]
+
+        def call(X, P):
+            out = fun(X, P)
+            return [out[:, offs[k]:offs[k + 1]] for k in range(len(offs) - 1)]
+
+        return call
+
+    def _diag_inputs(self, x: Dict[str, ArrayType], p: Dict[str, ArrayType]):
+        X, bx = pack_batch(self.opt.decision_variables, x)
+        P, bp = pack_batch(self.opt.parameters, p)
+        B = bx or bp
+        if B is None:
+            return None
+        return np.ascontiguousarray(np.broadcast_to(X, (B, X.shape[1]))), np.ascontiguousarray(np.broadcast_to(P, (B, P.shape[1]))), B
+
+    def evaluate_cost_terms(self, x: Dict[str, ArrayType], p: Dict[str, ArrayType]) -> List:
+        """Reference semantics for one instance (ref :303-314); with a batch axis on any value every cost term is
+        evaluated for the whole batch by one launch of the streaming kernel and comes back as a ``[B]`` array."""
+        packed = self._diag_inputs(x, p)
+        if packed is None:
+            return super().evaluate_cost_terms(x, p)
+        X, P, B = packed
+        terms = list(self.opt.cost_terms.values())
+        if not terms:
+            return []
+        out = self._diagnostic_function("cost_terms", terms)(X, P)
+        return [o[:, 0] if o.shape[1] == 1 else o for o in out]
+
+    def evaluate_cost(self, x: Dict[str, ArrayType], p: Dict[str, ArrayType]):
+        packed = self._diag_inputs(x, p)
+        if packed is None:
+            return super().evaluate_cost(x, p)
+        X, P, B = packed
+        return self._diagnostic_function("cost", [self.opt.f(self.opt.x, self.opt.p)])(X, P)[0][:, 0]
+
+    def violated_constraints(self, x: Dict[str, ArrayType], p: Dict[str, ArrayType]) -> Tuple:
+        """Reference semantics for one instance (ref :167-238).  Batched: every constraint family is evaluated on the
+        GPU; ``diff`` is ``[B, m, n]`` and ``pattern`` the boolean ``diff >= 0`` (the reference's convention)."""
+        packed = self._diag_inputs(x, p)
+        if packed is None:
+            return super().violated_constraints(x, p)
+        X, P, B = packed
+
+        @dataclass
+        class ViolatedConstraintBatch:
+            label: str
+            ctype: str
+            diff: np.ndarray
+            pattern: np.ndarray
+
+            @property
+            def n_violated(self) -> np.ndarray:  # per instance
+                bad = self.diff < 0.0 if self.ctype.endswith("ineq") else self.diff != 0.0
+                return bad.reshape(bad.shape[0], -1).sum(axis=1)
+
+        def family(container, ctype) -> List:
+            items = list(container.items())
+            if not items:
+                return []
+            out = self._diagnostic_function("constraints_" + ctype, [e for _, e in items])(X, P)
+            res = []
+            for (label, expr), o in zip(items, out):
+                m, n = cs.SX(expr).shape
+                diff = o.reshape(B, n, m).transpose(0, 2, 1)  # column-major flattening per instance
+                res.append(ViolatedConstraintBatch(label, ctype, diff, diff >= 0.0))
+            return res
+
+        return (family(self.opt.lin_eq_constraints, "lin_eq"), family(self.opt.eq_constraints, "eq"),
+                family(self.opt.lin_ineq_constraints, "lin_ineq"), family(self.opt.ineq_constraints, "ineq"))
+
+    # -- closed-loop residency (SURVEY.md 8f-2) ---------------------------------------------------
+    def capture_tick(self, P, X0, X, status=None, iters=None, lam=None, f=None, kkt=None):
+        """Capture one solve on device-resident tensors into a CUDA graph and return it (``graph.replay()`` runs a
+        tick: counter reset + the solver kernel, no host work but the replay call).  The tensors are the graph's
+        fixed buffers: write the new parameters into ``P`` (and the seed into ``X0``; pass ``X0 = X`` to warm-start
+        every tick from the previous solution, example/point_mass_mpc.py:156-175) before each replay."""
+        import torch
+
+        self.solve_raw(P, X0, X, lam, f, status, iters, kkt, stream=torch.cuda.current_stream().cuda_stream)  # warm-up: allocations
+        torch.cuda.synchronize()
+        graph = torch.cuda.CUDAGraph()
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.graph(graph, stream=side):
+            self.solve_raw(P, X0, X, lam, f, status, iters, kkt, stream=side.cuda_stream)
+        return graph
+
     def kernel_info(self) -> Dict:
         return self._handle.kernel_info()
 

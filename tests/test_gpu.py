@@ -364,6 +364,75 @@ def test_mpc_warm_start_device_resident(torch_cuda):
     assert iters[1] <= iters[0] and iters[2] <= iters[0]   # warm start never needs more iterations than the cold tick
 
 
+def test_mpc_tick_as_cuda_graph(torch_cuda):
+    """the whole tick (counter reset + solver kernel) captured once, replayed per tick with the
+    solution buffer as the next seed; the replay must give the bits of a plain call."""
+    import optas_b200
+    from optas_b200 import problems
+
+    torch = torch_cuda
+    prob = problems.point_mass_mpc()
+    solver = optas_b200.B200Solver(prob.opt).setup("ipopt")
+    B = 128
+    P, X0 = prob.sample(B, seed=2)
+    Pd = torch.from_numpy(P).cuda()
+    X = torch.from_numpy(X0).cuda()          # seed and solution share one buffer: warm start from the last tick
+    st = torch.empty(B, dtype=torch.int32, device="cuda")
+    it = torch.empty(B, dtype=torch.int32, device="cuda")
+    ref = torch.from_numpy(X0).cuda()
+    solver.solve_raw(Pd, ref, ref, None, None, st, it, None, stream=torch.cuda.current_stream().cuda_stream)
+    torch.cuda.synchronize()
+    first_iters = it.clone()
+    graph = solver.capture_tick(Pd, X, X, status=st, iters=it)   # (its warm-up call already solved tick 0 in place)
+    X.copy_(torch.from_numpy(X0).cuda())
+    graph.replay()
+    torch.cuda.synchronize()
+    assert (st <= 1).all()
+    assert torch.equal(X, ref) and torch.equal(it, first_iters)
+    # next tick: the plant moved a little; warm-started replay needs fewer iterations than the cold tick
+    Pd[:, 0:2] += 0.01
+    graph.replay()
+    torch.cuda.synchronize()
+    assert (st <= 1).float().mean() > 0.95
+    assert it.float().mean() < first_iters.float().mean()
+
+
+def test_batched_diagnostics(torch_cuda):
+    """evaluate_cost_terms / violated_constraints for a whole batch through the streaming kernel,
+    against the reference's one-instance-at-a-time evaluation on the host graph layer."""
+    import optas_b200
+    from optas_b200 import problems
+
+    prob = problems.point_mass_mpc()
+    solver = optas_b200.B200Solver(prob.opt).setup("ipopt")
+    B = 64
+    P, X0 = prob.sample(B, seed=3)
+    r = _solve_host(solver, P, X0)
+    xd, pd = prob.seed_dict(r["x"]), prob.param_dict(P)
+    terms = solver.evaluate_cost_terms(xd, pd)
+    assert len(terms) == len(prob.opt.cost_terms) and all(t.shape == (B,) for t in terms)
+    assert np.abs(sum(terms) - r["f"]).max() < 1e-10
+    assert np.abs(solver.evaluate_cost(xd, pd) - r["f"]).max() < 1e-10
+    lin_eq, eq, lin_ineq, ineq = solver.violated_constraints(xd, pd)
+    assert [c.label for c in ineq] == list(prob.opt.ineq_constraints.keys())
+    ok = r["status"] <= 1
+    for c in lin_eq + eq:
+        assert np.abs(c.diff[ok]).max() < 1e-7
+    for c in lin_ineq + ineq:
+        assert c.diff[ok].min() > -1e-7 and c.pattern.shape == c.diff.shape
+    # one instance, reference path (host): same numbers
+    i = 5
+    x1 = {k: v[i] for k, v in xd.items()}
+    p1 = {k: v[i] for k, v in pd.items()}
+    for tb, t1 in zip(terms, solver.evaluate_cost_terms(x1, p1)):
+        assert abs(tb[i] - float(t1)) < 1e-12
+    one = solver.violated_constraints(x1, p1)
+    for fam_b, fam_1 in zip((lin_eq, eq, lin_ineq, ineq), one):
+        for cb, c1 in zip(fam_b, fam_1):
+            assert cb.label == c1.label
+            assert np.abs(cb.diff[i] - c1.diff.toarray()).max() < 1e-12
+
+
 def test_qp_drop_in_classes(torch_cuda):
     """OSQPSolver / CVXOPTSolver spellings (optas/solver.py:426-580) on the differential-IK QP of
     example/planar_idk.py; the reference asserts QP-only for both."""
