@@ -176,6 +176,29 @@ def _batch_of(value: np.ndarray, m: int, n: int) -> Optional[int]:
     return None
 
 
+_PINNED = None  # None: not probed yet; False: unavailable
+
+
+def host_array(shape, dtype=np.float64, zero: bool = False) -> np.ndarray:
+    """Host array for data that crosses PCIe: page-locked (torch's caching host allocator) when a CUDA device is
+    present, so that the library's cuMemcpy*Async runs at DMA speed; plain numpy otherwise.  The numpy view keeps
+    the pinned block alive, a later solve never overwrites an array handed to the caller."""
+    global _PINNED
+    n = int(np.prod(shape))
+    if _PINNED is None:
+        try:
+            import torch
+
+            _PINNED = torch if torch.cuda.is_available() else False
+        except Exception:  # torch is plumbing, not a requirement
+            _PINNED = False
+    if _PINNED and n * np.dtype(dtype).itemsize >= (1 << 16):
+        tdt = {np.dtype(np.float64): _PINNED.float64, np.dtype(np.int32): _PINNED.int32}[np.dtype(dtype)]
+        t = _PINNED.zeros(shape, dtype=tdt, pin_memory=True) if zero else _PINNED.empty(shape, dtype=tdt, pin_memory=True)
+        return t.numpy()
+    return np.zeros(shape, dtype=dtype) if zero else np.empty(shape, dtype=dtype)
+
+
 def pack_batch(container, d: Dict[str, ArrayType]) -> Tuple[np.ndarray, Optional[int]]:
     """Vectorised ``SXContainer.dict2vec`` (ref sx_container.py:113-123) over a batch.
 
@@ -195,7 +218,7 @@ def pack_batch(container, d: Dict[str, ArrayType]) -> Tuple[np.ndarray, Optional
                 raise ValueError(f"'{label}': batch size {b} does not match {B}")
             B = b
         values[label] = (v, b)
-    out = np.zeros((B or 1, total))
+    out = host_array((B or 1, total), zero=True)
     for label, (v, b) in values.items():
         off, m, n = layout[label]
         if m * n == 0:
@@ -334,8 +357,8 @@ class B200Solver(Solver):
         n = int(P.shape[0]) if lo.np_ else int(X0.shape[0])
         P = np.ascontiguousarray(P, dtype=np.float64)
         X0 = None if X0 is None else np.ascontiguousarray(X0, dtype=np.float64)
-        out = {"x": np.empty((n, lo.nx)), "lam": np.empty((n, lo.n_eq + lo.n_ineq)), "f": np.empty(n),
-               "status": np.empty(n, dtype=np.int32), "iters": np.empty(n, dtype=np.int32), "kkt": np.empty(n)}
+        out = {"x": host_array((n, lo.nx)), "lam": host_array((n, lo.n_eq + lo.n_ineq)), "f": host_array((n,)),
+               "status": host_array((n,), np.int32), "iters": host_array((n,), np.int32), "kkt": host_array((n,))}
         self._handle.solve(n, P if lo.np_ else None, X0, out["x"], out["lam"], out["f"], out["status"], out["iters"],
                            out["kkt"])
         return out
@@ -349,8 +372,14 @@ class B200Solver(Solver):
             raise ValueError(f"seed batch {self._x0_batched} != parameter batch {self._p_batched}")
         self._batch = B
         n = B or 1
-        X0 = np.ascontiguousarray(np.broadcast_to(self._X0, (n, self.opt.nx)))
-        P = np.ascontiguousarray(np.broadcast_to(self._P, (n, self.opt.np)))
+        def rows(M, width):
+            if M.shape == (n, width) and M.flags.c_contiguous:
+                return M
+            out = host_array((n, width))
+            out[...] = M
+            return out
+
+        X0, P = rows(self._X0, self.opt.nx), rows(self._P, self.opt.np)
         lo = self._lowered
         r = self.solve_arrays(P, X0)
         X, lam, f, status, iters, kkt = r["x"], r["lam"], r["f"], r["status"], r["iters"], r["kkt"]
