@@ -230,6 +230,8 @@ struct bo_cta_state {
   bool recalc_y, ls_mode;
   double phi0, theta0, dw, dc, rho;
   int attempt, heavy;
+  int n_singular;       // consecutive iterations whose unperturbed KKT matrix was singular (rank-deficient JE)
+  bool jac_degenerate, first_singular;
   double a, a_trial, dphi, th_soc;
   int ls, soc;
 };
@@ -648,6 +650,8 @@ BO_DEVICE void bo_cta_init(bo_cta_state& S, const bo_cta& C, const bo_solver_par
   S.n_acceptable = 0;
   S.recalc_y = false;
   S.ls_mode = false;
+  S.n_singular = 0;
+  S.jac_degenerate = false;
   S.phase = BO_PH_EVAL;
   S.trips = 0;
   bo_cta_pre(C);
@@ -767,7 +771,10 @@ BO_DEVICE int bo_cta_trip_eval(bo_cta_state& S, const bo_cta& C, const bo_solver
     S.theta_min = 1e-4 * fmax(1.0, S.theta0);
   }
   S.dw = 0.0;
-  S.dc = 0.0;
+  // IPOPT's degeneracy heuristic (PDPerturbationHandler): once the constraint Jacobian has been found rank deficient
+  // in three consecutive iterations, the constraint block is perturbed from the first attempt on
+  S.dc = S.jac_degenerate ? BO_DC_SCALE * sqrt(sqrt(S.mu)) : 0.0;
+  S.first_singular = false;
   S.attempt = 0;
   S.heavy = 0;
   S.ls_mode = false;
@@ -809,6 +816,7 @@ BO_DEVICE int bo_cta_trip_factor(bo_cta_state& S, const bo_cta& C, const bo_solv
   if (inertia != 0) {
     if (inertia < 0 && BO_ME > 0 && S.dc == 0.0) {
       S.dc = BO_DC_SCALE * sqrt(sqrt(S.mu));
+      if (S.attempt == 0) S.first_singular = true;
     } else if (S.dw == 0.0) {
       S.dw = (S.dw_last == 0.0) ? 1e-4 : fmax(1e-20, S.dw_last / 3.0);
     } else {
@@ -818,6 +826,10 @@ BO_DEVICE int bo_cta_trip_factor(bo_cta_state& S, const bo_cta& C, const bo_solv
     return -1;
   }
   if (S.dw > 0.0 && S.heavy == 0) S.dw_last = S.dw;
+  if (S.heavy == 0 && !S.jac_degenerate) {
+    S.n_singular = S.first_singular ? S.n_singular + 1 : 0;
+    if (S.n_singular >= 3) S.jac_degenerate = true;
+  }
   BO_PAR(j, BO_ME) W[BO_OFF_RE + j] = W[BO_OFF_CE + j];
   BO_PAR(i, BO_MI) W[BO_OFF_RI + i] = W[BO_OFF_CI + i] - W[BO_OFF_S + i];
   bo_sync();

@@ -558,6 +558,8 @@ struct bo_ipm_state {
 #endif
   double phi0, theta0, dw, dc, rho;
   int attempt, heavy;
+  int n_singular;       // consecutive iterations whose unperturbed KKT matrix was singular (rank-deficient JE)
+  bool jac_degenerate, first_singular;
   // step and line search
   double sol[BO_NK], dx[BO_NX], ds[BO_DIM(BO_MI)], y_step[BO_DIM(BO_ME)];
   double dx0[BO_NX], ds0[BO_DIM(BO_MI)], rE[BO_DIM(BO_ME)], rI[BO_DIM(BO_MI)];
@@ -583,6 +585,8 @@ BO_DEVICE void bo_ipm_init(bo_ipm_state& S, const bo_solver_params prm) {
   S.recalc_y = false;
   S.ls_mode = false;
   S.static_fac = false;
+  S.n_singular = 0;
+  S.jac_degenerate = false;
   S.phase = BO_PH_EVAL;
   S.trips = 0;
   bo_eval_fc(S.x, S.p, &S.f, S.cE, S.cI);
@@ -727,7 +731,10 @@ BO_DEVICE int bo_trip_eval(bo_ipm_state& S, const bo_solver_params prm) {
         S.theta_min = 1e-4 * fmax(1.0, S.theta0);
       }
       S.dw = 0.0;
-      S.dc = 0.0;
+      // IPOPT's degeneracy heuristic (PDPerturbationHandler): once the constraint Jacobian has been found rank
+      // deficient in three consecutive iterations, the constraint block is perturbed from the first attempt on
+      S.dc = S.jac_degenerate ? BO_DC_SCALE * sqrt(sqrt(S.mu)) : 0.0;
+      S.first_singular = false;
       S.attempt = 0;
       S.heavy = 0;
       S.ls_mode = false;
@@ -797,6 +804,7 @@ BO_DEVICE int bo_trip_factor(bo_ipm_state& S, const bo_solver_params prm) {
       // ---- inertia correction (IPOPT Algorithm IC); retried on the next trip ----
       if (inertia < 0 && BO_ME > 0 && S.dc == 0.0) {
         S.dc = BO_DC_SCALE * sqrt(sqrt(S.mu));  // IPOPT: 1e-8 mu^(1/4)  // singular: perturb the constraint block first
+      if (S.attempt == 0) S.first_singular = true;
       } else if (S.dw == 0.0) {
         S.dw = (S.dw_last == 0.0) ? 1e-4 : fmax(1e-20, S.dw_last / 3.0);
       } else {
@@ -806,6 +814,10 @@ BO_DEVICE int bo_trip_factor(bo_ipm_state& S, const bo_solver_params prm) {
       return -1;
     }
     if (S.dw > 0.0 && S.heavy == 0) S.dw_last = S.dw;
+    if (S.heavy == 0 && !S.jac_degenerate) {
+      S.n_singular = S.first_singular ? S.n_singular + 1 : 0;
+      if (S.n_singular >= 3) S.jac_degenerate = true;
+    }
     BO_UNROLL
     for (int j = 0; j < BO_ME; ++j) S.rE[j] = S.cE[j];
     BO_UNROLL
