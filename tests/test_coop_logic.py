@@ -152,3 +152,34 @@ def test_coop_tier_table_indices_are_in_bounds():
                 assert (a <= nvals).all() and (b <= (nk if solve else nvals)).all() and (c <= nvals).all()
                 i += K + 1
             assert i == n
+
+
+@pytest.mark.parametrize("with_eq,with_ineq", [(False, True), (True, False), (False, False)])
+def test_coop_tier_without_equalities_or_inequalities(with_eq, with_ineq):
+    """Edge cases of the problem shape (n_eq = 0 and / or n_ineq = 0) through the cooperative tier, on a synthetic
+    chain problem straight through the C ABI (lower_nlp -> bo_problem_create), against the thread-per-instance tier."""
+    from optas_b200 import _capi, sym as cs
+    from optas_b200.lowering import lower_nlp
+
+    n = 24
+    x, p = cs.SX.sym("x", n), cs.SX.sym("p", n)
+    f = cs.sumsqr(x - p) + 0.5 * cs.sumsqr(cs.sin(x[1:]) - x[:-1]) + 0.1 * cs.sumsqr(x[1:] * x[:-1])
+    c_eq = cs.vertcat(*[x[3 * k] + x[3 * k + 1] * x[3 * k + 2] - 0.3 for k in range(n // 3)]) if with_eq else cs.SX(0, 1)
+    c_in = cs.vertcat(*[1.2 - x[k] * x[k] - 0.5 * x[k + 1] for k in range(n - 1)]) if with_ineq else cs.SX(0, 1)
+    lo = lower_nlp(x, p, f, c_eq, c_in)
+    assert (lo.n_eq > 0) == with_eq and (lo.n_ineq > 0) == with_ineq
+    rng = np.random.default_rng(11)
+    P = 0.6 * rng.standard_normal((6, n))
+    X0 = np.zeros((6, n))
+    res = {}
+    for name, flag in (("coop", _capi.BO_FLAG_COOP), ("thread", _capi.BO_FLAG_NO_COOP)):
+        h = _capi.ProblemHandle(lo, flags=_capi.BO_FLAG_COMPILE_ONLY | flag)
+        assert h.tier_info()["tier"] == ("coop" if name == "coop" else "sparse")
+        sim = HostSim(h.source(), lo.nx, lo.np_, lo.n_eq, lo.n_ineq, ldl_table=h.ldl_table(), dtable=h.dtable())
+        res[name] = sim.solve(P, X0)
+        assert (res[name]["status"] <= 1).all(), res[name]["status"]
+    assert np.abs(res["coop"]["x"] - res["thread"]["x"]).max() < 1e-7
+    assert np.abs(res["coop"]["f"] - res["thread"]["f"]).max() < 1e-9
+    if with_ineq:
+        xs = res["coop"]["x"]
+        assert (1.2 - xs[:, :-1] ** 2 - 0.5 * xs[:, 1:] > -1e-8).all()
