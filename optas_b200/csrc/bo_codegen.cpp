@@ -259,6 +259,14 @@ static void emit_sparse_helpers(std::ostringstream& o, const char* tag, const Sp
   o << "  (void)J; (void)x; (void)out;\n}\n";
 }
 
+bool hessian_depends_on_eq_multipliers(const ProblemSource& ps) {
+  for (int64_t i = 0; i < ps.kkt.n_instr(); ++i) {
+    const int32_t* r = &ps.kkt.instr[4 * i];
+    if ((r[0] & 0xFF) == BO_OP_INPUT && r[3] == 2) return true;  // input segment 2 of the kkt tape = y
+  }
+  return false;
+}
+
 std::string emit_problem_source(const ProblemSource& ps, int tpb, bool pivoted_ldl, const SparsePlan* sparse, bool large) {
   std::ostringstream o;
   o << "// generated by libb200optas (bo_codegen.cpp): tier-S solver, one instance per thread\n";
@@ -266,6 +274,7 @@ std::string emit_problem_source(const ProblemSource& ps, int tpb, bool pivoted_l
     << ps.n_ineq << "\n#define BO_NNZ_JE " << ps.jac_eq.nnz() << "\n#define BO_NNZ_JI " << ps.jac_ineq.nnz()
     << "\n#define BO_NNZ_H " << ps.hess.nnz() << "\n#define BO_TPB " << tpb << "\n";
   if (pivoted_ldl) o << "#define BO_USE_BK 1\n";
+  if (!hessian_depends_on_eq_multipliers(ps)) o << "#define BO_RECALC_DC_ONLY 1\n";
   if (sparse) o << "#define BO_SPARSE_LDL 1\n#define BO_SPARSE_VALS " << sparse->vals_size() << "\n";
   if (large) {
     // table-driven tier: no generated code at all, only the sizes

@@ -51,6 +51,10 @@ struct ProblemSource {
   Sparsity jac_eq, jac_ineq, hess;
 };
 
+// Linear equality constraints: y does not enter the Hessian of the Lagrangian, so the least-squares multiplier
+// re-estimate after a convexified step (which exists to break the dw -> y -> Hessian -> dw feedback) is skipped.
+bool hessian_depends_on_eq_multipliers(const ProblemSource& ps);
+
 // Full translation unit of the tier-S (thread-per-instance) solver for this problem.
 struct SparsePlan;
 std::string emit_problem_source(const ProblemSource& ps, int threads_per_block, bool pivoted_ldl,

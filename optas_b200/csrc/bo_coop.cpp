@@ -1227,6 +1227,7 @@ std::string emit_coop_source(const ProblemSource& ps, const CoopPlan& pl, int tp
     o << "#define BO_MIN_CTAS " << min_ctas << "\n#define BO_FAC_G " << pl.ldl_g << "\n#define BO_FWD_G " << pl.solve_g
       << "\n#define BO_BWD_G " << pl.solve_bwd_g << "\n";
   }
+  if (!hessian_depends_on_eq_multipliers(ps)) o << "#define BO_RECALC_DC_ONLY 1\n";
   o << "#include \"bo_common.cuh\"\n";
   if (pl.gen_tapes) o << "#define BO_GEN_TAPES 1\n" << pl.gen_code;
   o << "#include \"bo_ipm_cta.cuh\"\n";

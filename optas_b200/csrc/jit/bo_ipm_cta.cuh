@@ -922,7 +922,11 @@ BO_DEVICE int bo_cta_trip_trial(bo_cta_state& S, const bo_cta& C, const bo_solve
       W[BO_OFF_Z + i] = z;
     }
     BO_PAR(j, BO_ME) W[BO_OFF_Y + j] += S.a * W[BO_OFF_YST + j];
+    #ifdef BO_RECALC_DC_ONLY  /* y does not enter the Hessian (linear equalities): only the rank-deficient case needs it */
+    S.recalc_y = S.dc > 0.0;
+#else
     S.recalc_y = S.dw > 0.0 || S.dc > 0.0;
+#endif
     S.it += 1;
     S.phase = BO_PH_EVAL;
     bo_sync();

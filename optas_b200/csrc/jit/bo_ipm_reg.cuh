@@ -915,7 +915,11 @@ BO_DEVICE int bo_trip_trial(bo_ipm_state& S, const bo_solver_params prm) {
       for (int j = 0; j < BO_ME; ++j) S.y[j] += S.a * S.y_step[j];
       // regularised step (dw: nonconvex; dc: rank-deficient JE, whose multipliers are undetermined along
       // null(JE') and would otherwise drift by residual/dc): re-estimate y by least squares next trip
-      S.recalc_y = S.dw > 0.0 || S.dc > 0.0;
+      #ifdef BO_RECALC_DC_ONLY  /* y does not enter the Hessian (linear equalities): only the rank-deficient case needs it */
+    S.recalc_y = S.dc > 0.0;
+#else
+    S.recalc_y = S.dw > 0.0 || S.dc > 0.0;
+#endif
       S.it += 1;
       S.phase = BO_PH_EVAL;
       return -1;

@@ -131,9 +131,9 @@ class HostSim:
             wrap = os.path.join(d, f"wrap_{os.getpid()}.cpp")
             open(gen, "w").write(generated_source)
             open(wrap, "w").write((_WRAPPER_COOP if coop else _WRAPPER) % {"gen": gen, "trace": ("#define BO_HOST_TRACE 1\n" if trace else "") + defines})
-            subprocess.run(["/usr/bin/g++", "-O1", "-shared", "-fPIC", "-std=c++17", "-I", _JIT_INC, "-I", os.path.join(_HERE, "..", "include"), wrap, "-o", so + ".tmp"],
+            subprocess.run(["/usr/bin/g++", "-O1", "-shared", "-fPIC", "-std=c++17", "-I", _JIT_INC, "-I", os.path.join(_HERE, "..", "include"), wrap, "-o", so + f".tmp{os.getpid()}"],
                            check=True)
-            os.replace(so + ".tmp", so)
+            os.replace(so + f".tmp{os.getpid()}", so)
         self.lib = C.CDLL(so)
         vp = C.c_void_p
         self.lib.hostsim_solve.argtypes = [C.c_longlong] + [vp] * 9 + [C.c_int, C.c_double, C.c_double, C.c_double, C.c_double, C.c_int, vp, vp, vp]
