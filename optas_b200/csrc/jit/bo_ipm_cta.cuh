@@ -803,6 +803,22 @@ BO_DEVICE int bo_cta_trip_factor(bo_cta_state& S, const bo_cta& C, const bo_solv
       bo_reduce<1>(v, op, BO_RED_P(C));
       if (v[0] == 0.0) {
         BO_PAR(j, BO_ME) W[BO_OFF_Y + j] = W[BO_OFF_SOL + BO_NX + j];
+        // One step of iterative refinement towards the UNregularised least-squares multipliers: the factorised
+        // system carries -dc on the constraint block, which scales every component of y by s^2 / (s^2 + dc)
+        // (s: singular value of JE) -- a relative error of dc / s^2 ~ 1e-8 that would otherwise sit in the dual
+        // infeasibility as a floor just above tol (C4 stalled at 2.7e-8 and ended "acceptable").
+        BO_PAR(c, BO_NX) W[BO_OFF_DX0 + c] = W[BO_OFF_SOL + c];
+        bo_sync();
+        BO_PAR(c, BO_NX)
+          W[BO_OFF_SOL + c] = (W[BO_OFF_G + c] - BO_JI_T(c, W + BO_OFF_Z)) - (S.dw * W[BO_OFF_DX0 + c] + BO_JE_T(c, W + BO_OFF_Y));
+        BO_PAR(j, BO_ME)
+          W[BO_OFF_SOL + BO_NX + j] = -bo_gather(C.tab + C.tab[CT_JE_RPTR], C.tab + C.tab[CT_JE_RENT], j, W + BO_OFF_JE, W + BO_OFF_DX0);
+        bo_sync();
+        bo_cta_ldl_solve(C, W + BO_OFF_SOL);
+        BO_PAR(j, BO_ME) {
+          const double d = W[BO_OFF_SOL + BO_NX + j];
+          if (bo_isfinite(d)) W[BO_OFF_Y + j] += d;
+        }
       }
       bo_sync();
     }
