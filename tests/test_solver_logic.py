@@ -173,10 +173,12 @@ def test_c4_figure_eight_large_tier():
     sim, lo = _sim(prob)
     P, X0 = prob.sample(2, seed=2)
     r = sim.solve(P, X0, max_iter=400, max_trips=2500)
-    assert (r["status"] <= 1).all(), r["status"]
+    # converged to tol = 1e-8, not merely "acceptable": the least-squares multipliers are refined towards the
+    # unregularised solution, so the dc regularisation no longer leaves a 2.7e-8 floor in the dual infeasibility
+    assert (r["status"] == 0).all(), r["status"]
     for i in range(2):
         k = problems_ref.sparse_kkt_residual(lo, r["x"][i], P[i], r["lam"][i, :lo.n_eq], r["lam"][i, lo.n_eq:])
-        assert k["eq"] < 1e-6 and k["ineq"] < 1e-9 and k["stationarity"] < 1e-4 * max(1.0, np.abs(r["lam"][i]).max())
+        assert k["eq"] < 1e-9 and k["ineq"] < 1e-9 and k["stationarity"] < 1e-8 and k["complementarity"] < 1e-8
 
 
 def test_planar_differential_ik_qp():
