@@ -218,7 +218,9 @@ def pack_batch(container, d: Dict[str, ArrayType]) -> Tuple[np.ndarray, Optional
                 raise ValueError(f"'{label}': batch size {b} does not match {B}")
             B = b
         values[label] = (v, b)
-    out = host_array((B or 1, total), zero=True)
+    # zero-fill only when some label is missing (the reference's dict2vec semantics: missing labels become zeros)
+    covered = sum(m * n for label, (off, m, n) in layout.items() if label in values)
+    out = host_array((B or 1, total), zero=covered < total)
     for label, (v, b) in values.items():
         off, m, n = layout[label]
         if m * n == 0:
