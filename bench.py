@@ -230,6 +230,15 @@ def run_other_config(args) -> None:
     else:
         P, X0 = prob.sample(total, seed=rank + 1)
     B = X0.shape[0]
+    # the e2e leg copies its inputs from page-locked host memory (as the bench contract says)
+    from optas_b200.solver import host_array
+
+    def pinned(a):
+        out = host_array(a.shape)
+        out[...] = a
+        return out
+
+    P, X0 = pinned(P), pinned(X0)
     solver = optas_b200.B200Solver(prob.opt).setup("ipopt", opts, timing=True)
     Pd, X0d = torch.from_numpy(P).to(dev), torch.from_numpy(X0).to(dev)
     Xd = torch.empty_like(X0d)
