@@ -259,6 +259,7 @@ def run_other_config(args) -> None:
     torch.cuda.synchronize()
     dev_ms = e0.elapsed_time(e1)
     n_conv = int((std <= 1).sum().item())
+    solver.solve_arrays(P, X0)  # untimed: first use of the page-locked result buffers
     t0 = time.perf_counter()
     for _ in range(steps):
         r = solver.solve_arrays(P, X0)

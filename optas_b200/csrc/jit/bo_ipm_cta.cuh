@@ -40,6 +40,9 @@
 #define BO_HEAVY_MAX 5
 #endif
 #define BO_IC_MAX 60
+#ifndef BO_REFINE_BELOW
+#define BO_REFINE_BELOW 1e-4 /* refine the least-squares multipliers once the KKT error is below this */
+#endif
 #define BO_PH_EVAL 0
 #define BO_PH_FACTOR 1
 #define BO_PH_TRIAL 2
@@ -806,7 +809,9 @@ BO_DEVICE int bo_cta_trip_factor(bo_cta_state& S, const bo_cta& C, const bo_solv
         // One step of iterative refinement towards the UNregularised least-squares multipliers: the factorised
         // system carries -dc on the constraint block, which scales every component of y by s^2 / (s^2 + dc)
         // (s: singular value of JE) -- a relative error of dc / s^2 ~ 1e-8 that would otherwise sit in the dual
-        // infeasibility as a floor just above tol (C4 stalled at 2.7e-8 and ended "acceptable").
+        // infeasibility as a floor just above tol (C4 stalled at 2.7e-8 and ended "acceptable").  Only near
+        // convergence: far from it the extra accuracy buys nothing and costs a solve per iteration.
+        if (S.err0 < BO_REFINE_BELOW) {
         BO_PAR(c, BO_NX) W[BO_OFF_DX0 + c] = W[BO_OFF_SOL + c];
         bo_sync();
         BO_PAR(c, BO_NX)
@@ -818,6 +823,7 @@ BO_DEVICE int bo_cta_trip_factor(bo_cta_state& S, const bo_cta& C, const bo_solv
         BO_PAR(j, BO_ME) {
           const double d = W[BO_OFF_SOL + BO_NX + j];
           if (bo_isfinite(d)) W[BO_OFF_Y + j] += d;
+        }
         }
       }
       bo_sync();

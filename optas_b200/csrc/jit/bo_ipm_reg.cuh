@@ -510,6 +510,9 @@ BO_NOINLINE void bo_measures(double f, const double* cE, const double* cI, const
 #define BO_HEAVY_MAX 5  /* re-solves with dw = 1, 1e2, 1e4, 1e6 when no step is acceptable */
 #endif
 #define BO_IC_MAX 60    /* inertia-correction attempts per iteration */
+#ifndef BO_REFINE_BELOW
+#define BO_REFINE_BELOW 1e-4 /* refine the least-squares multipliers once the KKT error is below this */
+#endif
 #ifndef BO_INNER_ROUNDS
 /* FACTOR/TRIAL repetitions per trip before the warp moves on to the next EVAL.  Pays when EVAL dominates
  * (sparse / large tiers: C4 1.7x faster); for the dense tier the phases cost about the same and waiting
@@ -796,7 +799,7 @@ BO_DEVICE int bo_trip_factor(bo_ipm_state& S, const bo_solver_params prm) {
           // system carries -dc on the constraint block, which scales every component of y by s^2 / (s^2 + dc)
           // (s: singular value of JE) -- a relative error of dc / s^2 ~ 1e-8 that would otherwise sit in the dual
           // infeasibility as a floor just above tol (C4 stalled at 2.7e-8 and ended "acceptable").
-          if (S.static_fac) {
+          if (S.static_fac && S.err0 < BO_REFINE_BELOW) {  // only near convergence: elsewhere the accuracy buys nothing
             BO_UNROLL
             for (int i = 0; i < BO_NX; ++i) S.dx0[i] = S.sol[i];
             double ny[BO_DIM(BO_ME)];
