@@ -31,6 +31,16 @@ import sys
 import threading
 import time
 
+# Exactly ONE line goes to stdout (the JSON result of rank 0): everything else that libraries write to file descriptor 1
+# (NCCL prints its version banner there) is sent to stderr.
+_RESULT_OUT = os.fdopen(os.dup(1), "w")
+os.dup2(2, 1)
+
+
+def emit(result: dict) -> None:
+    _RESULT_OUT.write(json.dumps(result) + "\n")
+    _RESULT_OUT.flush()
+
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
@@ -190,7 +200,7 @@ def run_reference(args) -> None:
         "e2e": {"value": value, "unit": "instances/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line))
+    emit(line)
 
 
 OTHER_CONFIGS = {
@@ -270,7 +280,7 @@ def run_other_config(args) -> None:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         dist.all_reduce(c, op=dist.ReduceOp.SUM)
     if rank == 0:
-        print(json.dumps({
+        emit({
             "metric": "problem-instances solved/sec", "value": float(c[0]) * steps / (float(t[0]) * 1e-3), "unit": "instances/s",
             "n_gpus": world, "steps": steps, "warmup": warmup, "ms_per_step": float(t[0]) / steps, "higher_is_better": True,
             "scaling": scaling, "vs_baseline": None, "dtype": "f64", "data": "synthetic",
@@ -282,7 +292,7 @@ def run_other_config(args) -> None:
             "tier": {k: v for k, v in solver.tier_info().items() if k in (
                 "tier", "threads_per_block", "smem_dynamic", "blocks_per_sm", "levels", "segments", "factor_vals",
                 "factor_madds", "factor_steps", "solve_steps", "ldl_warps", "ldl_g", "solve_g", "generated_tapes",
-                "kkt_components", "kkt_classes", "kkt_code_rows", "kkt_total_instr")}}))
+                "kkt_components", "kkt_classes", "kkt_code_rows", "kkt_total_instr")}})
     if dist is not None:
         dist.barrier()
         dist.destroy_process_group()
@@ -457,7 +467,7 @@ def main() -> None:
         }
         if not args.no_cpu_baseline and world == 1:
             line["cpu_baseline"] = cpu_baseline(CPU_SAMPLE, os.cpu_count() or 1)
-        print(json.dumps(line))
+        emit(line)
     if dist is not None:
         dist.barrier()
         dist.destroy_process_group()
