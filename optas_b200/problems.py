@@ -339,4 +339,146 @@ def planar_idk() -> Problem:
     return Problem("planar_idk", opt, sample, {"J": J}, {"robot": robot})
 
 
-ALL_BUILDERS = [lwr_ik, booth, point_mass_mpc, figure_eight, dual_arm, planar_idk]
+# ----------------------------------------------------------------------------------------------
+# "Next" row 8f-3: the rest of the RobotModel surface through the same solver
+#   joint-space planner to an end-effector POSE with height constraints on two links
+#     (reference: example/simple_joint_space_planner.py:14-71)
+#   trajectory optimisation with sphere collision avoidance, three derivative orders
+#     (reference: example/sphere_collision_avoidance.py:54-98, builder.py:366-417)
+# ----------------------------------------------------------------------------------------------
+
+
+def joint_space_planner(T: int = 20) -> Problem:
+    duration, zpad = 4.0, 0.05
+    dt = duration / float(T - 1)
+    robot = RobotModel(urdf_filename=MED7_URDF, time_derivs=[0, 1])
+    name = robot.get_name()
+    builder = OptimizationBuilder(T=T, robots=robot, derivs_align=True)
+    qn = builder.add_parameter("nominal_joint_state", robot.ndof)
+    qc = builder.add_parameter("current_joint_state", robot.ndof)
+    pg = builder.add_parameter("position_goal", 3)
+    og = builder.add_parameter("orientation_goal", 4)
+    builder.fix_configuration(name, config=qc)
+    qF = builder.get_model_state(name, -1)
+    builder.add_equality_constraint("final_position", robot.get_global_link_position(MED7_EE, qF), pg)
+    builder.add_equality_constraint("final_orientation", robot.get_global_link_quaternion(MED7_EE, qF), og)
+    builder.integrate_model_states(name, time_deriv=1, dt=dt)
+    for t in range(T):
+        q = builder.get_model_state(name, t)
+        builder.add_cost_term(f"nominal_{t}", 0.1 * cs.sumsqr(q - qn))
+        builder.add_geq_inequality_constraint(f"eff_safe_{t}", robot.get_global_link_position(MED7_EE, q)[2] + zpad)
+        builder.add_geq_inequality_constraint(f"elbow_safe_{t}", robot.get_global_link_position("lbr_link_3", q)[2] + zpad)
+    dQ = builder.get_model_states(name, time_deriv=1)
+    builder.add_cost_term("minimize_velocity", 0.1 * cs.sumsqr(dQ))
+    ddQ = (dQ[:, 1:] - dQ[:, :-1]) / dt
+    builder.add_cost_term("minimize_acceleration", 10 * cs.sumsqr(ddQ))
+    builder.fix_configuration(name, t=-1, time_deriv=1)
+    opt = builder.build()
+
+    qs = cs.SX.sym("q", robot.ndof)
+    pose = cs.Function("pose", [qs], [cs.vertcat(robot.get_global_link_position(MED7_EE, qs),
+                                                  robot.get_global_link_quaternion(MED7_EE, qs))])
+    lo = robot.lower_actuated_joint_limits.toarray().flatten()
+    up = robot.upper_actuated_joint_limits.toarray().flatten()
+
+    def sample(B: int, seed: int = 6):
+        """Current configuration = the script's q0 = deg2rad[0,45,0,-90,0,-45,0] + N(0, 0.05^2); the goal POSE is
+        the forward kinematics of a second configuration q0 + N(0, 0.3^2) (reachable by construction; the script's
+        single goal is p = [0.4, 0.3, 0.4], quat = [0, 1, 0, 0]); seed: hold the current configuration."""
+        rng = np.random.default_rng(seed)
+        q0 = np.deg2rad([0.0, 45.0, 0.0, -90.0, 0.0, -45.0, 0.0])
+        qc_ = np.clip(q0 + 0.05 * rng.standard_normal((B, 7)), 0.95 * lo, 0.95 * up)
+        qg_ = np.clip(q0 + 0.3 * rng.standard_normal((B, 7)), 0.95 * lo, 0.95 * up)
+        goal = _eval_rows(pose, qg_)
+        P = np.concatenate([np.tile(q0, (B, 1)), qc_, goal], axis=1)
+        X0 = np.concatenate([np.tile(qc_, (1, T)), np.zeros((B, 7 * T))], axis=1)
+        return np.ascontiguousarray(P), np.ascontiguousarray(X0)
+
+    return Problem("joint_space_planner", opt, sample, {"pose": pose}, {"robot": robot})
+
+
+SPHERE_LINKS = ["end_effector_ball", "lwr_arm_7_link", "lwr_arm_5_link", "lwr_arm_6_link"]
+SPHERE_Q_NOMINAL = np.deg2rad([0.0, -45.0, 0.0, 90.0, 0.0, 45.0, 0.0])
+# solution of the script's first stage (`lwr_axis_ik` at start_eff_position = [0.825, -0.35, 0.2], seed = nominal);
+# tests/test_solver_logic.py::test_sphere_collision_first_stage_ik re-derives it
+SPHERE_Q_START = np.array([-0.38934800247392193, -1.1451497139998776, -0.3501660198135529, 1.2868149461781317,
+                           -0.5796474583683217, 1.0978271686956158, 0.0])
+
+
+def lwr_axis_ik() -> Problem:
+    """First stage of example/sphere_collision_avoidance.py (:20-42, `compute_initial_configuration`): IK to an
+    end-effector position with the tool z axis kept at its nominal direction, joint limits, nominal-posture cost."""
+    robot = RobotModel(urdf_filename=LWR_URDF, time_derivs=[0, 1, 2])
+    name = robot.get_name()
+    z0 = robot.get_global_link_transform(LWR_EE, SPHERE_Q_NOMINAL)[:3, 2]
+    builder = OptimizationBuilder(1, robots=robot, derivs_align=True)
+    start = builder.add_parameter("start_eff_position", 3)  # the constant [0.825, -0.35, 0.2] in the script
+    q = builder.get_model_state(name, 0)
+    Tq = robot.get_global_link_transform(LWR_EE, q)
+    builder.enforce_model_limits(name)
+    builder.add_equality_constraint("eff_pos", Tq[:3, 3], start)
+    builder.add_equality_constraint("eff_ori", Tq[:3, 2], z0)
+    builder.initial_configuration(name, time_deriv=1)
+    builder.initial_configuration(name, time_deriv=2)
+    builder.add_cost_term("nominal", cs.sumsqr(q - SPHERE_Q_NOMINAL))
+    opt = builder.build()
+
+    def sample(B: int, seed: int = 8):
+        rng = np.random.default_rng(seed)
+        P = np.array([0.825, -0.35, 0.2]) + 0.02 * rng.standard_normal((B, 3))
+        X0 = np.concatenate([np.tile(SPHERE_Q_NOMINAL, (B, 1)), np.zeros((B, 14))], axis=1)
+        return np.ascontiguousarray(P), np.ascontiguousarray(X0)
+
+    return Problem("lwr_axis_ik", opt, sample, {}, {"robot": robot})
+
+
+
+def sphere_collision_avoidance(T: int = 20, n_obstacles: int = 6, reduce_constraint: bool = True) -> Problem:
+    duration = 10.0
+    dt = duration / float(T - 1)
+    robot = RobotModel(urdf_filename=LWR_URDF, time_derivs=[0, 1, 2])
+    name = robot.get_name()
+    qnom = SPHERE_Q_NOMINAL
+    z0 = robot.get_global_link_transform(LWR_EE, qnom)[:3, 2]
+    builder = OptimizationBuilder(T, robots=robot, derivs_align=True)
+    q0 = builder.add_parameter("q0", robot.ndof)  # the script computes it with a first IK solve and bakes it in
+    pgoal = builder.add_parameter("goal_eff_position", 3)  # a constant [0.825, 0.35, 0.2] in the script
+    builder.enforce_model_limits(name)
+    builder.integrate_model_states(name, 2, dt)
+    builder.integrate_model_states(name, 1, dt)
+    builder.initial_configuration(name, init=q0)
+    builder.initial_configuration(name, time_deriv=1)
+    builder.initial_configuration(name, time_deriv=2)
+    qf = builder.get_model_state(name, t=-1)
+    Tf = robot.get_global_link_transform(LWR_EE, qf)
+    builder.add_equality_constraint("eff_pos", Tf[:3, 3], pgoal, reduce_constraint=reduce_constraint)
+    builder.add_equality_constraint("eff_ori", Tf[:3, 2], z0, reduce_constraint=reduce_constraint)
+    builder.add_cost_term("min_vel", cs.sumsqr(builder.get_model_states(name, time_deriv=1)))
+    builder.add_cost_term("min_acc", 100 * cs.sumsqr(builder.get_model_states(name, time_deriv=2)))
+    builder.add_cost_term("nominal", 1e2 * cs.sumsqr(qf - qnom))
+    obstacle_names = [f"obs{i}" for i in range(n_obstacles)]
+    builder.sphere_collision_avoidance_constraints(name, obstacle_names, link_names=SPHERE_LINKS)
+    opt = builder.build()
+
+    def sample(B: int, seed: int = 7):
+        """The script's scene: a column of six spheres (radius 0.1) at x = 0.55, y = 0, z = 0.1 .. 0.6, link radius
+        0.15, start at the first stage's IK solution + N(0, 0.02^2), goal position [0.825, 0.35, 0.2] + N(0, 0.02^2)."""
+        rng = np.random.default_rng(seed)
+        d: Dict[str, np.ndarray] = {"q0": SPHERE_Q_START + 0.02 * rng.standard_normal((B, 7)),
+                                    "goal_eff_position": np.array([0.825, 0.35, 0.2]) + 0.02 * rng.standard_normal((B, 3))}
+        for ln in SPHERE_LINKS:
+            d[ln + "_radii"] = np.full((B, 1), 0.15)
+        for i, on in enumerate(obstacle_names):
+            d[on + "_position"] = np.tile(np.array([0.55, 0.0, 0.1 * (i + 1)]), (B, 1))
+            d[on + "_radii"] = np.full((B, 1), 0.1)
+        from .solver import pack_batch
+
+        P, _ = pack_batch(opt.parameters, d)
+        X0d = {f"{name}/q/x": np.repeat(d["q0"][:, :, None], T, axis=2)}
+        X0, _ = pack_batch(opt.decision_variables, X0d)
+        return np.ascontiguousarray(P), np.ascontiguousarray(X0)
+
+    return Problem("sphere_collision_avoidance", opt, sample, {}, {"robot": robot})
+
+
+ALL_BUILDERS = [lwr_ik, booth, point_mass_mpc, figure_eight, dual_arm, planar_idk, joint_space_planner, lwr_axis_ik]

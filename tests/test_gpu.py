@@ -454,6 +454,58 @@ def test_qp_drop_in_classes(torch_cuda):
         optas.OSQPSolver(problems.dual_arm().opt).setup(use_warm_start=False)
 
 
+def test_joint_space_planner_batch(torch_cuda):
+    """SURVEY.md 8f-3 -- example/simple_joint_space_planner.py (pose goal = position + quaternion equalities on the
+    last knot, link-height inequalities on every knot) as a batch on the cooperative tier; checked by the oracle's KKT
+    residual and the independent numpy kinematics."""
+    import fk_ref
+    import kkt_check
+    import optas_b200
+    from optas_b200 import problems
+
+    prob = problems.joint_space_planner()
+    solver = optas_b200.B200Solver(prob.opt).setup("ipopt")
+    assert solver.tier_info()["tier"] == "coop"
+    B = 1024
+    P, X0 = prob.sample(B)
+    r = _solve_host(solver, P, X0)
+    ok = r["status"] <= 1
+    assert ok.mean() >= 0.99, np.bincount(r["status"])
+    lo = solver._lowered
+    idx = np.where(ok)[0][:16]
+    res = kkt_check.kkt_residual(prob, r["x"][idx], P[idx], r["lam"][idx][:, :lo.n_eq], r["lam"][idx][:, lo.n_eq:])
+    assert res.max() < KKT_TOL, res.max()
+    sol = prob.seed_dict(r["x"][ok])
+    Q, dQ = sol["med7/q/x"], sol["med7/dq/x"]
+    chain = fk_ref.Chain(problems.MED7_URDF, problems.MED7_EE)
+    assert np.abs(chain.fk(Q[:, :, -1])[1] - P[ok, 14:17]).max() < 1e-7
+    assert np.abs(chain.quaternion(Q[:, :, -1]) - P[ok, 17:21]).max() < 1e-7
+    assert np.abs(Q[:, :, 0] - P[ok, 7:14]).max() < 1e-9 and np.abs(dQ[:, :, -1]).max() < 1e-9
+    assert np.abs(Q[:, :, 1:] - Q[:, :, :-1] - (4.0 / 19.0) * dQ[:, :, :-1]).max() < 1e-9
+
+
+def test_axis_ik_first_stage_batch(torch_cuda):
+    """SURVEY.md 8f-3 -- first stage of example/sphere_collision_avoidance.py (:20-42): position + tool-axis IK through
+    `get_global_link_transform`; a rank-deficient equality block (unit vector)."""
+    import kkt_check
+    import optas_b200
+    from optas_b200 import problems
+
+    prob = problems.lwr_axis_ik()
+    solver = optas_b200.B200Solver(prob.opt).setup("ipopt")
+    B = 4096
+    P, X0 = prob.sample(B)
+    P[0] = [0.825, -0.35, 0.2]
+    r = _solve_host(solver, P, X0)
+    ok = r["status"] <= 1
+    assert ok.mean() >= 0.99, np.bincount(r["status"])
+    assert np.abs(r["x"][0, :7] - problems.SPHERE_Q_START).max() < 1e-7
+    lo = solver._lowered
+    idx = np.where(ok)[0][:32]
+    res = kkt_check.kkt_residual(prob, r["x"][idx], P[idx], r["lam"][idx][:, :lo.n_eq], r["lam"][idx][:, lo.n_eq:])
+    assert res.max() < KKT_TOL, res.max()
+
+
 def test_error_on_fail(torch_cuda):
     import optas_b200
     from optas_b200 import problems

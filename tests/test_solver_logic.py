@@ -197,3 +197,72 @@ def test_planar_differential_ik_qp():
     assert (rb["status"] == 0).all()
     res = kkt_check.kkt_residual(prob, rb["x"][:32], P[:32], rb["lam"][:32, :lo.n_eq], rb["lam"][:32, lo.n_eq:])
     assert res.max() < 1e-7
+
+
+# ---- the rest of the RobotModel surface through the same solver --------------------------------
+
+
+@pytest.mark.parametrize("coop", [True, False])
+def test_joint_space_planner_to_a_pose(coop):
+    """example/simple_joint_space_planner.py:14-71 (med7, T = 20, derivs_align): 280 variables, 147 linear
+    equalities, 7 pose equalities on the last knot (position + quaternion), 40 link-height inequalities."""
+    prob = problems.joint_space_planner()
+    opt = prob.opt
+    assert (opt.nx, opt.np, opt.nk, opt.na, opt.ng, opt.nh, opt.nv) == (280, 21, 0, 147, 40, 7, 348)
+    assert type(opt).__name__ == "QuadraticCostNonlinearConstraints"
+    sim, lo = _sim(prob, coop=coop)
+    P, X0 = prob.sample(6)
+    r = sim.solve(P, X0)
+    assert (r["status"] == 0).all(), r["status"]
+    res = kkt_check.kkt_residual(prob, r["x"], P, r["lam"][:, :lo.n_eq], r["lam"][:, lo.n_eq:])
+    assert res.max() < 1e-7
+    # the last knot reaches the goal pose (the quaternion up to sign is fixed by the equality itself), the first is
+    # the current configuration, the last velocity is zero, and both links stay above z = -0.05
+    sol = prob.seed_dict(r["x"])
+    Q, dQ = sol["med7/q/x"], sol["med7/dq/x"]
+    import fk_ref
+
+    chain_ee, chain_3 = fk_ref.Chain(problems.MED7_URDF, problems.MED7_EE), fk_ref.Chain(problems.MED7_URDF, "lbr_link_3")
+    qF = Q[:, :, -1]
+    assert np.abs(chain_ee.fk(qF)[1] - P[:, 14:17]).max() < 1e-8          # independent numpy kinematics (oracle/fk_ref.py)
+    assert np.abs(chain_ee.quaternion(qF) - P[:, 17:21]).max() < 1e-8
+    for t in range(Q.shape[2]):
+        assert chain_ee.fk(Q[:, :, t])[1][:, 2].min() > -0.05 - 1e-8 and chain_3.fk(Q[:, :, t])[1][:, 2].min() > -0.05 - 1e-8
+    assert np.abs(Q[:, :, 0] - P[:, 7:14]).max() < 1e-9 and np.abs(dQ[:, :, -1]).max() < 1e-9
+    # (no SLSQP polish here: position + unit quaternion are 7 equalities of rank 6, on which scipy's SLSQP stops with
+    #  "inequality constraints incompatible"; the oracle KKT residual and the independent kinematics stand in)
+
+
+def test_sphere_collision_first_stage_ik():
+    """example/sphere_collision_avoidance.py:20-42: IK to a position with the tool z axis held (three equalities of
+    rank two -- a unit vector), joint limits on q, zero velocity / acceleration knots; its solution at the script's
+    start position is the constant the second stage starts from."""
+    prob = problems.lwr_axis_ik()
+    opt = prob.opt
+    assert (opt.nx, opt.np, opt.nk, opt.na, opt.ng, opt.nh) == (21, 3, 14, 14, 0, 6)
+    sim, lo = _sim(prob)
+    P, X0 = prob.sample(16)
+    P[0] = [0.825, -0.35, 0.2]
+    r = sim.solve(P, X0)
+    assert (r["status"] == 0).all()
+    assert np.abs(r["x"][0, :7] - problems.SPHERE_Q_START).max() < 1e-7
+    res = kkt_check.kkt_residual(prob, r["x"], P, r["lam"][:, :lo.n_eq], r["lam"][:, lo.n_eq:])
+    assert res.max() < 1e-7
+    robot = prob.models["robot"]
+    Tq = robot.get_global_link_transform(problems.LWR_EE, r["x"][3, :7]).toarray()
+    T0 = robot.get_global_link_transform(problems.LWR_EE, problems.SPHERE_Q_NOMINAL).toarray()
+    assert np.abs(Tq[:3, 3] - P[3]).max() < 1e-8 and np.abs(Tq[:3, 2] - T0[:3, 2]).max() < 1e-8
+
+
+def test_sphere_collision_problem_dimensions_and_seed():
+    """example/sphere_collision_avoidance.py:54-98 builds through `sphere_collision_avoidance_constraints`
+    (builder.py:366-417): 20 knots x 4 link spheres x 6 obstacles = 480 inequalities, two reduced (sum-of-squares)
+    equalities; the seed (hold the start configuration) is collision free."""
+    prob = problems.sphere_collision_avoidance()
+    opt = prob.opt
+    assert (opt.nx, opt.np, opt.nk, opt.na, opt.ng, opt.nh, opt.nv) == (420, 38, 280, 287, 480, 2, 1338)
+    P, X0 = prob.sample(4)
+    op = slsqp_driver.OracleProblem(opt)
+    g = np.array([np.asarray(opt.g(X0[b], P[b])).flatten() for b in range(4)])
+    assert g.shape == (4, 480) and g.min() > 0.0
+    assert op is not None
