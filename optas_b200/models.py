@@ -13,8 +13,8 @@ RobotModel :233-1729) so problem-building scripts read the same:
   (ref :1199-1264).
 
 The whole ``get_[global_]link_<quantity>[_function]`` family is generated from one table instead
-of being spelled out method by method.  Inverse dynamics (RNEA, ref :1731-1884) is out of scope
-(SURVEY.md section 8f-3).
+of being spelled out method by method.  Inverse dynamics: ``rnea`` (ref :1731-1884) as one
+outward / inward sweep over per-body records.
 """
 
 from __future__ import annotations
@@ -553,8 +553,62 @@ class RobotModel(Model):
         return self.make_function("a", link, functools.partial(self.get_global_link_axis, axis=axis), n=n,
                                   numpy_output=numpy_output)
 
-    def rnea(self, q, qd, qdd):
-        raise NotImplementedError("inverse dynamics (RNEA) is outside the scope of the B200 solver backend")
+    # -- inverse dynamics ----------------------------------------------------------------------------
+    def _rnea_bodies(self):
+        """Per-body records for ``rnea``: (xyz, rpy, axis of the joint the body hangs on, mass, centre of mass,
+        inertia tensor), base to tip.  As in the reference (:1743-1791): serial chain root -> last link, first joint
+        fixed (its body is the base and carries no dynamics), every link with an <inertial> element after the first
+        is a body, the inertial origin's rpy is not applied."""
+        for joint in self.urdf.joint_map.values():
+            if joint.type not in ("revolute", "continuous", "fixed"):
+                raise JointTypeNotSupported(joint.type)
+        if next(iter(self.urdf.joint_map.values())).type != "fixed":
+            raise JointTypeNotSupported("First joint should be fixed")
+        inert = [link.inertial for link in self.urdf.links if link.inertial is not None][1:]
+        chain = self.urdf.get_chain(self.urdf.get_root(), self.link_names[-1], links=False)[1:]
+        bodies = []
+        for k, joint_name in enumerate(chain):
+            joint = self.urdf.joint_map[joint_name]
+            xyz, rpy = self.get_joint_origin(joint)
+            bodies.append(dict(r=xyz, R0=rpy2r(rpy), axis=self.get_joint_axis(joint), m=float(inert[k].mass),
+                               c=DM(inert[k].origin.xyz), I=DM(inert[k].inertia.to_matrix())))
+        return bodies
+
+    @arrayify_args
+    def rnea(self, q: ArrayType, qd: ArrayType, qdd: ArrayType) -> CasADiArrayType:
+        """Joint torques for (q, qd, qdd) by the recursive Newton-Euler algorithm (Craig, Introduction to
+        Robotics, ch. 6; ref :1731-1884).  Revolute / continuous joints only; the chain's last joint is the fixed
+        tool joint; gravity is -9.81 along the base z axis, entering as an upward base acceleration."""
+        cross = lambda a, b: cs.cross(a, b)
+        bodies = self._rnea_bodies()
+        n = len(bodies)
+        # parent -> child rotation of every joint (the tool joint does not move)
+        R = [b["R0"] @ angvec2r(q[k], b["axis"]) if k < n - 1 else b["R0"] for k, b in enumerate(bodies)]
+        # outward sweep: velocities / accelerations of each body frame, then the inertial force and moment
+        w, dw, dv = DM.zeros(3), DM.zeros(3), DM([0.0, 0.0, 9.81])
+        F, N = [], []
+        for k, b in enumerate(bodies):
+            E = R[k].T
+            w_in = E @ w
+            dv = E @ (dv + cross(dw, b["r"]) + cross(w, cross(w, b["r"])))
+            if k < n - 1:
+                z = E @ b["axis"]
+                dw = E @ dw + cross(w_in, z * qd[k]) + z * qdd[k]
+                w = w_in + z * qd[k]
+            else:
+                w, dw = w_in, E @ dw
+            F.append(b["m"] * (dv + cross(dw, b["c"]) + cross(w, cross(w, b["c"]))))
+            N.append(b["I"] @ dw + cross(w, b["I"] @ w))
+        # inward sweep: force / moment each body passes to its parent, projected on the joint axis
+        f = F[n - 1]
+        m = N[n - 1] + cross(bodies[n - 1]["c"], F[n - 1])
+        tau = [None] * (n - 1)
+        for k in range(n - 2, -1, -1):
+            Rf = R[k + 1] @ f
+            m = N[k] + R[k + 1] @ m + cross(bodies[k]["c"], F[k]) + cross(bodies[k + 1]["r"], Rf)
+            f = Rf + F[k]
+            tau[k] = m.T @ (R[k].T @ bodies[k]["axis"])
+        return cs.vertcat(*tau)
 
 
 def _install_function_factories():

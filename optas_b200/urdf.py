@@ -6,8 +6,9 @@ is absent from this image, so this module provides the small surface RobotModel 
 ``URDF.from_xml_file/from_xml_string``, ``.name/.joints/.links/.joint_map/.link_map``,
 ``get_root()``, ``get_chain(root, tip, joints=True, links=True, fixed=True)``,
 ``add_link/add_joint`` and the ``Joint/Link/Pose/JointLimit`` records.
-Only kinematic information is kept (inertial / visual / collision elements are ignored, apart
-from a link's visual origin).
+Kinematic information plus each link's ``<inertial>`` element (mass, centre-of-mass origin, inertia
+tensor -- what ``RobotModel.rnea`` reads, ref :1753-1768) and a link's visual origin are kept;
+collision geometry, meshes and transmissions are ignored.
 """
 
 from __future__ import annotations
@@ -54,10 +55,42 @@ class Visual:
         self.origin = origin
 
 
+class Inertia:
+    """The six independent entries of a link's inertia tensor about its centre of mass."""
+
+    def __init__(self, ixx=0.0, ixy=0.0, ixz=0.0, iyy=0.0, iyz=0.0, izz=0.0):
+        self.ixx, self.ixy, self.ixz, self.iyy, self.iyz, self.izz = ixx, ixy, ixz, iyy, iyz, izz
+
+    def to_matrix(self) -> List[List[float]]:
+        return [[self.ixx, self.ixy, self.ixz], [self.ixy, self.iyy, self.iyz], [self.ixz, self.iyz, self.izz]]
+
+    @staticmethod
+    def from_xml(el: Optional[ET.Element]) -> "Inertia":
+        if el is None:
+            return Inertia()
+        return Inertia(*(float(el.get(k, 0.0)) for k in ("ixx", "ixy", "ixz", "iyy", "iyz", "izz")))
+
+
+class Inertial:
+    def __init__(self, mass: float = 0.0, inertia: Optional[Inertia] = None, origin: Optional[Pose] = None):
+        self.mass = mass
+        self.inertia = inertia if inertia is not None else Inertia()
+        self.origin = origin if origin is not None else Pose()
+
+    @staticmethod
+    def from_xml(el: Optional[ET.Element]) -> Optional["Inertial"]:
+        if el is None:
+            return None
+        mass = el.find("mass")
+        return Inertial(float(mass.get("value", 0.0)) if mass is not None else 0.0, Inertia.from_xml(el.find("inertia")),
+                        Pose.from_xml(el.find("origin")))
+
+
 class Link:
-    def __init__(self, name: str, visual: Optional[Visual] = None):
+    def __init__(self, name: str, visual: Optional[Visual] = None, inertial: Optional[Inertial] = None):
         self.name = name
         self.visual = visual
+        self.inertial = inertial
 
 
 class Joint:
@@ -105,7 +138,7 @@ class URDF:
         for el in root.findall("link"):
             vis = el.find("visual")
             visual = Visual(Pose.from_xml(vis.find("origin"))) if vis is not None else None
-            out.add_link(Link(el.get("name"), visual))
+            out.add_link(Link(el.get("name"), visual, Inertial.from_xml(el.find("inertial"))))
         for el in root.findall("joint"):
             if el.get("type") is None:
                 continue  # <joint name=.../> references inside <transmission> etc.

@@ -6,8 +6,9 @@ Run in the build container only (reads /root/reference, which does not exist on 
 
 For each robot the config scripts use (KUKA LWR for C1/C2/C5, LBR Med7 for
 C4) it parses the reference URDF with this repo's reader and re-emits ONLY what forward kinematics
-needs -- joint name / type / parent / child / origin / axis / limits -- as a minimal URDF under
-optas_b200/robots/.  Meshes, inertias, visuals, collision geometry, transmissions and gazebo tags
+needs -- joint name / type / parent / child / origin / axis / limits -- plus each link's inertial
+element (mass, centre of mass, inertia tensor: read by RobotModel.rnea) as a minimal URDF under
+optas_b200/robots/.  Meshes, visuals, collision geometry, transmissions and gazebo tags
 are dropped.  The numbers are printed with repr() so they round-trip exactly; tests/test_models.py
 checks that FK on the derived file is bit-identical to FK on the original when that is present.
 """
@@ -37,7 +38,17 @@ def emit(urdf: URDF) -> str:
            "<!-- kinematics-only description derived by tests/golden/make_robot_assets.py -->",
            f'<robot name="{urdf.name}">']
     for link in urdf.links:
-        out.append(f'  <link name="{link.name}"/>')
+        if link.inertial is None:
+            out.append(f'  <link name="{link.name}"/>')
+            continue
+        i, n = link.inertial, link.inertial.inertia
+        out.append(f'  <link name="{link.name}">')
+        out.append("    <inertial>")
+        out.append(f'      <origin xyz="{fmt(i.origin.xyz)}" rpy="{fmt(i.origin.rpy)}"/>')
+        out.append(f'      <mass value="{i.mass!r}"/>')
+        out.append(f'      <inertia ixx="{n.ixx!r}" ixy="{n.ixy!r}" ixz="{n.ixz!r}" iyy="{n.iyy!r}" iyz="{n.iyz!r}" izz="{n.izz!r}"/>')
+        out.append("    </inertial>")
+        out.append("  </link>")
     for j in urdf.joints:
         out.append(f'  <joint name="{j.name}" type="{j.type}">')
         out.append(f'    <parent link="{j.parent}"/>')
@@ -54,10 +65,13 @@ def emit(urdf: URDF) -> str:
     return "\n".join(out) + "\n"
 
 
+# the reference's RNEA test robot (tests/test_models.py:1012-1052): a fixture, not a product asset
+FIXTURES = {"tester_robot_revolute.urdf": "/root/reference/tests/tester_robot_revolute.urdf"}
+
 if __name__ == "__main__":
-    for name, src in SOURCES.items():
+    for name, src in list(SOURCES.items()) + list(FIXTURES.items()):
         urdf = URDF.from_xml_file(src)
-        dst = os.path.join(ROOT, "optas_b200", "robots", name)
+        dst = os.path.join(ROOT, "tests", "golden", name) if name in FIXTURES else os.path.join(ROOT, "optas_b200", "robots", name)
         with open(dst, "w") as fh:
             fh.write(emit(urdf))
         print(f"{src} -> {dst}: {len(urdf.links)} links, {len(urdf.joints)} joints")
