@@ -209,6 +209,11 @@ OTHER_CONFIGS = {
     "c4": ("figure_eight", 4096, "weak", {"max_iter": 400, "max_trips": 2500},
            "C4: figure_eight_plan.py T=50 + joint-limit bounds (nx 693, 557 eq, 700 ineq)"),
     "c5": ("dual_arm", 32768, "strong", {}, "C5: dual_arm.py T=50 (nx 1386, 700 eq), 32768 instances sharded over the GPUs"),
+    # SURVEY.md 8f-3 rows (not BASELINE configs): the rest of the RobotModel surface through the same solver
+    "jsp": ("joint_space_planner", 8192, "weak", {},
+            "8f-3: simple_joint_space_planner.py T=20 (nx 280, 154 eq incl. pose goal, 40 link-height ineq)"),
+    "aik": ("lwr_axis_ik", 65536, "weak", {},
+            "8f-3: sphere_collision_avoidance.py first stage, position + tool-axis IK (nx 21, 20 eq, 14 bounds)"),
 }
 
 
@@ -306,7 +311,7 @@ def main() -> None:
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--batch", type=int, default=BATCH_PER_GPU)
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--config", default="c2", choices=["c2", "c3", "c4", "c5"],
+    ap.add_argument("--config", default="c2", choices=["c2", "c3", "c4", "c5", "jsp", "aik"],
                     help="c2 (default) is the headline line the driver reads; c3/c4/c5 print an extra line for the other "
                          "BASELINE.json configs (device-resident value + e2e only)")
     args = ap.parse_args()
