@@ -27,6 +27,21 @@ for stub in ("matplotlib", "matplotlib.pyplot", "matplotlib.animation", "pybulle
 sys.path.insert(0, "/root/reference/example")
 
 
+def _xacro_process(filename):
+    """xacro is absent: figure_eight_plan.py asks for med7.urdf.xacro; the reference ships its expansion med7.urdf in
+    the same directory (the file torque_control_example.py loads), which is what this returns."""
+    assert filename.endswith(".urdf.xacro"), filename
+    return open(filename[:-len(".xacro")]).read()
+
+
+xacro_stub = types.ModuleType("xacro")
+xacro_stub.process = _xacro_process
+sys.modules["xacro"] = xacro_stub
+import optas.models  # noqa: E402
+
+optas.models.xacro = xacro_stub
+
+
 def probe_vectors(nv, nx):
     return np.cos(0.37 * np.arange(nx) + 0.1), np.sin(0.23 * np.arange(nv) + 0.2)
 
