@@ -835,15 +835,23 @@ int bo_function_create(const bo_tape* tape, const bo_options* opts_in, bo_functi
   size_t per_instance = 0;
   for (int s : fn->tape.in_sizes) per_instance += (size_t)s;
   for (int s : fn->tape.out_sizes) per_instance += (size_t)s;
-  // two pipeline stages of BO_TPB instances must fit in shared memory (227 KB per CTA on sm_100)
+  // the pipeline stages of BO_TPB instances must fit in shared memory (227 KB per CTA on sm_100): inputs are always
+  // double-buffered; outputs double-buffered (default) or single-buffered (B200OPTAS_K1_OUT_STAGES=1: less shared
+  // memory per CTA, more resident CTAs per SM; the stores of a tile then drain before the next tile computes)
+  size_t in_doubles = 0, out_doubles = 0;
+  for (int s : fn->tape.in_sizes) in_doubles += (size_t)s;
+  for (int s : fn->tape.out_sizes) out_doubles += (size_t)s;
+  const char* os_env = getenv("B200OPTAS_K1_OUT_STAGES");
+  const int out_stages = (os_env && atoi(os_env) == 1) ? 1 : 2;
+  auto smem_for = [&](int t) { return (size_t)t * (2 * in_doubles + (size_t)out_stages * out_doubles) * sizeof(double) + 64; };
   int tpb = fn->opts.threads_per_block > 0 ? fn->opts.threads_per_block : 128;
-  while (tpb > 32 && 2 * (size_t)tpb * per_instance * sizeof(double) + 64 > 200 * 1024) tpb /= 2;
-  if (2 * (size_t)tpb * per_instance * sizeof(double) + 64 > 220 * 1024)
+  while (tpb > 32 && smem_for(tpb) > 200 * 1024) tpb /= 2;
+  if (smem_for(tpb) > 220 * 1024)
     return set_err(BO_ERR_UNSUPPORTED, "bo_function_create: %zu doubles per instance do not fit the shared-memory pipeline",
                    per_instance);
   fn->tpb = tpb;
-  fn->smem_dynamic = (int)(2 * (size_t)tpb * per_instance * sizeof(double) + 64);
-  fn->source = bo::emit_function_source(fn->tape, tpb);
+  fn->smem_dynamic = (int)smem_for(tpb);
+  fn->source = bo::emit_function_source(fn->tape, tpb, out_stages);
   int rc = jit_compile(fn->source, "bo_eval", "bo_eval_kernel", fn->opts, &fn->compiled);
   if (rc != BO_OK) return rc;
   fn->kernel.regs = fn->compiled.regs;

@@ -336,14 +336,15 @@ std::string emit_problem_source(const ProblemSource& ps, int tpb, bool pivoted_l
   return o.str();
 }
 
-std::string emit_function_source(const Tape& tape, int tpb) {
+std::string emit_function_source(const Tape& tape, int tpb, int out_stages) {
   std::ostringstream o;
   o << "// generated by libb200optas (bo_codegen.cpp): streaming evaluation kernel\n";
   int tot_in = 0, tot_out = 0;
   for (int s : tape.in_sizes) tot_in += s;
   for (int s : tape.out_sizes) tot_out += s;
   o << "#define BO_NIN " << tape.in_sizes.size() << "\n#define BO_NOUT " << tape.out_sizes.size() << "\n#define BO_TPB "
-    << tpb << "\n#define BO_IN_TOTAL " << tot_in << "\n#define BO_OUT_TOTAL " << tot_out << "\n";
+    << tpb << "\n#define BO_IN_TOTAL " << tot_in << "\n#define BO_OUT_TOTAL " << tot_out << "\n#define BO_OUT_STAGES "
+    << out_stages << "\n";
   o << "#include \"bo_common.cuh\"\n";
   auto arr = [&](const char* nm, const std::vector<int32_t>& v) {
     o << "__device__ constexpr int " << nm << "[" << (v.empty() ? 1 : v.size()) << "] = {";

@@ -60,6 +60,6 @@ struct SparsePlan;
 std::string emit_problem_source(const ProblemSource& ps, int threads_per_block, bool pivoted_ldl,
                                 const SparsePlan* sparse = nullptr, bool large = false);
 // Full translation unit of the streaming evaluation kernel for one tape.
-std::string emit_function_source(const Tape& tape, int threads_per_block);
+std::string emit_function_source(const Tape& tape, int threads_per_block, int out_stages = 2);
 
 }  // namespace bo

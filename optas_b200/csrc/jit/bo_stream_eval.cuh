@@ -24,7 +24,11 @@ struct bo_eval_args {
   int use_bulk;  // 0: all pointers are only 8-byte aligned -> plain coalesced copies
 };
 
-#define BO_STAGE_DOUBLES (BO_TPB * (BO_IN_TOTAL + BO_OUT_TOTAL))
+#ifndef BO_OUT_STAGES
+#define BO_OUT_STAGES 2  // 2: outputs double-buffered like the inputs; 1: one output buffer (more resident CTAs per SM)
+#endif
+#define BO_IN_STAGE_DOUBLES (BO_TPB * BO_IN_TOTAL)
+#define BO_OUT_STAGE_DOUBLES (BO_TPB * BO_OUT_TOTAL)
 
 __device__ __forceinline__ unsigned bo_smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
 
@@ -67,19 +71,26 @@ __device__ __forceinline__ void bo_bulk_wait_read() {
 __device__ __forceinline__ void bo_bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 __device__ __forceinline__ void bo_fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
-extern "C" __global__ void __launch_bounds__(BO_TPB) bo_eval_kernel(long long B, const bo_eval_args args) {
+#ifdef BO_MIN_BLOCKS  // experiment knob (-DBO_MIN_BLOCKS=n via B200OPTAS_JIT_DEFINES): register cap for n resident CTAs per SM
+#define BO_EVAL_BOUNDS __launch_bounds__(BO_TPB, BO_MIN_BLOCKS)
+#else
+#define BO_EVAL_BOUNDS __launch_bounds__(BO_TPB)
+#endif
+extern "C" __global__ void BO_EVAL_BOUNDS bo_eval_kernel(long long B, const bo_eval_args args) {
   extern __shared__ __align__(128) unsigned char bo_smem_raw[];
   double* const stage_base = reinterpret_cast<double*>(bo_smem_raw);
-  unsigned long long* const full = reinterpret_cast<unsigned long long*>(stage_base + 2 * BO_STAGE_DOUBLES);
+  double* const out_base = stage_base + 2 * BO_IN_STAGE_DOUBLES;
+  unsigned long long* const full = reinterpret_cast<unsigned long long*>(out_base + BO_OUT_STAGES * BO_OUT_STAGE_DOUBLES);
 
   // shared-memory segment pointers of one stage
   auto stage_ptrs = [&](int s, double** si, double** so) {
-    double* ptr = stage_base + s * BO_STAGE_DOUBLES;
+    double* ptr = stage_base + s * BO_IN_STAGE_DOUBLES;
     BO_UNROLL
     for (int k = 0; k < BO_NIN; ++k) {
       si[k] = ptr;
       ptr += BO_TPB * BO_IN_SIZE[k];
     }
+    ptr = out_base + (BO_OUT_STAGES == 2 ? s : 0) * BO_OUT_STAGE_DOUBLES;
     BO_UNROLL
     for (int k = 0; k < BO_NOUT; ++k) {
       so[k] = ptr;
@@ -122,8 +133,9 @@ extern "C" __global__ void __launch_bounds__(BO_TPB) bo_eval_kernel(long long B,
     const int count = (int)((B - tile * BO_TPB) < (long long)BO_TPB ? (B - tile * BO_TPB) : (long long)BO_TPB);
 
     if (tid == 0) {
-      // stores of the tile that used stage s two tiles ago must have finished reading smem
-      bo_bulk_wait_read<1>();
+      // stores of the tile that last used this output buffer (two tiles ago, or the previous tile when there is
+      // only one output buffer) must have finished reading smem
+      bo_bulk_wait_read<BO_OUT_STAGES - 1>();
     }
     __syncthreads();  // everyone is done computing the previous tile (stage s^1 inputs are free)
     if (bulk && tid == 0 && next < n_full_tiles) issue_loads(next, s ^ 1);

@@ -23,6 +23,7 @@ import numpy as np
 import optas_b200
 sys.modules["optas"] = optas_b200
 sys.modules["optas.templates"] = optas_b200.templates
+sys.modules["optas.spatialmath"] = optas_b200.spatialmath
 
 
 class _Anything(types.ModuleType):
@@ -79,6 +80,23 @@ CASES = {
         q0 = np.deg2rad([0, 45, 0, -90, 0, -45, 0])
         planner.reset(q0, [0.4, 0.3, 0.4], [0, 1, 0, 0], q0)
         assert s.p.shape == (21, 1)
+    """,
+    "other_scripts": """
+        # every other script whose planner / controller class can be constructed without a simulator
+        import point_mass_planner, figure_eight_plan_6dof, pushing, TrackingBall, torque_control_example
+        got = {}
+        for label, make in [("point_mass_planner", lambda: point_mass_planner.Planner()),
+                            ("figure_eight_plan_6dof", lambda: figure_eight_plan_6dof.Planner()),
+                            ("pushing.TOMPCCPlanner", lambda: pushing.TOMPCCPlanner(0.1, 0.2, 0.1)),
+                            ("pushing.IK", lambda: pushing.IK(0.02, 0.5)),
+                            ("TrackingBall", lambda: TrackingBall.TrackingController(0.02)),          # setup("sqpmethod")
+                            ("torque_control", lambda: torque_control_example.TrackingController(0.02))]:
+            s = make().solver
+            assert isinstance(s, optas_b200.B200Solver), label
+            got[label] = (type(s).__name__, s.opt.nx, s.opt.nv, type(s.opt).__name__)
+        assert got["point_mass_planner"] == ("CasADiSolver", 180, 593, "QuadraticCostNonlinearConstraints"), got
+        assert got["figure_eight_plan_6dof"][1] == 594 and got["pushing.TOMPCCPlanner"][0] == "ScipyMinimizeSolver", got
+        assert got["TrackingBall"][1:3] == (7, 3) and got["torque_control"][1:3] == (7, 3), got
     """,
     "example": """
         # example/example.py is a flat script ending in solver.solve() + a VTK window: run its lines up to the solve
