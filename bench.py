@@ -212,6 +212,8 @@ OTHER_CONFIGS = {
     # SURVEY.md 8f-3 rows (not BASELINE configs): the rest of the RobotModel surface through the same solver
     "jsp": ("joint_space_planner", 8192, "weak", {},
             "8f-3: simple_joint_space_planner.py T=20 (nx 280, 154 eq incl. pose goal, 40 link-height ineq)"),
+    "qp": ("planar_idk", 65536, "weak", {},
+           "8f-1: planar_idk.py differential-IK QP (QuadraticCostLinearConstraints: nx 3, 2 eq, 8 ineq) through the general kernel"),
     "aik": ("lwr_axis_ik", 65536, "weak", {},
             "8f-3: sphere_collision_avoidance.py first stage, position + tool-axis IK (nx 21, 20 eq, 14 bounds)"),
 }
@@ -311,7 +313,7 @@ def main() -> None:
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--batch", type=int, default=BATCH_PER_GPU)
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--config", default="c2", choices=["c2", "c3", "c4", "c5", "jsp", "aik"],
+    ap.add_argument("--config", default="c2", choices=["c2", "c3", "c4", "c5", "jsp", "aik", "qp"],
                     help="c2 (default) is the headline line the driver reads; c3/c4/c5 print an extra line for the other "
                          "BASELINE.json configs (device-resident value + e2e only)")
     args = ap.parse_args()
