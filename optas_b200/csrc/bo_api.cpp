@@ -589,6 +589,13 @@ int bo_problem_create(const bo_problem_desc* desc, const bo_options* opts_in, bo
     BO_CU(g_drv.cuDeviceGetAttribute(&pr->n_sm, CU_DEVICE_ATTRIBUTE_MULTIPROCESSOR_COUNT, dev));
     if (pr->smem_dynamic > 0)
       BO_CU(g_drv.cuFuncSetAttribute(pr->kernel.fn, CU_FUNC_ATTRIBUTE_MAX_DYNAMIC_SHARED_SIZE_BYTES, pr->smem_dynamic));
+    // thread-per-instance tiers keep their state in thread-local memory: ask for the largest L1 split
+    // (B200OPTAS_L1_CARVEOUT = shared-memory percentage 0..100 overrides; -1 leaves the driver's heuristic)
+    if (!pr->coop && pr->smem_dynamic == 0) {
+      const char* cv = getenv("B200OPTAS_L1_CARVEOUT");
+      const int carve = cv ? atoi(cv) : -1;
+      if (carve >= 0) BO_CU(g_drv.cuFuncSetAttribute(pr->kernel.fn, CU_FUNC_ATTRIBUTE_PREFERRED_SHARED_MEMORY_CARVEOUT, carve));
+    }
     BO_CU(g_drv.cuOccupancyMaxActiveBlocksPerMultiprocessor(&pr->blocks_per_sm, pr->kernel.fn, pr->tpb, (size_t)pr->smem_dynamic));
     if (pr->blocks_per_sm < 1) pr->blocks_per_sm = 1;
     if (pr->opts.blocks_per_sm > 0 && pr->opts.blocks_per_sm < pr->blocks_per_sm) pr->blocks_per_sm = pr->opts.blocks_per_sm;

@@ -433,6 +433,27 @@ def test_batched_diagnostics(torch_cuda):
             assert np.abs(cb.diff[i] - c1.diff.toarray()).max() < 1e-12
 
 
+def test_c3_graphs_match_the_reference_script_golden(torch_cuda):
+    """C3's cost and stacked constraint vector v = [k; g; a; -a; h; -h], evaluated by the streaming kernel from this
+    package's problem, against tests/golden/config_golden.json -- values produced by the unmodified reference script's
+    `point_mass_mpc.Controller` (tests/golden/make_config_golden.py)."""
+    import json
+    import os
+    from optas_b200 import problems, sym as cs
+    from optas_b200.function import B200Function
+
+    g = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "config_golden.json")))["c3_point_mass_mpc"]
+    opt = problems.point_mass_mpc().opt
+    x, p = cs.SX.sym("x", opt.nx), cs.SX.sym("p", opt.np)
+    fun = B200Function(cs.Function("fv", [x, p], [opt.f(x, p), opt.v(x, p)]))
+    X = np.array([c["x"] for c in g["cases"]])
+    P = np.array([c["p"] for c in g["cases"]])
+    f_gpu, v_gpu = fun(X, P)
+    for i, c in enumerate(g["cases"]):
+        assert abs(f_gpu[i, 0] - c["f"]) < 1e-12 * max(1.0, abs(c["f"]))
+        assert np.abs(v_gpu[i] - np.array(c["v"])).max() < 1e-12
+
+
 def test_qp_drop_in_classes(torch_cuda):
     """OSQPSolver / CVXOPTSolver spellings (optas/solver.py:426-580) on the differential-IK QP of
     example/planar_idk.py; the reference asserts QP-only for both."""
