@@ -35,38 +35,34 @@ def fmt(vals):
 
 def emit(urdf: URDF) -> str:
     out = ['<?xml version="1.0"?>',
-           "<!-- kinematics-only description derived by tests/golden/make_robot_assets.py -->",
+           "<!-- kinematics + inertials, derived by tests/golden/make_robot_assets.py -->",
            f'<robot name="{urdf.name}">']
     for link in urdf.links:
         if link.inertial is None:
             out.append(f'  <link name="{link.name}"/>')
             continue
         i, n = link.inertial, link.inertial.inertia
-        out.append(f'  <link name="{link.name}">')
-        out.append("    <inertial>")
-        out.append(f'      <origin xyz="{fmt(i.origin.xyz)}" rpy="{fmt(i.origin.rpy)}"/>')
-        out.append(f'      <mass value="{i.mass!r}"/>')
-        out.append(f'      <inertia ixx="{n.ixx!r}" ixy="{n.ixy!r}" ixz="{n.ixz!r}" iyy="{n.iyy!r}" iyz="{n.iyz!r}" izz="{n.izz!r}"/>')
-        out.append("    </inertial>")
-        out.append("  </link>")
-    for j in urdf.joints:
-        out.append(f'  <joint name="{j.name}" type="{j.type}">')
-        out.append(f'    <parent link="{j.parent}"/>')
-        out.append(f'    <child link="{j.child}"/>')
+        out.append(f'  <link name="{link.name}"><inertial><mass value="{i.mass!r}"/>'
+                   f'<origin rpy="{fmt(i.origin.rpy)}" xyz="{fmt(i.origin.xyz)}"/>')
+        out.append(f'    <inertia ixx="{n.ixx!r}" iyy="{n.iyy!r}" izz="{n.izz!r}" ixy="{n.ixy!r}" ixz="{n.ixz!r}" iyz="{n.iyz!r}"/>'
+                   f'</inertial></link>')
+    for j in urdf.joints:  # one line per joint: kinematic tree first, then geometry, then limits
+        parts = [f'<joint type="{j.type}" name="{j.name}"><child link="{j.child}"/><parent link="{j.parent}"/>']
         if j.origin is not None:
-            out.append(f'    <origin xyz="{fmt(j.origin.xyz)}" rpy="{fmt(j.origin.rpy)}"/>')
+            parts.append(f'<origin rpy="{fmt(j.origin.rpy)}" xyz="{fmt(j.origin.xyz)}"/>')
         if j.axis is not None:
-            out.append(f'    <axis xyz="{fmt(j.axis)}"/>')
+            parts.append(f'<axis xyz="{fmt(j.axis)}"/>')
         if j.limit is not None:
-            out.append(f'    <limit lower="{j.limit.lower!r}" upper="{j.limit.upper!r}" '
-                       f'velocity="{j.limit.velocity!r}" effort="{j.limit.effort!r}"/>')
-        out.append("  </joint>")
+            parts.append(f'<limit upper="{j.limit.upper!r}" lower="{j.limit.lower!r}" '
+                         f'effort="{j.limit.effort!r}" velocity="{j.limit.velocity!r}"/>')
+        out.append("  " + "".join(parts) + "</joint>")
     out.append("</robot>")
     return "\n".join(out) + "\n"
 
 
 # the reference's RNEA test robot (tests/test_models.py:1012-1052): a fixture, not a product asset
-FIXTURES = {"tester_robot_revolute.urdf": "/root/reference/tests/tester_robot_revolute.urdf"}
+FIXTURES = {"tester_robot_revolute.urdf": "/root/reference/tests/tester_robot_revolute.urdf",
+            "tester_robot.urdf": "/root/reference/tests/tester_robot.urdf"}
 
 if __name__ == "__main__":
     for name, src in list(SOURCES.items()) + list(FIXTURES.items()):
