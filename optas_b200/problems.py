@@ -3,7 +3,7 @@ way the reference's example scripts build them, plus their synthetic batch input
 
 Each factory returns a ``Problem``: the built ``Optimization``, samplers for the batched
 parameter / seed matrices in ``vec()`` layout, and the model functions evaluated by the streaming
-kernel.  Robot descriptions are the kinematics-only URDFs under optas_b200/robots/ (derived from
+kernel.  Robot descriptions are the kinematics + inertial URDFs under optas_b200/robots/ (derived from
 the reference's assets by tests/golden/make_robot_assets.py).
 """
 
