@@ -557,7 +557,11 @@ int bo_problem_create(const bo_problem_desc* desc, const bo_options* opts_in, bo
     const size_t smem = (size_t)cp.smem_doubles * sizeof(double);
     // worth it when the tapes split into enough independent pieces to occupy the CTA (horizon problems do: one
     // piece per stage), or when the problem is too large for a thread anyway
-    const bool wanted = pr->large || (pr->opts.flags & BO_FLAG_COOP) || cp.kkt.n_components >= 16;
+    // ... and the KKT system is big enough that a CTA beats a thread.  Measured on B200 (tools/tier_choice.py,
+    // profiles/r01_tier_choice.txt): 41 rows (position + axis IK) 15.8 M inst/s per thread vs 1.16 M/s per CTA;
+    // 122 rows (MPC tick) 0.12 M/s per thread vs 0.81 M/s per CTA.
+    const bool big_enough = ps.nx + ps.n_eq > 64;
+    const bool wanted = pr->large || (pr->opts.flags & BO_FLAG_COOP) || (cp.kkt.n_components >= 16 && big_enough);
     if (wanted && cp.vals_size() + 1 < 32767 && ps.nx + ps.n_eq + 1 < 32767 && smem <= 227 * 1024) {
       pr->coop = true;
       pr->large = false;
