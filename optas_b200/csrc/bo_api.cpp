@@ -557,10 +557,14 @@ int bo_problem_create(const bo_problem_desc* desc, const bo_options* opts_in, bo
     const size_t smem = (size_t)cp.smem_doubles * sizeof(double);
     // worth it when the tapes split into enough independent pieces to occupy the CTA (horizon problems do: one
     // piece per stage), or when the problem is too large for a thread anyway
-    // ... and the KKT system is big enough that a CTA beats a thread.  Measured on B200 (tools/tier_choice.py,
-    // profiles/r01_tier_choice.txt): 41 rows (position + axis IK) 15.8 M inst/s per thread vs 1.16 M/s per CTA;
-    // 122 rows (MPC tick) 0.12 M/s per thread vs 0.81 M/s per CTA.
-    const bool big_enough = ps.nx + ps.n_eq > 64;
+    // ... and the per-instance state is big enough that a CTA beats a thread (the thread-per-instance tiers keep it in
+    // thread-local memory and fall off a cliff once that stops fitting L1).  Measured on B200 (tools/tier_choice.py,
+    // tools/tier_break_even.py; profiles/r01_tier_choice.txt, r01_tier_break_even.txt), thread vs CTA in inst/s:
+    //   position + axis IK  nx 21, 20 eq, 14 ineq (5.4 KB per lane)   15.8 M  vs 1.16 M
+    //   MPC tick T = 6      nx 24, 14 eq, 54 ineq (10 KB per lane)     2.23 M vs 2.52 M
+    //   MPC tick T = 10     nx 40, 22 eq, 90 ineq (17 KB per lane)     0.74 M vs 1.64 M
+    //   MPC tick T = 20     nx 80, 42 eq, 180 ineq                     0.12 M vs 0.81 M
+    const bool big_enough = ps.nx + ps.n_eq + ps.n_ineq > 64;
     const bool wanted = pr->large || (pr->opts.flags & BO_FLAG_COOP) || (cp.kkt.n_components >= 16 && big_enough);
     if (wanted && cp.vals_size() + 1 < 32767 && ps.nx + ps.n_eq + 1 < 32767 && smem <= 227 * 1024) {
       pr->coop = true;
