@@ -276,8 +276,8 @@ def run_other_config(args) -> None:
     torch.cuda.synchronize()
     dev_ms = e0.elapsed_time(e1)
     n_conv = int((std <= 1).sum().item())
-    for _ in range(3):  # untimed: the page-locked result buffers only recycle from the third call on (torch's caching
-        solver.solve_arrays(P, X0)  # host allocator frees lazily; tools/e2e_probe.py: 56 / 41 / 5.1 / 5.1 ms per call)
+    for _ in range(3):  # untimed, and holding the result like the timed loop does: two sets of page-locked result buffers
+        r = solver.solve_arrays(P, X0)  # exist only from the third call on (tools/e2e_probe.py: 56 / 41 / 5.1 / 5.1 ms per call)
     t0 = time.perf_counter()
     for _ in range(steps):
         r = solver.solve_arrays(P, X0)
