@@ -266,3 +266,16 @@ def test_sphere_collision_problem_dimensions_and_seed():
     g = np.array([np.asarray(opt.g(X0[b], P[b])).flatten() for b in range(4)])
     assert g.shape == (4, 480) and g.min() > 0.0
     assert op is not None
+
+
+def test_tier_choice_follows_the_measured_rule():
+    """bo_problem_create picks the kernel tier from the problem sizes alone (measured on B200 in
+    profiles/r01_tier_choice.txt / r01_tier_break_even.txt): dense up to 14 KKT rows, thread-per-instance sparse for
+    small problems, one instance per CTA once nx + n_eq + n_ineq > 64 and the tapes split into stages."""
+    expect = [(problems.lwr_ik(), "dense"), (problems.planar_idk(), "dense"), (problems.lwr_axis_ik(), "sparse"),
+              (problems.point_mass_mpc(T=6), "coop"), (problems.point_mass_mpc(), "coop"), (problems.joint_space_planner(), "coop")]
+    for prob, tier in expect:
+        s = optas_b200.B200Solver(prob.opt).setup("ipopt", compile_only=True)
+        assert s.tier_info()["tier"] == tier, (prob.name, s.tier_info()["tier"])
+    forced = optas_b200.B200Solver(problems.lwr_axis_ik().opt).setup("ipopt", compile_only=True, coop=True)
+    assert forced.tier_info()["tier"] == "coop"   # BO_FLAG_COOP still overrides
