@@ -113,15 +113,18 @@ typedef struct bo_options {
   double tol;              /* <=0: default 1e-8  (scaled KKT error, as IPOPT's `tol`)      */
   double acceptable_tol;   /* <=0: default 1e-6                                             */
   double mu_init;          /* <=0: default 0.1   (as IPOPT's `mu_init`)                    */
-  double max_step;         /* cap on ||alpha*dx||_inf per iteration; 0: default 0.5, <0: unlimited */
+  double max_step;         /* cap on ||alpha*dx||_inf per iteration; 0: default = 0.5 when the tapes contain
+                              sin/cos/tan (kinematics), unlimited otherwise; <0: unlimited                  */
   const char* cache_dir;   /* NULL: <directory of libb200optas.so>/_jitcache               */
   const char* include_dir; /* NULL: <directory of libb200optas.so>/csrc/jit                */
   int32_t threads_per_block; /* <=0: tier default                                           */
-  int32_t max_trips;       /* <=0: default 250.  Budget of solver trips per instance (one trip = at most
+  int32_t max_trips;       /* <=0: default 250, or max(250, 2.5 max_iter) when max_iter is given.  Budget of solver trips per instance (one trip = at most
                               one KKT evaluation + one factorisation + one trial point); an instance
                               over budget ends with BO_MAX_ITER.  Bounds the tail latency of a batch. */
   int32_t blocks_per_sm;   /* <=0: as many as fit (occupancy); else cap on resident CTAs per SM       */
-  int32_t reserved[5];
+  int32_t device;          /* 0: the CUDA context current on the calling thread (none: device 0); k > 0: device
+                              ordinal k-1.  The handle stays bound to that device's primary context.          */
+  int32_t reserved[4];
 } bo_options;
 
 typedef struct bo_problem bo_problem;   /* opaque, owned by the library */
@@ -160,6 +163,10 @@ int bo_problem_kernel_info(const bo_problem* prob, int32_t* regs, int32_t* local
  *  [29] tapes compiled per component class (1) or interpreted (0)  [30]/[31] classes / generated rows of kkt         */
 #define BO_TIER_INFO_LEN 32
 int bo_problem_tier_info(const bo_problem* prob, int64_t* info, int32_t cap);
+
+/* The options in effect after defaults were resolved (max_iter, max_trips, tol, max_step ...): what the reference's
+ * `solver_options` dict (optas/solver.py:333-384) became on this back-end.                                    */
+int bo_problem_options(const bo_problem* prob, bo_options* out);
 
 /* Replaces optas/solver.py:395-396 (one nlpsol call + stats) for B instances at once.
  *   p   [B][np]        parameters                      (may be NULL iff np == 0)

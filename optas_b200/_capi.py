@@ -28,7 +28,7 @@ STATUS_NAMES = {0: "converged", 1: "acceptable", 2: "max_iter", 3: "line_search"
 EXPORTS = [
     "bo_abi_version", "bo_last_error", "bo_device_count",
     "bo_problem_create", "bo_problem_destroy", "bo_problem_source", "bo_problem_ldl_table", "bo_problem_dtable", "bo_problem_kernel_info",
-    "bo_problem_tier_info",
+    "bo_problem_tier_info", "bo_problem_options",
     "bo_solve", "bo_problem_kernel_time",
     "bo_function_create", "bo_function_destroy", "bo_function_eval", "bo_function_source",
     "bo_function_kernel_info", "bo_function_kernel_time",
@@ -68,7 +68,8 @@ class bo_options(C.Structure):
         ("flags", C.c_uint32), ("max_iter", C.c_int32),
         ("tol", C.c_double), ("acceptable_tol", C.c_double), ("mu_init", C.c_double), ("max_step", C.c_double),
         ("cache_dir", C.c_char_p), ("include_dir", C.c_char_p),
-        ("threads_per_block", C.c_int32), ("max_trips", C.c_int32), ("blocks_per_sm", C.c_int32), ("reserved", C.c_int32 * 5),
+        ("threads_per_block", C.c_int32), ("max_trips", C.c_int32), ("blocks_per_sm", C.c_int32), ("device", C.c_int32),
+        ("reserved", C.c_int32 * 4),
     ]
 
 
@@ -98,6 +99,7 @@ def load() -> C.CDLL:
     lib.bo_problem_dtable.restype = C.c_int64
     lib.bo_problem_kernel_info.argtypes = [vp, i32p, i32p, i32p]
     lib.bo_problem_tier_info.argtypes = [vp, C.POINTER(C.c_int64), C.c_int32]
+    lib.bo_problem_options.argtypes = [vp, C.POINTER(bo_options)]
     lib.bo_solve.argtypes = [vp, C.c_int64] + [vp] * 8 + [vp]
     lib.bo_problem_kernel_time.argtypes = [vp, f64p, C.POINTER(C.c_int64)]
     lib.bo_function_create.argtypes = [C.POINTER(bo_tape), C.POINTER(bo_options), C.POINTER(vp)]
@@ -151,13 +153,29 @@ def tape_struct(t: Tape, keep: _Keep) -> bo_tape:
 
 def options_struct(flags: int = 0, max_iter: int = 0, tol: float = 0.0, acceptable_tol: float = 0.0,
                    mu_init: float = 0.0, max_step: float = 0.0, cache_dir: Optional[str] = None, include_dir: Optional[str] = None,
-                   threads_per_block: int = 0, max_trips: int = 0, blocks_per_sm: int = 0) -> bo_options:
+                   threads_per_block: int = 0, max_trips: int = 0, blocks_per_sm: int = 0, device: Optional[int] = None) -> bo_options:
     return bo_options(
         flags=flags, max_iter=max_iter, tol=tol, acceptable_tol=acceptable_tol, mu_init=mu_init, max_step=max_step,
         cache_dir=cache_dir.encode() if cache_dir else None,
         include_dir=include_dir.encode() if include_dir else None,
         threads_per_block=threads_per_block, max_trips=max_trips, blocks_per_sm=blocks_per_sm,
+        device=_current_device_plus_one() if device is None else int(device) + 1,
     )
+
+
+def _current_device_plus_one() -> int:
+    """Device ordinal + 1 the caller has selected through torch (``torch.cuda.set_device`` is lazy: no context may be
+    current yet, and the library would otherwise bind the handle to device 0); 0 = let the library look at the thread's
+    current context."""
+    import sys
+
+    torch = sys.modules.get("torch")
+    try:
+        if torch is not None and torch.cuda.is_available():
+            return int(torch.cuda.current_device()) + 1
+    except Exception:
+        pass
+    return 0
 
 
 def _source(getter, handle) -> str:
@@ -182,6 +200,31 @@ def _ptr(a) -> Optional[int]:
     if hasattr(a, "data_ptr"):
         return int(a.data_ptr())
     raise TypeError(f"cannot take the address of {type(a)}")
+
+
+def _check_buffer(name: str, a, rows: int, width: Optional[int], kind: str) -> None:
+    """The library takes raw addresses: refuse anything that is not a C-contiguous ``[rows, width]`` (or ``[rows]``)
+    array of the expected element type -- a float32 or transposed tensor would be read / written out of bounds."""
+    if a is None:
+        return
+    want = {"f64": "float64", "i32": "int32"}[kind]
+    dt = str(a.dtype).replace("torch.", "")
+    if dt != want:
+        raise ValueError(f"{name}: expected {want}, got {dt}")
+    contiguous = a.flags.c_contiguous if isinstance(a, np.ndarray) else bool(a.is_contiguous())
+    if not contiguous:
+        raise ValueError(f"{name}: must be C-contiguous")
+    shape = tuple(int(d) for d in a.shape)
+    numel = int(np.prod(shape)) if shape else 1
+    need = rows * (width if width is not None else 1)
+    if numel != need or (len(shape) >= 1 and shape[0] != rows and need > 0):
+        raise ValueError(f"{name}: expected {rows} rows of {width if width is not None else 1} elements, got shape {list(shape)}")
+
+
+def _check_devices(arrays) -> None:
+    devs = {str(a.device) for a in arrays if a is not None and hasattr(a, "data_ptr") and getattr(a, "is_cuda", False)}
+    if len(devs) > 1:
+        raise ValueError(f"buffers live on different devices: {sorted(devs)}")
 
 
 class ProblemHandle:
@@ -235,7 +278,26 @@ class ProblemHandle:
         d["tier"] = TIER_NAMES[d["tier"]]
         return d
 
+    def options(self) -> dict:
+        """The options in effect after the library resolved its defaults."""
+        o = bo_options()
+        check(load().bo_problem_options(self._h, C.byref(o)))
+        return {k: getattr(o, k) for k in ("flags", "max_iter", "tol", "acceptable_tol", "mu_init", "max_step",
+                                           "threads_per_block", "max_trips", "blocks_per_sm", "device")}
+
     def solve(self, B: int, p, x0, x, lam=None, f=None, status=None, iters=None, kkt=None, stream: int = 0) -> None:
+        lo = self.lowered
+        if lo.np_ > 0 and p is None:
+            raise ValueError("p: required (np > 0)")
+        _check_buffer("p", p if lo.np_ > 0 else None, B, lo.np_, "f64")
+        _check_buffer("x0", x0, B, lo.nx, "f64")
+        _check_buffer("x", x, B, lo.nx, "f64")
+        _check_buffer("lam", lam, B, lo.n_eq + lo.n_ineq, "f64")
+        _check_buffer("f", f, B, None, "f64")
+        _check_buffer("status", status, B, None, "i32")
+        _check_buffer("iters", iters, B, None, "i32")
+        _check_buffer("kkt", kkt, B, None, "f64")
+        _check_devices([p, x0, x, lam, f, status, iters, kkt])
         check(load().bo_solve(self._h, B, _ptr(p), _ptr(x0), _ptr(x), _ptr(lam), _ptr(f), _ptr(status), _ptr(iters),
                               _ptr(kkt), stream or None))
 
@@ -279,6 +341,11 @@ class FunctionHandle:
         n_in, n_out = len(self.tape.in_sizes), len(self.tape.out_sizes)
         if len(ins) != n_in or len(outs) != n_out:
             raise ValueError(f"expected {n_in} inputs and {n_out} outputs")
+        for k, a in enumerate(ins):
+            _check_buffer(f"in[{k}]", a, B, int(self.tape.in_sizes[k]), "f64")
+        for k, a in enumerate(outs):
+            _check_buffer(f"out[{k}]", a, B, int(self.tape.out_sizes[k]), "f64")
+        _check_devices(list(ins) + list(outs))
         in_arr = (C.c_void_p * n_in)(*[_ptr(a) for a in ins])
         out_arr = (C.c_void_p * n_out)(*[_ptr(a) for a in outs])
         check(load().bo_function_eval(self._h, B, in_arr, out_arr, stream or None))

@@ -25,6 +25,7 @@
 #include "b200optas.h"
 #include "bo_codegen.h"
 #include "bo_coop.h"
+#include "bo_opcodes.h"
 #include "bo_sparse.h"
 
 namespace {
@@ -56,6 +57,8 @@ struct Driver {
   BO_DRV(cuCtxGetCurrent)
   BO_DRV(cuCtxSetCurrent)
   BO_DRV(cuCtxGetDevice)
+  BO_DRV(cuCtxPushCurrent_v2)
+  BO_DRV(cuCtxPopCurrent_v2)
   BO_DRV(cuDevicePrimaryCtxRetain)
   BO_DRV(cuModuleLoadData)
   BO_DRV(cuModuleUnload)
@@ -101,6 +104,8 @@ bool load_driver() {
   BO_SYM(cuCtxGetCurrent, "cuCtxGetCurrent")
   BO_SYM(cuCtxSetCurrent, "cuCtxSetCurrent")
   BO_SYM(cuCtxGetDevice, "cuCtxGetDevice")
+  BO_SYM(cuCtxPushCurrent_v2, "cuCtxPushCurrent_v2")
+  BO_SYM(cuCtxPopCurrent_v2, "cuCtxPopCurrent_v2")
   BO_SYM(cuDevicePrimaryCtxRetain, "cuDevicePrimaryCtxRetain")
   BO_SYM(cuModuleLoadData, "cuModuleLoadData")
   BO_SYM(cuModuleUnload, "cuModuleUnload")
@@ -148,22 +153,55 @@ const char* cu_err(CUresult r) {
     if (_r != CUDA_SUCCESS) return set_err(BO_ERR_CUDA, "%s failed: %s", #call, cu_err(_r)); \
   } while (0)
 
-// Make sure a context is current on this thread (torch's primary context if it exists).
-int ensure_context(CUdevice* dev_out) {
+// Make sure a context is current on this thread.  `device` >= 0 names the ordinal explicitly (bo_options.device =
+// ordinal + 1); otherwise the context already current on the thread is used (torch's primary context of the device the
+// caller selected and touched), and only when there is none the primary context of device 0.
+int ensure_context(CUdevice* dev_out, int device = -1, CUcontext* ctx_out = nullptr) {
   if (!load_driver()) return set_err(BO_ERR_NO_DEVICE, "%s", g_drv.why.c_str());
   int n = 0;
   if (g_drv.cuDeviceGetCount(&n) != CUDA_SUCCESS || n == 0) return set_err(BO_ERR_NO_DEVICE, "no CUDA device");
   CUcontext ctx = nullptr;
   g_drv.cuCtxGetCurrent(&ctx);
-  if (!ctx) {
+  if (device >= 0) {
+    if (device >= n) return set_err(BO_ERR_INVALID, "device ordinal %d out of range (%d devices)", device, n);
+    CUdevice cur = -1;
+    if (!ctx || g_drv.cuCtxGetDevice(&cur) != CUDA_SUCCESS || cur != device) {
+      CUdevice dev;
+      BO_CU(g_drv.cuDeviceGet(&dev, device));
+      BO_CU(g_drv.cuDevicePrimaryCtxRetain(&ctx, dev));
+      BO_CU(g_drv.cuCtxSetCurrent(ctx));
+    }
+  } else if (!ctx) {
     CUdevice dev;
     BO_CU(g_drv.cuDeviceGet(&dev, 0));
     BO_CU(g_drv.cuDevicePrimaryCtxRetain(&ctx, dev));
     BO_CU(g_drv.cuCtxSetCurrent(ctx));
   }
   if (dev_out) BO_CU(g_drv.cuCtxGetDevice(dev_out));
+  if (ctx_out) *ctx_out = ctx;
   return BO_OK;
 }
+
+// A handle's module, buffers and events belong to the context it was created in: make that context current for the
+// duration of a call that arrives on a thread whose current context is another one (or none).
+struct CtxScope {
+  bool pushed = false;
+  int enter(CUcontext want) {
+    if (!want) return BO_OK;
+    CUcontext cur = nullptr;
+    g_drv.cuCtxGetCurrent(&cur);
+    if (cur == want) return BO_OK;
+    BO_CU(g_drv.cuCtxPushCurrent_v2(want));
+    pushed = true;
+    return BO_OK;
+  }
+  ~CtxScope() {
+    if (pushed) {
+      CUcontext old;
+      g_drv.cuCtxPopCurrent_v2(&old);
+    }
+  }
+};
 
 // ------------------------------------------------------------------------------------------
 // paths, hashing, files
@@ -429,13 +467,27 @@ bo_options normalise(const bo_options* in) {
   bo_options o;
   memset(&o, 0, sizeof o);
   if (in) o = *in;
+  const bool user_max_iter = o.max_iter > 0;
   if (o.max_iter <= 0) o.max_iter = 100;
-  if (o.max_trips <= 0) o.max_trips = 250;
+  // every iteration costs at least one trip: a caller who raises max_iter without naming a trip budget must not be
+  // cut off by the default one
+  if (o.max_trips <= 0) o.max_trips = user_max_iter ? std::max(250, (5 * o.max_iter) / 2) : 250;
   if (!(o.tol > 0)) o.tol = 1e-8;
   if (!(o.acceptable_tol > 0)) o.acceptable_tol = 1e-6;
   if (!(o.mu_init > 0)) o.mu_init = 0.1;
-  if (o.max_step == 0.0) o.max_step = 0.5;
+  // max_step == 0 ("default") is resolved per problem in bo_problem_create: 0.5 when the tapes contain trigonometric
+  // kinematics, unlimited otherwise
   return o;
+}
+
+// The step cap exists for Newton steps of several radians through trigonometric kinematics; on problems without any
+// (QPs, linear models, unscaled task-space variables) it would only limit how far from the seed an optimum may lie.
+bool tape_has_trig(const bo::Tape& t) {
+  for (int64_t i = 0; i < t.n_instr(); ++i) {
+    const int op = t.instr[4 * i] & 0xFF;
+    if (op == BO_OP_SIN || op == BO_OP_COS || op == BO_OP_TAN) return true;
+  }
+  return false;
 }
 
 struct SolverParams {  // must match bo_solver_params in csrc/jit/bo_common.cuh
@@ -469,6 +521,7 @@ struct bo_problem {
   int smem_dynamic = 0;
   DevBuf d_dtab, d_scratch;
   int blocks_per_sm = 1, n_sm = 1;
+  CUcontext ctx = nullptr;
   Timer timer;
 };
 
@@ -484,6 +537,7 @@ struct bo_function {
   int smem_dynamic = 0;
   int blocks_per_sm = 1, n_sm = 1;
   std::vector<DevBuf> d_in, d_out;
+  CUcontext ctx = nullptr;
   Timer timer;
 };
 
@@ -541,7 +595,9 @@ int bo_problem_create(const bo_problem_desc* desc, const bo_options* opts_in, bo
   if (ps.nx + ps.n_eq > 8192 || ps.n_ineq > 16384)
     return set_err(BO_ERR_UNSUPPORTED, "bo_problem_create: nx+n_eq=%d, n_ineq=%d exceeds the built tiers", ps.nx + ps.n_eq,
                    ps.n_ineq);
-  pr->tpb = pr->opts.threads_per_block > 0 ? pr->opts.threads_per_block : 64;
+  // whole warps only: the kernels use full-mask warp votes
+  pr->tpb = pr->opts.threads_per_block > 0 ? ((pr->opts.threads_per_block + 31) / 32) * 32 : 64;
+  if (pr->opts.max_step == 0.0) pr->opts.max_step = (tape_has_trig(ps.kkt) || tape_has_trig(ps.fc)) ? 0.5 : -1.0;
   if (getenv("BO_DEBUG")) fprintf(stderr, "[bo] emitting source\n");
   // KKT systems beyond a dozen rows are factored sparsely: symbolic analysis here, once
   const bool pivoted = (pr->opts.flags & BO_FLAG_PIVOTED_LDL) != 0;
@@ -587,10 +643,8 @@ int bo_problem_create(const bo_problem_desc* desc, const bo_options* opts_in, bo
   pr->kernel.local_bytes = pr->compiled.local_bytes;
   pr->kernel.smem_bytes = pr->compiled.smem_bytes;
   if (!(pr->opts.flags & BO_FLAG_COMPILE_ONLY)) {
-    rc = ensure_context(nullptr);
-    if (rc != BO_OK) return rc;
     CUdevice dev;
-    rc = ensure_context(&dev);
+    rc = ensure_context(&dev, pr->opts.device - 1, &pr->ctx);
     if (rc != BO_OK) return rc;
     rc = load_kernel(pr->compiled, "bo_solve_kernel", &pr->kernel);
     if (rc != BO_OK) return rc;
@@ -648,6 +702,8 @@ int bo_problem_create(const bo_problem_desc* desc, const bo_options* opts_in, bo
 int bo_problem_destroy(bo_problem* pr) {
   if (!pr) return BO_OK;
   if (pr->loaded) {
+    CtxScope scope;
+    scope.enter(pr->ctx);
     for (DevBuf* b : {&pr->d_p, &pr->d_x0, &pr->d_x, &pr->d_lam, &pr->d_f, &pr->d_status, &pr->d_iters, &pr->d_kkt, &pr->d_counter, &pr->d_ldl_tab, &pr->d_dtab, &pr->d_scratch})
       b->release();
     pr->timer.release();
@@ -692,6 +748,14 @@ int bo_problem_kernel_info(const bo_problem* pr, int32_t* regs, int32_t* local_b
   if (regs) *regs = pr->kernel.regs;
   if (local_bytes) *local_bytes = pr->kernel.local_bytes;
   if (smem_bytes) *smem_bytes = pr->kernel.smem_bytes;
+  return BO_OK;
+}
+
+int bo_problem_options(const bo_problem* pr, bo_options* out) {
+  if (!pr || !out) return set_err(BO_ERR_INVALID, "null argument");
+  *out = pr->opts;
+  out->cache_dir = nullptr;  // borrowed strings are not handed back
+  out->include_dir = nullptr;
   return BO_OK;
 }
 
@@ -747,7 +811,8 @@ int bo_solve(bo_problem* pr, int64_t B, const double* p, const double* x0, doubl
   if (!pr->loaded) return set_err(BO_ERR_NO_DEVICE, "bo_solve: problem was created compile-only or without a device");
   if (pr->ps.np > 0 && !p) return set_err(BO_ERR_INVALID, "bo_solve: p is NULL but np > 0");
   if (B == 0) return BO_OK;
-  int rc = ensure_context(nullptr);
+  CtxScope scope;
+  int rc = scope.enter(pr->ctx);
   if (rc != BO_OK) return rc;
   CUstream st = (CUstream)cuda_stream;
   const size_t nx = pr->ps.nx, np = pr->ps.np, nl = pr->ps.n_eq + pr->ps.n_ineq;
@@ -825,6 +890,8 @@ int bo_solve(bo_problem* pr, int64_t B, const double* p, const double* x0, doubl
 int bo_problem_kernel_time(bo_problem* pr, double* ms_total, int64_t* n_launches) {
   if (!pr || !ms_total) return set_err(BO_ERR_INVALID, "null argument");
   if (!pr->loaded) return set_err(BO_ERR_NO_DEVICE, "problem not loaded on a device");
+  CtxScope scope;
+  scope.enter(pr->ctx);
   int64_t n = 0;
   int rc = pr->timer.collect(ms_total, &n);
   if (n_launches) *n_launches = n;
@@ -874,7 +941,7 @@ int bo_function_create(const bo_tape* tape, const bo_options* opts_in, bo_functi
   fn->kernel.smem_bytes = fn->compiled.smem_bytes;
   if (!(fn->opts.flags & BO_FLAG_COMPILE_ONLY)) {
     CUdevice dev;
-    rc = ensure_context(&dev);
+    rc = ensure_context(&dev, fn->opts.device - 1, &fn->ctx);
     if (rc != BO_OK) return rc;
     rc = load_kernel(fn->compiled, "bo_eval_kernel", &fn->kernel);
     if (rc != BO_OK) return rc;
@@ -894,6 +961,8 @@ int bo_function_create(const bo_tape* tape, const bo_options* opts_in, bo_functi
 int bo_function_destroy(bo_function* fn) {
   if (!fn) return BO_OK;
   if (fn->loaded) {
+    CtxScope scope;
+    scope.enter(fn->ctx);
     for (auto& b : fn->d_in) b.release();
     for (auto& b : fn->d_out) b.release();
     fn->timer.release();
@@ -920,7 +989,8 @@ int bo_function_eval(bo_function* fn, int64_t B, const double* const* in, double
   if (!fn || !in || !out || B < 0) return set_err(BO_ERR_INVALID, "bo_function_eval: bad argument");
   if (!fn->loaded) return set_err(BO_ERR_NO_DEVICE, "bo_function_eval: function was created compile-only or without a device");
   if (B == 0) return BO_OK;
-  int rc = ensure_context(nullptr);
+  CtxScope scope;
+  int rc = scope.enter(fn->ctx);
   if (rc != BO_OK) return rc;
   CUstream st = (CUstream)cuda_stream;
   const size_t n_in = fn->tape.in_sizes.size(), n_out = fn->tape.out_sizes.size();
@@ -982,6 +1052,8 @@ int bo_function_eval(bo_function* fn, int64_t B, const double* const* in, double
 int bo_function_kernel_time(bo_function* fn, double* ms_total, int64_t* n_launches) {
   if (!fn || !ms_total) return set_err(BO_ERR_INVALID, "null argument");
   if (!fn->loaded) return set_err(BO_ERR_NO_DEVICE, "function not loaded on a device");
+  CtxScope scope;
+  scope.enter(fn->ctx);
   int64_t n = 0;
   int rc = fn->timer.collect(ms_total, &n);
   if (n_launches) *n_launches = n;

@@ -702,10 +702,13 @@ BO_DEVICE int bo_cta_trip_eval(bo_cta_state& S, const bo_cta& C, const bo_solver
   const double kappa_eps = 10.0, kappa_mu = 0.2, tau_min = 0.99, s_max = 100.0;
   const double mu_min = prm.tol * 0.1;
   double* W = C.W;
-  if (++S.trips > prm.max_trips) return BO_ST_MAX_ITER;
+  // trip budget: an instance over budget right after an accepted step is evaluated once more, so that f / err0 /
+  // multipliers reported belong to the x returned (see bo_ipm_reg.cuh)
+  const bool over = ++S.trips > prm.max_trips;
+  if (over && S.phase != BO_PH_EVAL) return BO_ST_MAX_ITER;
   if (S.phase != BO_PH_EVAL) return -1;
   S.f = bo_cta_eval_kkt(C);
-  if (S.recalc_y && BO_ME > 0) {
+  if (S.recalc_y && BO_ME > 0 && !over) {
     // least-squares multiplier estimate after a regularised step (see bo_ipm_reg.cuh)
     S.recalc_y = false;
     S.ls_mode = true;
@@ -749,7 +752,7 @@ BO_DEVICE int bo_cta_trip_eval(bo_cta_state& S, const bo_cta& C, const bo_solver
   if (S.err0 <= prm.tol) return BO_ST_CONVERGED;
   S.n_acceptable = (S.err0 <= prm.acceptable_tol) ? S.n_acceptable + 1 : 0;
   if (S.n_acceptable >= 15) return BO_ST_ACCEPTABLE;
-  if (S.it >= prm.max_iter) return BO_ST_MAX_ITER;
+  if (S.it >= prm.max_iter || over) return BO_ST_MAX_ITER;
   // barrier parameter update (monotone Fiacco-McCormick); resets the filter
   if (BO_MI > 0) {
     for (int rep = 0; rep < 8; ++rep) {

@@ -651,12 +651,15 @@ BO_NOINLINE double bo_ipm_step(bo_ipm_state& S, const bo_solver_params& prm) {
 BO_DEVICE int bo_trip_eval(bo_ipm_state& S, const bo_solver_params prm) {
   const double kappa_eps = 10.0, kappa_mu = 0.2, tau_min = 0.99, s_max = 100.0;
   const double mu_min = prm.tol * 0.1;
-  if (++S.trips > prm.max_trips) return BO_ST_MAX_ITER;
+  // Trip budget.  Between an accepted step and the next evaluation S.f / S.err0 still describe the previous iterate:
+  // an instance that runs out of budget there is evaluated once more so that what is reported belongs to the x returned.
+  const bool over = ++S.trips > prm.max_trips;
+  if (over && S.phase != BO_PH_EVAL) return BO_ST_MAX_ITER;
 
   // =========================== PH_EVAL ===========================
   if (S.phase == BO_PH_EVAL) {
     bo_tape_kkt(S.x, S.p, S.y, S.z, &S.f, S.g, S.cE, S.cI, S.JE, S.JI, S.H);
-    if (S.recalc_y && BO_ME > 0) {
+    if (S.recalc_y && BO_ME > 0 && !over) {
       // The last step needed Hessian convexification (dw > 0): its Newton multipliers scale with dw
       // and feed back into the Hessian.  Replace y by the least-squares estimate
       //   [ I  JE' ; JE  -dc ] [ r ; y ] = [ grad f - JI' z ; 0 ]
@@ -709,7 +712,7 @@ BO_DEVICE int bo_trip_eval(bo_ipm_state& S, const bo_solver_params prm) {
       if (S.err0 <= prm.tol) return BO_ST_CONVERGED;
       S.n_acceptable = (S.err0 <= prm.acceptable_tol) ? S.n_acceptable + 1 : 0;
       if (S.n_acceptable >= 15) return BO_ST_ACCEPTABLE;
-      if (S.it >= prm.max_iter) return BO_ST_MAX_ITER;
+      if (S.it >= prm.max_iter || over) return BO_ST_MAX_ITER;
 
       // ---- barrier parameter update (monotone Fiacco-McCormick, IPOPT eq. 7); resets the filter ----
       if (BO_MI > 0) {

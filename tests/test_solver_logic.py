@@ -279,3 +279,65 @@ def test_tier_choice_follows_the_measured_rule():
         assert s.tier_info()["tier"] == tier, (prob.name, s.tier_info()["tier"])
     forced = optas_b200.B200Solver(problems.lwr_axis_ik().opt).setup("ipopt", compile_only=True, coop=True)
     assert forced.tier_info()["tier"] == "coop"   # BO_FLAG_COOP still overrides
+
+
+# ---- option defaults (round-1 advisor findings) ----------------------------------------------------------------------
+def _far_qp(g=100.0):
+    """min ||x - g||^2 s.t. x0 + x1 = 2 g, x >= -1: a convex QP whose optimum lies ~g away from the zero seed."""
+    import optas_b200.sym as cs
+    from optas_b200.lowering import lower_nlp
+
+    x = cs.SX.sym("x", 2)
+    p = cs.SX.sym("p", 1)
+    f = cs.sumsqr(x - p[0])
+    return lower_nlp(x, p, f, cs.vertcat(x[0] + x[1] - 2.0 * p[0]), x + 1.0)
+
+
+def test_step_cap_is_off_for_problems_without_trigonometry():
+    """The default step cap (0.5, absolute) made any optimum further than max_iter/2 from the seed unreachable.  It now
+    applies only when the tapes contain sin/cos/tan; an explicit max_step is always honoured."""
+    from optas_b200 import _capi
+
+    lo = _far_qp()
+    h = _capi.ProblemHandle(lo, flags=_capi.BO_FLAG_COMPILE_ONLY)
+    o = h.options()
+    assert o["max_step"] < 0 and o["max_iter"] == 100 and o["max_trips"] == 250
+    sim = HostSim(h.source(), lo.nx, lo.np_, lo.n_eq, lo.n_ineq)
+    r = sim.solve(np.array([[100.0]]), np.zeros((1, 2)), max_step=o["max_step"])
+    assert r["status"][0] == 0 and r["iters"][0] <= 12
+    assert np.allclose(r["x"][0], [100.0, 100.0], atol=1e-6)
+    # the old default reproduces the advisor's failure: 100 iterations x 0.5 = 50
+    r_old = sim.solve(np.array([[100.0]]), np.zeros((1, 2)), max_step=0.5)
+    assert r_old["status"][0] == 2 and np.abs(r_old["x"][0]).max() <= 50.0 + 1e-9
+    assert _capi.ProblemHandle(lo, flags=_capi.BO_FLAG_COMPILE_ONLY, max_step=0.25).options()["max_step"] == 0.25
+    # kinematics keep the cap
+    ik = optas_b200.B200Solver(problems.lwr_ik().opt).setup("ipopt", compile_only=True)
+    assert ik._handle.options()["max_step"] == 0.5
+
+
+def test_trip_budget_follows_max_iter():
+    """`ipopt.max_iter` / scipy `maxiter` above the default trip budget used to be silently ineffective."""
+    prob = problems.booth()
+    s = optas_b200.B200Solver(prob.opt).setup("ipopt", {"ipopt.max_iter": 1000}, compile_only=True)
+    o = s._handle.options()
+    assert o["max_iter"] == 1000 and o["max_trips"] == 2500
+    s = optas_b200.ScipyMinimizeSolver(prob.opt).setup(method="SLSQP", options={"maxiter": 40}, compile_only=True)
+    assert s._handle.options()["max_trips"] == 250
+    s = optas_b200.B200Solver(prob.opt).setup("ipopt", {"ipopt.max_iter": 1000, "max_trips": 77}, compile_only=True)
+    assert s._handle.options()["max_trips"] == 77
+    assert optas_b200.B200Solver(prob.opt).setup("ipopt", compile_only=True, threads_per_block=48)._handle.tier_info()["threads_per_block"] == 64
+
+
+def test_raw_buffers_are_validated_before_the_library_sees_them():
+    prob = problems.lwr_ik()
+    s = optas_b200.B200Solver(prob.opt).setup("ipopt", compile_only=True)
+    P, X0 = prob.sample(4, seed=0)
+    X = np.empty_like(X0)
+    with pytest.raises(ValueError, match="float64"):
+        s.solve_raw(P.astype(np.float32), X0, X)
+    with pytest.raises(ValueError, match="contiguous"):
+        s.solve_raw(np.asfortranarray(P), X0, X)
+    with pytest.raises(ValueError, match="rows"):
+        s.solve_raw(P[:3], X0, X)
+    with pytest.raises(ValueError, match="int32"):
+        s.solve_raw(P, X0, X, status=np.zeros(4, dtype=np.int64))
