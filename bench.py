@@ -163,7 +163,185 @@ def workload_config(batch: int, world: int) -> dict:
     return {"workload": "C2: KUKA LWR 7-DoF IK (example/example.py), random reachable p_goal, seed q_nominal",
             "instances_per_gpu": batch, "global_instances": batch * world, "parallelism": f"batch-sharded x{world}",
             "l2_flush_between_steps": True, "solver_tolerance": 1e-8,
-            "counted": "instances reported converged only"}
+            "counted": "instances with status 0 (scaled KKT error <= 1e-8); status 1 (<= 1e-6, stalled) is reported "
+                       "separately as acceptable_fraction and NOT counted"}
+
+
+# The other BASELINE.json configs, reported inside the headline line under "configs" (and alone with --config NAME).
+#   factory, BASELINE batch, scaling over --gpus N, solver options, seed ("own": the sampler's; "zeros": x0 = 0 as the
+#   reference script's first call has it, optas/solver.py:76), timed steps, CPU-baseline solver and sample per core, label
+CONFIGS = {
+    "c3": dict(factory="point_mass_mpc", batch=16384, scaling="weak", opts={}, seed="own", steps=3, cpu=("slsqp", 64),
+               label="C3: point_mass_mpc.py Controller tick, T=20 (nx 80, 42 eq, 180 ineq), seed = hold-position trajectory"),
+    "c3_zero_seed": dict(factory="point_mass_mpc", batch=16384, scaling="weak", opts={}, seed="zeros", steps=3, cpu=None,
+                         label="C3 as SURVEY 8d defines it: x0 = 0 (the script's cold first tick, point_mass_mpc.py:157-161)"),
+    "c4": dict(factory="figure_eight", batch=4096, scaling="weak", opts={"max_iter": 400, "max_trips": 2500}, seed="own", steps=1,
+               cpu=("ipm", 2),
+               label="C4: figure_eight_plan.py T=50 + joint-limit bounds (nx 693, 557 eq, 700 ineq), seed q = qc tiled, dq = 0 "
+                     "(figure_eight_plan.py:123-124); the reference script has no joint limits, BASELINE.json adds them"),
+    "c5": dict(factory="dual_arm", batch=32768, scaling="strong", opts={}, seed="own", steps=1, cpu=("ipm", 4),
+               label="C5: dual_arm.py T=50 (nx 1386, 700 eq), 32768 instances sharded over the GPUs, seed q = qc tiled, dq = 0"),
+    "c5_zero_seed": dict(factory="dual_arm", batch=32768, scaling="strong", opts={}, seed="zeros", steps=1, cpu=None,
+                         label="C5 with the reference script's own seed x0 = 0 (dual_arm.py never calls reset_initial_seed)"),
+    # SURVEY.md 8f rows (not BASELINE configs; only with --config NAME)
+    "jsp": dict(factory="joint_space_planner", batch=8192, scaling="weak", opts={}, seed="own", steps=3, cpu=None,
+                label="8f-3: simple_joint_space_planner.py T=20 (nx 280, 154 eq incl. pose goal, 40 link-height ineq)"),
+    "qp": dict(factory="planar_idk", batch=65536, scaling="weak", opts={}, seed="own", steps=3, cpu=None,
+               label="8f-1: planar_idk.py differential-IK QP (QuadraticCostLinearConstraints: nx 3, 2 eq, 8 ineq)"),
+    "aik": dict(factory="lwr_axis_ik", batch=65536, scaling="weak", opts={}, seed="own", steps=3, cpu=None,
+                label="8f-3: sphere_collision_avoidance.py first stage, position + tool-axis IK (nx 21, 20 eq, 14 bounds)"),
+}
+DEFAULT_CONFIGS = ["c3", "c3_zero_seed", "c4", "c5", "c5_zero_seed"]
+
+
+def config_inputs(name: str, rank: int, world: int):
+    """(problem, P, X0) of this rank for one config: weak = the BASELINE batch per rank, strong = a contiguous shard."""
+    import numpy as np
+    from optas_b200 import problems
+    from optas_b200.distributed import shard_slice
+
+    cfg = CONFIGS[name]
+    prob = getattr(problems, cfg["factory"])()
+    if cfg["scaling"] == "strong":
+        lo_, hi_ = shard_slice(cfg["batch"], rank, world)
+        P, X0 = prob.sample(cfg["batch"])
+        P, X0 = np.ascontiguousarray(P[lo_:hi_]), np.ascontiguousarray(X0[lo_:hi_])
+    else:
+        P, X0 = prob.sample(cfg["batch"], seed=rank + 1)
+    if cfg["seed"] == "zeros":
+        X0 = np.zeros_like(X0)
+    return prob, P, X0
+
+
+def config_cpu_baseline(name: str, workers: int) -> dict:
+    """CPU arm of one config on a bounded sample: C3 = the reference's runnable SLSQP formulation (oracle/slsqp_driver.py);
+    C4 / C5 (nx 693 / 1386, where dense SLSQP is O(n^3) per iteration) = the oracle's restatement of the interior-point
+    algorithm the reference calls there (oracle/ipm_ref.py).  One instance at a time per worker process."""
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import numpy as np
+    from optas_b200 import problems
+
+    cfg = CONFIGS[name]
+    kind, per_core = cfg["cpu"]
+    factory = getattr(problems, cfg["factory"])
+    n = per_core * workers
+    P, X0 = factory().sample(n, seed=4242)
+    if cfg["seed"] == "zeros":
+        X0 = np.zeros_like(X0)
+    if kind == "slsqp":
+        import slsqp_driver as drv
+
+        how = "scipy SLSQP, the reference's ScipyMinimizeSolver formulation with scipy defaults (oracle/slsqp_driver.py)"
+        kw = {}
+    else:
+        import ipm_ref as drv
+
+        how = ("sparse interior point restating the reference's nlpsol('ipopt') call (Waechter-Biegler Algorithm A, "
+               "scipy SuperLU; oracle/ipm_ref.py), tol 1e-8, step cap 0.5 as on the GPU")
+        kw = {"max_step": 0.5}
+    drv.solve_batch(factory, P[:workers], X0[:workers], workers=workers, **kw)  # builds the tapes in every worker once
+    t0 = time.perf_counter()
+    X, ok, nit = drv.solve_batch(factory, P, X0, workers=workers, **kw)
+    dt = time.perf_counter() - t0
+    return {"value": float(ok.sum() / dt), "unit": "instances/s", "cores": workers, "kind": "port",
+            "sample": f"{n} instances of the workload ({per_core} per core; FLAGGED: a sample, not the {cfg['batch']}-instance "
+                      f"batch), {how}, {workers} worker processes; {int(ok.sum())}/{n} converged, mean {float(nit.mean()):.1f} iterations",
+            "seconds": dt}
+
+
+def run_config(name: str, rank: int, world: int, dev, dist, fp64_tflops, with_cpu: bool) -> dict:
+    """One BASELINE config on this job's GPUs: device-resident `value`, `e2e` from page-locked host arrays through
+    B200Solver.solve_arrays, an FP64 `roofline` (these kernels move ~KB per instance: FP64 issue / latency bound, not
+    HBM) and, at N=1, the CPU arm on a bounded sample.  Collective calls inside: every rank must call it."""
+    import numpy as np
+    import torch
+    import optas_b200
+    from optas_b200.solver import host_array
+
+    cfg = CONFIGS[name]
+    prob, P, X0 = config_inputs(name, rank, world)
+    B = X0.shape[0]
+
+    def pinned(a):
+        out = host_array(a.shape)
+        out[...] = a
+        return out
+
+    P, X0 = pinned(P), pinned(X0)
+    solver = optas_b200.B200Solver(prob.opt).setup("ipopt", cfg["opts"], timing=True)
+    lo = solver._lowered
+    Pd, X0d = torch.from_numpy(P).to(dev), torch.from_numpy(X0).to(dev)
+    Xd = torch.empty_like(X0d)
+    std = torch.empty(B, dtype=torch.int32, device=dev)
+    itd = torch.empty(B, dtype=torch.int32, device=dev)
+    stream = torch.cuda.current_stream().cuda_stream
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    steps = cfg["steps"]
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    solver.solve_raw(Pd, X0d, Xd, None, None, std, itd, None, stream=stream)  # warm-up (also sizes the scratch)
+    barrier()
+    solver._handle.kernel_time()
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
+    for a, b in ev:
+        flush.zero_()
+        a.record()
+        solver.solve_raw(Pd, X0d, Xd, None, None, std, itd, None, stream=stream)
+        b.record()
+    barrier()
+    dev_ms = float(sum(a.elapsed_time(b) for a, b in ev))
+    kernel_ms, kernel_n = solver._handle.kernel_time()
+    n_conv = int((std == 0).sum().item())
+    n_acc = int((std == 1).sum().item())
+    iters_total = int(itd.sum().item())
+    # end to end: page-locked host arrays in, page-locked results out (two warm calls: the second set of result buffers
+    # of torch's caching host allocator exists from then on, tools/e2e_probe.py)
+    for _ in range(2 if steps > 1 else 1):
+        r = solver.solve_arrays(P, X0)
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        r = solver.solve_arrays(P, X0)
+    e2e_s = time.perf_counter() - t0
+    n_conv_e2e = int((r["status"] == 0).sum())
+    t = torch.tensor([dev_ms, e2e_s], dtype=torch.float64, device=dev)
+    c = torch.tensor([n_conv, n_acc, iters_total, B, n_conv_e2e], dtype=torch.float64, device=dev)
+    if dist is not None:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dist.all_reduce(c, op=dist.ReduceOp.SUM)
+    dev_ms, e2e_s = float(t[0]), float(t[1])
+    conv, acc, its, total, conv_e2e = (float(v) for v in c)
+    tier = solver.tier_info()
+    # FP64 work per interior-point iteration that the plan makes explicit: both tapes once, one factorisation
+    # (multiply-add = 2 flop); re-factorisations, substitutions and the extra trial points are NOT counted, so this is
+    # a lower bound on the arithmetic actually done
+    flop_iter = tape_flops(lo.kkt) + tape_flops(lo.fc) + 2 * int(tier.get("factor_madds", 0))
+    achieved = its / world * flop_iter / (kernel_ms / max(1, kernel_n) * 1e-3) / 1e12  # this rank's launch, TFLOP/s
+    out = {
+        "workload": cfg["label"], "scaling": cfg["scaling"], "global_instances": int(total), "n_gpus": world,
+        "value": conv * steps / (dev_ms * 1e-3), "unit": "instances/s", "steps": steps, "ms_per_step": dev_ms / steps,
+        "converged_fraction": conv / total, "acceptable_fraction": acc / total, "mean_iterations": its / total,
+        "e2e": {"value": conv_e2e * steps / e2e_s, "unit": "instances/s", "h2d_bytes_per_step": int(P.nbytes + X0.nbytes),
+                "d2h_bytes_per_step": int(r["x"].nbytes + r["lam"].nbytes + 28 * B), "api": "B200Solver.solve_arrays (page-locked host arrays)"},
+        "gpu_launches": int(kernel_n),
+        "roofline": {"kernel": f"bo_solve_kernel ({tier['tier']} tier)", "bound": "fp64 issue / dependent-instruction latency (not HBM, not tensor)",
+                     "achieved": achieved, "peak": fp64_tflops, "unit": "TFLOP/s", "frac": achieved / fp64_tflops if fp64_tflops else None,
+                     "traffic": None, "flop_per_iteration": flop_iter, "factor_madds": int(tier.get("factor_madds", 0)),
+                     "ms_per_launch": kernel_ms / max(1, kernel_n),
+                     "peak_source": "FP64 FMA microbenchmark of this run (fp64_peak_measured); MEASURED_PEAKS.json has no FP64 figure",
+                     "algorithmic_io_bytes_per_instance": 8 * (lo.np_ + 2 * lo.nx) + 8},
+        "tier": {k: v for k, v in tier.items() if k in ("tier", "threads_per_block", "smem_dynamic", "blocks_per_sm", "levels",
+                                                          "factor_vals", "factor_madds", "kkt_total_instr")},
+        "solve_kernel": solver.kernel_info(),
+    }
+    if with_cpu and cfg["cpu"] is not None and rank == 0:
+        out["cpu_baseline"] = config_cpu_baseline(name, os.cpu_count() or 1)
+    del solver
+    return out
 
 
 def run_reference(args) -> None:
@@ -188,11 +366,14 @@ def run_reference(args) -> None:
             solved.append(int(ok.sum()))
     total_t = sum(times)
     value = sum(solved) / total_t
+    cfg = workload_config(args.batch, max(1, args.gpus))
+    cfg["reference_arm_sample"] = (f"each step solves a {sample}-instance sample of the {args.batch}-instance batch on {workers} host "
+                                   "cores (ms_per_step is for that sample); rates compare, batch sizes do not")
     line = {
         "impl": "reference", "metric": "IK problem-instances solved/sec", "value": value, "unit": "instances/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * total_t / max(1, args.steps),
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": workload_config(args.batch, max(1, args.gpus)),
+        "config": cfg,
         "cpu_baseline": {"value": value, "unit": "instances/s", "cores": workers, "kind": "port",
                          "sample": f"{sample} instances of the workload per step (bounded sample of the {args.batch}-instance "
                                    f"batch), {workers} worker processes; reference's ScipyMinimizeSolver('SLSQP') formulation "
@@ -200,28 +381,19 @@ def run_reference(args) -> None:
         "e2e": {"value": value, "unit": "instances/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
+    if not args.no_configs:
+        line["configs"] = {}
+        for name in DEFAULT_CONFIGS:
+            if CONFIGS[name]["cpu"] is None:
+                continue
+            cb = config_cpu_baseline(name, workers)
+            line["configs"][name] = {"workload": CONFIGS[name]["label"], "value": cb["value"], "unit": "instances/s",
+                                     "cpu_baseline": cb}
     emit(line)
 
 
-OTHER_CONFIGS = {
-    # name: (problem factory, total batch of BASELINE.json, scaling, solver options, label)
-    "c3": ("point_mass_mpc", 16384, "weak", {}, "C3: point_mass_mpc.py Controller tick, T=20 (nx 80, 42 eq, 180 ineq)"),
-    "c4": ("figure_eight", 4096, "weak", {"max_iter": 400, "max_trips": 2500},
-           "C4: figure_eight_plan.py T=50 + joint-limit bounds (nx 693, 557 eq, 700 ineq)"),
-    "c5": ("dual_arm", 32768, "strong", {}, "C5: dual_arm.py T=50 (nx 1386, 700 eq), 32768 instances sharded over the GPUs"),
-    # SURVEY.md 8f-3 rows (not BASELINE configs): the rest of the RobotModel surface through the same solver
-    "jsp": ("joint_space_planner", 8192, "weak", {},
-            "8f-3: simple_joint_space_planner.py T=20 (nx 280, 154 eq incl. pose goal, 40 link-height ineq)"),
-    "qp": ("planar_idk", 65536, "weak", {},
-           "8f-1: planar_idk.py differential-IK QP (QuadraticCostLinearConstraints: nx 3, 2 eq, 8 ineq) through the general kernel"),
-    "aik": ("lwr_axis_ik", 65536, "weak", {},
-            "8f-3: sphere_collision_avoidance.py first stage, position + tool-axis IK (nx 21, 20 eq, 14 bounds)"),
-}
-
-
 def run_other_config(args) -> None:
-    """Extra bench lines for C3 / C4 / C5 (not read by the driver): device-resident `value` and `e2e`."""
-    import numpy as np
+    """`--config NAME`: one config alone, printed as a full bench line."""
     import torch
 
     rank = int(os.environ.get("RANK", "0"))
@@ -234,73 +406,18 @@ def run_other_config(args) -> None:
         import torch.distributed as dist
 
         dist.init_process_group("nccl", device_id=dev)
-    import optas_b200
-    from optas_b200 import problems
-    from optas_b200.distributed import shard_slice
-
-    factory, total, scaling, opts, label = OTHER_CONFIGS[args.config]
-    prob = getattr(problems, factory)()
-    if scaling == "strong":
-        lo_, hi_ = shard_slice(total, rank, world)
-        P, X0 = prob.sample(total)
-        P, X0 = np.ascontiguousarray(P[lo_:hi_]), np.ascontiguousarray(X0[lo_:hi_])
-    else:
-        P, X0 = prob.sample(total, seed=rank + 1)
-    B = X0.shape[0]
-    # the e2e leg copies its inputs from page-locked host memory (as the bench contract says)
-    from optas_b200.solver import host_array
-
-    def pinned(a):
-        out = host_array(a.shape)
-        out[...] = a
-        return out
-
-    P, X0 = pinned(P), pinned(X0)
-    solver = optas_b200.B200Solver(prob.opt).setup("ipopt", opts, timing=True)
-    Pd, X0d = torch.from_numpy(P).to(dev), torch.from_numpy(X0).to(dev)
-    Xd = torch.empty_like(X0d)
-    std = torch.empty(B, dtype=torch.int32, device=dev)
-    itd = torch.empty(B, dtype=torch.int32, device=dev)
-    stream = torch.cuda.current_stream().cuda_stream
-    steps, warmup = max(1, min(args.steps, 3)), 1
-    for _ in range(warmup):
-        solver.solve_raw(Pd, X0d, Xd, None, None, std, itd, None, stream=stream)
-    torch.cuda.synchronize()
-    if dist is not None:
-        dist.barrier()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for _ in range(steps):
-        solver.solve_raw(Pd, X0d, Xd, None, None, std, itd, None, stream=stream)
-    e1.record()
-    torch.cuda.synchronize()
-    dev_ms = e0.elapsed_time(e1)
-    n_conv = int((std <= 1).sum().item())
-    for _ in range(3):  # untimed, and holding the result like the timed loop does: two sets of page-locked result buffers
-        r = solver.solve_arrays(P, X0)  # exist only from the third call on (tools/e2e_probe.py: 56 / 41 / 5.1 / 5.1 ms per call)
-    t0 = time.perf_counter()
-    for _ in range(steps):
-        r = solver.solve_arrays(P, X0)
-    e2e_s = time.perf_counter() - t0
-    t = torch.tensor([dev_ms, e2e_s], dtype=torch.float64, device=dev)
-    c = torch.tensor([float(n_conv), float(B)], dtype=torch.float64, device=dev)
-    if dist is not None:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        dist.all_reduce(c, op=dist.ReduceOp.SUM)
+    fp64 = fp64_peak_tflops(dev, torch.cuda.current_stream().cuda_stream)
+    with ClockSampler(local_rank) as clocks:
+        r = run_config(args.config, rank, world, dev, dist, fp64["tflops"], with_cpu=not args.no_cpu_baseline and world == 1)
     if rank == 0:
-        emit({
-            "metric": "problem-instances solved/sec", "value": float(c[0]) * steps / (float(t[0]) * 1e-3), "unit": "instances/s",
-            "n_gpus": world, "steps": steps, "warmup": warmup, "ms_per_step": float(t[0]) / steps, "higher_is_better": True,
-            "scaling": scaling, "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": label, "global_instances": int(c[1]), "parallelism": f"batch-sharded x{world}"},
-            "converged_fraction": float(c[0]) / float(c[1]), "mean_iterations": float(itd.float().mean().item()),
-            "e2e": {"value": float(c[0]) * steps / float(t[1]), "unit": "instances/s",
-                    "h2d_bytes_per_step": int(P.nbytes + X0.nbytes), "d2h_bytes_per_step": int(r["x"].nbytes + r["lam"].nbytes + 28 * B)},
-            "gpu_launches": steps, "solve_kernel": solver.kernel_info(),
-            "tier": {k: v for k, v in solver.tier_info().items() if k in (
-                "tier", "threads_per_block", "smem_dynamic", "blocks_per_sm", "levels", "segments", "factor_vals",
-                "factor_madds", "factor_steps", "solve_steps", "ldl_warps", "ldl_g", "solve_g", "generated_tapes",
-                "kkt_components", "kkt_classes", "kkt_code_rows", "kkt_total_instr")}})
+        line = {"metric": "problem-instances solved/sec", "value": r["value"], "unit": "instances/s", "n_gpus": world,
+                "steps": r["steps"], "warmup": 1, "ms_per_step": r["ms_per_step"], "higher_is_better": True, "scaling": r["scaling"],
+                "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+                "config": {"workload": r["workload"], "global_instances": r["global_instances"], "parallelism": f"batch-sharded x{world}",
+                           "l2_flush_between_steps": True, "counted": "status 0 only"},
+                "fp64_peak_measured": fp64, "clocks": clocks.summary()}
+        line.update({k: v for k, v in r.items() if k not in ("value", "unit", "steps", "ms_per_step", "scaling", "workload", "n_gpus", "global_instances")})
+        emit(line)
     if dist is not None:
         dist.barrier()
         dist.destroy_process_group()
@@ -314,15 +431,16 @@ def main() -> None:
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--batch", type=int, default=BATCH_PER_GPU)
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--config", default="c2", choices=["c2", "c3", "c4", "c5", "jsp", "aik", "qp"],
-                    help="c2 (default) is the headline line the driver reads; c3/c4/c5 print an extra line for the other "
-                         "BASELINE.json configs (device-resident value + e2e only)")
+    ap.add_argument("--no-configs", action="store_true", help="headline C2 only: skip the `configs` block (C3 / C4 / C5)")
+    ap.add_argument("--config", default="c2", choices=["c2"] + sorted(CONFIGS),
+                    help="c2 (default) is the line the driver reads; it carries the other BASELINE.json configs under "
+                         "`configs`.  Any other name prints that config alone as a full line.")
     args = ap.parse_args()
-    if args.config != "c2":
-        run_other_config(args)
-        return
     if args.impl == "reference":
         run_reference(args)
+        return
+    if args.config != "c2":
+        run_other_config(args)
         return
     args.warmup = max(args.warmup, 3)
 
@@ -388,7 +506,8 @@ def main() -> None:
         step_ms = [a.elapsed_time(b) for a, b in ev]
         dev_ms = float(sum(step_ms))
         kernel_ms, kernel_n = solver._handle.kernel_time()
-        n_conv = int((std <= 1).sum().item())
+        n_conv = int((std == 0).sum().item())
+        n_acc = int((std == 1).sum().item())
         iters_total = int(itd.sum().item())
 
         # ---------------- end-to-end arm (`e2e`): public API, host arrays ----------------
@@ -403,7 +522,7 @@ def main() -> None:
             solver.reset_parameters(p_dict)
             solver.reset_initial_seed(x0_dict)
             sol = solver.solve()
-            n_conv_e2e = solver.stats()["n_converged"]
+            n_conv_e2e = int((solver.stats()["status"] == 0).sum())
         torch.cuda.synchronize()
         e2e_s = time.perf_counter() - t0
 
@@ -425,15 +544,26 @@ def main() -> None:
         fk_ms_total, fk_n = fk.kernel_time()
         fp64 = fp64_peak_tflops(dev, stream)
     fk_ms = fk_ms_total / fk_n
+    del fk, q, p_out, J_out
 
     # max over ranks of the device time, sum over ranks of the solved instances
     t = torch.tensor([dev_ms, e2e_s], dtype=torch.float64, device=dev)
-    c = torch.tensor([n_conv, n_conv_e2e], dtype=torch.float64, device=dev)
+    c = torch.tensor([n_conv, n_conv_e2e, n_acc, iters_total], dtype=torch.float64, device=dev)
     if dist is not None:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         dist.all_reduce(c, op=dist.ReduceOp.SUM)
     dev_ms_max, e2e_s_max = float(t[0]), float(t[1])
-    conv_total, conv_e2e_total = float(c[0]), float(c[1])
+    conv_total, conv_e2e_total, acc_total, iters_all = (float(v) for v in c)
+    info = solver.kernel_info()
+    tier = solver.tier_info()
+    kkt_flops, fc_flops = tape_flops(solver._lowered.kkt), tape_flops(solver._lowered.fc)
+    del solver, Pd, X0d, Xd, lamd
+
+    # ---------------- the other BASELINE configs (every rank takes part) ----------------
+    configs = {}
+    if not args.no_configs:
+        for name in DEFAULT_CONFIGS:
+            configs[name] = run_config(name, rank, world, dev, dist, fp64["tflops"], with_cpu=not args.no_cpu_baseline and world == 1)
 
     if rank == 0:
         peaks = measured_peaks()
@@ -443,6 +573,7 @@ def main() -> None:
         if os.path.exists(prof):
             with open(prof) as fh:
                 traffic = json.load(fh).get("dram_bytes_per_launch")
+        ms_launch = kernel_ms / max(1, kernel_n)
         line = {
             "metric": "IK problem-instances solved/sec", "value": conv_total * args.steps / (dev_ms_max * 1e-3),
             "unit": "instances/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
@@ -450,7 +581,8 @@ def main() -> None:
             "dtype": "f64", "data": "synthetic",
             "config": workload_config(B, world),
             "converged_fraction": conv_total / (B * world),
-            "mean_iterations": iters_total / B,
+            "acceptable_fraction": acc_total / (B * world),
+            "mean_iterations": iters_all / (B * world),
             "e2e": {"value": conv_e2e_total * args.steps / e2e_s_max, "unit": "instances/s",
                     "h2d_bytes_per_step": B * (npar + nx) * 8,
                     "d2h_bytes_per_step": B * (nx * 8 + nlam * 8 + 8 + 4 + 4 + 8),
@@ -461,18 +593,21 @@ def main() -> None:
                          "traffic": traffic, "peak_source": peaks["source"] + " (burst copy figure; kernel timed alone)",
                          "bytes_per_eval": FK_BYTES_PER_EVAL, "evals_per_launch": FK_BATCH, "ms_per_launch": fk_ms,
                          "launches_timed": int(fk_n)},
-            "solve_kernel": {"kernel": "bo_solve_kernel", "bound": "fp64 issue / iteration latency (not HBM)",
-                             "ms_per_launch": kernel_ms / max(1, kernel_n),
+            "solve_kernel": {"kernel": f"bo_solve_kernel ({tier['tier']} tier)", "bound": "fp64 issue / iteration latency (not HBM)",
+                             "ms_per_launch": ms_launch,
                              "algorithmic_io_bytes_per_launch": B * 200,
-                             "io_gbs": B * 200 / (kernel_ms / max(1, kernel_n) * 1e-3) / 1e9,
-                             "registers": solver.kernel_info()["registers"],
-                             "local_bytes": solver.kernel_info()["local_bytes"],
-                             "tape_flop_per_iteration": tape_flops(solver._lowered.kkt) + tape_flops(solver._lowered.fc),
-                             "achieved_tflops_tapes_only": iters_total * (tape_flops(solver._lowered.kkt) + tape_flops(solver._lowered.fc))
-                             / (kernel_ms / max(1, kernel_n) * 1e-3) / 1e12,
+                             "io_gbs": B * 200 / (ms_launch * 1e-3) / 1e9,
+                             "registers": info["registers"], "local_bytes": info["local_bytes"],
+                             "smem_bytes_per_cta": tier.get("smem_dynamic", 0) + max(0, info.get("smem_bytes", 0)),
+                             "threads_per_block": tier.get("threads_per_block"), "blocks_per_sm": tier.get("blocks_per_sm"),
+                             "tape_flop_per_iteration": kkt_flops + fc_flops,
+                             "achieved_tflops_tapes_only": iters_all / world * (kkt_flops + fc_flops) / (ms_launch * 1e-3) / 1e12,
                              "fp64_peak_measured": fp64},
             "clocks": clocks.summary(),
         }
+        line["solve_kernel"]["frac_of_fp64_peak_tapes_only"] = line["solve_kernel"]["achieved_tflops_tapes_only"] / fp64["tflops"]
+        if configs:
+            line["configs"] = configs
         if not args.no_cpu_baseline and world == 1:
             line["cpu_baseline"] = cpu_baseline(CPU_SAMPLE, os.cpu_count() or 1)
         emit(line)

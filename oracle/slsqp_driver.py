@@ -114,8 +114,20 @@ def solve_slsqp(prob: OracleProblem, p: np.ndarray, x0: np.ndarray, form: str = 
     return minimize(**kw)
 
 
+def _one_blas_thread():
+    """One BLAS / OpenMP thread per worker process: the batch is parallel over instances (one process per core), nested
+    library threads would only fight over the same cores."""
+    try:
+        from threadpoolctl import threadpool_limits
+
+        threadpool_limits(1)
+    except Exception:
+        pass
+
+
 def _worker(args):
     opt_factory, P, X0, form, tol, options = args
+    _one_blas_thread()
     prob = OracleProblem(opt_factory().opt)
     out = np.empty_like(X0)
     ok = np.zeros(len(X0), dtype=bool)
