@@ -27,6 +27,7 @@
 #include "bo_coop.h"
 #include "bo_opcodes.h"
 #include "bo_sparse.h"
+#include "bo_team.h"
 
 namespace {
 
@@ -294,7 +295,7 @@ int jit_compile(const std::string& source, const char* unit_name, const char* ke
 
   // hash = source + every header it may include + compiler version
   uint64_t h = fnv1a(source);
-  for (const char* hdr : {"bo_common.cuh", "bo_ipm_reg.cuh", "bo_ipm_cta.cuh", "bo_stream_eval.cuh"}) {
+  for (const char* hdr : {"bo_common.cuh", "bo_ipm_reg.cuh", "bo_ipm_cta.cuh", "bo_stream_eval.cuh", "bo_ipm_team.cuh", "bo_team_layout.cuh"}) {
     std::string text;
     if (!read_file(inc + "/" + hdr, &text)) return set_err(BO_ERR_INVALID, "JIT header %s/%s not found", inc.c_str(), hdr);
     h = fnv1a(text, h);
@@ -517,7 +518,8 @@ struct bo_problem {
   DevBuf d_p, d_x0, d_x, d_lam, d_f, d_status, d_iters, d_kkt, d_counter, d_ldl_tab;
   bo::SparsePlan plan;
   bo::CoopPlan coop_plan;
-  bool sparse = false, large = false, coop = false;
+  bool sparse = false, large = false, coop = false, team = false;
+  bo::TeamPlan team_plan;
   int smem_dynamic = 0;
   DevBuf d_dtab, d_scratch;
   int blocks_per_sm = 1, n_sm = 1;
@@ -630,7 +632,23 @@ int bo_problem_create(const bo_problem_desc* desc, const bo_options* opts_in, bo
       pr->coop_plan = std::move(cp);
     }
   }
-  if (pr->coop) {
+  // Team tier (csrc/jit/bo_ipm_team.cuh): small dense problems, G threads in G warps per instance, state in shared memory
+  if (!pr->sparse && !pivoted && !(pr->opts.flags & BO_FLAG_NO_TEAM)) {
+    int G = pr->opts.threads_per_block > 0 ? pr->opts.threads_per_block / 32 : 4;
+    G = std::max(1, std::min(G, 8));
+    std::string why;
+    const size_t smem = ((size_t)bo::team_smem_elems(ps, G) * 32 + 2 * 32 * (size_t)(ps.np + ps.nx)) * sizeof(double) + 32 * sizeof(int) + 128;
+    if (smem <= 227 * 1024 && bo::make_team_plan(ps, G, &pr->team_plan, &why)) {
+      pr->team = true;
+      pr->tpb = 32 * G;
+      pr->smem_dynamic = (int)smem;
+    } else if (pr->opts.flags & BO_FLAG_VERBOSE) {
+      fprintf(stderr, "[b200optas] team tier not used: %s\n", why.empty() ? "shared memory" : why.c_str());
+    }
+  }
+  if (pr->team) {
+    pr->source = bo::emit_team_source(ps, pr->team_plan);
+  } else if (pr->coop) {
     pr->source = bo::emit_coop_source(ps, pr->coop_plan, pr->tpb);
   } else {
     if (pr->sparse) pr->plan = bo::make_sparse_plan(ps, pr->large);
@@ -762,7 +780,7 @@ int bo_problem_options(const bo_problem* pr, bo_options* out) {
 int bo_problem_tier_info(const bo_problem* pr, int64_t* info, int32_t cap) {
   if (!pr) return set_err(BO_ERR_INVALID, "null problem");
   int64_t v[BO_TIER_INFO_LEN] = {0};
-  v[0] = pr->coop ? 3 : (pr->large ? 2 : (pr->sparse ? 1 : 0));
+  v[0] = pr->team ? 4 : (pr->coop ? 3 : (pr->large ? 2 : (pr->sparse ? 1 : 0)));
   v[1] = pr->tpb;
   v[2] = pr->smem_dynamic;
   if (pr->coop) {
@@ -797,6 +815,16 @@ int bo_problem_tier_info(const bo_problem* pr, int64_t* info, int32_t cap) {
   } else if (pr->sparse) {
     v[12] = pr->plan.flops;
     v[19] = pr->plan.vals_size();
+  } else if (pr->team) {
+    const bo::TeamPlan& tp = pr->team_plan;
+    v[10] = tp.G;
+    v[8] = *std::max_element(tp.kkt.cost.begin(), tp.kkt.cost.end());
+    v[9] = tp.kkt.total_cost;
+    v[15] = *std::max_element(tp.fc.cost.begin(), tp.fc.cost.end());
+    v[16] = tp.fc.total_cost;
+    v[18] = bo::team_smem_elems(pr->ps, tp.G);
+    const int nk = pr->ps.nx + pr->ps.n_eq;
+    v[12] = (int64_t)nk * (nk + 1) * (nk + 2) / 6;  // multiply-adds of one dense LDL'
   }
   v[20] = pr->blocks_per_sm;
   v[21] = pr->n_sm;
@@ -870,7 +898,8 @@ int bo_solve(bo_problem* pr, int64_t B, const double* p, const double* x0, doubl
   CUdeviceptr dcounter = pr->d_counter.ptr;
   BO_CU(g_drv.cuMemsetD8Async(dcounter, 0, sizeof(unsigned long long), st));
   long long grid_ll = (long long)pr->n_sm * pr->blocks_per_sm;
-  const long long need = pr->coop ? (long long)B : (B + pr->tpb - 1) / pr->tpb;  // coop: one instance per CTA
+  // coop: one instance per CTA; team: 32 instances per CTA; else one per thread
+  const long long need = pr->coop ? (long long)B : (pr->team ? (B + 31) / 32 : (B + pr->tpb - 1) / pr->tpb);
   if (grid_ll > need) grid_ll = need;
   const unsigned grid = (unsigned)grid_ll;
   SolverParams prm{pr->opts.max_iter, pr->opts.tol, pr->opts.acceptable_tol, pr->opts.mu_init, pr->opts.max_step,

@@ -14,6 +14,7 @@
 #define BO_RESTRICT __restrict__
 #define BO_UNROLL
 #define BO_NOUNROLL
+#define BO_CONSTANT static const
 #define BO_INF (std::numeric_limits<double>::infinity())
 #define BO_NAN (std::numeric_limits<double>::quiet_NaN())
 static inline void bo_sincos(double a, double* s, double* c) { *s = std::sin(a); *c = std::cos(a); }
@@ -27,6 +28,7 @@ using std::asin; using std::acos; using std::atan; using std::sinh; using std::c
 #define BO_RESTRICT __restrict__
 #define BO_UNROLL _Pragma("unroll")
 #define BO_NOUNROLL _Pragma("unroll 1") /* loops whose body is a long libm expansion (div, log): keep one copy */
+#define BO_CONSTANT __constant__
 #define BO_INF (__longlong_as_double(0x7ff0000000000000LL))
 #define BO_NAN (__longlong_as_double(0x7ff8000000000000LL))
 typedef int int32_t;

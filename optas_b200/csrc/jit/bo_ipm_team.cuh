@@ -17,14 +17,21 @@
 //     The per-row barrier work of the inequality rows (1/s, log s, |c - s|) rides in the slice that owns the row.
 //   * state lives in shared memory as [element][32 lanes]: every access of a warp is 256 contiguous bytes
 //     (conflict-free), nothing spills: x, s, y, z, the evaluation (g, c, J, H), the packed LDL' factor, the step
-//     and the filter.  ~2.9 KB per instance for C2 => 2 CTAs (64 instances, 8 warps) per SM.
+//     and the filter.  ~3.4 KB per instance for C2 => 2 CTAs (64 instances, 8 warps) per SM.
 //   * warp 0 is the MASTER of its 32 instances: it owns the scalar state machine in registers (phase, mu, filter
 //     sizes ...), assembles and factors the KKT matrix in registers (unrolled, unpivoted LDL' on the rho-augmented
 //     system -- see bo_ipm_reg.cuh for why that is valid) and takes every decision; the other warps only ever
 //     execute slices, so no decision is computed twice with possibly different rounding.
-//   * one trip of the loop = W1 (KKT tape slices) | M1 (residuals, convergence test, mu, factor, step) |
-//     W2 (f / c slices at the trial point) | M2 (filter acceptance, SOC, backtracking), four CTA barriers.
+//   * one trip of the loop = W1 (KKT tape slices, which also assemble the (1,1) block of the KKT matrix and the row
+//     sums / maxima of the convergence test) | M1 (residuals, convergence test, mu, LDL', step) | W2a (trial point and
+//     its sin / cos: computed once, shared by all slices and by the next iteration's W1) | W2b (f / c slices, logs and
+//     reciprocals of the slack rows) | M2 (filter acceptance, SOC, backtracking): five CTA barriers.
 //     As in bo_ipm_reg.cuh every data-dependent retry is a state transition that takes effect on the next trip.
+//   * code size matters as much as instruction count: every warp runs its own straight-line code, so the instruction
+//     working set of an SM is the whole kernel.  The first version (250 KB of SASS: sin / cos and log expanded in every
+//     slice) spent 17 of every 43 cycles per issued instruction waiting for instruction fetch
+//     (profiles/r02_team_v0_ncu.txt); transcendental functions now exist once (non-inlined helpers, shared sin / cos),
+//     loops with a division or a logarithm in the body are not unrolled, constants come from the constant bank.
 //   * persistent CTAs; a team that finishes fetches the next instance (global counter) -- with TMA staging:
 //     the CTA pulls TILES of 32 consecutive instances (p and x0 rows are contiguous byte ranges) into shared memory
 //     with cp.async.bulk on an mbarrier, one tile ahead, and hands them out one by one.
@@ -34,83 +41,123 @@
 #pragma once
 #include "bo_common.cuh"
 
-#define BO_NK (BO_NX + BO_ME)
-#define BO_KSZ ((BO_NK * (BO_NK + 1)) / 2)
-#define BO_KIDX(i, j) (((i) * ((i) + 1)) / 2 + (j)) /* packed lower triangle, i >= j */
-#define BO_DIM(n) ((n) > 0 ? (n) : 1)
-
-#ifndef BO_DC_SCALE
-#define BO_DC_SCALE 1e-8
-#endif
-#ifndef BO_STATIC_RHO
-#define BO_STATIC_RHO 1.0e6
-#endif
-#define BO_NFILTER 8
-#ifndef BO_LS_MAX
-#define BO_LS_MAX 16
-#endif
-#ifndef BO_HEAVY_MAX
-#define BO_HEAVY_MAX 5
-#endif
-#define BO_IC_MAX 60
-#ifndef BO_REFINE_BELOW
-#define BO_REFINE_BELOW 1e-4
-#endif
-
-#define BO_PH_IDLE (-1)
-#define BO_PH_EVAL 0
-#define BO_PH_FACTOR 1
-#define BO_PH_TRIAL 2
-#define BO_PH_INIT 3
-
-// ---- shared-memory layout: offsets in "elements" (one element = BO_LS doubles, one per lane) ----
-#define BO_OFF_P 0
-#define BO_OFF_X (BO_OFF_P + BO_NP)
-#define BO_OFF_S (BO_OFF_X + BO_NX)
-#define BO_OFF_Y (BO_OFF_S + BO_MI)
-#define BO_OFF_Z (BO_OFF_Y + BO_ME)
-#define BO_OFF_RS (BO_OFF_Z + BO_MI)      /* 1 / s */
-#define BO_OFF_F0 (BO_OFF_RS + BO_MI)     /* f at x */
-#define BO_OFF_G (BO_OFF_F0 + 1)
-#define BO_OFF_CE (BO_OFF_G + BO_NX)
-#define BO_OFF_CI (BO_OFF_CE + BO_ME)
-#define BO_OFF_JE (BO_OFF_CI + BO_MI)
-#define BO_OFF_JI (BO_OFF_JE + BO_NNZ_JE)
-#define BO_OFF_H (BO_OFF_JI + BO_NNZ_JI)
-#define BO_OFF_SIG (BO_OFF_H + BO_NNZ_H)
-#define BO_OFF_RD (BO_OFF_SIG + BO_MI)
-#define BO_OFF_LD (BO_OFF_RD + BO_NX)     /* packed factor: 1/D on the diagonal, unit-lower L below */
-#define BO_OFF_DX (BO_OFF_LD + BO_KSZ)
-#define BO_OFF_DS (BO_OFF_DX + BO_NX)
-#define BO_OFF_YST (BO_OFF_DS + BO_MI)
-#define BO_OFF_DX0 (BO_OFF_YST + BO_ME)
-#define BO_OFF_DS0 (BO_OFF_DX0 + BO_NX)
-#define BO_OFF_RE (BO_OFF_DS0 + BO_MI)
-#define BO_OFF_RI (BO_OFF_RE + BO_ME)
-#define BO_OFF_FT (BO_OFF_RI + BO_MI)     /* f at the trial point */
-#define BO_OFF_CET (BO_OFF_FT + 1)
-#define BO_OFF_CIT (BO_OFF_CET + BO_ME)
-#define BO_OFF_PART (BO_OFF_CIT + BO_MI)  /* per role: sum log(s), sum |c| */
-#define BO_OFF_AT (BO_OFF_PART + 2 * BO_G) /* trial step length, published by the master */
-#define BO_OFF_FTH (BO_OFF_AT + 1)
-#define BO_OFF_FPH (BO_OFF_FTH + BO_NFILTER)
-#define BO_SM_ELEMS (BO_OFF_FPH + BO_NFILTER)
-
-#ifdef BO_HOST_SIM
-#define BO_LS 1
-#else
-#define BO_LS 32
-#endif
-#define SM(off, i) sm[((off) + (i)) * BO_LS]
-#define SMP(off) (sm + (off) * BO_LS)
+#include "bo_team_layout.cuh"
 
 // Master-only scalar state of one instance (registers of warp 0).
 struct bo_tm {
   double f, mu, tau, dw_last, err0, theta_max, theta_min, phi0, theta0, dw, dc, rho, a, a_trial, dphi, th_soc;
+  double a_ftype;  // step lengths above this make the switching condition of the filter hold for the current direction
+  double lgs;      // sum log(s) at the current iterate (from the slices that evaluated the accepted trial point)
   int nf, it, n_acceptable, phase, trips, attempt, heavy, n_singular, ls, soc;
   bool recalc_y, ls_mode, jac_degenerate, first_singular;
   long long b;
 };
+
+#ifdef BO_HOST_SIM
+#define BO_CTZLL(m) __builtin_ctzll(m)
+static inline double bo_rcp(double d) { return 1.0 / d; }
+static double bo_log_ni(double v) { return std::log(v); }
+static double bo_exp_ni(double v) { return std::exp(v); }
+#else
+#define BO_CTZLL(m) (__ffsll((long long)(m)) - 1)
+// Reciprocal without the IEEE slow path: hardware seed (MUFU.RCP64H, ~20 bits) + two Newton steps, within 2 ulp for
+// normal arguments.  ~6 instructions instead of ~40, and the factorisation alone needs one per pivot.
+__device__ __forceinline__ double bo_rcp(double d) {
+  double r;
+  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(d));
+  if (r != 0.0 && fabs(r) < BO_INF) {  // seed 0 / inf (huge, infinite, zero or denormal argument) and NaN are final
+    double e = fma(-d, r, 1.0);
+    r = fma(r, e, r);
+    e = fma(-d, r, 1.0);
+    r = fma(r, e, r);
+  }
+  return r;
+}
+// one copy of the logarithm / exponential (~100 instructions each when inlined) for all their call sites
+__device__ __noinline__ double bo_log_ni(double v) { return log(v); }
+__device__ __noinline__ double bo_exp_ni(double v) { return exp(v); }
+#endif
+
+// ---- W2a: trial point and the shared sin / cos of its components (one copy of this code serves every role) ----
+BO_NOINLINE void bo_team_pre(double* BO_RESTRICT sm, const double at, const int role) {
+  BO_NOUNROLL
+  for (int k = role; k < BO_NX; k += BO_G) {
+    const double xt = SM(BO_OFF_X, k) + at * SM(BO_OFF_DX, k);
+    SM(BO_OFF_XT, k) = xt;
+    if ((BO_TRIG_MASK >> k) & 1u) {
+      double sn, cs;
+      bo_sincos(xt, &sn, &cs);
+      SM(BO_OFF_SH, 2 * k) = sn;
+      SM(BO_OFF_SH, 2 * k + 1) = cs;
+    }
+  }
+}
+
+// ---- W2b tail: per-row barrier work of the rows a slice owns (its f / c outputs are already in shared memory) ----
+// trial slack st = s + a ds, log st, |c - st|; and, in case the step is accepted, the reset slack max(st, c), its
+// reciprocal and its log -- so that the iteration that follows needs no division and no logarithm at all.
+BO_NOINLINE void bo_team_rows(double* BO_RESTRICT sm, double at, bool rows, int role, unsigned long long mask_e,
+                              unsigned long long mask_i) {
+  double lg = 0.0, th = 0.0, lgn = 0.0;
+  while (mask_e) {
+    const int j = BO_CTZLL(mask_e);
+    mask_e &= mask_e - 1;
+    th += fabs(SM(BO_OFF_CET, j));
+  }
+  if (rows) {
+    while (mask_i) {
+      const int i = BO_CTZLL(mask_i);
+      mask_i &= mask_i - 1;
+      const double st = SM(BO_OFF_S, i) + at * SM(BO_OFF_DS, i);
+      const double cit = SM(BO_OFF_CIT, i);
+      const double l = bo_log_ni(st);
+      lg += l;
+      th += fabs(cit - st);
+      const double sn = fmax(st, cit);  // slack reset: lowers theta, never raises the barrier objective
+      const double rsn = bo_rcp(sn);
+      SM(BO_OFF_SN, i) = sn;
+      SM(BO_OFF_RSN, i) = rsn;
+      // log(sn) = log(st) - log(1 - d), d = (sn - st) / sn >= 0.  For linear rows c and st differ by rounding only: d is
+      // 0 or ~1e-16 and the first-order term is exact to double precision; a second logarithm only for a real reset.
+      const double d = (sn - st) * rsn;
+      lgn += (d < 1e-9) ? l + d : bo_log_ni(sn);
+    }
+  }
+  SM(BO_OFF_PART, 5 * role) = lg;
+  SM(BO_OFF_PART, 5 * role + 1) = th;
+  SM(BO_OFF_PART, 5 * role + 2) = lgn;
+}
+
+// ---- W1 tail: the part of the convergence test that is a sum / max over the constraint rows a slice owns ----
+// also leaves the linearisation residuals RE = cE, RI = cI - s for the step computation
+BO_NOINLINE void bo_team_rows_kkt(double* BO_RESTRICT sm, int role, unsigned long long mask_e, unsigned long long mask_i) {
+  double e_prim = 0.0, theta = 0.0, sz_min = BO_INF, sz_max = 0.0, sum_z = 0.0;
+  while (mask_e) {
+    const int j = BO_CTZLL(mask_e);
+    mask_e &= mask_e - 1;
+    const double c = SM(BO_OFF_CE, j);
+    SM(BO_OFF_RE, j) = c;
+    e_prim = fmax(e_prim, fabs(c));
+    theta += fabs(c);
+  }
+  while (mask_i) {
+    const int i = BO_CTZLL(mask_i);
+    mask_i &= mask_i - 1;
+    const double s = SM(BO_OFF_S, i), z = SM(BO_OFF_Z, i);
+    const double r = SM(BO_OFF_CI, i) - s;
+    SM(BO_OFF_RI, i) = r;
+    e_prim = fmax(e_prim, fabs(r));
+    theta += fabs(r);
+    sz_min = fmin(sz_min, s * z);
+    sz_max = fmax(sz_max, s * z);
+    sum_z += fabs(z);
+  }
+  SM(BO_OFF_PART, 5 * role) = e_prim;
+  SM(BO_OFF_PART, 5 * role + 1) = theta;
+  SM(BO_OFF_PART, 5 * role + 2) = sz_min;
+  SM(BO_OFF_PART, 5 * role + 3) = sz_max;
+  SM(BO_OFF_PART, 5 * role + 4) = sum_z;
+}
 
 // ---- unpivoted LDL' of the packed matrix in registers (see bo_ipm_reg.cuh: valid on the rho-augmented system) ----
 // On exit A holds 1/D on the diagonal and the unit-lower L below it.
@@ -130,18 +177,17 @@ BO_DEVICE int bo_tm_ldl(double* BO_RESTRICT A) {
     } else {
       if (!(d < -1e-13) && bad == 0) bad = 2;
     }
-    const double dinv = 1.0 / d;
+    const double dinv = bo_rcp(d);
     BO_UNROLL
     for (int i = j + 1; i < BO_NK; ++i) {
       double v = A[BO_KIDX(i, j)];
       BO_UNROLL
       for (int k = 0; k < j; ++k) v -= A[BO_KIDX(i, k)] * A[BO_KIDX(j, k)] * A[BO_KIDX(k, k)];
-      A[BO_KIDX(i, j)] = v;  // unscaled C(i,j); scaled to L once column j is complete (below)
+      A[BO_KIDX(i, j)] = v;  // unscaled C(i,j) = L(i,j) D(j): L(i,k) L(j,k) D(k) = C(i,k) C(j,k) / D(k)
     }
-    // rows > j of columns < j are still unscaled C; the products above used C(i,k) * C(j,k) / D(k) = L(i,k) C(j,k)
     A[BO_KIDX(j, j)] = dinv;
   }
-  // scale C -> L
+  // C -> L
   BO_UNROLL
   for (int j = 0; j < BO_NK; ++j) {
     BO_UNROLL
@@ -150,8 +196,12 @@ BO_DEVICE int bo_tm_ldl(double* BO_RESTRICT A) {
   return bad;
 }
 
-// Solve with the factor stored in shared memory (1/D on the diagonal): b is a register array.
-BO_DEVICE void bo_tm_ldl_solve(const double* BO_RESTRICT sm, double* BO_RESTRICT b) {
+// Solve K sol = sol in place on the SOL vector in shared memory, with the factor stored there too (1/D on the
+// diagonal).  Fully unrolled: the vector is loaded once, lives in registers, and is stored once.
+BO_NOINLINE void bo_tm_ldl_solve(double* BO_RESTRICT sm) {
+  double b[BO_NK];
+  BO_UNROLL
+  for (int i = 0; i < BO_NK; ++i) b[i] = SM(BO_OFF_SOL, i);
   BO_UNROLL
   for (int i = 1; i < BO_NK; ++i) {
     BO_UNROLL
@@ -164,39 +214,95 @@ BO_DEVICE void bo_tm_ldl_solve(const double* BO_RESTRICT sm, double* BO_RESTRICT
     BO_UNROLL
     for (int k = i + 1; k < BO_NK; ++k) b[i] -= SM(BO_OFF_LD, BO_KIDX(k, i)) * b[k];
   }
+  BO_UNROLL
+  for (int i = 0; i < BO_NK; ++i) SM(BO_OFF_SOL, i) = b[i];
 }
 
 // Step for the constraint residuals (RE, RI) with the current factorisation: writes DX, DS (and, when y_step is
-// set, YST) and returns the fraction-to-the-boundary primal step length.
-BO_NOINLINE double bo_tm_step(const bo_tm& M, double* BO_RESTRICT sm, const bool y_step) {
-  double sol[BO_NK];
-  BO_UNROLL
-  for (int i = 0; i < BO_NX; ++i) sol[i] = -SM(BO_OFF_RD, i);
-  // t = -(z - mu / s + sigma * rI), parked in DS (overwritten by the real ds below)
-  BO_UNROLL
-  for (int i = 0; i < BO_MI; ++i)
-    SM(BO_OFF_DS, i) = -(SM(BO_OFF_Z, i) - M.mu * SM(BO_OFF_RS, i) + SM(BO_OFF_SIG, i) * SM(BO_OFF_RI, i));
-  bo_JIt_acc_t(SMP(BO_OFF_JI), SMP(BO_OFF_DS), BO_LS, 1.0, sol, 1);
-  BO_UNROLL
-  for (int j = 0; j < BO_ME; ++j) sol[BO_NX + j] = -SM(BO_OFF_RE, j);
-  bo_JEt_acc_t(SMP(BO_OFF_JE), SMP(BO_OFF_RE), BO_LS, -M.rho, sol, 1);  // first block row += rho JE' (second block rhs)
-  bo_tm_ldl_solve(sm, sol);
-  const double undo = 1.0 / (1.0 - M.rho * M.dc);
-  BO_UNROLL
-  for (int i = 0; i < BO_NX; ++i) SM(BO_OFF_DX, i) = sol[i];
-  if (y_step) {
+// set, YST) and returns the fraction-to-the-boundary primal step length; SOL[0] carries sum ds / s back.
+BO_NOINLINE double bo_tm_step(double* BO_RESTRICT sm, const double mu, const double rho, const double dc, const double tau,
+                              const bool y_step) {
+  {
+    double sol[BO_NX];
     BO_UNROLL
-    for (int j = 0; j < BO_ME; ++j) SM(BO_OFF_YST, j) = -sol[BO_NX + j] * undo;
+    for (int i = 0; i < BO_NX; ++i) sol[i] = -SM(BO_OFF_RD, i);
+    // t = -(z - mu / s + sigma * rI), parked in DS (overwritten by the real ds below)
+    BO_NOUNROLL
+    for (int i = 0; i < BO_MI; ++i)
+      SM(BO_OFF_DS, i) = -(SM(BO_OFF_Z, i) - mu * SM(BO_OFF_RS, i) + SM(BO_OFF_SIG, i) * SM(BO_OFF_RI, i));
+    bo_JIt_acc_t(SMP(BO_OFF_JI), SMP(BO_OFF_DS), BO_LS, 1.0, sol, 1);
+    bo_JEt_acc_t(SMP(BO_OFF_JE), SMP(BO_OFF_RE), BO_LS, -rho, sol, 1);  // first block row += rho JE' (second block rhs)
+    BO_UNROLL
+    for (int i = 0; i < BO_NX; ++i) SM(BO_OFF_SOL, i) = sol[i];
+    BO_UNROLL
+    for (int j = 0; j < BO_ME; ++j) SM(BO_OFF_SOL, BO_NX + j) = -SM(BO_OFF_RE, j);
   }
-  bo_JI_mul_t(SMP(BO_OFF_JI), sol, 1, SMP(BO_OFF_DS), BO_LS);
-  double worst = 0.0;  // max over rows of -ds / s
+  bo_tm_ldl_solve(sm);
   BO_UNROLL
+  for (int i = 0; i < BO_NX; ++i) SM(BO_OFF_DX, i) = SM(BO_OFF_SOL, i);
+  if (y_step) {
+    const double undo = bo_rcp(1.0 - rho * dc);
+    BO_UNROLL
+    for (int j = 0; j < BO_ME; ++j) SM(BO_OFF_YST, j) = -SM(BO_OFF_SOL, BO_NX + j) * undo;
+  }
+  bo_JI_mul_t(SMP(BO_OFF_JI), SMP(BO_OFF_SOL), BO_LS, SMP(BO_OFF_DS), BO_LS);
+  double worst = 0.0, dsr = 0.0;  // max over rows of -ds / s; sum ds / s (directional derivative of the barrier term)
+  BO_NOUNROLL
   for (int i = 0; i < BO_MI; ++i) {
     const double ds = SM(BO_OFF_DS, i) + SM(BO_OFF_RI, i);
     SM(BO_OFF_DS, i) = ds;
-    worst = fmax(worst, -ds * SM(BO_OFF_RS, i));
+    const double q = ds * SM(BO_OFF_RS, i);
+    worst = fmax(worst, -q);
+    dsr += q;
   }
-  return worst * 1.0 > M.tau ? M.tau / worst : 1.0;
+  SM(BO_OFF_SOL, 0) = dsr;  // the solution vector is consumed: its first slot carries sum ds / s back to the caller
+  return worst > tau ? tau / worst : 1.0;  // min(1, min_i -tau s_i / ds_i)
+}
+
+// Least-squares multiplier estimate (bo_ipm_reg.cuh): with [I JE'; JE -dc] factored, solve for [r; y] = K \ [g - JI'z; 0],
+// optionally followed by one step of iterative refinement towards the unregularised solution.
+BO_NOINLINE void bo_tm_ls_multipliers(double* BO_RESTRICT sm, const double dw, const bool refine) {
+  {
+    double sol[BO_NX];
+    BO_UNROLL
+    for (int i = 0; i < BO_NX; ++i) sol[i] = SM(BO_OFF_G, i);
+    bo_JIt_acc_t(SMP(BO_OFF_JI), SMP(BO_OFF_Z), BO_LS, -1.0, sol, 1);
+    BO_UNROLL
+    for (int i = 0; i < BO_NX; ++i) SM(BO_OFF_SOL, i) = sol[i];
+    BO_UNROLL
+    for (int j = 0; j < BO_ME; ++j) SM(BO_OFF_SOL, BO_NX + j) = 0.0;
+  }
+  bo_tm_ldl_solve(sm);
+  bool fin = true;
+  BO_UNROLL
+  for (int j = 0; j < BO_ME; ++j) fin = fin && bo_isfinite(SM(BO_OFF_SOL, BO_NX + j));
+  if (!fin) return;
+  BO_UNROLL
+  for (int j = 0; j < BO_ME; ++j) SM(BO_OFF_Y, j) = SM(BO_OFF_SOL, BO_NX + j);
+  if (!refine) return;
+  {
+    double sol[BO_NX];
+    BO_UNROLL
+    for (int i = 0; i < BO_NX; ++i) {
+      const double r = SM(BO_OFF_SOL, i);
+      SM(BO_OFF_DX0, i) = r;
+      sol[i] = SM(BO_OFF_G, i) - dw * r;
+    }
+    bo_JIt_acc_t(SMP(BO_OFF_JI), SMP(BO_OFF_Z), BO_LS, -1.0, sol, 1);
+    bo_JEt_acc_t(SMP(BO_OFF_JE), SMP(BO_OFF_Y), BO_LS, -1.0, sol, 1);
+    BO_UNROLL
+    for (int i = 0; i < BO_NX; ++i) SM(BO_OFF_SOL, i) = sol[i];
+    // second block: -(JE r), formed in shared memory (SOL tail), read back negated
+    bo_JE_mul_t(SMP(BO_OFF_JE), SMP(BO_OFF_DX0), BO_LS, SMP(BO_OFF_SOL) + BO_NX * BO_LS, BO_LS);
+    BO_UNROLL
+    for (int j = 0; j < BO_ME; ++j) SM(BO_OFF_SOL, BO_NX + j) = -SM(BO_OFF_SOL, BO_NX + j);
+  }
+  bo_tm_ldl_solve(sm);
+  BO_UNROLL
+  for (int j = 0; j < BO_ME; ++j) {
+    const double d = SM(BO_OFF_SOL, BO_NX + j);
+    if (bo_isfinite(d)) SM(BO_OFF_Y, j) += d;
+  }
 }
 
 // A fresh instance: the master has put p and the seed into P / X.
@@ -218,6 +324,8 @@ BO_DEVICE void bo_tm_begin(bo_tm& M, double* BO_RESTRICT sm, const bo_solver_par
   M.trips = 0;
   M.f = 0.0;
   M.a_trial = 0.0;
+  M.a_ftype = BO_INF;
+  M.lgs = 0.0;
   M.phase = BO_PH_INIT;
   BO_UNROLL
   for (int i = 0; i < BO_NX; ++i) SM(BO_OFF_DX, i) = 0.0;  // the INIT evaluation reads x + 0 * dx
@@ -226,8 +334,8 @@ BO_DEVICE void bo_tm_begin(bo_tm& M, double* BO_RESTRICT sm, const bo_solver_par
 
 // ---- M1: EVAL part (results of the KKT slices are in shared memory) and FACTOR part ----
 // Returns -1 to continue or the final status.
-BO_NOINLINE int bo_tm_m1(bo_tm& M, double* BO_RESTRICT sm, const bo_solver_params& prm) {
-  const double kappa_eps = 10.0, kappa_mu = 0.2, tau_min = 0.99, s_max = 100.0;
+BO_DEVICE int bo_tm_m1(bo_tm& M, double* BO_RESTRICT sm, const bo_solver_params& prm) {
+  const double kappa_eps = 10.0, kappa_mu = 0.2, tau_min = 0.99, s_max = 100.0, s_phi = 2.3, s_theta = 1.1;
   const double mu_min = prm.tol * 0.1;
   const bool over = ++M.trips > prm.max_trips;
   if (over && M.phase != BO_PH_EVAL) return BO_ST_MAX_ITER;
@@ -242,7 +350,7 @@ BO_NOINLINE int bo_tm_m1(bo_tm& M, double* BO_RESTRICT sm, const bo_solver_param
       M.dc = 1e-10;
       M.phase = BO_PH_FACTOR;
     } else {
-      double e_dual = 0.0, e_prim = 0.0, e_comp0 = 0.0, sum_mult = 0.0, sum_z = 0.0;
+      double e_dual = 0.0, e_prim = 0.0, e_comp0 = 0.0, sum_mult = 0.0, sum_z = 0.0, theta = 0.0, sz_min = BO_INF;
       {
         double rd[BO_NX];
         BO_UNROLL
@@ -256,24 +364,23 @@ BO_NOINLINE int bo_tm_m1(bo_tm& M, double* BO_RESTRICT sm, const bo_solver_param
         }
       }
       BO_UNROLL
-      for (int j = 0; j < BO_ME; ++j) {
-        e_prim = fmax(e_prim, fabs(SM(BO_OFF_CE, j)));
-        sum_mult += fabs(SM(BO_OFF_Y, j));
+      for (int r = 0; r < BO_G; ++r) {  // partial results of the slices' row work
+        e_prim = fmax(e_prim, SM(BO_OFF_PART, 5 * r));
+        theta += SM(BO_OFF_PART, 5 * r + 1);
+        sz_min = fmin(sz_min, SM(BO_OFF_PART, 5 * r + 2));
+        e_comp0 = fmax(e_comp0, SM(BO_OFF_PART, 5 * r + 3));
+        sum_z += SM(BO_OFF_PART, 5 * r + 4);
       }
       BO_UNROLL
-      for (int i = 0; i < BO_MI; ++i) {
-        const double s = SM(BO_OFF_S, i), z = SM(BO_OFF_Z, i);
-        e_prim = fmax(e_prim, fabs(SM(BO_OFF_CI, i) - s));
-        e_comp0 = fmax(e_comp0, s * z);
-        sum_z += fabs(z);
-      }
+      for (int j = 0; j < BO_ME; ++j) sum_mult += fabs(SM(BO_OFF_Y, j));
       sum_mult += sum_z;
-      const double s_d = (BO_ME + BO_MI) > 0 ? fmax(s_max, sum_mult / (double)BO_DIM(BO_ME + BO_MI)) / s_max : 1.0;
-      const double s_c = BO_MI > 0 ? fmax(s_max, sum_z / (double)BO_DIM(BO_MI)) / s_max : 1.0;
-      M.err0 = fmax(fmax(e_dual / s_d, e_prim), e_comp0 / s_c);
+      // scaling of the dual / complementarity errors (Waechter & Biegler eq. 6), as reciprocals: 1 / s_d, 1 / s_c
+      const double rs_d = (BO_ME + BO_MI) > 0 ? bo_rcp(fmax(1.0, sum_mult * (1.0 / (s_max * (double)BO_DIM(BO_ME + BO_MI))))) : 1.0;
+      const double rs_c = BO_MI > 0 ? bo_rcp(fmax(1.0, sum_z * (1.0 / (s_max * (double)BO_DIM(BO_MI))))) : 1.0;
+      M.err0 = fmax(fmax(e_dual * rs_d, e_prim), e_comp0 * rs_c);
 #ifdef BO_HOST_TRACE
       printf("it %3d f %.6e err0 %.3e (dual %.3e prim %.3e comp %.3e) mu %.2e nf %d dw_last %.2e\n", M.it, M.f, M.err0,
-             e_dual / s_d, e_prim, e_comp0 / s_c, M.mu, M.nf, M.dw_last);
+             e_dual * rs_d, e_prim, e_comp0 * rs_c, M.mu, M.nf, M.dw_last);
 #endif
       if (!bo_isfinite(M.err0) || !bo_isfinite(M.f)) return BO_ST_NUMERICAL;
       if (M.err0 <= prm.tol) return BO_ST_CONVERGED;
@@ -283,11 +390,10 @@ BO_NOINLINE int bo_tm_m1(bo_tm& M, double* BO_RESTRICT sm, const bo_solver_param
 
       // barrier parameter update (monotone Fiacco-McCormick, Waechter & Biegler eq. 7); resets the filter
       if (BO_MI > 0) {
+        BO_NOUNROLL
         for (int rep = 0; rep < 8; ++rep) {
-          double e_comp = 0.0;
-          BO_UNROLL
-          for (int i = 0; i < BO_MI; ++i) e_comp = fmax(e_comp, fabs(SM(BO_OFF_S, i) * SM(BO_OFF_Z, i) - M.mu));
-          const double err_mu = fmax(fmax(e_dual / s_d, e_prim), e_comp / s_c);
+          const double e_comp = fmax(e_comp0 - M.mu, M.mu - sz_min);  // max_i |s_i z_i - mu|
+          const double err_mu = fmax(fmax(e_dual * rs_d, e_prim), e_comp * rs_c);
           if (err_mu <= kappa_eps * M.mu && M.mu > mu_min) {
             M.mu = fmax(mu_min, fmin(kappa_mu * M.mu, M.mu * sqrt(M.mu)));
             M.nf = 0;
@@ -297,17 +403,8 @@ BO_NOINLINE int bo_tm_m1(bo_tm& M, double* BO_RESTRICT sm, const bo_solver_param
         }
       }
       M.tau = fmax(tau_min, 1.0 - M.mu);
-      BO_UNROLL
-      for (int i = 0; i < BO_MI; ++i) SM(BO_OFF_SIG, i) = SM(BO_OFF_Z, i) * SM(BO_OFF_RS, i);
-      // barrier objective and l1 violation from the partial sums of the slices
-      double lg = 0.0, th = 0.0;
-      BO_UNROLL
-      for (int r = 0; r < BO_G; ++r) {
-        lg += SM(BO_OFF_PART, 2 * r);
-        th += SM(BO_OFF_PART, 2 * r + 1);
-      }
-      M.theta0 = th;
-      M.phi0 = M.f - M.mu * lg;
+      M.theta0 = theta;
+      M.phi0 = M.f - M.mu * M.lgs;
       if (M.it == 0) {
         M.theta_max = 1e4 * fmax(1.0, M.theta0);
         M.theta_min = 1e-4 * fmax(1.0, M.theta0);
@@ -327,8 +424,15 @@ BO_NOINLINE int bo_tm_m1(bo_tm& M, double* BO_RESTRICT sm, const bo_solver_param
     M.rho = rho;
     int bad;
     {
+      // K = [ KX + dw I , JE' ; JE , -dc' I ]: the (1,1) block comes assembled from the KKT slices
       double K[BO_KSZ];
-      bo_kkt_fill_t(SMP(BO_OFF_H), SMP(BO_OFF_JE), SMP(BO_OFF_JI), SMP(BO_OFF_SIG), M.ls_mode ? 0.0 : 1.0, rho, K);
+      BO_UNROLL
+      for (int i = 0; i < BO_KSZ; ++i) K[i] = 0.0;
+      if (!M.ls_mode) {
+        BO_UNROLL
+        for (int i = 0; i < (BO_NX * (BO_NX + 1)) / 2; ++i) K[i] = SM(BO_OFF_KX, i);
+      }
+      bo_kkt_je_t(SMP(BO_OFF_JE), K);
       const double dcp = M.dc / (1.0 - rho * M.dc);
       BO_UNROLL
       for (int i = 0; i < BO_NX; ++i) K[BO_KIDX(i, i)] += M.dw;
@@ -340,38 +444,7 @@ BO_NOINLINE int bo_tm_m1(bo_tm& M, double* BO_RESTRICT sm, const bo_solver_param
     }
     const int inertia = bad == 0 ? 0 : (bad == 1 ? 1 : -1);
     if (M.ls_mode) {
-      if (inertia == 0) {
-        double sol[BO_NK];
-        BO_UNROLL
-        for (int i = 0; i < BO_NX; ++i) sol[i] = SM(BO_OFF_G, i);
-        bo_JIt_acc_t(SMP(BO_OFF_JI), SMP(BO_OFF_Z), BO_LS, -1.0, sol, 1);
-        BO_UNROLL
-        for (int j = 0; j < BO_ME; ++j) sol[BO_NX + j] = 0.0;
-        bo_tm_ldl_solve(sm, sol);
-        bool fin = true;
-        BO_UNROLL
-        for (int j = 0; j < BO_ME; ++j) fin = fin && bo_isfinite(sol[BO_NX + j]);
-        if (fin) {
-          BO_UNROLL
-          for (int j = 0; j < BO_ME; ++j) SM(BO_OFF_Y, j) = sol[BO_NX + j];
-          if (M.err0 < BO_REFINE_BELOW) {
-            // one step of iterative refinement towards the unregularised least-squares multipliers (bo_ipm_reg.cuh)
-            BO_UNROLL
-            for (int i = 0; i < BO_NX; ++i) SM(BO_OFF_DX0, i) = sol[i];
-            BO_UNROLL
-            for (int i = 0; i < BO_NX; ++i) sol[i] = SM(BO_OFF_G, i) - M.dw * SM(BO_OFF_DX0, i);
-            bo_JIt_acc_t(SMP(BO_OFF_JI), SMP(BO_OFF_Z), BO_LS, -1.0, sol, 1);
-            bo_JEt_acc_t(SMP(BO_OFF_JE), SMP(BO_OFF_Y), BO_LS, -1.0, sol, 1);
-            bo_JE_mul_t(SMP(BO_OFF_JE), SMP(BO_OFF_DX0), BO_LS, sol + BO_NX, 1);
-            BO_UNROLL
-            for (int j = 0; j < BO_ME; ++j) sol[BO_NX + j] = -sol[BO_NX + j];
-            bo_tm_ldl_solve(sm, sol);
-            BO_UNROLL
-            for (int j = 0; j < BO_ME; ++j)
-              if (bo_isfinite(sol[BO_NX + j])) SM(BO_OFF_Y, j) += sol[BO_NX + j];
-          }
-        }
-      }
+      if (inertia == 0) bo_tm_ls_multipliers(sm, M.dw, M.err0 < BO_REFINE_BELOW);
       M.ls_mode = false;
       M.phase = BO_PH_EVAL;  // re-evaluate the Hessian with the new multipliers on the next trip
       return -1;
@@ -397,21 +470,29 @@ BO_NOINLINE int bo_tm_m1(bo_tm& M, double* BO_RESTRICT sm, const bo_solver_param
       M.n_singular = M.first_singular ? M.n_singular + 1 : 0;
       if (M.n_singular >= 3) M.jac_degenerate = true;
     }
-    BO_UNROLL
-    for (int j = 0; j < BO_ME; ++j) SM(BO_OFF_RE, j) = SM(BO_OFF_CE, j);
-    BO_UNROLL
-    for (int i = 0; i < BO_MI; ++i) SM(BO_OFF_RI, i) = SM(BO_OFF_CI, i) - SM(BO_OFF_S, i);
-    const double a_p = bo_tm_step(M, sm, true);
-    double dphi = 0.0, dxn = 0.0, dsr = 0.0;
+    if (M.heavy > 0) {
+      // RE / RI were left by the KKT slices; the second-order corrections of an earlier direction overwrote them
+      BO_UNROLL
+      for (int j = 0; j < BO_ME; ++j) SM(BO_OFF_RE, j) = SM(BO_OFF_CE, j);
+      BO_NOUNROLL
+      for (int i = 0; i < BO_MI; ++i) SM(BO_OFF_RI, i) = SM(BO_OFF_CI, i) - SM(BO_OFF_S, i);
+    }
+    const double a_p = bo_tm_step(sm, M.mu, M.rho, M.dc, M.tau, true);
+    const double dsr = SM(BO_OFF_SOL, 0);
+    double dphi = 0.0, dxn = 0.0;
     BO_UNROLL
     for (int i = 0; i < BO_NX; ++i) {
       const double dx = SM(BO_OFF_DX, i);
       dphi += SM(BO_OFF_G, i) * dx;
       dxn = fmax(dxn, fabs(dx));
     }
-    BO_UNROLL
-    for (int i = 0; i < BO_MI; ++i) dsr += SM(BO_OFF_DS, i) * SM(BO_OFF_RS, i);
     M.dphi = dphi - M.mu * dsr;
+    // Switching condition (Waechter & Biegler eq. 19): a (-dphi)^s_phi > theta0^s_theta, kept as a threshold on a so that
+    // the trial points of this direction need no logarithm
+    if (M.dphi < 0.0 && M.theta0 <= M.theta_min)
+      M.a_ftype = M.theta0 <= 0.0 ? 0.0 : bo_exp_ni(s_theta * bo_log_ni(M.theta0) - s_phi * bo_log_ni(-M.dphi));
+    else
+      M.a_ftype = BO_INF;
     M.a = a_p;
     if (prm.max_step > 0.0 && M.a * dxn > prm.max_step) M.a = prm.max_step / dxn;
     M.a_trial = M.a;
@@ -423,37 +504,45 @@ BO_NOINLINE int bo_tm_m1(bo_tm& M, double* BO_RESTRICT sm, const bo_solver_param
 }
 
 // ---- M2: the trial point has been evaluated by the f / c slices ----
-BO_NOINLINE int bo_tm_m2(bo_tm& M, double* BO_RESTRICT sm, const bo_solver_params& prm) {
+BO_DEVICE int bo_tm_m2(bo_tm& M, double* BO_RESTRICT sm, const bo_solver_params& prm) {
   const double kappa_sigma = 1e10, gamma_theta = 1e-5, gamma_phi = 1e-5, eta_phi = 1e-8;
-  const double s_phi = 2.3, s_theta = 1.1, kappa_soc = 0.99;
+  const double kappa_soc = 0.99;
   if (M.phase == BO_PH_INIT) {
     // start of an instance: slacks from c_I(x0) pushed into the interior, z on the central path, y = 0
     M.f = SM(BO_OFF_FT, 0);
-    BO_UNROLL
+    double lgs = 0.0;
+    BO_NOUNROLL
     for (int i = 0; i < BO_MI; ++i) {
       const double ci = SM(BO_OFF_CIT, i);
       const double s = fmax(ci, 1e-2 * fmax(1.0, fabs(ci)));
+      const double rs = bo_rcp(s);
       SM(BO_OFF_S, i) = s;
-      SM(BO_OFF_Z, i) = M.mu / s;
+      SM(BO_OFF_RS, i) = rs;
+      SM(BO_OFF_Z, i) = M.mu * rs;
+      SM(BO_OFF_SIG, i) = M.mu * rs * rs;
+      lgs += bo_log_ni(s);
     }
+    M.lgs = lgs;
     BO_UNROLL
     for (int j = 0; j < BO_ME; ++j) SM(BO_OFF_Y, j) = 0.0;
+    BO_UNROLL
+    for (int i = 0; i < BO_NX; ++i) SM(BO_OFF_X, i) = SM(BO_OFF_XT, i);
     M.phase = BO_PH_EVAL;
     return -1;
   }
   if (M.phase != BO_PH_TRIAL) return -1;
   const double at = M.a_trial;
   const double ft = SM(BO_OFF_FT, 0);
-  double lg = 0.0, thetat = 0.0;
+  double lg = 0.0, thetat = 0.0, lgn = 0.0;
   BO_UNROLL
   for (int r = 0; r < BO_G; ++r) {
-    lg += SM(BO_OFF_PART, 2 * r);
-    thetat += SM(BO_OFF_PART, 2 * r + 1);
+    lg += SM(BO_OFF_PART, 5 * r);
+    thetat += SM(BO_OFF_PART, 5 * r + 1);
+    lgn += SM(BO_OFF_PART, 5 * r + 2);
   }
   const double phit = ft - M.mu * lg;
   const bool finite = bo_isfinite(phit) && bo_isfinite(thetat);
-  const bool ftype = M.dphi < 0.0 && M.theta0 <= M.theta_min &&
-                     (M.theta0 <= 0.0 || log(M.a) + s_phi * log(-M.dphi) > s_theta * log(M.theta0));
+  const bool ftype = M.a > M.a_ftype;
   const double slack = 10.0 * 2.2e-16 * fabs(M.phi0);
   bool ok = false, armijo = false;
   if (finite && thetat <= M.theta_max) {
@@ -491,7 +580,7 @@ BO_NOINLINE int bo_tm_m2(bo_tm& M, double* BO_RESTRICT sm, const bo_solver_param
     // dual step with its own fraction-to-the-boundary rule: a_d = min(1, tau * min_i z_i / (-dz_i)); the minimum
     // of the ratios is tracked by cross-multiplication (one division in total)
     double num = 1.0, den = 0.0;  // best ratio num / den (den > 0), none yet
-    BO_UNROLL
+    BO_NOUNROLL
     for (int i = 0; i < BO_MI; ++i) {
       const double z = SM(BO_OFF_Z, i);
       const double dz = -z + M.mu * SM(BO_OFF_RS, i) - SM(BO_OFF_SIG, i) * SM(BO_OFF_DS, i);
@@ -503,19 +592,21 @@ BO_NOINLINE int bo_tm_m2(bo_tm& M, double* BO_RESTRICT sm, const bo_solver_param
     }
     const double a_d = (den > 0.0 && M.tau * num < den) ? M.tau * num / den : 1.0;
     BO_UNROLL
-    for (int i = 0; i < BO_NX; ++i) SM(BO_OFF_X, i) = SM(BO_OFF_X, i) + at * SM(BO_OFF_DX, i);
-    BO_UNROLL
+    for (int i = 0; i < BO_NX; ++i) SM(BO_OFF_X, i) = SM(BO_OFF_XT, i);
+    BO_NOUNROLL
     for (int i = 0; i < BO_MI; ++i) {
-      const double st = SM(BO_OFF_S, i) + at * SM(BO_OFF_DS, i);
-      const double s = fmax(st, SM(BO_OFF_CIT, i));  // slack reset: lowers theta, never raises the barrier objective
+      const double s = SM(BO_OFF_SN, i), rs = SM(BO_OFF_RSN, i);  // reset slack and its reciprocal, from the slices
       SM(BO_OFF_S, i) = s;
+      SM(BO_OFF_RS, i) = rs;
       double z = SM(BO_OFF_Z, i) + a_d * SM(BO_OFF_RI, i);
       // keep z within a factor kappa_sigma of the central-path value mu/s (IPOPT eq. 16); the test is division-free
       const double sz = s * z;
-      if (sz > kappa_sigma * M.mu) z = kappa_sigma * M.mu / s;
-      else if (sz * kappa_sigma < M.mu) z = M.mu / (kappa_sigma * s);
+      if (sz > kappa_sigma * M.mu) z = kappa_sigma * M.mu * rs;
+      else if (sz * kappa_sigma < M.mu) z = M.mu * rs / kappa_sigma;
       SM(BO_OFF_Z, i) = z;
+      SM(BO_OFF_SIG, i) = z * rs;
     }
+    M.lgs = lgn;
     BO_UNROLL
     for (int j = 0; j < BO_ME; ++j) SM(BO_OFF_Y, j) += M.a * SM(BO_OFF_YST, j);
 #ifdef BO_RECALC_DC_ONLY
@@ -535,13 +626,12 @@ BO_NOINLINE int bo_tm_m2(bo_tm& M, double* BO_RESTRICT sm, const bo_solver_param
       BO_UNROLL
       for (int i = 0; i < BO_NX; ++i) SM(BO_OFF_DX0, i) = SM(BO_OFF_DX, i);
       BO_UNROLL
-      for (int i = 0; i < BO_MI; ++i) SM(BO_OFF_DS0, i) = SM(BO_OFF_DS, i);
-      BO_UNROLL
       for (int j = 0; j < BO_ME; ++j) SM(BO_OFF_RE, j) = M.a * SM(BO_OFF_CE, j) + SM(BO_OFF_CET, j);
-      BO_UNROLL
+      BO_NOUNROLL
       for (int i = 0; i < BO_MI; ++i) {
-        const double s = SM(BO_OFF_S, i);
-        SM(BO_OFF_RI, i) = M.a * (SM(BO_OFF_CI, i) - s) + (SM(BO_OFF_CIT, i) - (s + at * SM(BO_OFF_DS, i)));
+        const double s = SM(BO_OFF_S, i), ds = SM(BO_OFF_DS, i);
+        SM(BO_OFF_DS0, i) = ds;
+        SM(BO_OFF_RI, i) = M.a * (SM(BO_OFF_CI, i) - s) + (SM(BO_OFF_CIT, i) - (s + at * ds));
       }
       M.th_soc = thetat;
       try_soc = true;
@@ -549,21 +639,21 @@ BO_NOINLINE int bo_tm_m2(bo_tm& M, double* BO_RESTRICT sm, const bo_solver_param
   } else if (M.soc < 4 && finite && thetat <= kappa_soc * M.th_soc) {
     BO_UNROLL
     for (int j = 0; j < BO_ME; ++j) SM(BO_OFF_RE, j) = at * SM(BO_OFF_RE, j) + SM(BO_OFF_CET, j);
-    BO_UNROLL
+    BO_NOUNROLL
     for (int i = 0; i < BO_MI; ++i)
       SM(BO_OFF_RI, i) = at * SM(BO_OFF_RI, i) + (SM(BO_OFF_CIT, i) - (SM(BO_OFF_S, i) + at * SM(BO_OFF_DS, i)));
     M.th_soc = thetat;
     try_soc = true;
   }
   if (try_soc) {
-    M.a_trial = bo_tm_step(M, sm, false);  // corrected direction; tried on the next trip
+    M.a_trial = bo_tm_step(sm, M.mu, M.rho, M.dc, M.tau, false);  // corrected direction; tried on the next trip
     M.soc += 1;
     return -1;
   }
-  if (M.soc > 0) {  // corrections did not help: back to the uncorrected direction
+  if (M.soc > 0) {  // corrections did not help: back to the uncorrected direction (and its residuals)
     BO_UNROLL
     for (int i = 0; i < BO_NX; ++i) SM(BO_OFF_DX, i) = SM(BO_OFF_DX0, i);
-    BO_UNROLL
+    BO_NOUNROLL
     for (int i = 0; i < BO_MI; ++i) SM(BO_OFF_DS, i) = SM(BO_OFF_DS0, i);
     M.soc = 0;
   }
@@ -590,8 +680,11 @@ static int bo_team_solve_host(bo_tm& M, double* sm, const bo_solver_params& prm)
     if (M.phase != BO_PH_INIT) status = bo_tm_m1(M, sm, prm);
     if (status >= 0) break;
     SM(BO_OFF_AT, 0) = M.a_trial;
-    if (M.phase == BO_PH_TRIAL || M.phase == BO_PH_INIT)
-      for (int r = 0; r < BO_G; ++r) bo_team_fc(r, sm, M.phase == BO_PH_INIT ? 0.0 : M.a_trial, M.phase == BO_PH_TRIAL);
+    if (M.phase == BO_PH_TRIAL || M.phase == BO_PH_INIT) {
+      const double at = M.phase == BO_PH_INIT ? 0.0 : M.a_trial;
+      for (int r = 0; r < BO_G; ++r) bo_team_pre(sm, at, r);
+      for (int r = 0; r < BO_G; ++r) bo_team_fc(r, sm, at, M.phase == BO_PH_TRIAL);
+    }
     status = bo_tm_m2(M, sm, prm);
   }
   return status;
@@ -673,6 +766,8 @@ bo_solve_kernel(long long B, const double* __restrict__ p_all, const double* __r
     sc->tile_n[s] = n;
     sc->tile_used[s] = 0;
     double* dst = stage + s * BO_STAGE_DOUBLES;
+    // the previous tenant of this buffer was read through the generic proxy: order those reads before the engine's writes
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     const bool bulk = aligned && n == BO_TILE;  // full tiles of 16-byte aligned rows go through the bulk-copy engine
     sc->bulk[s] = bulk ? 1 : 0;
     if (bulk) {
@@ -736,6 +831,7 @@ bo_solve_kernel(long long B, const double* __restrict__ p_all, const double* __r
           b0 = sc->tile_b[s];
         }
       }
+      __syncwarp();
       s = __shfl_sync(0xffffffffu, s, 0);
       first = __shfl_sync(0xffffffffu, first, 0);
       take = __shfl_sync(0xffffffffu, take, 0);
@@ -786,26 +882,29 @@ bo_solve_kernel(long long B, const double* __restrict__ p_all, const double* __r
     if (ctrl[lane] == BO_PH_EVAL) bo_team_kkt(role, sm);
     __syncthreads();
     // ---- M1 ----
+    int status = -1;
     if (role == 0) {
       if (M.phase == BO_PH_EVAL || M.phase == BO_PH_FACTOR || M.phase == BO_PH_TRIAL) {
-        const int status = bo_tm_m1(M, sm, prm);
-        if (status >= 0) finish(status);
+        status = bo_tm_m1(M, sm, prm);
+        if (status >= 0) M.phase = BO_PH_DONE;
       }
-      fetch();  // a team that just finished starts its next instance in this trip's W2
       SM(BO_OFF_AT, 0) = M.a_trial;
       ctrl[lane] = M.phase;
     }
     __syncthreads();
-    // ---- W2: f / c slices at the trial point (or at the seed of a fresh instance) ----
-    {
-      const int ph = ctrl[lane];
-      if (ph == BO_PH_TRIAL || ph == BO_PH_INIT) bo_team_fc(role, sm, SM(BO_OFF_AT, 0), ph == BO_PH_TRIAL);
-    }
+    // ---- W2a: trial point (or the seed of a fresh instance) and the shared sin / cos of its components ----
+    const int ph2 = ctrl[lane];
+    const bool w2 = ph2 == BO_PH_TRIAL || ph2 == BO_PH_INIT;
+    const double at2 = w2 ? SM(BO_OFF_AT, 0) : 0.0;
+    if (w2) bo_team_pre(sm, at2, role);
+    __syncthreads();
+    // ---- W2b: f / c slices there, then the barrier work of the inequality rows each slice owns ----
+    if (w2) bo_team_fc(role, sm, at2, ph2 == BO_PH_TRIAL);
     __syncthreads();
     // ---- M2 ----
-    if (role == 0 && (M.phase == BO_PH_TRIAL || M.phase == BO_PH_INIT)) {
-      const int status = bo_tm_m2(M, sm, prm);
-      if (status >= 0) finish(status);
+    if (role == 0) {
+      if (M.phase == BO_PH_TRIAL || M.phase == BO_PH_INIT) status = bo_tm_m2(M, sm, prm);
+      if (status >= 0) finish(status);  // one copy of the write-out: instances that ended in M1 are parked in PH_DONE
     }
   }
 }

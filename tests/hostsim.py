@@ -46,6 +46,34 @@ extern "C" void hostsim_solve(long long B, const double* p, const double* x0, do
 }
 """
 
+_WRAPPER_TEAM = r"""
+#define BO_HOST_SIM 1
+#include <cstdio>
+#include <vector>
+%(trace)s
+#include "%(gen)s"
+// team tier: the G roles of a team run one after the other where the kernel has a CTA barrier (bo_team_solve_host)
+extern "C" void hostsim_solve(long long B, const double* p, const double* x0, double* x, double* lam, double* f,
+                              int* status, int* iters, double* kkt, int* trips, int max_iter, double tol, double acc_tol,
+                              double mu_init, double max_step, int max_trips, const int* ldl_tab, const double* dtab, double* scratch) {
+  bo_solver_params prm;
+  prm.max_iter = max_iter; prm.tol = tol; prm.acceptable_tol = acc_tol; prm.mu_init = mu_init; prm.max_step = max_step; prm.max_trips = max_trips; prm.ldl_tab = ldl_tab; prm.dtab = dtab; prm.scratch = scratch; prm.scratch_stride = 1;
+  std::vector<double> smv(BO_SM_ELEMS + 1);
+  double* sm = smv.data();
+  for (long long b = 0; b < B; ++b) {
+    for (auto& v : smv) v = 0.0 / 0.0;  // anything read before it is written shows up as NaN
+    bo_tm M;
+    for (int i = 0; i < BO_NP; ++i) SM(BO_OFF_P, i) = p[b * BO_NP + i];
+    for (int i = 0; i < BO_NX; ++i) SM(BO_OFF_X, i) = x0 ? x0[b * BO_NX + i] : 0.0;
+    status[b] = bo_team_solve_host(M, sm, prm);
+    for (int i = 0; i < BO_NX; ++i) x[b * BO_NX + i] = SM(BO_OFF_X, i);
+    for (int j = 0; j < BO_ME; ++j) lam[b * (BO_ME + BO_MI) + j] = SM(BO_OFF_Y, j);
+    for (int i = 0; i < BO_MI; ++i) lam[b * (BO_ME + BO_MI) + BO_ME + i] = SM(BO_OFF_Z, i);
+    f[b] = M.f; iters[b] = M.it; kkt[b] = M.err0; if (trips) trips[b] = M.trips;
+  }
+}
+"""
+
 _WRAPPER_COOP = r"""
 #define BO_HOST_SIM 1
 #include <cstdio>
@@ -120,8 +148,9 @@ class HostSim:
         self.nx, self.np_, self.nl = nx, np_, n_eq + n_ineq
         key = hashlib.sha1(generated_source.encode()).hexdigest()[:16] + str(trace) + defines
         coop = "#define BO_COOP 1" in generated_source
-        key += hashlib.sha1((_WRAPPER_COOP if coop else _WRAPPER).encode()).hexdigest()[:8]
-        for name in ("bo_common.cuh", "bo_ipm_reg.cuh", "bo_ipm_cta.cuh"):
+        wrapper = _WRAPPER_TEAM if "#define BO_TEAM 1" in generated_source else (_WRAPPER_COOP if coop else _WRAPPER)
+        key += hashlib.sha1(wrapper.encode()).hexdigest()[:8]
+        for name in ("bo_common.cuh", "bo_ipm_reg.cuh", "bo_ipm_cta.cuh", "bo_ipm_team.cuh", "bo_team_layout.cuh"):
             key += hashlib.sha1(open(os.path.join(_JIT_INC, name), "rb").read()).hexdigest()[:8]
         d = os.path.join(tempfile.gettempdir(), "b200optas_hostsim")
         os.makedirs(d, exist_ok=True)
@@ -130,7 +159,7 @@ class HostSim:
             gen = os.path.join(d, f"gen_{os.getpid()}.cu")
             wrap = os.path.join(d, f"wrap_{os.getpid()}.cpp")
             open(gen, "w").write(generated_source)
-            open(wrap, "w").write((_WRAPPER_COOP if coop else _WRAPPER) % {"gen": gen, "trace": ("#define BO_HOST_TRACE 1\n" if trace else "") + defines})
+            open(wrap, "w").write(wrapper % {"gen": gen, "trace": ("#define BO_HOST_TRACE 1\n" if trace else "") + defines})
             subprocess.run(["/usr/bin/g++", "-O1", "-shared", "-fPIC", "-std=c++17", "-I", _JIT_INC, "-I", os.path.join(_HERE, "..", "include"), wrap, "-o", so + f".tmp{os.getpid()}"],
                            check=True)
             os.replace(so + f".tmp{os.getpid()}", so)
