@@ -57,7 +57,12 @@ def test_compile_only_generates_sm100a_kernels():
     info = solver.kernel_info()
     assert 0 < info["registers"] <= 255
     src = solver.kernel_source()
-    assert "bo_tape_kkt" in src and '#include "bo_ipm_reg.cuh"' in src
+    # small dense problems run on the team tier: tape slices per warp, state in shared memory, no thread-local state
+    assert solver.tier_info()["tier"] == "team"
+    assert "bo_kkt_r0" in src and "bo_kkt_r3" in src and '#include "bo_ipm_team.cuh"' in src
+    assert info["local_bytes"] <= 64
+    old = optas_b200.B200Solver(prob.opt).setup("ipopt", compile_only=True, team=False)
+    assert old.tier_info()["tier"] == "dense" and '#include "bo_ipm_reg.cuh"' in old.kernel_source()
     fk = B200Function(prob.functions["fk_jac"], compile_only=True)
     assert 0 < fk.kernel_info()["registers"] <= 255
     assert "bo_sincos" in fk.kernel_source()

@@ -71,8 +71,8 @@ def test_horizon_problems_compile_to_a_few_classes():
     assert info["kkt_components"] > 1000 and info["kkt_classes"] <= 32
     assert info["kkt_code_rows"] < info["kkt_total_instr"] / 10
     assert info["smem_dynamic"] <= 227 * 1024
-    # the IK problem (one kinematic chain, 10 x 10 KKT system) stays on the thread-per-instance dense tier
-    assert optas_b200.B200Solver(problems.lwr_ik().opt).setup("ipopt", compile_only=True).tier_info()["tier"] == "dense"
+    # the IK problem (one kinematic chain, 10 x 10 KKT system) runs on the team tier (4 threads per instance, shared memory)
+    assert optas_b200.B200Solver(problems.lwr_ik().opt).setup("ipopt", compile_only=True).tier_info()["tier"] == "team"
 
 
 @pytest.mark.parametrize("segments", ["1", "2", "3"])

@@ -270,15 +270,39 @@ def test_sphere_collision_problem_dimensions_and_seed():
 
 def test_tier_choice_follows_the_measured_rule():
     """bo_problem_create picks the kernel tier from the problem sizes alone (measured on B200 in
-    profiles/r01_tier_choice.txt / r01_tier_break_even.txt): dense up to 14 KKT rows, thread-per-instance sparse for
-    small problems, one instance per CTA once nx + n_eq + n_ineq > 64 and the tapes split into stages."""
-    expect = [(problems.lwr_ik(), "dense"), (problems.planar_idk(), "dense"), (problems.lwr_axis_ik(), "sparse"),
+    profiles/r01_tier_choice.txt / r01_tier_break_even.txt): the team tier (state in shared memory) up to 14 KKT rows,
+    thread-per-instance sparse for small problems, one instance per CTA once nx + n_eq + n_ineq > 64 and the tapes split
+    into stages."""
+    expect = [(problems.lwr_ik(), "team"), (problems.planar_idk(), "team"), (problems.lwr_axis_ik(), "sparse"),
               (problems.point_mass_mpc(T=6), "coop"), (problems.point_mass_mpc(), "coop"), (problems.joint_space_planner(), "coop")]
     for prob, tier in expect:
         s = optas_b200.B200Solver(prob.opt).setup("ipopt", compile_only=True)
         assert s.tier_info()["tier"] == tier, (prob.name, s.tier_info()["tier"])
     forced = optas_b200.B200Solver(problems.lwr_axis_ik().opt).setup("ipopt", compile_only=True, coop=True)
     assert forced.tier_info()["tier"] == "coop"   # BO_FLAG_COOP still overrides
+    old = optas_b200.B200Solver(problems.lwr_ik().opt).setup("ipopt", compile_only=True, team=False)
+    assert old.tier_info()["tier"] == "dense"     # BO_FLAG_NO_TEAM: the round-1 thread-per-instance kernel
+
+
+def test_team_tier_takes_the_same_iterations_as_the_thread_tier():
+    """The team tier (bo_ipm_team.cuh) is the same algorithm as the thread-per-instance dense tier: on the host build
+    of both generated sources every instance ends with the same status after the same number of iterations and trips."""
+    from optas_b200 import _capi
+    from optas_b200.lowering import lower_problem
+
+    for prob, B in ((problems.lwr_ik(), 1024), (problems.planar_idk(), 256), (problems.booth(), 16)):
+        lo = lower_problem(prob.opt)
+        P, X0 = prob.sample(B, seed=3)
+        res = {}
+        for label, flag in (("team", 0), ("thread", _capi.BO_FLAG_NO_TEAM)):
+            h = _capi.ProblemHandle(lo, flags=_capi.BO_FLAG_COMPILE_ONLY | flag)
+            assert h.tier_info()["tier"] == ("team" if flag == 0 else "dense")
+            res[label] = HostSim(h.source(), lo.nx, lo.np_, lo.n_eq, lo.n_ineq).solve(P, X0, max_step=h.options()["max_step"])
+        a, b = res["team"], res["thread"]
+        assert np.array_equal(a["status"], b["status"]) and np.array_equal(a["iters"], b["iters"])
+        assert np.array_equal(a["trips"], b["trips"])
+        ok = a["status"] == 0
+        assert ok.mean() > 0.99 and np.abs(a["x"][ok] - b["x"][ok]).max() < 1e-9
 
 
 # ---- option defaults (round-1 advisor findings) ----------------------------------------------------------------------
