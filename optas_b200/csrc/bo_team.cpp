@@ -442,6 +442,36 @@ std::string emit_team_source(const ProblemSource& ps, const TeamPlan& plan) {
     o << "  K[" << i * (i + 1) / 2 + j << "] += JE[" << k << " * BO_LS];\n";
   }
   o << "  (void)JE; (void)K;\n}\n\n";
+  // Gauss-Newton (1,1) block of the restoration phase: JI' diag(w) JI + rho JE'JE into the packed lower triangle
+  // (K: strided shared memory, e.g. the KX array)
+  o << "BO_NOINLINE void bo_kkt_gn_t(const double* BO_RESTRICT JE, const double* BO_RESTRICT JI, const double* BO_RESTRICT w, const double rho, double* BO_RESTRICT K) {\n";
+  o << "  BO_NOUNROLL\n  for (int i = 0; i < " << ps.nx * (ps.nx + 1) / 2 << "; ++i) K[i * BO_LS] = 0.0;\n";
+  {
+    auto kidx = [](int i, int j) { return i * (i + 1) / 2 + j; };
+    std::vector<std::vector<int>> by_row(ps.n_ineq > 0 ? ps.n_ineq : 1);
+    for (int k = 0; k < ps.jac_ineq.nnz(); ++k) by_row[ps.jac_ineq.row[k]].push_back(k);
+    for (int r = 0; r < ps.n_ineq; ++r) {
+      const auto& ks = by_row[r];
+      for (size_t u = 0; u < ks.size(); ++u)
+        for (size_t v = 0; v < ks.size(); ++v) {
+          const int cu = ps.jac_ineq.col[ks[u]], cv = ps.jac_ineq.col[ks[v]];
+          if (cu < cv || (cu == cv && u != v)) continue;
+          o << "  K[" << kidx(cu, cv) << " * BO_LS] += w[" << r << " * BO_LS] * (JI[" << ks[u] << " * BO_LS] * JI[" << ks[v] << " * BO_LS]);\n";
+        }
+    }
+    std::vector<std::vector<int>> by_row_e(ps.n_eq > 0 ? ps.n_eq : 1);
+    for (int k = 0; k < ps.jac_eq.nnz(); ++k) by_row_e[ps.jac_eq.row[k]].push_back(k);
+    for (int r = 0; r < ps.n_eq; ++r) {
+      const auto& ks = by_row_e[r];
+      for (size_t u = 0; u < ks.size(); ++u)
+        for (size_t v = 0; v < ks.size(); ++v) {
+          const int cu = ps.jac_eq.col[ks[u]], cv = ps.jac_eq.col[ks[v]];
+          if (cu < cv || (cu == cv && u != v)) continue;
+          o << "  K[" << kidx(cu, cv) << " * BO_LS] += rho * (JE[" << ks[u] << " * BO_LS] * JE[" << ks[v] << " * BO_LS]);\n";
+        }
+    }
+  }
+  o << "  (void)JE; (void)JI; (void)w; (void)rho; (void)K;\n}\n\n";
   o << "#include \"bo_ipm_team.cuh\"\n";
   return o.str();
 }

@@ -33,6 +33,23 @@
 #define BO_STATIC_RHO 1.0e6
 #endif
 #define BO_NFILTER 8
+// feasibility restoration: see bo_ipm_reg.cuh (same algorithm, same constants)
+#ifndef BO_RESTO_KAPPA
+#define BO_RESTO_KAPPA 0.1
+#endif
+#ifndef BO_RESTO_ZETA
+#define BO_RESTO_ZETA 1e-4
+#endif
+#ifndef BO_RESTO_MAX_IT
+#define BO_RESTO_MAX_IT 40
+#endif
+#ifndef BO_RESTO_MAX_PHASES
+#define BO_RESTO_MAX_PHASES 3
+#endif
+#define BO_RESTO_DC (1.0 - 1e-8)
+#ifndef BO_ALPHA_MIN
+#define BO_ALPHA_MIN 5e-7
+#endif
 #ifndef BO_LS_MAX
 #define BO_LS_MAX 16
 #endif
@@ -237,6 +254,8 @@ struct bo_cta_state {
   bool jac_degenerate, first_singular;
   double a, a_trial, dphi, th_soc;
   int ls, soc;
+  int resto, n_resto;  // feasibility restoration: iterations in the current phase (0: regular mode), phases so far
+  double thr, thr0;    // theta_r at x / at entry
 };
 
 // ---------------------------------------------------------------------------------------------------
@@ -657,6 +676,8 @@ BO_DEVICE void bo_cta_init(bo_cta_state& S, const bo_cta& C, const bo_solver_par
   S.jac_degenerate = false;
   S.phase = BO_PH_EVAL;
   S.trips = 0;
+  S.resto = 0;
+  S.n_resto = 0;
   bo_cta_pre(C);
   S.f = bo_cta_eval_fc(C, W + BO_OFF_X, W + BO_OFF_CE, W + BO_OFF_CI);
   BO_PAR(i, BO_MI) {
@@ -667,6 +688,32 @@ BO_DEVICE void bo_cta_init(bo_cta_state& S, const bo_cta& C, const bo_solver_par
   }
   BO_PAR(j, BO_ME) W[BO_OFF_Y + j] = 0.0;
   bo_sync();
+}
+
+// Restoration step data at x (bo_ipm_reg.cuh: bo_resto_prepare): weights / residuals of the violated inequality rows,
+// no Hessian, no barrier, no multipliers.  Returns theta_r; ends with a CTA barrier.
+BO_NOINLINE double bo_cta_resto_prepare(const bo_cta& C) {
+  double* W = C.W;
+  double v[1] = {0.0};
+  BO_PAR(j, BO_ME) {
+    const double c = W[BO_OFF_CE + j];
+    W[BO_OFF_RE + j] = c;
+    v[0] += c * c;
+  }
+  BO_PAR(i, BO_MI) {
+    const double r = fmin(W[BO_OFF_CI + i], 0.0);
+    W[BO_OFF_SIG + i] = r < 0.0 ? 1.0 : 0.0;
+    W[BO_OFF_RI + i] = r;
+    W[BO_OFF_Z + i] = 0.0;
+    W[BO_OFF_S + i] = BO_INF;  // mu / s = 0, no fraction-to-the-boundary limit
+    v[0] += r * r;
+  }
+  BO_PAR(c, BO_NX) W[BO_OFF_RD + c] = 0.0;
+  BO_PAR(i, BO_NNZ_H) W[BO_OFF_H + i] = 0.0;
+  const int op[1] = {BO_RED_SUM};
+  bo_reduce<1>(v, op, BO_RED_P(C));
+  bo_sync();
+  return sqrt(v[0]);
 }
 
 // Step for the residuals (rE, rI) with the current factorisation: fills sol (dx, -dy), dx, ds; returns the
@@ -708,6 +755,21 @@ BO_DEVICE int bo_cta_trip_eval(bo_cta_state& S, const bo_cta& C, const bo_solver
   if (over && S.phase != BO_PH_EVAL) return BO_ST_MAX_ITER;
   if (S.phase != BO_PH_EVAL) return -1;
   S.f = bo_cta_eval_kkt(C);
+  if (S.resto > 0) {
+    // restoration: next Levenberg-Marquardt step on the infeasibility from the fresh Jacobians
+    if (!bo_isfinite(S.f)) return BO_ST_NUMERICAL;
+    if (over || S.it >= prm.max_iter) return BO_ST_MAX_ITER;
+    if (S.resto > BO_RESTO_MAX_IT) return BO_ST_LINE_SEARCH;
+    S.thr = bo_cta_resto_prepare(C);
+    S.dw = BO_RESTO_ZETA;
+    S.dc = BO_RESTO_DC;
+    S.first_singular = false;
+    S.attempt = 0;
+    S.heavy = 0;
+    S.ls_mode = false;
+    S.phase = BO_PH_FACTOR;
+    return -1;
+  }
   if (S.recalc_y && BO_ME > 0 && !over) {
     // least-squares multiplier estimate after a regularised step (see bo_ipm_reg.cuh)
     S.recalc_y = false;
@@ -792,7 +854,7 @@ BO_DEVICE int bo_cta_trip_eval(bo_cta_state& S, const bo_cta& C, const bo_solver
 BO_DEVICE int bo_cta_trip_factor(bo_cta_state& S, const bo_cta& C, const bo_solver_params& prm) {
   double* W = C.W;
   if (S.phase != BO_PH_FACTOR) return -1;
-  const double rho = S.ls_mode ? 0.0 : BO_STATIC_RHO;
+  const double rho = S.ls_mode ? 0.0 : (S.resto > 0 ? 1.0 : BO_STATIC_RHO);
   S.rho = rho;
   bo_cta_assemble(C, rho, S.dw, S.dc / (1.0 - rho * S.dc));
   const int bad = bo_cta_factor(C);
@@ -850,13 +912,15 @@ BO_DEVICE int bo_cta_trip_factor(bo_cta_state& S, const bo_cta& C, const bo_solv
     if (++S.attempt > BO_IC_MAX || S.dw > 1e40) return S.err0 <= prm.acceptable_tol ? BO_ST_ACCEPTABLE : BO_ST_NUMERICAL;
     return -1;
   }
-  if (S.dw > 0.0 && S.heavy == 0) S.dw_last = S.dw;
+  if (S.dw > 0.0 && S.heavy == 0 && S.resto == 0) S.dw_last = S.dw;
   if (S.heavy == 0 && !S.jac_degenerate) {
     S.n_singular = S.first_singular ? S.n_singular + 1 : 0;
     if (S.n_singular >= 3) S.jac_degenerate = true;
   }
-  BO_PAR(j, BO_ME) W[BO_OFF_RE + j] = W[BO_OFF_CE + j];
-  BO_PAR(i, BO_MI) W[BO_OFF_RI + i] = W[BO_OFF_CI + i] - W[BO_OFF_S + i];
+  if (S.resto == 0) {
+    BO_PAR(j, BO_ME) W[BO_OFF_RE + j] = W[BO_OFF_CE + j];
+    BO_PAR(i, BO_MI) W[BO_OFF_RI + i] = W[BO_OFF_CI + i] - W[BO_OFF_S + i];
+  }
   bo_sync();
   const double a_p = bo_cta_step(S, C);
   BO_PAR(j, BO_ME) W[BO_OFF_YST + j] = -W[BO_OFF_SOL + BO_NX + j];
@@ -891,6 +955,56 @@ BO_DEVICE int bo_cta_trip_trial(bo_cta_state& S, const bo_cta& C, const bo_solve
   BO_PAR(i, BO_MI) W[BO_OFF_ST + i] = W[BO_OFF_S + i] + S.a_trial * W[BO_OFF_DS + i];
   bo_sync();
   const double ft = bo_cta_eval_fc(C, W + BO_OFF_XT, W + BO_OFF_CET, W + BO_OFF_CIT);
+  if (S.resto > 0) {
+    // restoration trial point: Armijo on theta_r
+    double v[1] = {0.0};
+    BO_PAR(j, BO_ME) v[0] += W[BO_OFF_CET + j] * W[BO_OFF_CET + j];
+    BO_PAR(i, BO_MI) {
+      const double r = fmin(W[BO_OFF_CIT + i], 0.0);
+      v[0] += r * r;
+    }
+    const int op[1] = {BO_RED_SUM};
+    bo_reduce<1>(v, op, BO_RED_P(C));
+    const double thr_t = sqrt(v[0]);
+#ifdef BO_HOST_TRACE
+    printf("     resto %d ls %d a %.3e theta_r %.3e -> %.3e (entry %.3e)\n", S.resto, S.ls, S.a_trial, S.thr, thr_t, S.thr0);
+#endif
+    if (bo_isfinite(thr_t) && thr_t <= (1.0 - 1e-4 * S.a_trial) * S.thr) {
+      BO_PAR(i, BO_NX) W[BO_OFF_X + i] = W[BO_OFF_XT + i];
+      S.it += 1;
+      if (thr_t <= fmax(BO_RESTO_KAPPA * S.thr0, 1e-10)) {
+        // feasible enough: back to the regular iteration from here, multipliers and filter start afresh
+        S.f = ft;
+        BO_PAR(i, BO_MI) {
+          const double ci = W[BO_OFF_CIT + i];
+          const double s = fmax(ci, 1e-2 * fmax(1.0, fabs(ci)));
+          W[BO_OFF_S + i] = s;
+          W[BO_OFF_Z + i] = S.mu / s;
+        }
+        BO_PAR(j, BO_ME) W[BO_OFF_Y + j] = 0.0;
+        S.resto = 0;
+        S.nf = 0;
+        S.dw_last = 0.0;
+        S.recalc_y = BO_ME > 0;  // least-squares equality multipliers at the new point
+      } else {
+        S.resto += 1;
+      }
+      S.phase = BO_PH_EVAL;
+      bo_sync();
+      return -1;
+    }
+    if (S.ls >= 2 && S.attempt < 4) {  // Levenberg-Marquardt: more damping, new direction
+      S.attempt += 1;
+      S.dw *= 100.0;
+      S.phase = BO_PH_FACTOR;
+      return -1;
+    }
+    S.a *= 0.5;
+    S.a_trial = S.a;
+    S.ls += 1;
+    if (S.ls >= 24 || S.a < 1e-10) return BO_ST_LINE_SEARCH;  // stationary point of the infeasibility
+    return -1;
+  }
   double phit, thetat;
   bo_cta_measures(C, ft, W + BO_OFF_CET, W + BO_OFF_CIT, W + BO_OFF_ST, S.mu, &phit, &thetat);
   const bool finite = bo_isfinite(phit) && bo_isfinite(thetat);
@@ -988,7 +1102,19 @@ BO_DEVICE int bo_cta_trip_trial(bo_cta_state& S, const bo_cta& C, const bo_solve
   S.a *= 0.5;
   S.a_trial = S.a;
   S.ls += 1;
-  if (S.ls >= BO_LS_MAX || S.a < 1e-12) {
+  if ((S.ls >= BO_LS_MAX || S.a < BO_ALPHA_MIN) && S.theta0 > 1e-7 * fmax(1.0, S.theta_min * 1e4) && S.n_resto < BO_RESTO_MAX_PHASES) {
+    // no acceptable step at an infeasible point: feasibility restoration (the evaluation at x is still valid)
+    S.n_resto += 1;
+    S.resto = 1;
+    S.thr0 = S.thr = bo_cta_resto_prepare(C);
+    S.dw = BO_RESTO_ZETA;
+    S.dc = BO_RESTO_DC;
+    S.attempt = 0;
+    S.heavy = 0;
+    S.phase = BO_PH_FACTOR;
+    return -1;
+  }
+  if (S.ls >= BO_LS_MAX || S.a < BO_ALPHA_MIN) {
     if (++S.heavy >= BO_HEAVY_MAX) return S.err0 <= prm.acceptable_tol ? BO_ST_ACCEPTABLE : BO_ST_LINE_SEARCH;  // IPOPT: a failed step at an acceptable point ends "solved to acceptable level"
     S.dw = fmax(S.dw * 100.0, 1.0);
     S.phase = BO_PH_FACTOR;

@@ -524,6 +524,34 @@ BO_NOINLINE void bo_measures(double f, const double* cE, const double* cI, const
 #endif
 #endif
 
+// ---- feasibility restoration (stands in for IPOPT's restoration phase, Waechter & Biegler section 3.3) ----
+// Entered when the line search finds no acceptable step at an infeasible point (typically: the fraction-to-the-boundary
+// rule leaves a step length of 1e-6 because a slack sits on its bound while its constraint is violated).  The iterate
+// then moves by Levenberg-Marquardt steps on the infeasibility alone,
+//     min_dx  1/2 || c_E + J_E dx ||^2 + 1/2 || min(c_I + J_I dx, 0) ||^2 + zeta/2 ||dx||^2
+// through the same KKT factorisation (H := zeta I, Sigma := indicator of the violated rows, z := 0, mu := 0, rho := 1 and
+// the constraint block made inert by dc -> 1), with an Armijo test on theta_r = || (c_E, min(c_I, 0)) ||_2; a step
+// that fails it twice is recomputed with 100 x the damping zeta.  It ends when theta_r has dropped to BO_RESTO_KAPPA of its
+// entry value: slacks and multipliers are re-initialised at the new point (as for a fresh instance, mu kept) and the
+// regular iteration resumes; or with BO_ST_LINE_SEARCH when theta_r cannot be reduced (a stationary point of the
+// infeasibility: what IPOPT reports as "converged to a point of local infeasibility").
+#ifndef BO_RESTO_KAPPA
+#define BO_RESTO_KAPPA 0.1
+#endif
+#ifndef BO_RESTO_ZETA
+#define BO_RESTO_ZETA 1e-4
+#endif
+#ifndef BO_RESTO_MAX_IT
+#define BO_RESTO_MAX_IT 40
+#endif
+#ifndef BO_RESTO_MAX_PHASES
+#define BO_RESTO_MAX_PHASES 3
+#endif
+#define BO_RESTO_DC (1.0 - 1e-8) /* with rho = 1: constraint block -dc / (1 - rho dc) = -1e8, i.e. inert */
+#ifndef BO_ALPHA_MIN
+#define BO_ALPHA_MIN 5e-7 /* IPOPT's alpha_min = gamma_alpha gamma_theta for a non-descent direction */
+#endif
+
 #define BO_PH_EVAL 0    /* evaluate f, grad, c, J, H at x; test convergence; assemble K */
 #define BO_PH_FACTOR 1  /* factor K + regularisation; on success compute the step */
 #define BO_PH_TRIAL 2   /* evaluate one trial point; accept / correct / backtrack */
@@ -569,6 +597,9 @@ struct bo_ipm_state {
   double dx0[BO_NX], ds0[BO_DIM(BO_MI)], rE[BO_DIM(BO_ME)], rI[BO_DIM(BO_MI)];
   double a, a_trial, dphi, th_soc;
   int ls, soc;  // soc: 0 = plain trial, k > 0 = k-th second-order-corrected trial
+  // feasibility restoration: iterations in the current phase (0: regular mode), phases so far, theta_r at x / at entry
+  int resto, n_resto;
+  double thr, thr0;
 };
 
 // The small tape is called from two places (start of an instance, every trial point): keep one copy.
@@ -593,6 +624,8 @@ BO_DEVICE void bo_ipm_init(bo_ipm_state& S, const bo_solver_params prm) {
   S.jac_degenerate = false;
   S.phase = BO_PH_EVAL;
   S.trips = 0;
+  S.resto = 0;
+  S.n_resto = 0;
   bo_eval_fc(S.x, S.p, &S.f, S.cE, S.cI);
   BO_NOUNROLL
   for (int i = 0; i < BO_MI; ++i) {
@@ -601,6 +634,31 @@ BO_DEVICE void bo_ipm_init(bo_ipm_state& S, const bo_solver_params prm) {
   }
   BO_UNROLL
   for (int j = 0; j < BO_ME; ++j) S.y[j] = 0.0;
+}
+
+// Restoration step data at x: weights / residuals of the violated inequality rows, no Hessian, no barrier, no multipliers.
+// Returns theta_r.  (s, z are re-initialised when the restoration phase ends.)
+BO_NOINLINE double bo_resto_prepare(bo_ipm_state& S) {
+  double thr = 0.0;
+  BO_UNROLL
+  for (int j = 0; j < BO_ME; ++j) {
+    S.rE[j] = S.cE[j];
+    thr += S.cE[j] * S.cE[j];
+  }
+  BO_NOUNROLL
+  for (int i = 0; i < BO_MI; ++i) {
+    const double v = fmin(S.cI[i], 0.0);
+    S.sigma[i] = v < 0.0 ? 1.0 : 0.0;
+    S.rI[i] = v;
+    S.z[i] = 0.0;
+    S.s[i] = BO_INF;  // mu / s = 0, no fraction-to-the-boundary limit
+    thr += v * v;
+  }
+  BO_UNROLL
+  for (int i = 0; i < BO_NX; ++i) S.rd[i] = 0.0;
+  BO_UNROLL
+  for (int i = 0; i < BO_DIM(BO_NNZ_H); ++i) S.H[i] = 0.0;
+  return sqrt(thr);
 }
 
 // Step for the constraint residuals (S.rE, S.rI) with the current factorisation: fills S.sol
@@ -659,7 +717,20 @@ BO_DEVICE int bo_trip_eval(bo_ipm_state& S, const bo_solver_params prm) {
   // =========================== PH_EVAL ===========================
   if (S.phase == BO_PH_EVAL) {
     bo_tape_kkt(S.x, S.p, S.y, S.z, &S.f, S.g, S.cE, S.cI, S.JE, S.JI, S.H);
-    if (S.recalc_y && BO_ME > 0 && !over) {
+    if (S.resto > 0) {
+      // restoration: next Levenberg-Marquardt step on the infeasibility from the fresh Jacobians
+      if (!bo_isfinite(S.f)) return BO_ST_NUMERICAL;
+      if (over || S.it >= prm.max_iter) return BO_ST_MAX_ITER;
+      if (S.resto > BO_RESTO_MAX_IT) return BO_ST_LINE_SEARCH;
+      S.thr = bo_resto_prepare(S);
+      S.dw = BO_RESTO_ZETA;
+      S.dc = BO_RESTO_DC;
+      S.first_singular = false;
+      S.attempt = 0;
+      S.heavy = 0;
+      S.ls_mode = false;
+      S.phase = BO_PH_FACTOR;
+    } else if (S.recalc_y && BO_ME > 0 && !over) {
       // The last step needed Hessian convexification (dw > 0): its Newton multipliers scale with dw
       // and feed back into the Hessian.  Replace y by the least-squares estimate
       //   [ I  JE' ; JE  -dc ] [ r ; y ] = [ grad f - JI' z ; 0 ]
@@ -763,7 +834,7 @@ BO_DEVICE int bo_trip_factor(bo_ipm_state& S, const bo_solver_params prm) {
 #else
     // unpivoted LDL' on the rho-augmented system (uniform control flow across the warp)
     S.static_fac = true;
-    const double rho = S.ls_mode ? 0.0 : BO_STATIC_RHO;
+    const double rho = S.ls_mode ? 0.0 : (S.resto > 0 ? 1.0 : BO_STATIC_RHO);
     S.rho = rho;
     if (!S.ls_mode) bo_JEtJE_acc(S.JE, rho, BO_LDP(S));
 #ifdef BO_SPARSE_LDL
@@ -842,15 +913,17 @@ BO_DEVICE int bo_trip_factor(bo_ipm_state& S, const bo_solver_params prm) {
       if (++S.attempt > BO_IC_MAX || S.dw > 1e40) return S.err0 <= prm.acceptable_tol ? BO_ST_ACCEPTABLE : BO_ST_NUMERICAL;
       return -1;
     }
-    if (S.dw > 0.0 && S.heavy == 0) S.dw_last = S.dw;
+    if (S.dw > 0.0 && S.heavy == 0 && S.resto == 0) S.dw_last = S.dw;
     if (S.heavy == 0 && !S.jac_degenerate) {
       S.n_singular = S.first_singular ? S.n_singular + 1 : 0;
       if (S.n_singular >= 3) S.jac_degenerate = true;
     }
-    BO_UNROLL
-    for (int j = 0; j < BO_ME; ++j) S.rE[j] = S.cE[j];
-    BO_UNROLL
-    for (int i = 0; i < BO_MI; ++i) S.rI[i] = S.cI[i] - S.s[i];
+    if (S.resto == 0) {
+      BO_UNROLL
+      for (int j = 0; j < BO_ME; ++j) S.rE[j] = S.cE[j];
+      BO_UNROLL
+      for (int i = 0; i < BO_MI; ++i) S.rI[i] = S.cI[i] - S.s[i];
+    }
     const double a_p = bo_ipm_step(S, prm);
     BO_UNROLL
     for (int j = 0; j < BO_ME; ++j) S.y_step[j] = -S.sol[BO_NX + j];
@@ -888,6 +961,56 @@ BO_DEVICE int bo_trip_trial(bo_ipm_state& S, const bo_solver_params prm) {
     BO_UNROLL
     for (int i = 0; i < BO_MI; ++i) st[i] = S.s[i] + S.a_trial * S.ds[i];
     bo_eval_fc(xt, S.p, &ft, cEt, cIt);
+    if (S.resto > 0) {
+      // restoration trial point: Armijo on theta_r
+      double thr_t = 0.0;
+      BO_UNROLL
+      for (int j = 0; j < BO_ME; ++j) thr_t += cEt[j] * cEt[j];
+      BO_NOUNROLL
+      for (int i = 0; i < BO_MI; ++i) {
+        const double v = fmin(cIt[i], 0.0);
+        thr_t += v * v;
+      }
+      thr_t = sqrt(thr_t);
+#ifdef BO_HOST_TRACE
+      printf("     resto %d ls %d a %.3e theta_r %.3e -> %.3e (entry %.3e)\n", S.resto, S.ls, S.a_trial, S.thr, thr_t, S.thr0);
+#endif
+      if (bo_isfinite(thr_t) && thr_t <= (1.0 - 1e-4 * S.a_trial) * S.thr) {
+        BO_UNROLL
+        for (int i = 0; i < BO_NX; ++i) S.x[i] = xt[i];
+        S.it += 1;
+        if (thr_t <= fmax(BO_RESTO_KAPPA * S.thr0, 1e-10)) {
+          // feasible enough: back to the regular iteration from here, multipliers and filter start afresh
+          S.f = ft;
+          BO_NOUNROLL
+          for (int i = 0; i < BO_MI; ++i) {
+            S.s[i] = fmax(cIt[i], 1e-2 * fmax(1.0, fabs(cIt[i])));
+            S.z[i] = S.mu / S.s[i];
+          }
+          BO_UNROLL
+          for (int j = 0; j < BO_ME; ++j) S.y[j] = 0.0;
+          S.resto = 0;
+          S.nf = 0;
+          S.dw_last = 0.0;
+          S.recalc_y = BO_ME > 0;  // least-squares equality multipliers at the new point
+        } else {
+          S.resto += 1;
+        }
+        S.phase = BO_PH_EVAL;
+        return -1;
+      }
+      if (S.ls >= 2 && S.attempt < 4) {  // Levenberg-Marquardt: more damping, new direction
+        S.attempt += 1;
+        S.dw *= 100.0;
+        S.phase = BO_PH_FACTOR;
+        return -1;
+      }
+      S.a *= 0.5;
+      S.a_trial = S.a;
+      S.ls += 1;
+      if (S.ls >= 24 || S.a < 1e-10) return BO_ST_LINE_SEARCH;  // stationary point of the infeasibility
+      return -1;
+    }
     bo_measures(ft, cEt, cIt, st, S.mu, &phit, &thetat);
     const bool finite = bo_isfinite(phit) && bo_isfinite(thetat);
     const bool ftype = S.dphi < 0.0 && S.theta0 <= S.theta_min &&
@@ -992,7 +1115,19 @@ BO_DEVICE int bo_trip_trial(bo_ipm_state& S, const bo_solver_params prm) {
     S.a *= 0.5;
     S.a_trial = S.a;
     S.ls += 1;
-    if (S.ls >= BO_LS_MAX || S.a < 1e-12) {
+    if ((S.ls >= BO_LS_MAX || S.a < BO_ALPHA_MIN) && S.theta0 > 1e-7 * fmax(1.0, S.theta_min * 1e4) && S.n_resto < BO_RESTO_MAX_PHASES) {
+      // no acceptable step at an infeasible point: feasibility restoration (the evaluation at x is still valid)
+      S.n_resto += 1;
+      S.resto = 1;
+      S.thr0 = S.thr = bo_resto_prepare(S);
+      S.dw = BO_RESTO_ZETA;
+      S.dc = BO_RESTO_DC;
+      S.attempt = 0;
+      S.heavy = 0;
+      S.phase = BO_PH_FACTOR;
+      return -1;
+    }
+    if (S.ls >= BO_LS_MAX || S.a < BO_ALPHA_MIN) {
       // no acceptable step along this direction: convexify harder (dw large => minimum-norm
       // feasibility step); this stands in for IPOPT's restoration phase on these small problems
       if (++S.heavy >= BO_HEAVY_MAX) return S.err0 <= prm.acceptable_tol ? BO_ST_ACCEPTABLE : BO_ST_LINE_SEARCH;  // IPOPT: a failed step at an acceptable point ends "solved to acceptable level"

@@ -48,10 +48,40 @@ struct bo_tm {
   double f, mu, tau, dw_last, err0, theta_max, theta_min, phi0, theta0, dw, dc, rho, a, a_trial, dphi, th_soc;
   double a_ftype;  // step lengths above this make the switching condition of the filter hold for the current direction
   double lgs;      // sum log(s) at the current iterate (from the slices that evaluated the accepted trial point)
+  double thr, thr0;  // feasibility restoration: l1 infeasibility of (c_E, min(c_I, 0)) at x, and at entry
   int nf, it, n_acceptable, phase, trips, attempt, heavy, n_singular, ls, soc;
+  int resto, n_resto;  // iterations spent in the current restoration phase (0: regular mode); phases entered so far
   bool recalc_y, ls_mode, jac_degenerate, first_singular;
   long long b;
 };
+
+// ---- feasibility restoration (stands in for IPOPT's restoration phase, Waechter & Biegler section 3.3) ----
+// Entered when the line search finds no acceptable step at an infeasible point (typically: the fraction-to-the-boundary
+// rule leaves a step length of 1e-6 because a slack sits on its bound while its constraint is violated).  The iterate
+// then moves by Levenberg-Marquardt steps on the infeasibility alone,
+//     min_dx  1/2 || c_E + J_E dx ||^2 + 1/2 || min(c_I + J_I dx, 0) ||^2 + zeta/2 ||dx||^2
+// through the same KKT factorisation (H := zeta I, Sigma := indicator of the violated rows, z := 0, mu := 0, rho := 1 and
+// the constraint block made inert by dc -> 1), with an Armijo test on theta_r = || (c_E, min(c_I, 0)) ||_2; a step
+// that fails it twice is recomputed with 100 x the damping zeta.  It ends when theta_r has dropped to BO_RESTO_KAPPA of its
+// entry value: slacks and multipliers are re-initialised at the new point (as for a fresh instance, mu kept) and the
+// regular iteration resumes; or with BO_ST_LINE_SEARCH when theta_r cannot be reduced (a stationary point of the
+// infeasibility: what IPOPT reports as "converged to a point of local infeasibility").
+#ifndef BO_RESTO_KAPPA
+#define BO_RESTO_KAPPA 0.1
+#endif
+#ifndef BO_RESTO_ZETA
+#define BO_RESTO_ZETA 1e-4
+#endif
+#ifndef BO_RESTO_MAX_IT
+#define BO_RESTO_MAX_IT 40
+#endif
+#ifndef BO_RESTO_MAX_PHASES
+#define BO_RESTO_MAX_PHASES 3
+#endif
+#define BO_RESTO_DC (1.0 - 1e-8) /* with rho = 1: constraint block -dc / (1 - rho dc) = -1e8, i.e. inert */
+#ifndef BO_ALPHA_MIN
+#define BO_ALPHA_MIN 5e-7 /* IPOPT's alpha_min = gamma_alpha gamma_theta for a non-descent direction */
+#endif
 
 #ifdef BO_HOST_SIM
 #define BO_CTZLL(m) __builtin_ctzll(m)
@@ -305,6 +335,52 @@ BO_NOINLINE void bo_tm_ls_multipliers(double* BO_RESTRICT sm, const double dw, c
   }
 }
 
+// Restoration step data at x: weights / residuals of the violated inequality rows in SIG / RI, no barrier, no multipliers.
+// Returns theta_r.  (S, Z, RS, SIG are re-initialised when the restoration phase ends.)
+BO_NOINLINE double bo_tm_resto_prepare(double* BO_RESTRICT sm) {
+  double thr = 0.0;
+  BO_UNROLL
+  for (int j = 0; j < BO_ME; ++j) {
+    const double c = SM(BO_OFF_CE, j);
+    SM(BO_OFF_RE, j) = c;
+    thr += c * c;
+  }
+  BO_NOUNROLL
+  for (int i = 0; i < BO_MI; ++i) {
+    const double v = fmin(SM(BO_OFF_CI, i), 0.0);
+    SM(BO_OFF_SIG, i) = v < 0.0 ? 1.0 : 0.0;
+    SM(BO_OFF_RI, i) = v;
+    SM(BO_OFF_Z, i) = 0.0;
+    SM(BO_OFF_RS, i) = 0.0;
+    thr += v * v;
+  }
+  BO_UNROLL
+  for (int i = 0; i < BO_NX; ++i) SM(BO_OFF_RD, i) = 0.0;
+  return sqrt(thr);
+}
+
+// Slacks pushed into the interior, z on the central path, y = 0, x := XT: start of an instance and end of a restoration
+// phase.  Needs c_I at XT in CIT.
+BO_NOINLINE double bo_tm_init_point(double* BO_RESTRICT sm, const double mu) {
+  double lgs = 0.0;
+  BO_NOUNROLL
+  for (int i = 0; i < BO_MI; ++i) {
+    const double ci = SM(BO_OFF_CIT, i);
+    const double s = fmax(ci, 1e-2 * fmax(1.0, fabs(ci)));
+    const double rs = bo_rcp(s);
+    SM(BO_OFF_S, i) = s;
+    SM(BO_OFF_RS, i) = rs;
+    SM(BO_OFF_Z, i) = mu * rs;
+    SM(BO_OFF_SIG, i) = mu * rs * rs;
+    lgs += bo_log_ni(s);
+  }
+  BO_UNROLL
+  for (int j = 0; j < BO_ME; ++j) SM(BO_OFF_Y, j) = 0.0;
+  BO_UNROLL
+  for (int i = 0; i < BO_NX; ++i) SM(BO_OFF_X, i) = SM(BO_OFF_XT, i);
+  return lgs;
+}
+
 // A fresh instance: the master has put p and the seed into P / X.
 BO_DEVICE void bo_tm_begin(bo_tm& M, double* BO_RESTRICT sm, const bo_solver_params& prm, long long b) {
   M.b = b;
@@ -326,6 +402,10 @@ BO_DEVICE void bo_tm_begin(bo_tm& M, double* BO_RESTRICT sm, const bo_solver_par
   M.a_trial = 0.0;
   M.a_ftype = BO_INF;
   M.lgs = 0.0;
+  M.resto = 0;
+  M.n_resto = 0;
+  M.thr = 0.0;
+  M.thr0 = 0.0;
   M.phase = BO_PH_INIT;
   BO_UNROLL
   for (int i = 0; i < BO_NX; ++i) SM(BO_OFF_DX, i) = 0.0;  // the INIT evaluation reads x + 0 * dx
@@ -342,7 +422,20 @@ BO_DEVICE int bo_tm_m1(bo_tm& M, double* BO_RESTRICT sm, const bo_solver_params&
 
   if (M.phase == BO_PH_EVAL) {
     M.f = SM(BO_OFF_F0, 0);
-    if (M.recalc_y && BO_ME > 0 && !over) {
+    if (M.resto > 0) {
+      // restoration: next Levenberg-Marquardt step on the infeasibility from the fresh Jacobians
+      if (!bo_isfinite(M.f)) return BO_ST_NUMERICAL;
+      if (over || M.it >= prm.max_iter) return BO_ST_MAX_ITER;
+      if (M.resto > BO_RESTO_MAX_IT) return BO_ST_LINE_SEARCH;
+      M.thr = bo_tm_resto_prepare(sm);
+      M.dw = BO_RESTO_ZETA;
+      M.dc = BO_RESTO_DC;
+      M.first_singular = false;
+      M.attempt = 0;
+      M.heavy = 0;
+      M.ls_mode = false;
+      M.phase = BO_PH_FACTOR;
+    } else if (M.recalc_y && BO_ME > 0 && !over) {
       // least-squares multiplier estimate after a regularised step (bo_ipm_reg.cuh): factor [I JE'; JE -dc]
       M.recalc_y = false;
       M.ls_mode = true;
@@ -420,7 +513,7 @@ BO_DEVICE int bo_tm_m1(bo_tm& M, double* BO_RESTRICT sm, const bo_solver_params&
   }
 
   if (M.phase == BO_PH_FACTOR) {
-    const double rho = M.ls_mode ? 0.0 : BO_STATIC_RHO;
+    const double rho = M.ls_mode ? 0.0 : (M.resto > 0 ? 1.0 : BO_STATIC_RHO);
     M.rho = rho;
     int bad;
     {
@@ -428,6 +521,7 @@ BO_DEVICE int bo_tm_m1(bo_tm& M, double* BO_RESTRICT sm, const bo_solver_params&
       double K[BO_KSZ];
       BO_UNROLL
       for (int i = 0; i < BO_KSZ; ++i) K[i] = 0.0;
+      if (M.resto > 0) bo_kkt_gn_t(SMP(BO_OFF_JE), SMP(BO_OFF_JI), SMP(BO_OFF_SIG), rho, SMP(BO_OFF_KX));  // JI' W JI + rho JE'JE
       if (!M.ls_mode) {
         BO_UNROLL
         for (int i = 0; i < (BO_NX * (BO_NX + 1)) / 2; ++i) K[i] = SM(BO_OFF_KX, i);
@@ -465,19 +559,19 @@ BO_DEVICE int bo_tm_m1(bo_tm& M, double* BO_RESTRICT sm, const bo_solver_params&
       if (++M.attempt > BO_IC_MAX || M.dw > 1e40) return M.err0 <= prm.acceptable_tol ? BO_ST_ACCEPTABLE : BO_ST_NUMERICAL;
       return -1;
     }
-    if (M.dw > 0.0 && M.heavy == 0) M.dw_last = M.dw;
+    if (M.dw > 0.0 && M.heavy == 0 && M.resto == 0) M.dw_last = M.dw;
     if (M.heavy == 0 && !M.jac_degenerate) {
       M.n_singular = M.first_singular ? M.n_singular + 1 : 0;
       if (M.n_singular >= 3) M.jac_degenerate = true;
     }
-    if (M.heavy > 0) {
+    if (M.heavy > 0 && M.resto == 0) {
       // RE / RI were left by the KKT slices; the second-order corrections of an earlier direction overwrote them
       BO_UNROLL
       for (int j = 0; j < BO_ME; ++j) SM(BO_OFF_RE, j) = SM(BO_OFF_CE, j);
       BO_NOUNROLL
       for (int i = 0; i < BO_MI; ++i) SM(BO_OFF_RI, i) = SM(BO_OFF_CI, i) - SM(BO_OFF_S, i);
     }
-    const double a_p = bo_tm_step(sm, M.mu, M.rho, M.dc, M.tau, true);
+    const double a_p = bo_tm_step(sm, M.resto > 0 ? 0.0 : M.mu, M.rho, M.dc, M.tau, true);
     const double dsr = SM(BO_OFF_SOL, 0);
     double dphi = 0.0, dxn = 0.0;
     BO_UNROLL
@@ -510,28 +604,56 @@ BO_DEVICE int bo_tm_m2(bo_tm& M, double* BO_RESTRICT sm, const bo_solver_params&
   if (M.phase == BO_PH_INIT) {
     // start of an instance: slacks from c_I(x0) pushed into the interior, z on the central path, y = 0
     M.f = SM(BO_OFF_FT, 0);
-    double lgs = 0.0;
-    BO_NOUNROLL
-    for (int i = 0; i < BO_MI; ++i) {
-      const double ci = SM(BO_OFF_CIT, i);
-      const double s = fmax(ci, 1e-2 * fmax(1.0, fabs(ci)));
-      const double rs = bo_rcp(s);
-      SM(BO_OFF_S, i) = s;
-      SM(BO_OFF_RS, i) = rs;
-      SM(BO_OFF_Z, i) = M.mu * rs;
-      SM(BO_OFF_SIG, i) = M.mu * rs * rs;
-      lgs += bo_log_ni(s);
-    }
-    M.lgs = lgs;
-    BO_UNROLL
-    for (int j = 0; j < BO_ME; ++j) SM(BO_OFF_Y, j) = 0.0;
-    BO_UNROLL
-    for (int i = 0; i < BO_NX; ++i) SM(BO_OFF_X, i) = SM(BO_OFF_XT, i);
+    M.lgs = bo_tm_init_point(sm, M.mu);
     M.phase = BO_PH_EVAL;
     return -1;
   }
   if (M.phase != BO_PH_TRIAL) return -1;
   const double at = M.a_trial;
+  if (M.resto > 0) {
+    // restoration trial point: Armijo on theta_r
+    double thr_t = 0.0;
+    BO_UNROLL
+    for (int j = 0; j < BO_ME; ++j) thr_t += SM(BO_OFF_CET, j) * SM(BO_OFF_CET, j);
+    BO_NOUNROLL
+    for (int i = 0; i < BO_MI; ++i) {
+      const double v = fmin(SM(BO_OFF_CIT, i), 0.0);
+      thr_t += v * v;
+    }
+    thr_t = sqrt(thr_t);
+#ifdef BO_HOST_TRACE
+    printf("     resto %d ls %d a %.3e theta_r %.3e -> %.3e (entry %.3e)\n", M.resto, M.ls, at, M.thr, thr_t, M.thr0);
+#endif
+    if (bo_isfinite(thr_t) && thr_t <= (1.0 - 1e-4 * at) * M.thr) {
+      M.it += 1;
+      if (thr_t <= fmax(BO_RESTO_KAPPA * M.thr0, 1e-10)) {
+        // feasible enough: back to the regular iteration from here, multipliers and filter start afresh
+        M.f = SM(BO_OFF_FT, 0);
+        M.lgs = bo_tm_init_point(sm, M.mu);
+        M.resto = 0;
+        M.nf = 0;
+        M.dw_last = 0.0;
+        M.recalc_y = BO_ME > 0;  // least-squares equality multipliers at the new point
+      } else {
+        BO_UNROLL
+        for (int i = 0; i < BO_NX; ++i) SM(BO_OFF_X, i) = SM(BO_OFF_XT, i);
+        M.resto += 1;
+      }
+      M.phase = BO_PH_EVAL;
+      return -1;
+    }
+    if (M.ls >= 2 && M.attempt < 4) {  // Levenberg-Marquardt: more damping, new direction
+      M.attempt += 1;
+      M.dw *= 100.0;
+      M.phase = BO_PH_FACTOR;
+      return -1;
+    }
+    M.a *= 0.5;
+    M.a_trial = M.a;
+    M.ls += 1;
+    if (M.ls >= 24 || M.a < 1e-10) return BO_ST_LINE_SEARCH;  // stationary point of the infeasibility
+    return -1;
+  }
   const double ft = SM(BO_OFF_FT, 0);
   double lg = 0.0, thetat = 0.0, lgn = 0.0;
   BO_UNROLL
@@ -660,7 +782,19 @@ BO_DEVICE int bo_tm_m2(bo_tm& M, double* BO_RESTRICT sm, const bo_solver_params&
   M.a *= 0.5;
   M.a_trial = M.a;
   M.ls += 1;
-  if (M.ls >= BO_LS_MAX || M.a < 1e-12) {
+  if (M.ls >= BO_LS_MAX || M.a < BO_ALPHA_MIN) {
+    if (M.theta0 > 1e-7 * fmax(1.0, M.theta_min * 1e4) && M.n_resto < BO_RESTO_MAX_PHASES) {
+      // no acceptable step at an infeasible point: feasibility restoration (the evaluation at x is still valid)
+      M.n_resto += 1;
+      M.resto = 1;
+      M.thr0 = M.thr = bo_tm_resto_prepare(sm);
+      M.dw = BO_RESTO_ZETA;
+      M.dc = BO_RESTO_DC;
+      M.attempt = 0;
+      M.heavy = 0;
+      M.phase = BO_PH_FACTOR;
+      return -1;
+    }
     // no acceptable step along this direction: convexify harder (see bo_ipm_reg.cuh)
     if (++M.heavy >= BO_HEAVY_MAX) return M.err0 <= prm.acceptable_tol ? BO_ST_ACCEPTABLE : BO_ST_LINE_SEARCH;
     M.dw = fmax(M.dw * 100.0, 1.0);

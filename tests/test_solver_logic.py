@@ -349,7 +349,9 @@ def test_trip_budget_follows_max_iter():
     assert s._handle.options()["max_trips"] == 250
     s = optas_b200.B200Solver(prob.opt).setup("ipopt", {"ipopt.max_iter": 1000, "max_trips": 77}, compile_only=True)
     assert s._handle.options()["max_trips"] == 77
-    assert optas_b200.B200Solver(prob.opt).setup("ipopt", compile_only=True, threads_per_block=48)._handle.tier_info()["threads_per_block"] == 64
+    # whole warps only (the kernels use full-mask warp votes): 48 -> 64 on the thread-per-instance tier, 32 G on the team tier
+    assert optas_b200.B200Solver(prob.opt).setup("ipopt", compile_only=True, threads_per_block=48, team=False)._handle.tier_info()["threads_per_block"] == 64
+    assert optas_b200.B200Solver(prob.opt).setup("ipopt", compile_only=True, threads_per_block=80)._handle.tier_info()["threads_per_block"] == 64
 
 
 def test_raw_buffers_are_validated_before_the_library_sees_them():
