@@ -187,6 +187,16 @@ int bo_solve(bo_problem* prob, int64_t B, const double* p, const double* x0, dou
  * CUDA events on the launching stream; resets the counters.  n_launches may be NULL.       */
 int bo_problem_kernel_time(bo_problem* prob, double* ms_total, int64_t* n_launches);
 
+/* Batched `SXContainer.dict2vec` (optas/sx_container.py:113-123; called by Solver.reset_parameters / reset_initial_seed,
+ * optas/solver.py:103-116): gathers n_seg label arrays into the row-major [B][total] matrix bo_solve takes.  Label k is
+ * an m_k x n_k matrix per instance; src[k] points at element (0, 0, 0) of a [B][m_k][n_k] array whose strides in doubles are
+ * stride[3k .. 3k+2] = (batch, row, column) -- any view, no contiguity needed; batch stride 0 broadcasts one matrix over the
+ * batch -- or is NULL (label missing: zeros, as the reference does).  The destination
+ * columns off_k .. off_k + m_k n_k - 1 receive the COLUMN-major flattening of each instance's matrix, which is the
+ * reference's vec() layout.  Host memory only; n_threads <= 0: one thread per core up to 16.                          */
+int bo_pack_rows(double* dst, int64_t B, int64_t total, int32_t n_seg, const double* const* src, const int64_t* stride,
+                 const int32_t* m, const int32_t* n, const int64_t* off, int32_t n_threads);
+
 /* Replaces optas/models.py:786-787 (`Function.map(n)` evaluation of an FK / Jacobian / cost
  * expression graph over n columns): a streaming kernel, one instance per thread, inputs and
  * outputs staged through shared memory with bulk async copies (TMA).

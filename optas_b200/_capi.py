@@ -29,7 +29,7 @@ EXPORTS = [
     "bo_abi_version", "bo_last_error", "bo_device_count",
     "bo_problem_create", "bo_problem_destroy", "bo_problem_source", "bo_problem_ldl_table", "bo_problem_dtable", "bo_problem_kernel_info",
     "bo_problem_tier_info", "bo_problem_options",
-    "bo_solve", "bo_problem_kernel_time",
+    "bo_solve", "bo_problem_kernel_time", "bo_pack_rows",
     "bo_function_create", "bo_function_destroy", "bo_function_eval", "bo_function_source",
     "bo_function_kernel_info", "bo_function_kernel_time",
 ]
@@ -102,6 +102,7 @@ def load() -> C.CDLL:
     lib.bo_problem_options.argtypes = [vp, C.POINTER(bo_options)]
     lib.bo_solve.argtypes = [vp, C.c_int64] + [vp] * 8 + [vp]
     lib.bo_problem_kernel_time.argtypes = [vp, f64p, C.POINTER(C.c_int64)]
+    lib.bo_pack_rows.argtypes = [vp, C.c_int64, C.c_int64, C.c_int32, C.POINTER(vp), C.POINTER(C.c_int64), i32p, i32p, C.POINTER(C.c_int64), C.c_int32]
     lib.bo_function_create.argtypes = [C.POINTER(bo_tape), C.POINTER(bo_options), C.POINTER(vp)]
     lib.bo_function_destroy.argtypes = [vp]
     lib.bo_function_eval.argtypes = [vp, C.c_int64, C.POINTER(vp), C.POINTER(vp), vp]
@@ -176,6 +177,19 @@ def _current_device_plus_one() -> int:
     except Exception:
         pass
     return 0
+
+
+def pack_rows(dst: np.ndarray, segments) -> None:
+    """``bo_pack_rows``: ``dst`` is ``[B, total]`` float64 C-contiguous; ``segments`` is a list of
+    ``(array or None, (batch, row, column) strides in elements, m, n, offset)``; arrays are float64 views of any layout."""
+    B, total = dst.shape
+    k = len(segments)
+    ptrs = (C.c_void_p * max(k, 1))(*[None if a is None else a.ctypes.data for a, _, _, _, _ in segments])
+    strides = (C.c_int64 * max(3 * k, 1))(*[int(v) for _, st, _, _, _ in segments for v in st])
+    ms = (C.c_int32 * max(k, 1))(*[int(m) for _, _, m, _, _ in segments])
+    ns = (C.c_int32 * max(k, 1))(*[int(n) for _, _, _, n, _ in segments])
+    offs = (C.c_int64 * max(k, 1))(*[int(o) for _, _, _, _, o in segments])
+    check(load().bo_pack_rows(dst.ctypes.data, B, total, k, ptrs, strides, ms, ns, offs, 0))
 
 
 def _source(getter, handle) -> str:

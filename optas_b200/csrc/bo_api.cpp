@@ -19,6 +19,7 @@
 #include <fstream>
 #include <memory>
 #include <sstream>
+#include <thread>
 #include <string>
 #include <vector>
 
@@ -925,6 +926,50 @@ int bo_problem_kernel_time(bo_problem* pr, double* ms_total, int64_t* n_launches
   int rc = pr->timer.collect(ms_total, &n);
   if (n_launches) *n_launches = n;
   return rc;
+}
+
+// ------------------------------------------------------------------------------------------
+// host-side marshalling: label arrays -> [B][total] rows (batched dict2vec)
+// ------------------------------------------------------------------------------------------
+int bo_pack_rows(double* dst, int64_t B, int64_t total, int32_t n_seg, const double* const* src, const int64_t* stride,
+                 const int32_t* m, const int32_t* n, const int64_t* off, int32_t n_threads) {
+  if (!dst || B < 0 || total < 0 || n_seg < 0 || (n_seg > 0 && (!src || !stride || !m || !n || !off)))
+    return set_err(BO_ERR_INVALID, "bo_pack_rows: bad argument");
+  for (int k = 0; k < n_seg; ++k)
+    if (m[k] < 0 || n[k] < 0 || off[k] < 0 || off[k] + (int64_t)m[k] * n[k] > total)
+      return set_err(BO_ERR_INVALID, "bo_pack_rows: segment %d does not fit a row of %lld", k, (long long)total);
+  if (B == 0 || total == 0) return BO_OK;
+  auto work = [&](int64_t b0, int64_t b1) {
+    for (int64_t b = b0; b < b1; ++b) {
+      double* row = dst + b * total;
+      for (int k = 0; k < n_seg; ++k) {
+        const int mk = m[k], nk = n[k];
+        double* out = row + off[k];
+        if (!src[k]) {
+          for (int e = 0; e < mk * nk; ++e) out[e] = 0.0;
+          continue;
+        }
+        const int64_t sb = stride[3 * k], sr = stride[3 * k + 1], sc = stride[3 * k + 2];
+        const double* in = src[k] + b * sb;
+        for (int c = 0; c < nk; ++c)  // column-major flattening of the instance's matrix
+          for (int r = 0; r < mk; ++r) out[c * mk + r] = in[r * sr + c * sc];
+      }
+    }
+  };
+  int nt = n_threads > 0 ? n_threads : (int)std::min<unsigned>(16u, std::max(1u, std::thread::hardware_concurrency()));
+  if ((int64_t)nt > B / 4096) nt = (int)std::max<int64_t>(1, B / 4096);  // a thread is not worth less than 4096 rows
+  if (nt <= 1) {
+    work(0, B);
+    return BO_OK;
+  }
+  std::vector<std::thread> pool;
+  const int64_t chunk = (B + nt - 1) / nt;
+  for (int t = 0; t < nt; ++t) {
+    const int64_t b0 = t * chunk, b1 = std::min<int64_t>(B, b0 + chunk);
+    if (b0 < b1) pool.emplace_back(work, b0, b1);
+  }
+  for (auto& th : pool) th.join();
+  return BO_OK;
 }
 
 // ------------------------------------------------------------------------------------------

@@ -218,24 +218,42 @@ def pack_batch(container, d: Dict[str, ArrayType]) -> Tuple[np.ndarray, Optional
                 raise ValueError(f"'{label}': batch size {b} does not match {B}")
             B = b
         values[label] = (v, b)
-    # zero-fill only when some label is missing (the reference's dict2vec semantics: missing labels become zeros)
-    covered = sum(m * n for label, (off, m, n) in layout.items() if label in values)
-    out = host_array((B or 1, total), zero=covered < total)
-    for label, (v, b) in values.items():
-        off, m, n = layout[label]
+    out = host_array((B or 1, total))
+    if total == 0:
+        return out, B
+    # one threaded pass of the library over all labels (bo_pack_rows): missing labels become zeros like the reference's
+    # dict2vec, [m, n] values are broadcast over the batch, every instance's matrix lands column-major (vec() layout)
+    from . import _capi
+
+    segments, keep = [], []
+    for label, (off, m, n) in layout.items():
         if m * n == 0:
             continue
+        if label not in values:
+            segments.append((None, (0, 0, 0), m, n, off))
+            continue
+        v, b = values[label]
+        if v.dtype != np.float64:
+            v = v.astype(np.float64)
+        keep.append(v)
+        e = v.itemsize
         if b is None:
             if v.size != m * n:
                 raise ValueError(f"'{label}': expected {m * n} elements, got {v.size}")
-            flat = v.reshape(-1, order="F") if v.ndim == 2 else v.reshape(-1)
-            out[:, off:off + m * n] = flat[None, :]
+            if v.ndim == 2 and v.shape == (m, n):
+                st = (0, v.strides[0] // e, v.strides[1] // e)
+            else:  # a flat vector is the column-major flattening (reference: cs.vec)
+                v = np.ascontiguousarray(v).reshape(-1)
+                keep.append(v)
+                st = (0, 1, m)
         elif v.ndim == 3:
             if v.shape[1:] != (m, n):
                 raise ValueError(f"'{label}': expected [B, {m}, {n}], got {list(v.shape)}")
-            out[:, off:off + m * n] = v.transpose(0, 2, 1).reshape(B, m * n)
-        else:
-            out[:, off:off + m * n] = v
+            st = (v.strides[0] // e, v.strides[1] // e, v.strides[2] // e)
+        else:  # [B, m*n]: every row already the column-major flattening of one instance
+            st = (v.strides[0] // e, v.strides[1] // e, m * (v.strides[1] // e))
+        segments.append((v, st, m, n, off))
+    _capi.pack_rows(out, segments)
     return out, B
 
 

@@ -8,7 +8,10 @@ problem's own IR functions through the oracle tape interpreter -- step (i) of th
     complementarity|| z * c_ineq ||_inf
 
 ``kkt_residual`` returns the max of those per instance.  If multipliers are not supplied they are
-estimated by non-negative least squares on the active set.
+estimated by non-negative least squares on the active set.  With ``scaled=True`` stationarity and
+complementarity are divided by IPOPT's scaling factors s_d = max(100, (|y|_1 + |z|_1) / (m + n)) / 100 and
+s_c = max(100, |z|_1 / n) / 100 (Waechter & Biegler 2006, eq. 6) -- the quantity IPOPT's ``tol`` (and the GPU
+back-end's) bounds, which is what "converged to 1e-8" means on the reference path.
 """
 
 from __future__ import annotations
@@ -24,7 +27,7 @@ sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
 from slsqp_driver import OracleProblem  # noqa: E402
 
 
-def kkt_terms(oprob: OracleProblem, x, p, y=None, z=None, active_tol: float = 1e-6):
+def kkt_terms(oprob: OracleProblem, x, p, y=None, z=None, active_tol: float = 1e-6, scaled: bool = False):
     g = oprob.df(x, p)
     ce, Je = oprob.c_eq(x, p) if oprob.constrained else (np.zeros(0), np.zeros((0, oprob.nx)))
     ci, Ji = oprob.c_ineq(x, p) if oprob.constrained else (np.zeros(0), np.zeros((0, oprob.nx)))
@@ -44,19 +47,29 @@ def kkt_terms(oprob: OracleProblem, x, p, y=None, z=None, active_tol: float = 1e
     y = np.asarray(y, dtype=float).reshape(-1)
     z = np.asarray(z, dtype=float).reshape(-1)
     stat = g - Je.T @ y - Ji.T @ z
+    s_d, s_c = ipopt_scaling(y, z) if scaled else (1.0, 1.0)
     return {
-        "stationarity": float(np.abs(stat).max(initial=0.0)),
+        "stationarity": float(np.abs(stat).max(initial=0.0)) / s_d,
         "eq": float(np.abs(ce).max(initial=0.0)),
         "ineq": float(np.abs(np.minimum(ci, 0.0)).max(initial=0.0)),
         "dual_sign": float(np.abs(np.minimum(z, 0.0)).max(initial=0.0)),
-        "complementarity": float(np.abs(z * ci).max(initial=0.0)),
+        "complementarity": float(np.abs(z * ci).max(initial=0.0)) / s_c,
     }
+
+
+def ipopt_scaling(y, z, s_max: float = 100.0):
+    """(s_d, s_c) of Waechter & Biegler 2006, eq. 6."""
+    n_mult = len(y) + len(z)
+    s_d = max(s_max, (np.abs(y).sum() + np.abs(z).sum()) / n_mult) / s_max if n_mult else 1.0
+    s_c = max(s_max, np.abs(z).sum() / len(z)) / s_max if len(z) else 1.0
+    return s_d, s_c
 
 
 _CACHE = {}
 
 
-def kkt_residual(prob, X, P, lam_eq: Optional[np.ndarray] = None, lam_ineq: Optional[np.ndarray] = None) -> np.ndarray:
+def kkt_residual(prob, X, P, lam_eq: Optional[np.ndarray] = None, lam_ineq: Optional[np.ndarray] = None,
+                 scaled: bool = False) -> np.ndarray:
     """Per-instance max KKT term.  ``prob``: an ``optas_b200.problems.Problem`` (only ``.opt`` is used)."""
     key = id(prob.opt)
     if key not in _CACHE:
@@ -68,5 +81,5 @@ def kkt_residual(prob, X, P, lam_eq: Optional[np.ndarray] = None, lam_ineq: Opti
     for i in range(X.shape[0]):
         y = None if lam_eq is None else lam_eq[i]
         z = None if lam_ineq is None else lam_ineq[i]
-        out[i] = max(kkt_terms(op, X[i], P[i] if P.shape[0] > 1 else P[0], y, z).values())
+        out[i] = max(kkt_terms(op, X[i], P[i] if P.shape[0] > 1 else P[0], y, z, scaled=scaled).values())
     return out

@@ -4,8 +4,9 @@
 Tolerances: all arithmetic is IEEE binary64.  FK / Jacobian values must agree with the numpy
 restatement to 1e-12 absolute (a few ulp of O(1) quantities: FMA contraction and the device sincos
 differ from libm in the last bits).  Converged decision variables must agree with the oracle's
-polished solution to 1e-6 relative and have oracle KKT residual <= 1e-6 (north_star: "1e-6 rel-tol
-on decision variables and KKT residual")."""
+polished solution to 1e-6 relative (north_star: "1e-6 rel-tol on decision variables and KKT residual"); the oracle KKT
+residual of an instance reported CONVERGED (status 0) must be <= 1e-8 in IPOPT's scaling, of one
+reported ACCEPTABLE (status 1) <= 1e-6.  The per-config parity protocol lives in tests/test_gpu_parity.py."""
 import numpy as np
 import pytest
 
@@ -13,7 +14,8 @@ pytestmark = pytest.mark.gpu
 
 FK_TOL = 1e-12
 X_RTOL = 1e-6
-KKT_TOL = 1e-6
+KKT_TOL = 1e-8            # status 0
+KKT_TOL_ACCEPTABLE = 1e-6  # status 1
 
 
 @pytest.fixture(scope="module")
@@ -44,6 +46,19 @@ def _solve_host(solver, P, X0):
     solver.solve_raw(np.ascontiguousarray(P), np.ascontiguousarray(X0), out["x"], out["lam"], out["f"], out["status"],
                      out["iters"], out["kkt"])
     return out
+
+
+def _assert_kkt(prob, lo, r, P, idx):
+    """Oracle KKT residual (IPOPT scaling): <= 1e-8 for status 0, <= 1e-6 for status 1 (counted separately)."""
+    import kkt_check
+
+    idx = np.asarray(idx)
+    res = kkt_check.kkt_residual(prob, r["x"][idx], P[idx], r["lam"][idx][:, :lo.n_eq], r["lam"][idx][:, lo.n_eq:], scaled=True)
+    conv = r["status"][idx] == 0
+    assert conv.any()
+    assert res[conv].max() <= KKT_TOL, res[conv].max()
+    if (~conv).any():
+        assert res[~conv].max() <= KKT_TOL_ACCEPTABLE, res[~conv].max()
 
 
 def test_fk_jacobian_matches_oracle_full_batch(ik):
@@ -135,8 +150,7 @@ def test_c2_batch_parity_protocol(ik):
     assert ok.mean() >= 0.995, ok.mean()
     lo = solver._lowered
     idx = np.where(ok)[0][:512]
-    res = kkt_check.kkt_residual(prob, r["x"][idx], P[idx], r["lam"][idx][:, :lo.n_eq], r["lam"][idx][:, lo.n_eq:])
-    assert res.max() < KKT_TOL, res.max()
+    _assert_kkt(prob, lo, r, P, idx)
     op = slsqp_driver.OracleProblem(prob.opt)
     worst = 0.0
     for i in idx[:96]:
@@ -252,8 +266,7 @@ def test_c3_point_mass_mpc_batch(torch_cuda, coop):
     assert ok.mean() >= 0.97, ok.mean()
     lo = solver._lowered
     idx = np.where(ok)[0][:24]
-    res = kkt_check.kkt_residual(prob, r["x"][idx], P[idx], r["lam"][idx][:, :lo.n_eq], r["lam"][idx][:, lo.n_eq:])
-    assert res.max() < KKT_TOL, res.max()
+    _assert_kkt(prob, lo, r, P, idx)
     # dynamics x_{t+1} = x_t + dt v_t and the initial state hold to round-off (linear equalities)
     sol = prob.seed_dict(r["x"][ok])
     Y, dY = sol["point_mass/y/x"], sol["point_mass/dy/x"]
@@ -279,8 +292,8 @@ def test_c5_dual_arm_batch(torch_cuda, coop):
     assert (r["status"] <= 1).all(), np.bincount(r["status"])
     lo = solver._lowered
     for i in (0, 17, 95):
-        k = problems_ref.sparse_kkt_residual(lo, r["x"][i], P[i], r["lam"][i, :lo.n_eq], r["lam"][i, lo.n_eq:])
-        assert max(k["stationarity"], k["eq"]) < KKT_TOL
+        k = problems_ref.sparse_kkt_residual(lo, r["x"][i], P[i], r["lam"][i, :lo.n_eq], r["lam"][i, lo.n_eq:], scaled=True)
+        assert max(k["stationarity"], k["eq"], k["complementarity"]) <= (KKT_TOL if r["status"][i] == 0 else KKT_TOL_ACCEPTABLE)
         assert abs(r["f"][i] - problems_ref.dual_arm_cost(r["x"][i], P[i])) < 1e-10
         assert np.abs(problems_ref.dual_arm_constraints(r["x"][i], P[i])).max() < 1e-8
     # dict API: trajectories come back as [B, 7, T] and the first knot is the commanded configuration
@@ -494,8 +507,7 @@ def test_joint_space_planner_batch(torch_cuda):
     assert ok.mean() >= 0.98, np.bincount(r["status"])  # measured on B200: 1011 of 1024 converge, 13 end in a line-search failure
     lo = solver._lowered
     idx = np.where(ok)[0][:16]
-    res = kkt_check.kkt_residual(prob, r["x"][idx], P[idx], r["lam"][idx][:, :lo.n_eq], r["lam"][idx][:, lo.n_eq:])
-    assert res.max() < KKT_TOL, res.max()
+    _assert_kkt(prob, lo, r, P, idx)
     sol = prob.seed_dict(r["x"][ok])
     Q, dQ = sol["med7/q/x"], sol["med7/dq/x"]
     chain = fk_ref.Chain(problems.MED7_URDF, problems.MED7_EE)
@@ -523,8 +535,7 @@ def test_axis_ik_first_stage_batch(torch_cuda):
     assert np.abs(r["x"][0, :7] - problems.SPHERE_Q_START).max() < 1e-7
     lo = solver._lowered
     idx = np.where(ok)[0][:32]
-    res = kkt_check.kkt_residual(prob, r["x"][idx], P[idx], r["lam"][idx][:, :lo.n_eq], r["lam"][idx][:, lo.n_eq:])
-    assert res.max() < KKT_TOL, res.max()
+    _assert_kkt(prob, lo, r, P, idx)
 
 
 def test_fk_jacobian_matches_reference_golden_vectors(ik):

@@ -159,3 +159,31 @@ def test_v_stacking_order():
     ce, _ = op.c_eq(x0, p)
     assert np.allclose(v, np.concatenate([ci, ce, -ce]))
     assert v.shape == (20,)
+
+
+@pytest.mark.parametrize("name, closed", [("point_mass_mpc", "point_mass_fc"), ("figure_eight", "figure_eight_fc"),
+                                          ("dual_arm", None)])
+def test_horizon_tapes_against_independent_closed_forms(name, closed):
+    """The lowered tapes of C3 / C4 / C5 (what the GPU kernels and the oracle's solvers both evaluate) against plain-numpy
+    closed forms written from the reference scripts: values directly, grad f and the constraint Jacobians by central
+    differences of the closed form, the Lagrangian Hessian by central differences of the pinned tape gradient.  This check
+    does not pass through optas_b200.sym.jacobian, the AD the tapes were derived with (round-1 verdict: the oracle's
+    derivative path was common-mode with the product's)."""
+    import problems_ref
+    from optas_b200 import problems
+    from optas_b200.lowering import lower_problem
+
+    prob = getattr(problems, name)()
+    lo = lower_problem(prob.opt)
+    if closed is None:
+        def fc(x, p):
+            return problems_ref.dual_arm_cost(x, p), problems_ref.dual_arm_constraints(x, p), np.zeros(0)
+    else:
+        fc = getattr(problems_ref, closed)
+    P, X0 = prob.sample(2, seed=3)
+    rng = np.random.default_rng(0)
+    x = X0[0] + 0.05 * rng.standard_normal(lo.nx)
+    y, z = rng.standard_normal(lo.n_eq), rng.uniform(0.1, 1.0, lo.n_ineq)
+    err = problems_ref.check_tapes_against_closed_form(lo, fc, x, P[0], y, z)
+    assert max(err["f"], err["c_eq"], err["c_ineq"]) < 1e-11, err
+    assert max(err["grad"], err["jac_eq"], err["jac_ineq"], err["hess"]) < 1e-7, err
