@@ -17,8 +17,9 @@
  *   - all numeric data is IEEE binary64, row-major with the INSTANCE index slowest:
  *     p[B][np], x[B][nx] ... (one OpTaS problem instance per row).
  *   - data pointers may be host or device memory (detected with cudaPointerGetAttributes);
- *     a call whose buffers are all device memory is asynchronous on `stream`, a call with any
- *     host buffer stages through pinned memory and returns after the results are on the host.
+ *     a call whose buffers are all device memory is asynchronous on `stream`; a call with any
+ *     host buffer stages through device buffers of the handle and returns after the results are on the
+ *     host (page-locked host memory makes the copies asynchronous; pageable memory works).
  *   - buffers are BORROWED for the duration of the call; nothing is retained.
  *   - a handle is bound to the CUDA device current at creation; handles are not thread-safe,
  *     distinct handles may be used from distinct threads / processes (one per GPU).
@@ -106,6 +107,8 @@ typedef struct bo_problem_desc {
 #define BO_FLAG_COOP 32u         /* use the cooperative tier (one instance per CTA, factor in shared memory) even for
                                    a problem small enough for the thread-per-instance sparse tier             */
 #define BO_FLAG_NO_COOP 64u      /* never use the cooperative tier (large problems then run thread-per-instance) */
+#define BO_FLAG_PIPELINE 256u    /* host-buffer calls: cut the batch into chunks on two internal streams so that uploads, kernels
+                                   and downloads overlap.  Off by default: measured slower on B200 (each chunk pays its own tail) */
 #define BO_FLAG_NO_TEAM 128u     /* small dense problems: run the round-1 thread-per-instance kernel (state in thread-local
                                    memory) instead of the team tier (state in shared memory, G threads per instance) */
 

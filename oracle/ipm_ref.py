@@ -80,10 +80,12 @@ class SparseIPM:
     # -- the iteration -----------------------------------------------------------------------------
     def solve(self, p, x0, tol: float = 1e-8, acceptable_tol: float = 1e-6, max_iter: int = 300, mu_init: float = 0.1,
               max_step: float = 0.0, y0: Optional[np.ndarray] = None, z0: Optional[np.ndarray] = None,
-              mu0: Optional[float] = None, trace: bool = False):
+              mu0: Optional[float] = None, fixed_mu: bool = False, trace: bool = False):
         """Returns dict(x, y, z, f, status, iters, kkt).  ``y0 / z0 / mu0`` warm-start the duals (used by the polish
         check, which starts at a candidate primal-dual solution); ``max_step`` > 0 caps ||alpha dx||_inf like the GPU
-        back-end's option of the same name (0: IPOPT behaviour, no cap)."""
+        back-end's option of the same name (0: IPOPT behaviour, no cap).  ``fixed_mu``: solve the barrier sub-problem of
+        ``mu0`` only -- mu is never reduced and convergence is measured by E_mu (Waechter & Biegler eq. 5 with the
+        complementarity residual s z - mu); the polish check uses this to refine a candidate on ITS central-path point."""
         kappa_eps, kappa_mu, theta_mu, tau_min, s_max = 10.0, 0.2, 1.5, 0.99, 100.0
         gamma_theta, gamma_phi, eta_phi, s_phi, s_theta, kappa_sigma = 1e-5, 1e-5, 1e-8, 2.3, 1.1, 1e10
         n, me, mi = self.nx, self.me, self.mi
@@ -110,7 +112,7 @@ class SparseIPM:
             sum_mult = np.abs(y).sum() + sum_z
             s_d = max(s_max, sum_mult / max(1, me + mi)) / s_max if me + mi else 1.0
             s_c = max(s_max, sum_z / max(1, mi)) / s_max if mi else 1.0
-            err0 = max(e_dual / s_d, e_prim, (s * z).max(initial=0.0) / s_c)
+            err0 = max(e_dual / s_d, e_prim, (np.abs(s * z - mu).max(initial=0.0) if fixed_mu else (s * z).max(initial=0.0)) / s_c)
             if trace:
                 print(f"it {it:3d} f {f:.6e} err0 {err0:.3e} (dual {e_dual / s_d:.3e} prim {e_prim:.3e}) mu {mu:.2e}")
             if not np.isfinite(err0) or not np.isfinite(f):
@@ -126,7 +128,7 @@ class SparseIPM:
             if it >= max_iter:
                 status = MAX_ITER
                 break
-            if mi:
+            if mi and not fixed_mu:
                 for _ in range(8):
                     err_mu = max(e_dual / s_d, e_prim, np.abs(s * z - mu).max() / s_c)
                     if err_mu <= kappa_eps * mu and mu > mu_min:

