@@ -107,6 +107,7 @@ typedef struct bo_problem_desc {
 #define BO_FLAG_COOP 32u         /* use the cooperative tier (one instance per CTA, factor in shared memory) even for
                                    a problem small enough for the thread-per-instance sparse tier             */
 #define BO_FLAG_NO_COOP 64u      /* never use the cooperative tier (large problems then run thread-per-instance) */
+#define BO_FLAG_TEAM 512u        /* use the team tier even for a problem small enough that the thread-per-instance kernel is faster */
 #define BO_FLAG_PIPELINE 256u    /* host-buffer calls: cut the batch into chunks on two internal streams so that uploads, kernels
                                    and downloads overlap.  Off by default: measured slower on B200 (each chunk pays its own tail) */
 #define BO_FLAG_NO_TEAM 128u     /* small dense problems: run the round-1 thread-per-instance kernel (state in thread-local

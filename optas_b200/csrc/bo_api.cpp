@@ -641,11 +641,15 @@ int bo_problem_create(const bo_problem_desc* desc, const bo_options* opts_in, bo
     }
   }
   // Team tier (csrc/jit/bo_ipm_team.cuh): small dense problems, G threads in G warps per instance, state in shared memory
-  if (!pr->sparse && !pivoted && !(pr->opts.flags & BO_FLAG_NO_TEAM)) {
+  // Measured on B200 (tools/team_check.py, profiles/r02_team_vs_thread.txt): the team tier wins once the per-instance state
+  // no longer fits a thread (C2: 24 rows of variables + constraints, 3 KB of thread-local state: 6.0 vs 10.2 ms per 65536)
+  // and loses below that (planar differential-IK QP, 13 rows, 1.7 KB: 0.51 vs 0.26 ms; Booth 14.5 vs 9.9 us per 4096).
+  const bool team_worth_it = ps.nx + ps.n_eq + ps.n_ineq >= 20 || (pr->opts.flags & BO_FLAG_TEAM);
+  if (!pr->sparse && !pivoted && team_worth_it && !(pr->opts.flags & BO_FLAG_NO_TEAM)) {
     int G = pr->opts.threads_per_block > 0 ? pr->opts.threads_per_block / 32 : 4;
     G = std::max(1, std::min(G, 8));
     std::string why;
-    const size_t smem = ((size_t)bo::team_smem_elems(ps, G) * 32 + 2 * 32 * (size_t)(ps.np + ps.nx)) * sizeof(double) + 32 * sizeof(int) + 128;
+    const size_t smem = ((size_t)bo::team_smem_elems(ps, G) * 32 + 2 * 32 * (size_t)(ps.np + ps.nx)) * sizeof(double) + 32 * sizeof(int) + 128 + 32 * sizeof(long long);
     if (smem <= 227 * 1024 && bo::make_team_plan(ps, G, &pr->team_plan, &why)) {
       pr->team = true;
       pr->tpb = 32 * G;

@@ -32,6 +32,7 @@
 #define BO_PH_TRIAL 2
 #define BO_PH_INIT 3
 #define BO_PH_DONE 4 /* finished in M1; results are written out at the end of the trip */
+#define BO_PH_FRESH 5 /* parameters and seed of a new instance are staged; the team's quad has not picked it up yet */
 
 // ---- shared-memory layout: offsets in "elements" (one element = BO_LS doubles, one per lane) ----
 #define BO_OFF_P 0

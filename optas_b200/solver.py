@@ -342,7 +342,7 @@ class B200Solver(Solver):
         flags = ((_capi.BO_FLAG_COMPILE_ONLY if compile_only else 0) | (_capi.BO_FLAG_TIMING if timing else 0)
                  | (_capi.BO_FLAG_PIVOTED_LDL if pivoted_ldl else 0)
                  | (_capi.BO_FLAG_COOP if coop else 0) | (_capi.BO_FLAG_NO_COOP if coop is False else 0)
-                 | (_capi.BO_FLAG_NO_TEAM if team is False else 0))
+                 | (_capi.BO_FLAG_NO_TEAM if team is False else 0) | (_capi.BO_FLAG_TEAM if team else 0))
         self._handle = _capi.ProblemHandle(self._lowered, flags=flags, max_iter=max_iter, tol=tol_use,
                                            acceptable_tol=acc_tol, mu_init=mu_init, max_step=max_step,
                                            threads_per_block=threads_per_block, max_trips=max_trips,

@@ -270,10 +270,10 @@ def test_sphere_collision_problem_dimensions_and_seed():
 
 def test_tier_choice_follows_the_measured_rule():
     """bo_problem_create picks the kernel tier from the problem sizes alone (measured on B200 in
-    profiles/r01_tier_choice.txt / r01_tier_break_even.txt): the team tier (state in shared memory) up to 14 KKT rows,
-    thread-per-instance sparse for small problems, one instance per CTA once nx + n_eq + n_ineq > 64 and the tapes split
-    into stages."""
-    expect = [(problems.lwr_ik(), "team"), (problems.planar_idk(), "team"), (problems.lwr_axis_ik(), "sparse"),
+    profiles/r01_tier_choice.txt / r01_tier_break_even.txt, r02_team_vs_thread.txt): up to 14 KKT rows the team tier (state in
+    shared memory) when variables + constraints >= 20, else the thread-per-instance dense tier; thread-per-instance sparse for
+    mid-size problems; one instance per CTA once nx + n_eq + n_ineq > 64 and the tapes split into stages."""
+    expect = [(problems.lwr_ik(), "team"), (problems.planar_idk(), "dense"), (problems.lwr_axis_ik(), "sparse"),
               (problems.point_mass_mpc(T=6), "coop"), (problems.point_mass_mpc(), "coop"), (problems.joint_space_planner(), "coop")]
     for prob, tier in expect:
         s = optas_b200.B200Solver(prob.opt).setup("ipopt", compile_only=True)
@@ -294,9 +294,9 @@ def test_team_tier_takes_the_same_iterations_as_the_thread_tier():
         lo = lower_problem(prob.opt)
         P, X0 = prob.sample(B, seed=3)
         res = {}
-        for label, flag in (("team", 0), ("thread", _capi.BO_FLAG_NO_TEAM)):
+        for label, flag in (("team", _capi.BO_FLAG_TEAM), ("thread", _capi.BO_FLAG_NO_TEAM)):
             h = _capi.ProblemHandle(lo, flags=_capi.BO_FLAG_COMPILE_ONLY | flag)
-            assert h.tier_info()["tier"] == ("team" if flag == 0 else "dense")
+            assert h.tier_info()["tier"] == ("team" if label == "team" else "dense")
             res[label] = HostSim(h.source(), lo.nx, lo.np_, lo.n_eq, lo.n_ineq).solve(P, X0, max_step=h.options()["max_step"])
         a, b = res["team"], res["thread"]
         assert np.array_equal(a["status"], b["status"]) and np.array_equal(a["iters"], b["iters"])
@@ -351,7 +351,7 @@ def test_trip_budget_follows_max_iter():
     assert s._handle.options()["max_trips"] == 77
     # whole warps only (the kernels use full-mask warp votes): 48 -> 64 on the thread-per-instance tier, 32 G on the team tier
     assert optas_b200.B200Solver(prob.opt).setup("ipopt", compile_only=True, threads_per_block=48, team=False)._handle.tier_info()["threads_per_block"] == 64
-    assert optas_b200.B200Solver(prob.opt).setup("ipopt", compile_only=True, threads_per_block=80)._handle.tier_info()["threads_per_block"] == 64
+    assert optas_b200.B200Solver(prob.opt).setup("ipopt", compile_only=True, threads_per_block=80, team=True)._handle.tier_info()["threads_per_block"] == 64
 
 
 def test_raw_buffers_are_validated_before_the_library_sees_them():
