@@ -99,10 +99,26 @@ def measured_peaks() -> dict:
     return {"hbm_gbs": 6650.0, "source": "fallback (B200_PROFILING.md)"}
 
 
+def fp64_microbench() -> dict:
+    """tools/fp64_microbench.cu (built by __graft_entry__.build()): scalar DFMA with 8 independent chains per thread and
+    mma.sync.m8n8k4.f64 (DMMA) with 8 accumulator tiles per warp, all SMs.  Returns {} when the binary is missing."""
+    exe = os.path.join(ROOT, "tools", "_build", "fp64_microbench")
+    if not os.path.exists(exe):
+        return {}
+    try:
+        out = subprocess.run([exe], capture_output=True, text=True, timeout=60).stdout
+        rows = [json.loads(line) for line in out.splitlines() if line.startswith("{")]
+        return {r["kernel"]: r["tflops"] for r in rows}
+    except Exception:
+        return {}
+
+
 def fp64_peak_tflops(dev, stream) -> dict:
-    """Measured FP64 FMA throughput of this GPU: a tape of 16 independent Horner chains (128 multiply-adds
-    each, 4096 flop per evaluation, 256 B of I/O) pushed through the same streaming kernel as K1.
-    MEASURED_PEAKS.json has no FP64 figure; this is the denominator for the solver kernel's FP64 fraction."""
+    """Measured FP64 throughput of this GPU (MEASURED_PEAKS.json has no FP64 figure): the denominator for the solver
+    kernels' FP64 fraction is the scalar-DFMA microbenchmark (tools/fp64_microbench.cu, 8 chains per thread); the DMMA
+    (mma.sync.m8n8k4.f64) figure is reported beside it.  Also kept: the same measurement through the product's own
+    streaming kernel K1 -- a tape of 16 independent Horner chains (128 multiply-adds each) -- which reaches less because
+    every evaluation also moves 256 B."""
     import torch
     import optas_b200.sym as cs
     from optas_b200.function import B200Function
@@ -127,8 +143,13 @@ def fp64_peak_tflops(dev, stream) -> dict:
     torch.cuda.synchronize()
     ms, n = fn.kernel_time()
     flops = Bf * 16 * 128 * 2
-    return {"tflops": flops / (ms / n * 1e-3) / 1e12, "how": "16x128 FMA Horner chains per evaluation, 2 Mi evaluations, bo_eval_kernel",
-            "registers": fn.kernel_info()["registers"]}
+    k1 = flops / (ms / n * 1e-3) / 1e12
+    mb = fp64_microbench()
+    out = {"tflops": max(k1, mb.get("dfma", 0.0)), "how": "max of: scalar DFMA microbenchmark (tools/fp64_microbench.cu, 8 chains per thread, all SMs); "
+           "16x128 FMA Horner chains per evaluation through bo_eval_kernel", "dfma_microbench_tflops": mb.get("dfma"),
+           "dmma_m8n8k4_microbench_tflops": mb.get("dmma m8n8k4"), "horner_through_k1_tflops": k1,
+           "registers": fn.kernel_info()["registers"]}
+    return out
 
 
 def tape_flops(tape) -> int:
@@ -608,6 +629,7 @@ def main() -> None:
         line["solve_kernel"]["frac_of_fp64_peak_tapes_only"] = line["solve_kernel"]["achieved_tflops_tapes_only"] / fp64["tflops"]
         if configs:
             line["configs"] = configs
+            line["gpu_launches_configs"] = int(sum(c.get("gpu_launches", 0) for c in configs.values()))
         if not args.no_cpu_baseline and world == 1:
             line["cpu_baseline"] = cpu_baseline(CPU_SAMPLE, os.cpu_count() or 1)
         emit(line)

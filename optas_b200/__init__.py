@@ -22,7 +22,6 @@ from .builder import OptimizationBuilder
 from .optimization import Optimization
 from .solver import B200Solver, CasADiSolver, CVXOPTSolver, OSQPSolver, ScipyMinimizeSolver, Solver
 from .nlpsol import nlpsol, qpsol
-from . import templates
 
 __version__ = "0.1.0"
 

@@ -1,4 +1,7 @@
-"""Loop glue between a task script and a solver: the ``Manager`` base class the reference's example scripts derive
+"""TEST SHIM (not part of the optas_b200 package; SURVEY.md section 2 marks optas/templates.py out of scope): exists only so
+that tests/test_scripts_unchanged.py can run the reference's example scripts, which subclass it, without editing them.
+
+Loop glue between a task script and a solver: the ``Manager`` base class the reference's example scripts derive
 their planners / controllers from (reference: optas/templates.py:10-105).  Host orchestration only -- it owns a
 ``Solver`` (here: the B200 back-end behind ``CasADiSolver`` & co.), calls ``solve()`` and keeps the last solution.
 

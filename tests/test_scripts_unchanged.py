@@ -22,7 +22,10 @@ sys.path.insert(0, {ROOT!r})
 import numpy as np
 import optas_b200
 sys.modules["optas"] = optas_b200
-sys.modules["optas.templates"] = optas_b200.templates
+sys.path.insert(0, {os.path.join(ROOT, "tests")!r})
+import shim_templates  # tests/ only: the reference's Manager glue (out of scope for the package, SURVEY.md 2 #13)
+optas_b200.templates = shim_templates
+sys.modules["optas.templates"] = shim_templates
 sys.modules["optas.spatialmath"] = optas_b200.spatialmath
 
 
