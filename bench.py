@@ -321,7 +321,7 @@ def run_config(name: str, rank: int, world: int, dev, dist, fp64_tflops, with_cp
     iters_total = int(itd.sum().item())
     # end to end: page-locked host arrays in, page-locked results out (two warm calls: the second set of result buffers
     # of torch's caching host allocator exists from then on, tools/e2e_probe.py)
-    for _ in range(2 if steps > 1 else 1):
+    for _ in range(2):
         r = solver.solve_arrays(P, X0)
     barrier()
     t0 = time.perf_counter()

@@ -620,7 +620,20 @@ int bo_problem_create(const bo_problem_desc* desc, const bo_options* opts_in, bo
   if (pr->sparse && !(pr->opts.flags & BO_FLAG_NO_COOP)) {
     const int tpb = pr->opts.threads_per_block > 0 ? ((pr->opts.threads_per_block + 31) / 32) * 32 : (pr->large ? 256 : 64);
     bo::CoopPlan cp = bo::make_coop_plan(ps, tpb);
-    const size_t smem = (size_t)cp.smem_doubles * sizeof(double);
+    size_t smem = (size_t)cp.smem_doubles * sizeof(double);
+    {
+      // Experiment knob B200OPTAS_COOP_W_SMEM=1: the vectors of the instance in shared memory as well (when they fit).
+      // Measured on B200 and left OFF: C3 789 k -> 582 k inst/s (35 KB per CTA: 6 resident CTAs per SM instead of 16; the
+      // tier is bound by dependent-instruction latency and lives on resident CTAs, not on the L2 round trips of its
+      // workspace), joint-space planner 51.0 k -> 52.2 k.
+      const size_t with_w = smem + bo::coop_scratch_doubles(ps, cp) * sizeof(double);
+      const char* env = getenv("B200OPTAS_COOP_W_SMEM");
+      const size_t limit = (env && atoi(env)) ? 200 * 1024 : 0;
+      if (with_w <= limit) {
+        cp.w_in_smem = true;
+        smem = with_w;
+      }
+    }
     // worth it when the tapes split into enough independent pieces to occupy the CTA (horizon problems do: one
     // piece per stage), or when the problem is too large for a thread anyway
     // ... and the per-instance state is big enough that a CTA beats a thread (the thread-per-instance tiers keep it in

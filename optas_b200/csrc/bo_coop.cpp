@@ -1221,13 +1221,15 @@ std::string emit_coop_source(const ProblemSource& ps, const CoopPlan& pl, int tp
   {
     // resident CTAs per SM the kernel is compiled for (register cap): as many as the shared memory allows, at least
     // 64 registers per thread
-    const int by_smem = (int)(227 * 1024 / std::max<size_t>(1, (size_t)pl.smem_doubles * 8 + 1024));
+    const size_t smem_total = ((size_t)pl.smem_doubles + (pl.w_in_smem ? coop_scratch_doubles(ps, pl) : 0)) * 8;
+    const int by_smem = (int)(227 * 1024 / std::max<size_t>(1, smem_total + 1024));
     const int by_regs = 65536 / (tpb * 64);
     const int min_ctas = std::max(1, std::min(std::min(by_smem, by_regs), 32));
     o << "#define BO_MIN_CTAS " << min_ctas << "\n#define BO_FAC_G " << pl.ldl_g << "\n#define BO_FWD_G " << pl.solve_g
       << "\n#define BO_BWD_G " << pl.solve_bwd_g << "\n";
   }
   if (!hessian_depends_on_eq_multipliers(ps)) o << "#define BO_RECALC_DC_ONLY 1\n";
+  if (pl.w_in_smem) o << "#define BO_W_IN_SMEM 1\n";
   o << "#include \"bo_common.cuh\"\n";
   if (pl.gen_tapes) o << "#define BO_GEN_TAPES 1\n" << pl.gen_code;
   o << "#include \"bo_ipm_cta.cuh\"\n";

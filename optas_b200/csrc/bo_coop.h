@@ -53,6 +53,8 @@ struct CoopPlan {
   int n_work_fc = 1, n_work_kkt = 1, n_work_pre = 1;  // interpreter work slots per sub-tape
   int fc_wstride = 0, kkt_wstride = 0;  // stride of the shared-memory work arrays w[slot][thread]; 0 = thread-local
   int smem_doubles = 0;        // dynamic shared memory of the kernel
+  bool w_in_smem = false;      // the per-instance vector workspace (coop_scratch_doubles) lives in shared memory too, after
+                               // those smem_doubles (small problems: C3); else in a per-CTA slice of global memory
   bool gen_tapes = false;      // tapes compiled to straight-line code per component class (else interpreted)
   std::string gen_code;        // the generated class functions + dispatchers
   int n_levels = 0;            // elimination-tree height (= barriers per factorisation)

@@ -1154,7 +1154,14 @@ bo_solve_kernel(long long B, const double* __restrict__ p_all, const double* __r
   __shared__ long long bo_prof[8];
   C.prof = bo_prof;
 #endif
+#ifdef BO_W_IN_SMEM
+  // small problems (C3: 27 KB of vectors per instance): the whole per-instance state stays on chip.  Round 1 kept it in a
+  // per-CTA slice of global memory "resident in L2": 5.6 GB of DRAM traffic per launch for 32 MB of algorithmic I/O
+  // (profiles/r01_coop_c3_details.txt) and an L2 round trip under every vector operation.
+  C.W = bo_smem + BO_SMEM_DOUBLES;
+#else
   C.W = prm.scratch + (long long)blockIdx.x * BO_SCRATCH_DOUBLES;
+#endif
   C.tab = prm.ldl_tab;
   C.dtab = prm.dtab;
   bo_cta_state S;
