@@ -378,11 +378,30 @@ class B200Solver(Solver):
         n = int(P.shape[0]) if lo.np_ else int(X0.shape[0])
         P = np.ascontiguousarray(P, dtype=np.float64)
         X0 = None if X0 is None else np.ascontiguousarray(X0, dtype=np.float64)
-        out = {"x": host_array((n, lo.nx)), "lam": host_array((n, lo.n_eq + lo.n_ineq)), "f": host_array((n,)),
-               "status": host_array((n,), np.int32), "iters": host_array((n,), np.int32), "kkt": host_array((n,))}
+        out = self._result_buffers(n)
         self._handle.solve(n, P if lo.np_ else None, X0, out["x"], out["lam"], out["f"], out["status"], out["iters"],
                            out["kkt"])
         return out
+
+    def _result_buffers(self, n: int) -> Dict[str, np.ndarray]:
+        """Page-locked result arrays for a batch of ``n``.  Allocating them costs 1.2 ms per call at n = 65536 (measured,
+        tools/e2e_breakdown2.py), so sets are recycled -- but only sets nobody else still holds: a set is reused when the
+        reference count of every array in it shows this pool as the only owner (views handed out by ``solve()`` keep
+        their base array alive, so a caller who still holds a solution keeps its buffers).  A result handed to the caller
+        is therefore never overwritten by a later solve."""
+        import sys
+
+        lo = self._lowered
+        pool = self.__dict__.setdefault("_pool", [])
+        for st in pool:
+            if st["n"] == n and all(sys.getrefcount(a) <= 3 for a in st["arrays"].values()):  # pool dict + loop variable + argument
+                return dict(st["arrays"])
+        arrays = {"x": host_array((n, lo.nx)), "lam": host_array((n, lo.n_eq + lo.n_ineq)), "f": host_array((n,)),
+                  "status": host_array((n,), np.int32), "iters": host_array((n,), np.int32), "kkt": host_array((n,))}
+        pool.append({"n": n, "arrays": arrays})
+        if len(pool) > 4:
+            pool.pop(0)
+        return dict(arrays)
 
     # -- solve --------------------------------------------------------------------------------
     def _run(self) -> np.ndarray:

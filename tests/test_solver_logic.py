@@ -367,3 +367,23 @@ def test_raw_buffers_are_validated_before_the_library_sees_them():
         s.solve_raw(P[:3], X0, X)
     with pytest.raises(ValueError, match="int32"):
         s.solve_raw(P, X0, X, status=np.zeros(4, dtype=np.int64))
+
+
+def test_result_buffers_are_recycled_only_when_nobody_holds_them():
+    """solve_arrays() recycles its page-locked result arrays (allocating them costs more than the PCIe copies), but never a
+    set the caller can still see: a live array or a live VIEW of one (what solve() hands out) keeps its set out of the pool."""
+    prob = problems.booth()
+    s = optas_b200.B200Solver(prob.opt).setup("ipopt", compile_only=True)
+    a = s._result_buffers(100)
+    ida = id(a["x"])
+    b = s._result_buffers(100)
+    assert id(b["x"]) != ida                      # first set still held
+    view = a["x"][:, 0]
+    del a
+    c = s._result_buffers(100)
+    assert id(c["x"]) != ida                      # a view of the first set is alive
+    del view, b, c
+    d = s._result_buffers(100)
+    assert id(d["x"]) in [id(st["arrays"]["x"]) for st in s._pool] and len(s._pool) == 3
+    e = s._result_buffers(7)
+    assert e["x"].shape == (7, 2)                 # another batch size gets its own set
