@@ -208,11 +208,14 @@ CONFIGS = {
     "jsp": dict(factory="joint_space_planner", batch=8192, scaling="weak", opts={}, seed="own", steps=3, cpu=None,
                 label="8f-3: simple_joint_space_planner.py T=20 (nx 280, 154 eq incl. pose goal, 40 link-height ineq)"),
     "qp": dict(factory="planar_idk", batch=65536, scaling="weak", opts={}, seed="own", steps=3, cpu=None,
-               label="8f-1: planar_idk.py differential-IK QP (QuadraticCostLinearConstraints: nx 3, 2 eq, 8 ineq)"),
+               label="8f-1: planar_idk.py differential-IK QP (QuadraticCostLinearConstraints: nx 3, 2 eq, 8 ineq), dedicated QP "
+                     "iteration (Mehrotra predictor-corrector, one tape evaluation per instance; csrc/jit/bo_qp_reg.cuh)"),
+    "qp_general": dict(factory="planar_idk", batch=65536, scaling="weak", opts={}, setup={"qp": False}, seed="own", steps=3, cpu=None,
+                       label="8f-1 comparison: the same QP batch through the general interior-point kernel (round 1's path)"),
     "aik": dict(factory="lwr_axis_ik", batch=65536, scaling="weak", opts={}, seed="own", steps=3, cpu=None,
                 label="8f-3: sphere_collision_avoidance.py first stage, position + tool-axis IK (nx 21, 20 eq, 14 bounds)"),
 }
-DEFAULT_CONFIGS = ["c3", "c3_zero_seed", "c4", "c5", "c5_zero_seed"]
+DEFAULT_CONFIGS = ["c3", "c3_zero_seed", "c4", "c5", "c5_zero_seed", "qp", "qp_general"]
 
 
 def config_inputs(name: str, rank: int, world: int):
@@ -289,7 +292,7 @@ def run_config(name: str, rank: int, world: int, dev, dist, fp64_tflops, with_cp
         return out
 
     P, X0 = pinned(P), pinned(X0)
-    solver = optas_b200.B200Solver(prob.opt).setup("ipopt", cfg["opts"], timing=True)
+    solver = optas_b200.B200Solver(prob.opt).setup("ipopt", cfg["opts"], timing=True, **cfg.get("setup", {}))
     lo = solver._lowered
     Pd, X0d = torch.from_numpy(P).to(dev), torch.from_numpy(X0).to(dev)
     Xd = torch.empty_like(X0d)
@@ -341,7 +344,14 @@ def run_config(name: str, rank: int, world: int, dev, dist, fp64_tflops, with_cp
     # (multiply-add = 2 flop); re-factorisations, substitutions and the extra trial points are NOT counted, so this is
     # a lower bound on the arithmetic actually done
     flop_iter = tape_flops(lo.kkt) + tape_flops(lo.fc) + 2 * int(tier.get("factor_madds", 0))
-    achieved = its / world * flop_iter / (kernel_ms / max(1, kernel_n) * 1e-3) / 1e12  # this rank's launch, TFLOP/s
+    flop_launch = its / world * flop_iter
+    if tier["tier"].startswith("qp"):
+        # QP iteration: the kkt tape twice per instance (seed, final check); per iteration one dense LDL' of the
+        # (nx + n_eq)-row system (n^3 / 3 multiply-adds) -- substitutions and the assembly not counted
+        nk = lo.nx + lo.n_eq
+        flop_iter = 2 * nk ** 3 // 3
+        flop_launch = its / world * flop_iter + 2 * tape_flops(lo.kkt) * B
+    achieved = flop_launch / (kernel_ms / max(1, kernel_n) * 1e-3) / 1e12  # this rank's launch, TFLOP/s
     out = {
         "workload": cfg["label"], "scaling": cfg["scaling"], "global_instances": int(total), "n_gpus": world,
         "value": conv * steps / (dev_ms * 1e-3), "unit": "instances/s", "steps": steps, "ms_per_step": dev_ms / steps,

@@ -107,6 +107,7 @@ typedef struct bo_problem_desc {
 #define BO_FLAG_COOP 32u         /* use the cooperative tier (one instance per CTA, factor in shared memory) even for
                                    a problem small enough for the thread-per-instance sparse tier             */
 #define BO_FLAG_NO_COOP 64u      /* never use the cooperative tier (large problems then run thread-per-instance) */
+#define BO_FLAG_NO_QP 1024u      /* run quadratic programs through the general interior-point kernel (no dedicated QP iteration) */
 #define BO_FLAG_TEAM 512u        /* use the team tier even for a problem small enough that the thread-per-instance kernel is faster */
 #define BO_FLAG_PIPELINE 256u    /* host-buffer calls: cut the batch into chunks on two internal streams so that uploads, kernels
                                    and downloads overlap.  Off by default: measured slower on B200 (each chunk pays its own tail) */
@@ -160,7 +161,8 @@ int bo_problem_kernel_info(const bo_problem* prob, int32_t* regs, int32_t* local
 /* Which tier the problem was lowered to and the sizes of its plan (diagnostics; copies min(cap, BO_TIER_INFO_LEN)):
  *  [0] tier 0 dense / 1 sparse / 2 large (thread per instance)  3 cooperative (CTA per instance)  4 team (G threads
  *      in G warps per instance, state in shared memory; then [10] = G, [8] / [9] = largest / unsliced cost of the kkt
- *      slices, [15] / [16] the same for fc, [18] = shared-memory doubles per instance)
+ *      slices, [15] / [16] the same for fc, [18] = shared-memory doubles per instance)  5 / 6 the dense / sparse
+ *      thread-per-instance tier running the QP iteration (quadratic cost, linear constraints)
  *  [1] threads per CTA  [2] dynamic shared memory bytes  [3] elimination-tree levels  [4]/[5] sub-tapes of fc / kkt
  *  [6] parameter-only values of kkt  [7] partial-sum slots  [8] longest kkt sub-tape  [9] kkt instructions over all
  *  sub-tapes  [10]/[11] lanes per factor target / solve row  [12] multiply-adds per factorisation  [13] work slots

@@ -21,8 +21,8 @@ LIB_PATH = os.path.join(_HERE, "libb200optas.so")
 BO_ABI_VERSION = 1
 BO_OK, BO_ERR_INVALID, BO_ERR_COMPILE, BO_ERR_CUDA, BO_ERR_NO_DEVICE, BO_ERR_UNSUPPORTED = 0, -1, -2, -3, -4, -5
 BO_FLAG_COMPILE_ONLY, BO_FLAG_VERBOSE, BO_FLAG_NO_CACHE, BO_FLAG_TIMING, BO_FLAG_PIVOTED_LDL = 1, 2, 4, 8, 16
-BO_FLAG_COOP, BO_FLAG_NO_COOP, BO_FLAG_NO_TEAM, BO_FLAG_PIPELINE, BO_FLAG_TEAM = 32, 64, 128, 256, 512
-TIER_NAMES = {0: "dense", 1: "sparse", 2: "large", 3: "coop", 4: "team"}
+BO_FLAG_COOP, BO_FLAG_NO_COOP, BO_FLAG_NO_TEAM, BO_FLAG_PIPELINE, BO_FLAG_TEAM, BO_FLAG_NO_QP = 32, 64, 128, 256, 512, 1024
+TIER_NAMES = {0: "dense", 1: "sparse", 2: "large", 3: "coop", 4: "team", 5: "qp", 6: "qp_sparse"}
 STATUS_NAMES = {0: "converged", 1: "acceptable", 2: "max_iter", 3: "line_search", 4: "numerical"}
 
 EXPORTS = [

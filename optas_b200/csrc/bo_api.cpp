@@ -302,7 +302,7 @@ int jit_compile(const std::string& source, const char* unit_name, const char* ke
 
   // hash = source + every header it may include + compiler version
   uint64_t h = fnv1a(source);
-  for (const char* hdr : {"bo_common.cuh", "bo_ipm_reg.cuh", "bo_ipm_cta.cuh", "bo_stream_eval.cuh", "bo_ipm_team.cuh", "bo_team_layout.cuh"}) {
+  for (const char* hdr : {"bo_common.cuh", "bo_ipm_reg.cuh", "bo_qp_reg.cuh", "bo_ipm_cta.cuh", "bo_stream_eval.cuh", "bo_ipm_team.cuh", "bo_team_layout.cuh"}) {
     std::string text;
     if (!read_file(inc + "/" + hdr, &text)) return set_err(BO_ERR_INVALID, "JIT header %s/%s not found", inc.c_str(), hdr);
     h = fnv1a(text, h);
@@ -525,7 +525,7 @@ struct bo_problem {
   DevBuf d_p, d_x0, d_x, d_lam, d_f, d_status, d_iters, d_kkt, d_counter, d_ldl_tab;
   bo::SparsePlan plan;
   bo::CoopPlan coop_plan;
-  bool sparse = false, large = false, coop = false, team = false;
+  bool sparse = false, large = false, coop = false, team = false, qp = false;
   bo::TeamPlan team_plan;
   int smem_dynamic = 0;
   DevBuf d_dtab, d_scratch;
@@ -653,12 +653,16 @@ int bo_problem_create(const bo_problem_desc* desc, const bo_options* opts_in, bo
       pr->coop_plan = std::move(cp);
     }
   }
+  // QP path (csrc/jit/bo_qp_reg.cuh): quadratic cost with linear constraints, decided from the tape.  The thread-per-instance
+  // tiers run it (it needs no trial points and no per-iteration tape, so its state is small); horizon-sized QPs that
+  // qualify for the cooperative tier stay there.
+  pr->qp = !pr->coop && !pr->large && !pivoted && !(pr->opts.flags & (BO_FLAG_NO_QP | BO_FLAG_TEAM)) && bo::problem_is_qp(ps);
   // Team tier (csrc/jit/bo_ipm_team.cuh): small dense problems, G threads in G warps per instance, state in shared memory
   // Measured on B200 (tools/team_check.py, profiles/r02_team_vs_thread.txt): the team tier wins once the per-instance state
   // no longer fits a thread (C2: 24 rows of variables + constraints, 3 KB of thread-local state: 6.0 vs 10.2 ms per 65536)
   // and loses below that (planar differential-IK QP, 13 rows, 1.7 KB: 0.51 vs 0.26 ms; Booth 14.5 vs 9.9 us per 4096).
   const bool team_worth_it = ps.nx + ps.n_eq + ps.n_ineq >= 20 || (pr->opts.flags & BO_FLAG_TEAM);
-  if (!pr->sparse && !pivoted && team_worth_it && !(pr->opts.flags & BO_FLAG_NO_TEAM)) {
+  if (!pr->sparse && !pivoted && !pr->qp && team_worth_it && !(pr->opts.flags & BO_FLAG_NO_TEAM)) {
     int G = pr->opts.threads_per_block > 0 ? pr->opts.threads_per_block / 32 : 4;
     G = std::max(1, std::min(G, 8));
     std::string why;
@@ -677,7 +681,7 @@ int bo_problem_create(const bo_problem_desc* desc, const bo_options* opts_in, bo
     pr->source = bo::emit_coop_source(ps, pr->coop_plan, pr->tpb);
   } else {
     if (pr->sparse) pr->plan = bo::make_sparse_plan(ps, pr->large);
-    pr->source = bo::emit_problem_source(ps, pr->tpb, pivoted, pr->sparse ? &pr->plan : nullptr, pr->large);
+    pr->source = bo::emit_problem_source(ps, pr->tpb, pivoted, pr->sparse ? &pr->plan : nullptr, pr->large, pr->qp);
   }
   if (getenv("BO_DEBUG")) fprintf(stderr, "[bo] source %zu bytes\n", pr->source.size());
   int rc = jit_compile(pr->source, "bo_solve", "bo_solve_kernel", pr->opts, &pr->compiled);
@@ -808,6 +812,7 @@ int bo_problem_tier_info(const bo_problem* pr, int64_t* info, int32_t cap) {
   if (!pr) return set_err(BO_ERR_INVALID, "null problem");
   int64_t v[BO_TIER_INFO_LEN] = {0};
   v[0] = pr->team ? 4 : (pr->coop ? 3 : (pr->large ? 2 : (pr->sparse ? 1 : 0)));
+  if (pr->qp) v[0] = pr->sparse ? 6 : 5;
   v[1] = pr->tpb;
   v[2] = pr->smem_dynamic;
   if (pr->coop) {

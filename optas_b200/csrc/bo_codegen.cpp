@@ -267,9 +267,33 @@ bool hessian_depends_on_eq_multipliers(const ProblemSource& ps) {
   return false;
 }
 
-std::string emit_problem_source(const ProblemSource& ps, int tpb, bool pivoted_ldl, const SparsePlan* sparse, bool large) {
+bool problem_is_qp(const ProblemSource& ps) {
+  // forward taint pass over the (slot-reusing) tape: bit k = "depends on input segment k" (0 x, 1 p, 2 y, 3 z)
+  std::vector<uint8_t> taint((size_t)std::max(ps.kkt.n_work, 1), 0);
+  for (int64_t i = 0; i < ps.kkt.n_instr(); ++i) {
+    const int32_t* r = &ps.kkt.instr[4 * i];
+    const int op = r[0] & 0xFF;
+    if (op == BO_OP_INPUT) {
+      taint[r[1]] = (uint8_t)(1u << r[3]);
+    } else if (op == BO_OP_CONST) {
+      taint[r[1]] = 0;
+    } else if (op == BO_OP_OUTPUT) {
+      if (r[3] >= 4 && (taint[r[1]] & 0x0D)) return false;  // output segments 4, 5, 6 = jac_eq, jac_ineq, hess
+    } else if (op == BO_OP_IF_ELSE) {
+      taint[r[1]] = taint[r[2]] | taint[r[3]] | taint[(uint32_t)r[0] >> 8];
+    } else if (is_unary(op)) {
+      taint[r[1]] = taint[r[2]];
+    } else {
+      taint[r[1]] = taint[r[2]] | taint[r[3]];
+    }
+  }
+  return true;
+}
+
+std::string emit_problem_source(const ProblemSource& ps, int tpb, bool pivoted_ldl, const SparsePlan* sparse, bool large, bool qp) {
   std::ostringstream o;
   o << "// generated by libb200optas (bo_codegen.cpp): tier-S solver, one instance per thread\n";
+  if (qp) o << "#define BO_QP 1\n";
   o << "#define BO_NX " << ps.nx << "\n#define BO_NP " << ps.np << "\n#define BO_ME " << ps.n_eq << "\n#define BO_MI "
     << ps.n_ineq << "\n#define BO_NNZ_JE " << ps.jac_eq.nnz() << "\n#define BO_NNZ_JI " << ps.jac_ineq.nnz()
     << "\n#define BO_NNZ_H " << ps.hess.nnz() << "\n#define BO_TPB " << tpb << "\n";
@@ -331,6 +355,14 @@ std::string emit_problem_source(const ProblemSource& ps, int tpb, bool pivoted_l
     }
   }
   o << "  (void)JE; (void)rho; (void)K;\n}\n";
+  // out = H v (H: lower triangle of a symmetric matrix) -- the QP path moves the gradient along a step with it
+  o << "BO_DEVICE void bo_H_mul(const double* BO_RESTRICT H, const double* BO_RESTRICT v, double* BO_RESTRICT out) {\n";
+  o << "  for (int i = 0; i < " << ps.nx << "; ++i) out[i] = 0.0;\n";
+  for (int k = 0; k < ps.hess.nnz(); ++k) {
+    o << "  out[" << ps.hess.row[k] << "] += H[" << k << "] * v[" << ps.hess.col[k] << "];\n";
+    if (ps.hess.row[k] != ps.hess.col[k]) o << "  out[" << ps.hess.col[k] << "] += H[" << k << "] * v[" << ps.hess.row[k] << "];\n";
+  }
+  o << "  (void)H; (void)v; (void)out;\n}\n";
   o << "\n";
   o << "#include \"bo_ipm_reg.cuh\"\n";
   return o.str();

@@ -58,7 +58,10 @@ bool hessian_depends_on_eq_multipliers(const ProblemSource& ps);
 // Full translation unit of the tier-S (thread-per-instance) solver for this problem.
 struct SparsePlan;
 std::string emit_problem_source(const ProblemSource& ps, int threads_per_block, bool pivoted_ldl,
-                                const SparsePlan* sparse = nullptr, bool large = false);
+                                const SparsePlan* sparse = nullptr, bool large = false, bool qp = false);
+// Quadratic cost, linear constraints: no Jacobian or Hessian output of the kkt tape depends on x, y or z (decided from the
+// tape, not from the declared problem class).  Such problems run the dedicated QP iteration (csrc/jit/bo_qp_reg.cuh).
+bool problem_is_qp(const ProblemSource& ps);
 // Full translation unit of the streaming evaluation kernel for one tape.
 std::string emit_function_source(const Tape& tape, int threads_per_block, int out_stages = 2);
 

@@ -607,6 +607,10 @@ struct bo_ipm_state {
 BO_NOINLINE void bo_eval_fc(const double* x, const double* p, double* f, double* cE, double* cI) { bo_tape_fc(x, p, f, cE, cI); }
 #endif
 
+#ifdef BO_QP
+// quadratic cost, linear constraints: the dedicated iteration replaces everything below (same state, same linear algebra)
+#include "bo_qp_reg.cuh"
+#else
 // Start an instance: S.p and S.x hold the parameters and the seed.
 BO_DEVICE void bo_ipm_init(bo_ipm_state& S, const bo_solver_params prm) {
   S.mu = prm.mu_init;
@@ -1231,3 +1235,4 @@ bo_solve_kernel(long long B, const double* __restrict__ p_all, const double* __r
   }
 }
 #endif
+#endif  // BO_QP

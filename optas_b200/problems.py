@@ -339,6 +339,65 @@ def planar_idk() -> Problem:
     return Problem("planar_idk", opt, sample, {"J": J}, {"robot": robot})
 
 
+def lwr_diff_ik_qp(dt: float = 0.01) -> Problem:
+    """Differential IK as a QP (reference: example/experiment1.py:14-128, class ExprIK / IK1 -- there on the OSQP interface,
+    3000 ticks): min |dq|^2 + 1000 |J(qc) dq - v_goal|^2  s.t.  joint limits on qc + dt dq, z-band on the end effector.
+    nx 7, no equalities, 16 inequality rows; J, the limits and the z-band depend on the parameters (qc, xydir) only."""
+    robot = RobotModel(urdf_filename=LWR_URDF, time_derivs=[1])
+    name = robot.get_name()
+    builder = OptimizationBuilder(T=1, robots=[robot], derivs_align=True)
+    qd = builder.get_model_state(name, 0, time_deriv=1)
+    qc = builder.add_parameter("qc", robot.ndof)
+    xydir = builder.add_parameter("xydir", 2)
+    J = robot.get_global_link_geometric_jacobian(LWR_EE, qc)
+    veff = J @ qd
+    builder.add_cost_term("min_qd", cs.sumsqr(qd))
+    vg = cs.vertcat(0.1 * xydir, cs.DM.zeros(4))
+    builder.add_cost_term("eff_motion", 1000.0 * cs.sumsqr(veff - vg))
+    lo, up = robot.lower_actuated_joint_limits, robot.upper_actuated_joint_limits
+    qn = qc + dt * qd
+    builder.add_leq_inequality_constraint("lower_qlim", lo, qn)
+    builder.add_leq_inequality_constraint("upper_qlim", qn, up)
+    pn = robot.get_global_link_position(LWR_EE, qc) + dt * veff[:3]
+    builder.add_leq_inequality_constraint("lower_zlim", 0.025, pn[2])
+    builder.add_leq_inequality_constraint("upper_zlim", pn[2], 1.5)
+    opt = builder.build()
+
+    def sample(B: int, seed: int = 6):
+        rng = np.random.default_rng(seed)
+        qc_ = LWR_Q_NOMINAL + 0.3 * rng.standard_normal((B, 7))
+        ang = rng.uniform(0.0, 2.0 * np.pi, B)
+        return np.ascontiguousarray(np.concatenate([qc_, np.cos(ang)[:, None], np.sin(ang)[:, None]], axis=1)), np.zeros((B, 7))
+
+    return Problem("lwr_diff_ik_qp", opt, sample, {}, {"robot": robot})
+
+
+def box_qp(n: int = 8, n_eq: int = 3, seed: int = 0) -> Problem:
+    """A family of strictly convex QPs with active bounds (test workload of the QP path): min x'Px + q'x  s.t.  A x = b,
+    -1 <= x <= 1, with P, A fixed and (q, b) the parameters -- about n/3 of the bounds are active at the solution."""
+    rng = np.random.default_rng(seed)
+    L = rng.standard_normal((n, n))
+    Pm = L @ L.T / n + 0.05 * np.eye(n)
+    A = rng.standard_normal((n_eq, n))
+    task = TaskModel("v", n, time_derivs=[0])
+    builder = OptimizationBuilder(T=1, tasks=[task])
+    x = builder.get_model_state("v", 0)
+    q = builder.add_parameter("q", n)
+    builder.add_cost_term("quad", x.T @ cs.DM(Pm) @ x + q.T @ x)
+    if n_eq > 0:
+        rhs = builder.add_parameter("rhs", n_eq)
+        builder.add_equality_constraint("lin", cs.DM(A) @ x, rhs)
+    builder.add_bound_inequality_constraint("box", [-1.0] * n, x, [1.0] * n)
+    opt = builder.build()
+
+    def sample(B: int, seed: int = 7):
+        r = np.random.default_rng(seed)
+        return (np.ascontiguousarray(np.concatenate([3.0 * r.standard_normal((B, n)), 0.3 * r.standard_normal((B, n_eq))], axis=1)),
+                np.zeros((B, n)))
+
+    return Problem(f"box_qp_{n}_{n_eq}", opt, sample, {}, {"P": Pm, "A": A})
+
+
 # ----------------------------------------------------------------------------------------------
 # "Next" row 8f-3: the rest of the RobotModel surface through the same solver
 #   joint-space planner to an end-effector POSE with height constraints on two links
@@ -481,4 +540,4 @@ def sphere_collision_avoidance(T: int = 20, n_obstacles: int = 6, reduce_constra
     return Problem("sphere_collision_avoidance", opt, sample, {}, {"robot": robot})
 
 
-ALL_BUILDERS = [lwr_ik, booth, point_mass_mpc, figure_eight, dual_arm, planar_idk, joint_space_planner, lwr_axis_ik]
+ALL_BUILDERS = [lwr_ik, booth, point_mass_mpc, figure_eight, dual_arm, planar_idk, joint_space_planner, lwr_axis_ik, lwr_diff_ik_qp]

@@ -302,7 +302,8 @@ class B200Solver(Solver):
     def setup(self, solver_name: Optional[str] = None, solver_options: Optional[Dict] = None, *,
               method: Optional[str] = None, tol: Optional[float] = None, options: Optional[Dict] = None,
               compile_only: bool = False, timing: bool = False, threads_per_block: int = 0, max_trips: int = 0,
-              blocks_per_sm: int = 0, pivoted_ldl: bool = False, coop: Optional[bool] = None, team: Optional[bool] = None):
+              blocks_per_sm: int = 0, pivoted_ldl: bool = False, coop: Optional[bool] = None, team: Optional[bool] = None,
+              qp: Optional[bool] = None):
         from . import _capi
 
         name = solver_name if solver_name is not None else (method if method is not None else "ipopt")
@@ -342,7 +343,8 @@ class B200Solver(Solver):
         flags = ((_capi.BO_FLAG_COMPILE_ONLY if compile_only else 0) | (_capi.BO_FLAG_TIMING if timing else 0)
                  | (_capi.BO_FLAG_PIVOTED_LDL if pivoted_ldl else 0)
                  | (_capi.BO_FLAG_COOP if coop else 0) | (_capi.BO_FLAG_NO_COOP if coop is False else 0)
-                 | (_capi.BO_FLAG_NO_TEAM if team is False else 0) | (_capi.BO_FLAG_TEAM if team else 0))
+                 | (_capi.BO_FLAG_NO_TEAM if team is False else 0) | (_capi.BO_FLAG_TEAM if team else 0)
+                 | (_capi.BO_FLAG_NO_QP if qp is False else 0))
         self._handle = _capi.ProblemHandle(self._lowered, flags=flags, max_iter=max_iter, tol=tol_use,
                                            acceptable_tol=acc_tol, mu_init=mu_init, max_step=max_step,
                                            threads_per_block=threads_per_block, max_trips=max_trips,

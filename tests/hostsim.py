@@ -150,7 +150,7 @@ class HostSim:
         coop = "#define BO_COOP 1" in generated_source
         wrapper = _WRAPPER_TEAM if "#define BO_TEAM 1" in generated_source else (_WRAPPER_COOP if coop else _WRAPPER)
         key += hashlib.sha1(wrapper.encode()).hexdigest()[:8]
-        for name in ("bo_common.cuh", "bo_ipm_reg.cuh", "bo_ipm_cta.cuh", "bo_ipm_team.cuh", "bo_team_layout.cuh"):
+        for name in ("bo_common.cuh", "bo_ipm_reg.cuh", "bo_qp_reg.cuh", "bo_ipm_cta.cuh", "bo_ipm_team.cuh", "bo_team_layout.cuh"):
             key += hashlib.sha1(open(os.path.join(_JIT_INC, name), "rb").read()).hexdigest()[:8]
         d = os.path.join(tempfile.gettempdir(), "b200optas_hostsim")
         os.makedirs(d, exist_ok=True)

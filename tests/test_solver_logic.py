@@ -273,7 +273,7 @@ def test_tier_choice_follows_the_measured_rule():
     profiles/r01_tier_choice.txt / r01_tier_break_even.txt, r02_team_vs_thread.txt): up to 14 KKT rows the team tier (state in
     shared memory) when variables + constraints >= 20, else the thread-per-instance dense tier; thread-per-instance sparse for
     mid-size problems; one instance per CTA once nx + n_eq + n_ineq > 64 and the tapes split into stages."""
-    expect = [(problems.lwr_ik(), "team"), (problems.planar_idk(), "dense"), (problems.lwr_axis_ik(), "sparse"),
+    expect = [(problems.lwr_ik(), "team"), (problems.planar_idk(), "qp"), (problems.booth(), "qp"), (problems.lwr_axis_ik(), "sparse"),
               (problems.point_mass_mpc(T=6), "coop"), (problems.point_mass_mpc(), "coop"), (problems.joint_space_planner(), "coop")]
     for prob, tier in expect:
         s = optas_b200.B200Solver(prob.opt).setup("ipopt", compile_only=True)
@@ -294,7 +294,7 @@ def test_team_tier_takes_the_same_iterations_as_the_thread_tier():
         lo = lower_problem(prob.opt)
         P, X0 = prob.sample(B, seed=3)
         res = {}
-        for label, flag in (("team", _capi.BO_FLAG_TEAM), ("thread", _capi.BO_FLAG_NO_TEAM)):
+        for label, flag in (("team", _capi.BO_FLAG_TEAM), ("thread", _capi.BO_FLAG_NO_TEAM | _capi.BO_FLAG_NO_QP)):
             h = _capi.ProblemHandle(lo, flags=_capi.BO_FLAG_COMPILE_ONLY | flag)
             assert h.tier_info()["tier"] == ("team" if label == "team" else "dense")
             res[label] = HostSim(h.source(), lo.nx, lo.np_, lo.n_eq, lo.n_ineq).solve(P, X0, max_step=h.options()["max_step"])
@@ -303,6 +303,117 @@ def test_team_tier_takes_the_same_iterations_as_the_thread_tier():
         assert np.array_equal(a["trips"], b["trips"])
         ok = a["status"] == 0
         assert ok.mean() > 0.99 and np.abs(a["x"][ok] - b["x"][ok]).max() < 1e-9
+
+
+# ---- the QP path (csrc/jit/bo_qp_reg.cuh) ------------------------------------------------------------
+def _sim_of(prob, **kw):
+    s = optas_b200.B200Solver(prob.opt).setup("ipopt", compile_only=True, **kw)
+    lo = s._lowered
+    return s, lo, HostSim(s.kernel_source(), lo.nx, lo.np_, lo.n_eq, lo.n_ineq, ldl_table=s.ldl_table())
+
+
+def test_qp_path_is_chosen_from_the_tape_not_from_the_class_name():
+    """bo_problem_create runs the QP iteration exactly when no Jacobian / Hessian output of the kkt tape depends on x, y, z
+    (reference: OSQPSolver / CVXOPTSolver take P, q, M, c, A, b as functions of p only, optas/solver.py:455-467, 540-551)."""
+    for prob, want in ((problems.planar_idk(), "qp"), (problems.lwr_diff_ik_qp(), "qp"), (problems.box_qp(), "qp"),
+                       (problems.booth(), "qp"), (problems.lwr_ik(), "team"), (problems.lwr_axis_ik(), "sparse")):
+        s = optas_b200.B200Solver(prob.opt).setup("ipopt", compile_only=True)
+        assert s.tier_info()["tier"] == want, (prob.name, s.tier_info())
+    off = optas_b200.B200Solver(problems.planar_idk().opt).setup("ipopt", compile_only=True, qp=False)
+    assert off.tier_info()["tier"] == "dense"  # BO_FLAG_NO_QP: the general interior-point kernel
+    mid = optas_b200.B200Solver(problems.box_qp(24, 4).opt).setup("ipopt", compile_only=True, coop=False)
+    assert mid.tier_info()["tier"] == "qp_sparse"
+
+
+@pytest.mark.parametrize("make", [problems.planar_idk, problems.lwr_diff_ik_qp, problems.box_qp, lambda: problems.box_qp(12, 0, seed=3)])
+def test_qp_path_matches_the_oracle_and_the_interior_point_kernel(make):
+    """Same minimiser as the general kernel and as scipy SLSQP on the numpy closed form of the QP, the oracle's KKT residual
+    at tol, fewer iterations, and f / kkt reported at the returned x (re-evaluated by the tape, not carried along)."""
+    from scipy.optimize import minimize
+
+    prob = make()
+    P, X0 = prob.sample(192)
+    s, lo, sim = _sim_of(prob)
+    assert s.tier_info()["tier"] == "qp"
+    r = sim.solve(P, X0, max_step=s._handle.options()["max_step"])
+    assert (r["status"] == 0).all() and r["kkt"].max() <= 1e-8
+    # IPOPT's scaled error (s_d, s_c: instances that start outside their limits carry large multipliers)
+    res = kkt_check.kkt_residual(prob, r["x"][:48], P[:48], r["lam"][:48, :lo.n_eq], r["lam"][:48, lo.n_eq:], scaled=True)
+    assert res.max() < 2e-8
+    _, _, gen = _sim_of(prob, qp=False)
+    g = gen.solve(P, X0, max_step=s._handle.options()["max_step"])
+    both = g["status"] == 0
+    assert both.mean() > 0.9 and r["iters"][both].mean() < g["iters"][both].mean()
+    assert np.abs(r["f"] - g["f"])[both].max() < 1e-6 * max(1.0, np.abs(g["f"][both]).max())
+    # f is evaluated AT x: re-evaluate the objective with the oracle's tape interpreter
+    import tape_vm
+    f_at_x = tape_vm.CTape(lo.fc)(r["x"][:8], P[:8])[0].ravel()
+    assert np.abs(f_at_x - r["f"][:8]).max() <= 1e-12 * max(1.0, np.abs(f_at_x).max())
+    if "P" in prob.models:  # the box family has a closed form: independent active-set solve (scipy SLSQP)
+        Pm, A = prob.models["P"], prob.models["A"]
+        n, me = Pm.shape[0], A.shape[0]
+        for i in range(6):
+            q, b = P[i, :n], P[i, n:]
+            cons = [{"type": "eq", "fun": lambda v: A @ v - b, "jac": lambda v: A}] if me else []
+            ref = minimize(lambda v: v @ Pm @ v + q @ v, np.zeros(n), jac=lambda v: 2 * Pm @ v + q, method="SLSQP",
+                           bounds=[(-1, 1)] * n, constraints=cons, options={"ftol": 1e-14, "maxiter": 500})
+            assert ref.status in (0, 8) and np.abs(ref.x - r["x"][i]).max() < 1e-6  # 8: no further descent at the minimiser
+
+
+def test_qp_path_edge_cases():
+    """Equality-only and unconstrained QPs take ONE Newton step; a semidefinite Hessian and linearly dependent equality rows
+    are regularised; an infeasible QP ends with a failure status instead of spinning."""
+    import optas_b200.sym as cs
+    from optas_b200.builder import OptimizationBuilder
+    from optas_b200.models import TaskModel
+
+    rng = np.random.default_rng(1)
+    n = 6
+
+    def build(Pm, A, box):
+        b = OptimizationBuilder(T=1, tasks=[TaskModel("v", n, time_derivs=[0])])
+        x = b.get_model_state("v", 0)
+        q = b.add_parameter("q", n)
+        b.add_cost_term("quad", x.T @ cs.DM(Pm) @ x + q.T @ x)
+        if A is not None:
+            b.add_equality_constraint("lin", cs.DM(A) @ x, b.add_parameter("rhs", A.shape[0]))
+        if box:
+            b.add_bound_inequality_constraint("box", [-1.0] * n, x, [1.0] * n)
+        return b.build()
+
+    def run(opt, P, X0, **kw):
+        s = optas_b200.B200Solver(opt).setup("ipopt", compile_only=True, **kw)
+        lo = s._lowered
+        sim = HostSim(s.kernel_source(), lo.nx, lo.np_, lo.n_eq, lo.n_ineq)
+        return s.tier_info()["tier"], sim.solve(P, X0, max_step=s._handle.options()["max_step"])
+
+    Ppd = np.eye(n) + 0.1 * np.ones((n, n))
+    # unconstrained: x = -(2P)^-1 q in one step, whatever the seed
+    Q = rng.standard_normal((16, n))
+    tier, r = run(build(Ppd, None, False), Q, rng.standard_normal((16, n)))
+    assert tier == "qp" and (r["status"] == 0).all() and (r["iters"] == 1).all()
+    assert np.abs(r["x"] - np.linalg.solve(2 * Ppd, -Q.T).T).max() < 1e-12
+    # equality-only
+    A = rng.standard_normal((2, n))
+    tier, r = run(build(Ppd, A, False), rng.standard_normal((16, n + 2)), rng.standard_normal((16, n)))
+    assert (r["status"] == 0).all() and (r["iters"] == 1).all()
+    # rank-2 Hessian inside a box
+    L = rng.standard_normal((n, 2))
+    opt = build(L @ L.T, None, True)
+    Q = rng.standard_normal((32, n))
+    _, r = run(opt, Q, np.zeros((32, n)))
+    _, g = run(opt, Q, np.zeros((32, n)), qp=False)
+    assert (r["status"] == 0).all() and np.abs(r["f"] - g["f"]).max() < 1e-6
+    # dependent equality rows (consistent right-hand sides)
+    a = rng.standard_normal((1, n))
+    rhs = rng.standard_normal((16, 1))
+    _, r = run(build(Ppd, np.concatenate([a, 2 * a]), True), np.concatenate([rng.standard_normal((16, n)), rhs, 2 * rhs], axis=1), np.zeros((16, n)))
+    assert (r["status"] <= 1).all()
+    # infeasible: x0 + x1 = 5 inside [-1, 1]^n
+    A = np.zeros((1, n))
+    A[0, :2] = 1.0
+    _, r = run(build(Ppd, A, True), np.concatenate([rng.standard_normal((4, n)), 5 * np.ones((4, 1))], axis=1), np.zeros((4, n)))
+    assert (r["status"] >= 2).all() and (r["trips"] <= 250).all()
 
 
 # ---- option defaults (round-1 advisor findings) ----------------------------------------------------------------------
