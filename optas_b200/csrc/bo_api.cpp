@@ -394,6 +394,18 @@ bool is_device_ptr(const void* p) {
   return type == CU_MEMORYTYPE_DEVICE || type == CU_MEMORYTYPE_UNIFIED;
 }
 
+// Page-locked host memory is mapped into the device address space (unified addressing): a kernel can read and write it in
+// place.  Returns the device-side address of such a buffer, 0 for anything else (pageable host memory, device memory).
+CUdeviceptr mapped_host_ptr(const void* p) {
+  if (!p) return 0;
+  unsigned int type = 0;
+  if (g_drv.cuPointerGetAttribute(&type, CU_POINTER_ATTRIBUTE_MEMORY_TYPE, (CUdeviceptr)(uintptr_t)p) != CUDA_SUCCESS) return 0;
+  if (type != CU_MEMORYTYPE_HOST) return 0;
+  CUdeviceptr d = 0;
+  if (g_drv.cuPointerGetAttribute(&d, CU_POINTER_ATTRIBUTE_DEVICE_POINTER, (CUdeviceptr)(uintptr_t)p) != CUDA_SUCCESS) return 0;
+  return d;
+}
+
 // grow-only device scratch buffer
 struct DevBuf {
   CUdeviceptr ptr = 0;
@@ -894,14 +906,31 @@ int bo_solve(bo_problem* pr, int64_t B, const double* p, const double* x0, doubl
   }
 
   CUdeviceptr dp, dx0, dx, dlam, df, dstat, dit, dkkt;
+  // Page-locked host buffers are handed to the kernel as they are (zero copy): every instance reads its p / x0 row once
+  // when it starts (the team tier by bulk copies a tile ahead) and writes its results once when it ends, so the PCIe
+  // traffic hides under the iterations of the other instances instead of two serial copies around the launch.
+  // B200OPTAS_ZERO_COPY = 0 none, 1 results only, 2 (default) inputs and results.  Pageable buffers are staged.
+  static const int zero_copy_mode = [] {
+    const char* e = getenv("B200OPTAS_ZERO_COPY");
+    return e ? atoi(e) : 2;
+  }();
+  bool any_mapped = false;
   // device staging buffers for the whole batch (chunks address them by offset)
-  auto stage = [&](const void* host, size_t bytes_per, DevBuf& buf, CUdeviceptr* dptr, bool* is_host) -> int {
+  auto stage = [&](const void* host, size_t bytes_per, DevBuf& buf, CUdeviceptr* dptr, bool* is_host, bool is_input = false) -> int {
     *dptr = 0;
     *is_host = false;
     if (!host || bytes_per == 0) return BO_OK;
     if (is_device_ptr(host)) {
       *dptr = (CUdeviceptr)(uintptr_t)host;
       return BO_OK;
+    }
+    if (n_chunks == 1 && zero_copy_mode >= (is_input ? 2 : 1)) {
+      const CUdeviceptr m = mapped_host_ptr(host);
+      if (m) {
+        *dptr = m;
+        any_mapped = true;
+        return BO_OK;
+      }
     }
     *is_host = true;
     int r = buf.reserve((size_t)B * bytes_per);
@@ -910,16 +939,16 @@ int bo_solve(bo_problem* pr, int64_t B, const double* p, const double* x0, doubl
     return BO_OK;
   };
   bool hp, hx0, hx, hlam, hf, hstat, hit, hkkt;
-  if ((rc = stage(p, np * sizeof(double), pr->d_p, &dp, &hp)) != BO_OK) return rc;
-  if ((rc = stage(x0, nx * sizeof(double), pr->d_x0, &dx0, &hx0)) != BO_OK) return rc;
+  if ((rc = stage(p, np * sizeof(double), pr->d_p, &dp, &hp, true)) != BO_OK) return rc;
+  if ((rc = stage(x0, nx * sizeof(double), pr->d_x0, &dx0, &hx0, true)) != BO_OK) return rc;
   if ((rc = stage(x, nx * sizeof(double), pr->d_x, &dx, &hx)) != BO_OK) return rc;
   if ((rc = stage(lam, nl * sizeof(double), pr->d_lam, &dlam, &hlam)) != BO_OK) return rc;
   if ((rc = stage(f, sizeof(double), pr->d_f, &df, &hf)) != BO_OK) return rc;
   if ((rc = stage(status, sizeof(int32_t), pr->d_status, &dstat, &hstat)) != BO_OK) return rc;
   if ((rc = stage(iters, sizeof(int32_t), pr->d_iters, &dit, &hit)) != BO_OK) return rc;
   if ((rc = stage(kkt_res, sizeof(double), pr->d_kkt, &dkkt, &hkkt)) != BO_OK) return rc;
-  const bool any_host = hp || hx0 || hx || hlam || hf || hstat || hit || hkkt;
-  if (!any_host) n_chunks = 1;
+  const bool any_host = hp || hx0 || hx || hlam || hf || hstat || hit || hkkt || any_mapped;
+  if (!(hp || hx0 || hx || hlam || hf || hstat || hit || hkkt)) n_chunks = 1;
 
   SolverParams prm{pr->opts.max_iter, pr->opts.tol, pr->opts.acceptable_tol, pr->opts.mu_init, pr->opts.max_step,
                    pr->opts.max_trips, pr->sparse ? pr->d_ldl_tab.ptr : 0, (pr->large || pr->coop) ? pr->d_dtab.ptr : 0,

@@ -65,3 +65,12 @@ struct bo_solver_params {
 #define BO_ST_MAX_ITER 2
 #define BO_ST_LINE_SEARCH 3
 #define BO_ST_NUMERICAL 4
+
+// IPOPT's Jacobian-degeneracy heuristic (PDPerturbationHandler) counts an iteration as "singular" when the KKT matrix
+// with dc = 0 was reported singular and dc > 0 cured it -- at whatever Hessian perturbation dw that happened, not only on
+// the unperturbed first attempt (1: any attempt; 0: round-1 behaviour, first attempt only).  Three such iterations in a
+// row switch dc on from the first attempt: in a non-convex region (dw > 0 every iteration) that saves the
+// (dw, 0) factorisation of every later iteration without changing the system that is finally solved.
+#ifndef BO_SINGULAR_ANY_ATTEMPT
+#define BO_SINGULAR_ANY_ATTEMPT 1
+#endif

@@ -903,7 +903,7 @@ BO_DEVICE int bo_cta_trip_factor(bo_cta_state& S, const bo_cta& C, const bo_solv
   if (inertia != 0) {
     if (inertia < 0 && BO_ME > 0 && S.dc == 0.0) {
       S.dc = BO_DC_SCALE * sqrt(sqrt(S.mu));
-      if (S.attempt == 0) S.first_singular = true;
+      if (S.attempt == 0 || BO_SINGULAR_ANY_ATTEMPT) S.first_singular = true;
     } else if (S.dw == 0.0) {
       S.dw = (S.dw_last == 0.0) ? 1e-4 : fmax(1e-20, S.dw_last / 3.0);
     } else {

@@ -43,6 +43,17 @@
 #endif
 #define BO_KIDX(i, j) (((i) * ((i) + 1)) / 2 + (j)) /* packed lower triangle, i >= j */
 #define BO_DIM(n) ((n) > 0 ? (n) : 1)
+// A pivot of the x block counts as "not positive" below this fraction of its diagonal entry.  The interior-point kernel
+// reads the inertia from it (a small pivot = a direction of negative / zero curvature: more dw).  The QP path knows its
+// matrix is positive semidefinite; there a small ratio is only the usual ill-conditioning of Z/S near the solution, and
+// regularising it away would spoil the Newton step: it accepts pivots down to rounding level.
+#ifndef BO_PIVOT_RTOL
+#ifdef BO_QP
+#define BO_PIVOT_RTOL 1e-16
+#else
+#define BO_PIVOT_RTOL 1e-13
+#endif
+#endif
 
 // ---- fast path: unpivoted LDL' with a fixed elimination order (x first, then y) ----
 // Every lane executes the same instruction sequence (no data-dependent pivoting), the loops have
@@ -87,7 +98,7 @@ BO_NOINLINE int bo_ldl_static(double* BO_RESTRICT A) {
       d -= l * l * A[BO_KIDX(k, k)];
     }
     if (j < BO_NX) {
-      if (!(d > 1e-13 * scale) && bad == 0) bad = 1;
+      if (!(d > BO_PIVOT_RTOL * scale) && bad == 0) bad = 1;
     } else {
       if (!(d < -1e-13) && bad == 0) bad = 2;
     }
@@ -162,7 +173,7 @@ BO_NOINLINE int bo_ldl_sparse(double* BO_RESTRICT vals, long long stride, const 
       for (; c < cnt; ++c, pc += 2) BO_V(prog[pc]) -= BO_V(prog[pc + 1]) * w;
     }
     if (sign[j] > 0) {
-      if (!(d > 1e-13 * scale) && bad == 0) bad = 1;
+      if (!(d > BO_PIVOT_RTOL * scale) && bad == 0) bad = 1;
     } else {
       if (!(d < -1e-13) && bad == 0) bad = 2;
     }
@@ -908,7 +919,7 @@ BO_DEVICE int bo_trip_factor(bo_ipm_state& S, const bo_solver_params prm) {
       // ---- inertia correction (IPOPT Algorithm IC); retried on the next trip ----
       if (inertia < 0 && BO_ME > 0 && S.dc == 0.0) {
         S.dc = BO_DC_SCALE * sqrt(sqrt(S.mu));  // IPOPT: 1e-8 mu^(1/4)  // singular: perturb the constraint block first
-      if (S.attempt == 0) S.first_singular = true;
+      if (S.attempt == 0 || BO_SINGULAR_ANY_ATTEMPT) S.first_singular = true;
       } else if (S.dw == 0.0) {
         S.dw = (S.dw_last == 0.0) ? 1e-4 : fmax(1e-20, S.dw_last / 3.0);
       } else {

@@ -550,7 +550,7 @@ BO_DEVICE int bo_tm_m1(bo_tm& M, double* BO_RESTRICT sm, const bo_solver_params&
       // inertia correction (IPOPT Algorithm IC); retried on the next trip
       if (inertia < 0 && BO_ME > 0 && M.dc == 0.0) {
         M.dc = BO_DC_SCALE * sqrt(sqrt(M.mu));
-        if (M.attempt == 0) M.first_singular = true;
+        if (M.attempt == 0 || BO_SINGULAR_ANY_ATTEMPT) M.first_singular = true;
       } else if (M.dw == 0.0) {
         M.dw = (M.dw_last == 0.0) ? 1e-4 : fmax(1e-20, M.dw_last / 3.0);
       } else {

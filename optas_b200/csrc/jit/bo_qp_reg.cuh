@@ -18,6 +18,16 @@
 // interior-point kernel's (scaled KKT error <= tol), so status / kkt_error mean the same on both paths.
 #pragma once
 
+#ifndef BO_QP_ALPHA_OK
+#define BO_QP_ALPHA_OK 0.1  /* below this step length the corrected step is replaced by a centring step */
+#endif
+// Weight of the second-order term ds_aff * dz_aff in the corrector.  Mehrotra's method uses 1; when the affine step is
+// cut short by the boundary (a_aff << 1) the full term describes a step that is never taken, and the plain method was
+// seen cycling on badly centred iterates (16 of 65536 box QPs, mu alternating 0.008 <-> 0.025).  Weighting by a_aff
+// removed every such case and lowers the mean iteration count (box QPs 7.37 -> 6.94).
+#ifndef BO_QP_CROSS
+#define BO_QP_CROSS(a) (a)
+#endif
 #ifndef BO_QP_IC_MAX
 #define BO_QP_IC_MAX 12  /* regularisation attempts (semidefinite H / dependent rows of A) before giving up */
 #endif
@@ -35,6 +45,7 @@ BO_DEVICE void bo_ipm_init(bo_ipm_state& S, const bo_solver_params prm) {
   S.dw = 0.0;
   S.dc = 0.0;
   S.attempt = 0;
+  S.ls = 0;
   S.soc = 1;  // "fresh": g, cE, cI, f were evaluated by the tape at the current x
   S.static_fac = true;
   BO_UNROLL
@@ -119,7 +130,8 @@ BO_DEVICE int bo_ipm_trip(bo_ipm_state& S, const bo_solver_params prm) {
     for (int i = 0; i < BO_MI; ++i) {
       S.rI[i] = S.cI[i] - S.s[i];
       e_prim = fmax(e_prim, fabs(S.rI[i]));
-      e_comp = fmax(e_comp, S.s[i] * S.z[i]);
+      // complementarity against the slack AND against the constraint value itself (what a checker without slacks sees)
+      e_comp = fmax(e_comp, fmax(S.s[i], fabs(S.cI[i])) * S.z[i]);
       mu += S.s[i] * S.z[i];
       sum_z += fabs(S.z[i]);
     }
@@ -168,6 +180,7 @@ BO_DEVICE int bo_ipm_trip(bo_ipm_state& S, const bo_solver_params prm) {
     // the same residuals, the optimality test above is unaffected
     if (bad == 2 && S.dc == 0.0) S.dc = 1e-9;
     else S.dw = S.dw == 0.0 ? 1e-8 : S.dw * 100.0;
+    S.ls = 1;  // regularised in this iteration
     if (++S.attempt > BO_QP_IC_MAX) return S.err0 <= prm.acceptable_tol ? BO_ST_ACCEPTABLE : BO_ST_NUMERICAL;
     return -1;
   }
@@ -185,11 +198,25 @@ BO_DEVICE int bo_ipm_trip(bo_ipm_state& S, const bo_solver_params prm) {
     for (int i = 0; i < BO_MI; ++i) mu_aff += (S.s[i] + a_aff * S.ds[i]) * (S.z[i] + a_aff * S.ds0[i]);
     mu_aff /= (double)BO_DIM(BO_MI);
     const double r = mu > 0.0 ? mu_aff / mu : 0.0;
-    const double smu = r * r * r * mu;
+    // centring target sigma mu, not below tol / 10 (IPOPT's mu_min): driving the products s z further down only blows up
+    // Z/S -- and with it the conditioning of the system -- while the dual residual is still converging
+    const double smu = fmax(r * r * r * mu, fmin(mu, 0.1 * prm.tol));
     BO_NOUNROLL
-    for (int i = 0; i < BO_MI; ++i) rcs[i] = S.z[i] + (S.ds[i] * S.ds0[i] - smu) / S.s[i];
+    for (int i = 0; i < BO_MI; ++i) rcs[i] = S.z[i] + (BO_QP_CROSS(a_aff) * S.ds[i] * S.ds0[i] - smu) / S.s[i];
     bo_qp_step(S, prm, rcs);
     alpha = bo_qp_max_step(S, fmax(0.99, 1.0 - mu));
+    if (alpha < BO_QP_ALPHA_OK) {
+      // Badly centred iterate (a few products s z far above the mean): the corrected direction runs into the boundary at
+      // once and the plain method can cycle.  Take a pure centring step instead (sigma = 1, no second-order term) with
+      // the same factorisation; the next iteration then starts from balanced products.
+      BO_NOUNROLL
+      for (int i = 0; i < BO_MI; ++i) rcs[i] = S.z[i] - mu / S.s[i];
+      bo_qp_step(S, prm, rcs);
+      alpha = bo_qp_max_step(S, fmax(0.99, 1.0 - mu));
+    }
+#ifdef BO_HOST_TRACE
+    printf("       a_aff %.3e sigma %.3e alpha %.3e\n", a_aff, r * r * r, alpha);
+#endif
   }
 
   // ---- move, carrying the function values along (exact for a quadratic cost and linear constraints) ----
@@ -228,6 +255,12 @@ BO_DEVICE int bo_ipm_trip(bo_ipm_state& S, const bo_solver_params prm) {
   }
   S.soc = 0;
   ++S.it;
+  // a regularisation that was needed once is tried smaller the next time (it is not a property of the instance: the
+  // conditioning of H + JI' (Z/S) JI changes with Z/S)
+  if (S.ls) S.dw *= 1e-2;
+  if (S.dw < 1e-8) S.dw = 0.0;
+  S.ls = 0;
+  S.attempt = 0;
   return -1;
 }
 
