@@ -357,7 +357,7 @@ def run_config(name: str, rank: int, world: int, dev, dist, fp64_tflops, with_cp
         "value": conv * steps / (dev_ms * 1e-3), "unit": "instances/s", "steps": steps, "ms_per_step": dev_ms / steps,
         "converged_fraction": conv / total, "acceptable_fraction": acc / total, "mean_iterations": its / total,
         "e2e": {"value": conv_e2e * steps / e2e_s, "unit": "instances/s", "h2d_bytes_per_step": int(P.nbytes + X0.nbytes),
-                "d2h_bytes_per_step": int(r["x"].nbytes + r["lam"].nbytes + 28 * B), "api": "B200Solver.solve_arrays (page-locked host arrays)"},
+                "d2h_bytes_per_step": int(r["x"].nbytes + r["lam"].nbytes + 28 * B), "api": "B200Solver.solve_arrays (page-locked host arrays, read / written in place by the kernel over PCIe)"},
         "gpu_launches": int(kernel_n),
         "roofline": {"kernel": f"bo_solve_kernel ({tier['tier']} tier)", "bound": "fp64 issue / dependent-instruction latency (not HBM, not tensor)",
                      "achieved": achieved, "peak": fp64_tflops, "unit": "TFLOP/s", "frac": achieved / fp64_tflops if fp64_tflops else None,
@@ -617,7 +617,10 @@ def main() -> None:
             "e2e": {"value": conv_e2e_total * args.steps / e2e_s_max, "unit": "instances/s",
                     "h2d_bytes_per_step": B * (npar + nx) * 8,
                     "d2h_bytes_per_step": B * (nx * 8 + nlam * 8 + 8 + 4 + 4 + 8),
-                    "api": "B200Solver.reset_parameters/reset_initial_seed/solve with host numpy arrays"},
+                    "api": "B200Solver.reset_parameters/reset_initial_seed/solve with host numpy arrays",
+                    "transfers": "dict arrays are packed into page-locked rows (bo_pack_rows), which the kernel reads and "
+                                 "whose page-locked result arrays it writes in place over PCIe (zero copy, inside the timed "
+                                 "region: the bytes above cross the bus every step); B200OPTAS_ZERO_COPY=0 = staged copies"},
             "gpu_launches": int(kernel_n),
             "roofline": {"kernel": "bo_eval_kernel (FK position + linear Jacobian, LWR 7-DoF)", "bound": "hbm",
                          "achieved": fk_gbs, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": fk_gbs / peaks["hbm_gbs"],

@@ -18,8 +18,10 @@
  *     p[B][np], x[B][nx] ... (one OpTaS problem instance per row).
  *   - data pointers may be host or device memory (detected with cudaPointerGetAttributes);
  *     a call whose buffers are all device memory is asynchronous on `stream`; a call with any
- *     host buffer stages through device buffers of the handle and returns after the results are on the
- *     host (page-locked host memory makes the copies asynchronous; pageable memory works).
+ *     host buffer returns after the results are on the host.  PAGE-LOCKED host buffers are used in place by the
+ *     kernel (zero copy: an instance reads its row when it starts and writes its results when it ends, so the PCIe
+ *     traffic overlaps the other instances' iterations; B200OPTAS_ZERO_COPY=0 in the environment restores staged
+ *     copies); pageable host buffers are staged through device buffers of the handle.
  *   - buffers are BORROWED for the duration of the call; nothing is retained.
  *   - a handle is bound to the CUDA device current at creation; handles are not thread-safe,
  *     distinct handles may be used from distinct threads / processes (one per GPU).

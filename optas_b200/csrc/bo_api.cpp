@@ -17,7 +17,10 @@
 #include <cstdlib>
 #include <cstring>
 #include <fstream>
+#include <condition_variable>
+#include <functional>
 #include <memory>
+#include <mutex>
 #include <sstream>
 #include <thread>
 #include <string>
@@ -619,6 +622,7 @@ int bo_problem_create(const bo_problem_desc* desc, const bo_options* opts_in, bo
                    ps.n_ineq);
   // whole warps only: the kernels use full-mask warp votes
   pr->tpb = pr->opts.threads_per_block > 0 ? ((pr->opts.threads_per_block + 31) / 32) * 32 : 64;
+  const bool auto_max_step = pr->opts.max_step == 0.0;
   if (pr->opts.max_step == 0.0) pr->opts.max_step = (tape_has_trig(ps.kkt) || tape_has_trig(ps.fc)) ? 0.5 : -1.0;
   if (getenv("BO_DEBUG")) fprintf(stderr, "[bo] emitting source\n");
   // KKT systems beyond a dozen rows are factored sparsely: symbolic analysis here, once
@@ -669,6 +673,7 @@ int bo_problem_create(const bo_problem_desc* desc, const bo_options* opts_in, bo
   // tiers run it (it needs no trial points and no per-iteration tape, so its state is small); horizon-sized QPs that
   // qualify for the cooperative tier stay there.
   pr->qp = !pr->coop && !pr->large && !pivoted && !(pr->opts.flags & (BO_FLAG_NO_QP | BO_FLAG_TEAM)) && bo::problem_is_qp(ps);
+  if (pr->qp && auto_max_step) pr->opts.max_step = -1.0;  // sin / cos of the parameters only: the step cap has no role in a QP
   // Team tier (csrc/jit/bo_ipm_team.cuh): small dense problems, G threads in G warps per instance, state in shared memory
   // Measured on B200 (tools/team_check.py, profiles/r02_team_vs_thread.txt): the team tier wins once the per-instance state
   // no longer fits a thread (C2: 24 rows of variables + constraints, 3 KB of thread-local state: 6.0 vs 10.2 ms per 65536)
@@ -1009,6 +1014,62 @@ int bo_problem_kernel_time(bo_problem* pr, double* ms_total, int64_t* n_launches
 // ------------------------------------------------------------------------------------------
 // host-side marshalling: label arrays -> [B][total] rows (batched dict2vec)
 // ------------------------------------------------------------------------------------------
+// Worker threads of bo_pack_rows, started on first use and kept: spawning 16 threads per call cost more than the copy
+// (0.3 of 0.47 ms for 65536 x 10 doubles).  The caller takes part in the work.  A forked child starts its own pool.
+namespace {
+struct PackPool {
+  std::mutex m;
+  std::condition_variable cv_work, cv_done;
+  std::vector<std::thread>* workers = new std::vector<std::thread>;
+  const std::function<void(int)>* job = nullptr;
+  int n_jobs = 0, next = 0, pending = 0;
+  uint64_t generation = 0;
+  pid_t owner = 0;
+  void worker() {
+    uint64_t seen = 0;
+    std::unique_lock<std::mutex> lk(m);
+    for (;;) {
+      cv_work.wait(lk, [&] { return generation != seen; });
+      seen = generation;
+      drain(lk);
+    }
+  }
+  void drain(std::unique_lock<std::mutex>& lk) {  // called with the lock held
+    while (next < n_jobs) {
+      const int t = next++;
+      const std::function<void(int)>* f = job;
+      lk.unlock();
+      (*f)(t);
+      lk.lock();
+      if (--pending == 0) cv_done.notify_all();
+    }
+  }
+  void run(int n, const std::function<void(int)>& f) {
+    std::unique_lock<std::mutex> lk(m);
+    if (owner != getpid()) {  // first use, or first use after fork(): the parent's threads do not exist here
+      if (owner != 0) workers = new std::vector<std::thread>;  // the old handles name threads of the parent: leave them alone
+      owner = getpid();
+    }
+    const int want = std::min(n - 1, 15);
+    while ((int)workers->size() < want) workers->emplace_back([this] { worker(); });
+    job = &f;
+    n_jobs = n;
+    next = 0;
+    pending = n;
+    ++generation;
+    cv_work.notify_all();
+    drain(lk);
+    cv_done.wait(lk, [&] { return pending == 0; });
+    job = nullptr;
+    n_jobs = 0;
+  }
+};
+PackPool& pack_pool() {
+  static PackPool* pool = new PackPool;  // never destroyed: its threads may outlive static destruction
+  return *pool;
+}
+}  // namespace
+
 int bo_pack_rows(double* dst, int64_t B, int64_t total, int32_t n_seg, const double* const* src, const int64_t* stride,
                  const int32_t* m, const int32_t* n, const int64_t* off, int32_t n_threads) {
   if (!dst || B < 0 || total < 0 || n_seg < 0 || (n_seg > 0 && (!src || !stride || !m || !n || !off)))
@@ -1029,6 +1090,11 @@ int bo_pack_rows(double* dst, int64_t B, int64_t total, int32_t n_seg, const dou
         }
         const int64_t sb = stride[3 * k], sr = stride[3 * k + 1], sc = stride[3 * k + 2];
         const double* in = src[k] + b * sb;
+        if (sr == 1 && (nk == 1 || sc == mk)) {  // the instance's block already lies in vec() order: straight copy
+          const int len = mk * nk;
+          for (int e = 0; e < len; ++e) out[e] = in[e];
+          continue;
+        }
         for (int c = 0; c < nk; ++c)  // column-major flattening of the instance's matrix
           for (int r = 0; r < mk; ++r) out[c * mk + r] = in[r * sr + c * sc];
       }
@@ -1040,13 +1106,11 @@ int bo_pack_rows(double* dst, int64_t B, int64_t total, int32_t n_seg, const dou
     work(0, B);
     return BO_OK;
   }
-  std::vector<std::thread> pool;
   const int64_t chunk = (B + nt - 1) / nt;
-  for (int t = 0; t < nt; ++t) {
+  pack_pool().run(nt, [&](int t) {
     const int64_t b0 = t * chunk, b1 = std::min<int64_t>(B, b0 + chunk);
-    if (b0 < b1) pool.emplace_back(work, b0, b1);
-  }
-  for (auto& th : pool) th.join();
+    if (b0 < b1) work(b0, b1);
+  });
   return BO_OK;
 }
 

@@ -219,6 +219,13 @@ BO_DEVICE int bo_ipm_trip(bo_ipm_state& S, const bo_solver_params prm) {
 #endif
   }
 
+  if (prm.max_step > 0.0) {  // an explicit step cap is honoured here as well (the default is off for problems without sin / cos)
+    double dxn = 0.0;
+    BO_UNROLL
+    for (int i = 0; i < BO_NX; ++i) dxn = fmax(dxn, fabs(S.dx[i]));
+    if (alpha * dxn > prm.max_step) alpha = prm.max_step / dxn;
+  }
+
   // ---- move, carrying the function values along (exact for a quadratic cost and linear constraints) ----
   {
     double hdx[BO_NX], t[BO_DIM(BO_ME > BO_MI ? BO_ME : BO_MI)];
