@@ -635,7 +635,7 @@ int bo_problem_create(const bo_problem_desc* desc, const bo_options* opts_in, bo
   // everything the large tier used to take, on request (BO_FLAG_COOP) for any sparse-tier problem.
   if (pr->sparse && !(pr->opts.flags & BO_FLAG_NO_COOP)) {
     const int tpb = pr->opts.threads_per_block > 0 ? ((pr->opts.threads_per_block + 31) / 32) * 32 : (pr->large ? 256 : 64);
-    bo::CoopPlan cp = bo::make_coop_plan(ps, tpb);
+    bo::CoopPlan cp = bo::make_coop_plan(ps, tpb, pr->opts.cache_dir ? std::string(pr->opts.cache_dir) : lib_dir() + "/_jitcache");
     size_t smem = (size_t)cp.smem_doubles * sizeof(double);
     {
       // Experiment knob B200OPTAS_COOP_W_SMEM=1: the vectors of the instance in shared memory as well (when they fit).

@@ -786,22 +786,24 @@ void append_tape_section(std::vector<int32_t>& t, int slot, const PartTape& pt, 
 // ======================================================================================
 // Lane programs: a warp-wide, fully pre-scheduled instruction stream
 // ======================================================================================
-// A stream is a sequence of ROUNDS; a round is one header word per lane followed by K operand words per lane
-// (8 bytes each, lane-interleaved: word i of lane l at [i][l]):
-//   header:  x = K | LEVEL_END << 31,  y = tgt | POSITIVE << 15      (tgt = 0x7FFF: this lane finalises nothing)
-//   operand: x = a | b << 16,          y = c
-// In a round every lane does K times acc += vals[a] * (factor: vals[b] * vals[c] | solve: bp[b]); then the G lanes of
-// a group add their accumulators up and lane 0 of the group finalises `tgt`; after a LEVEL_END round the
-// participating warps synchronise.  K and LEVEL_END are the same in all lanes of a warp.  POSITIVE marks a diagonal
-// factor target whose pivot must be positive (variable block).  Every warp stream ends with one padding word so the
-// executor may always fetch one word ahead.
+// A stream is a sequence of fixed-size PACKETS: one header word per lane followed by PK operand words per lane
+// (8 bytes each, lane-interleaved: word i of lane l at [i][l]).  A ROUND -- one target per group of G lanes -- is one or
+// more packets:
+//   header:  x = FIRST | LAST << 1 | LEVEL_END << 2 | EMPTY << 3 | log2(G) << 4,  y = tgt | POSITIVE << 15   (tgt = 0x7FFF: this lane finalises nothing)
+//   operand: x = a | b << 16,          y = c                                     (padding: the always-zero cells)
+// In a round every lane accumulates acc += vals[a] * (factor: vals[b] * vals[c] | solve: bp[b]); after the LAST packet the
+// G lanes of a group add their accumulators up and lane 0 of the group finalises `tgt`; after a LEVEL_END packet the
+// participating warps synchronise.  The flags are the same in all lanes of a warp.  POSITIVE marks a diagonal factor
+// target whose pivot must be positive (variable block).  Every warp stream ends with 8 padding packets (prefetched, never run).
 struct LaneTarget {
   int tgt;
   std::vector<std::array<int, 3>> con;
   bool positive = false;  // factor, diagonal target: pivot expected positive (variable block)
 };
 struct LaneProgram {
-  int W = 1, G = 1;
+  int W = 1, G = 1, PK = 4;
+  int pad_words = 0;  // words of trailing padding in every warp stream
+  bool aligned = false;
   std::vector<std::vector<int32_t>> words;  // per warp: [step][32][2]
   double cost = 0.0;
   int64_t max_steps() const {
@@ -811,18 +813,34 @@ struct LaneProgram {
   }
 };
 
-LaneProgram schedule_program(const std::vector<std::vector<LaneTarget>>& levels, int W, int G, int zero_a, int zero_b, int zero_c,
-                             bool emit) {
+// `aligned`: the targets of a level arrive column by column with operand lists aligned on the column's k-list (see the
+// factor program below); consecutive targets then go to consecutive lane groups of one warp, so that the second and
+// third operand of a step are the same shared-memory word in the lanes of a column with the same sub-index (a broadcast).
+// `sum_weight`: share of the OTHER warps' work that counts against a level (0: one CTA per SM, only the busiest warp
+// matters; 1: many small CTAs share the SM's issue slots, so the total instruction count is what is paid for).
+// G = 0: the lanes per target are chosen LEVEL BY LEVEL (the cheapest of 1..32 for that level under the same cost model;
+// the header carries log2 G in bits 4..6, the executor's group sum reads it from there): a level of 60 long targets wants
+// G = 4 on 8 warps, the level after it with 300 short ones G = 1.
+LaneProgram schedule_program(const std::vector<std::vector<LaneTarget>>& levels, int W, int G_fixed, int PK, int zero_a, int zero_b,
+                             int zero_c, bool emit, bool aligned = false, double sum_weight = 0.0) {
   LaneProgram pr;
   pr.W = W;
-  pr.G = G;
+  pr.G = G_fixed;
+  pr.PK = PK;
   pr.words.resize(W);
-  const int ngrp = 32 / G, slots = W * ngrp;
-  int log2g = 0;
-  while ((1 << log2g) < G) ++log2g;
-  // latency model of one warp (cycles): an operand step, a round (header, group sum, finalisation), a level barrier
-  const double c_step = 100.0, c_round = 250.0 + 40.0 * log2g, c_barrier = W > 1 ? 200.0 : 20.0;
-  auto header = [&](std::vector<int32_t>& out, int K, bool level_end, const LaneTarget* const* tg) {
+  // Cost model of one warp (cycles).  Measured on B200 (ncu, profiles/r02_coop_c5_packets_ncu.txt): the programs are
+  // bound by the INSTRUCTION ISSUE of the warp on the critical path -- a packet is ~12 instructions per operand step
+  // (index decode, three shared-memory loads, two FP64 operations) plus ~35 of bookkeeping (prefetch of the words
+  // BO_LP_DEPTH packets ahead, flags), a round ends with the group sum and the finalisation.  So the cost of a level is
+  // the instruction count of its busiest warp; padding operands cost as much as real ones.  (The absolute scale is off --
+  // a lone warp needs ~4.9 cycles per instruction, not 2.2 -- only ratios are used.)
+  const double cpi = 2.2;
+  // same packet count, measured on C5 / C4: the aligned form is 13 % / 9 % faster (two of its three operands are broadcasts,
+  // the unaligned lanes read three unrelated words: bank conflicts)
+  const double c_packet = cpi * (12.0 * PK + 35.0) * (aligned ? 1.0 : 1.12), c_barrier = W > 1 ? 80.0 : 10.0;
+  auto header = [&](std::vector<int32_t>& out, int G, unsigned flags, const LaneTarget* const* tg) {
+    int log2g = 0;
+    while ((1 << log2g) < G) ++log2g;
     for (int lane = 0; lane < 32; ++lane) {
       const int g = lane / G, sub = lane % G;
       int tgt = 0x7FFF, pos = 0;
@@ -830,16 +848,24 @@ LaneProgram schedule_program(const std::vector<std::vector<LaneTarget>>& levels,
         tgt = tg[g]->tgt;
         pos = tg[g]->positive ? 0x8000 : 0;
       }
-      out.push_back((int32_t)((uint32_t)K | (level_end ? 0x80000000u : 0u)));
+      out.push_back((int32_t)(flags | ((unsigned)log2g << 4)));
       out.push_back((int32_t)((uint32_t)tgt | (uint32_t)pos));
     }
   };
-  for (const auto& lv : levels) {
-    std::vector<int> order(lv.size());
-    for (size_t k = 0; k < lv.size(); ++k) order[k] = (int)k;
-    std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return lv[a].con.size() > lv[b].con.size(); });
+  auto zero_words = [&](std::vector<int32_t>& out, int count) {
+    for (int k = 0; k < count * 32; ++k) {
+      out.push_back((int32_t)((uint32_t)zero_a | ((uint32_t)zero_b << 16)));
+      out.push_back((int32_t)zero_c);
+    }
+  };
+  // one level with G lanes per target: returns its cost, emits its packets when asked to
+  auto do_level = [&](const std::vector<LaneTarget>& lv, const std::vector<int>& order, int G, bool emit_now) {
+    const int ngrp = 32 / G, slots = W * ngrp;
+    int log2g = 0;
+    while ((1 << log2g) < G) ++log2g;
+    const double c_round = cpi * (60.0 + 12.0 * log2g);
     const int rounds = ((int)lv.size() + slots - 1) / slots;
-    double worst = 0.0;
+    double worst = 0.0, total = 0.0;
     for (int w = 0; w < W; ++w) {
       double cost_w = 0.0;
       // rounds of this warp in this level
@@ -849,7 +875,8 @@ LaneProgram schedule_program(const std::vector<std::vector<LaneTarget>>& levels,
         tg.fill(nullptr);
         bool any = false;
         for (int g = 0; g < ngrp; ++g) {
-          const int q = g * W + w, k = r * slots + q;  // slot q of the round: warp = q % W, group = q / W
+          // slot q of the round: warp = q % W, group = q / W; aligned: 32 / G consecutive targets per warp
+          const int q = g * W + w, k = aligned ? (r * W + w) * ngrp + g : r * slots + q;
           if (k < (int)lv.size()) {
             tg[g] = &lv[order[k]];
             any = true;
@@ -858,73 +885,114 @@ LaneProgram schedule_program(const std::vector<std::vector<LaneTarget>>& levels,
         if (any) mine.push_back(tg);
       }
       if (mine.empty()) {
-        if (emit) header(pr.words[w], 0, true, nullptr);  // nothing to do in this level: only meet the barrier
-        cost_w += 30.0;
+        if (emit_now) {  // nothing to do in this level: only meet the barrier
+          header(pr.words[w], 1, 4u | 8u, nullptr);  // LEVEL_END | EMPTY
+          zero_words(pr.words[w], PK);
+        }
+        cost_w += cpi * 30.0;
       }
       for (size_t r = 0; r < mine.size(); ++r) {
         int maxlen = 0;
         for (int g = 0; g < ngrp; ++g)
           if (mine[r][g]) maxlen = std::max(maxlen, (int)mine[r][g]->con.size());
         const int K = (maxlen + G - 1) / G;
-        cost_w += K * c_step + c_round;
-        if (!emit) continue;
-        header(pr.words[w], K, r + 1 == mine.size(), mine[r].data());
-        for (int st = 0; st < K; ++st)
-          for (int lane = 0; lane < 32; ++lane) {
-            const int g = lane / G, sub = lane % G;
-            int a = zero_a, b = zero_b, c = zero_c;
-            const LaneTarget* tg = mine[r][g];
-            const int ci = st * G + sub;
-            if (tg && ci < (int)tg->con.size()) {
-              a = tg->con[ci][0];
-              b = tg->con[ci][1];
-              c = tg->con[ci][2];
+        const int np = std::max(1, (K + PK - 1) / PK);
+        cost_w += c_round + np * c_packet;
+        if (!emit_now) continue;
+        for (int pk = 0; pk < np; ++pk) {
+          const bool last = pk + 1 == np;
+          const unsigned flags = (pk == 0 ? 1u : 0u) | (last ? 2u : 0u) | (last && r + 1 == mine.size() ? 4u : 0u);
+          header(pr.words[w], G, flags, last ? mine[r].data() : nullptr);
+          for (int st = pk * PK; st < (pk + 1) * PK; ++st)
+            for (int lane = 0; lane < 32; ++lane) {
+              const int g = lane / G, sub = lane % G;
+              int a = zero_a, b = zero_b, c = zero_c;
+              const LaneTarget* tg = mine[r][g];
+              const int ci = st * G + sub;
+              if (tg && st < K && ci < (int)tg->con.size()) {
+                a = tg->con[ci][0];
+                b = tg->con[ci][1];
+                c = tg->con[ci][2];
+              }
+              pr.words[w].push_back((int32_t)((uint32_t)a | ((uint32_t)b << 16)));
+              pr.words[w].push_back((int32_t)c);
             }
-            pr.words[w].push_back((int32_t)((uint32_t)a | ((uint32_t)b << 16)));
-            pr.words[w].push_back((int32_t)c);
-          }
+        }
       }
       worst = std::max(worst, cost_w);
+      total += cost_w;
     }
-    pr.cost += worst + c_barrier;
+    return std::max(worst, sum_weight * total) + c_barrier;
+  };
+  for (const auto& lv : levels) {
+    std::vector<int> order(lv.size());
+    for (size_t k = 0; k < lv.size(); ++k) order[k] = (int)k;
+    std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return lv[a].con.size() > lv[b].con.size(); });
+    int G = G_fixed;
+    if (G_fixed == 0) {
+      double best = -1.0;
+      for (int g = 1; g <= 32; g *= 2) {
+        const double c = do_level(lv, order, g, false);
+        if (best < 0.0 || c < best) {
+          best = c;
+          G = g;
+        }
+      }
+    }
+    pr.cost += do_level(lv, order, G, emit);
   }
+  pr.pad_words = 8 * (PK + 1);  // BO_LP_PAD_PACKETS packets the executor may prefetch but never executes
   if (emit)
-    for (int w = 0; w < W; ++w) header(pr.words[w], 0, false, nullptr);  // trailing padding word (never executed)
+    for (int w = 0; w < W; ++w)
+      for (int k = 0; k < 8; ++k) {
+        header(pr.words[w], 1, 8u, nullptr);
+        zero_words(pr.words[w], PK);
+      }
   return pr;
 }
 
-LaneProgram best_program(const std::vector<std::vector<LaneTarget>>& levels, int max_warps, int zero_a, int zero_b, int zero_c,
-                         const char* env_w, const char* env_g) {
-  int bw = 1, bg = 1;
+// `pks`: candidate packet sizes (operand words per packet): long operand lists want large packets (less bookkeeping per
+// operand), short ones small packets (less padding)
+LaneProgram best_program(const std::vector<std::vector<LaneTarget>>& levels, int max_warps, const std::vector<int>& pks, int zero_a,
+                         int zero_b, int zero_c, const char* env_w, const char* env_g, double sum_weight = 0.0,
+                         const std::vector<std::vector<LaneTarget>>* levels_aligned = nullptr) {
+  int bw = 1, bg = 0, bpk = pks[0];
+  bool bal = false;
   double best = -1.0;
   // experiment hooks: force the number of warps / lanes per target of the factor program
   const int force_w = getenv(env_w) ? atoi(getenv(env_w)) : 0;
   const int force_g = getenv(env_g) ? atoi(getenv(env_g)) : 0;
-  for (int W = 1; W <= max_warps; W *= 2)
-    for (int G = 1; G <= 32; G *= 2) {
-      if ((force_w && W != force_w) || (force_g && G != force_g)) continue;
-      const LaneProgram p = schedule_program(levels, W, G, zero_a, zero_b, zero_c, false);
-      if (best < 0.0 || p.cost < best) {
-        best = p.cost;
-        bw = W;
-        bg = G;
-      }
-    }
-  return schedule_program(levels, bw, bg, zero_a, zero_b, zero_c, true);
+  for (int PK : pks)
+    for (int al = 0; al < (levels_aligned ? 2 : 1); ++al)
+      for (int W = 1; W <= max_warps; W *= 2)
+        for (int G = 0; G <= 32; G = G ? G * 2 : 1) {  // 0 = per-level choice
+          if ((force_w && W != force_w) || (force_g && G != (force_g < 0 ? 0 : force_g))) continue;
+          const LaneProgram p = schedule_program(al ? *levels_aligned : levels, W, G, PK, zero_a, zero_b, zero_c, false, al != 0, sum_weight);
+          if (best < 0.0 || p.cost < best) {
+            best = p.cost;
+            bw = W;
+            bg = G;
+            bpk = PK;
+            bal = al != 0;
+          }
+        }
+  LaneProgram out = schedule_program(bal ? *levels_aligned : levels, bw, bg, bpk, zero_a, zero_b, zero_c, true, bal, sum_weight);
+  out.aligned = bal;
+  return out;
 }
 
-// table section: [0] W  [1] G  [2] stream offset (absolute, 16-byte aligned)  [3] total steps, then per warp
+// table section: [0] W  [1] G | PK << 8  [2] stream offset (absolute, 16-byte aligned)  [3] total steps, then per warp
 // { first step, number of steps }
 void append_program(std::vector<int32_t>& t, int slot, const LaneProgram& pr) {
   t[slot] = (int32_t)t.size();
   const size_t h = t.size();
   t.resize(h + 4 + 2 * (size_t)pr.W, 0);
   t[h] = pr.W;
-  t[h + 1] = pr.G;
+  t[h + 1] = pr.G | (pr.PK << 8);  // G = 0: chosen per level (in the packet headers)
   int64_t first = 0;
   for (int w = 0; w < pr.W; ++w) {
     t[h + 4 + 2 * w] = (int32_t)first;
-    t[h + 5 + 2 * w] = (int32_t)(pr.words[w].size() / 64) - 1;  // words to execute (the trailing padding word excluded)
+    t[h + 5 + 2 * w] = (int32_t)(pr.words[w].size() / 64) - pr.pad_words;  // words to execute (the trailing padding excluded)
     first += (int64_t)pr.words[w].size() / 64;
   }
   t[h + 3] = (int32_t)first;
@@ -940,32 +1008,94 @@ static CoopPlan make_coop_plan_segments(const ProblemSource& ps, int tpb, int n_
 // The elimination order is chosen by trial: cutting every chain of the KKT graph into 2 (3) pieces that factor
 // independently roughly halves the elimination-tree height for a little extra fill; whichever variant gives the
 // shortest lane programs (factorisation + both substitutions, longest warp) and still fits shared memory wins.
-CoopPlan make_coop_plan(const ProblemSource& ps, int tpb) {
+// The search below builds up to eight symbolic factorisations (seconds each for C4 / C5), so its verdict -- one integer per
+// KKT structure -- is remembered: in the process, and in `cache_dir` (the JIT cache) across processes.
+static uint64_t structure_hash(const ProblemSource& ps, int tpb) {
+  uint64_t h = 1469598103934665603ull;
+  auto mix = [&](uint64_t v) {
+    h ^= v;
+    h *= 1099511628211ull;
+  };
+  mix(0x6c64ull << 8 | 4);  // version of the search (bump when the candidates or the cost model change)
+  for (int v : {ps.nx, ps.n_eq, ps.n_ineq, tpb}) mix((uint64_t)v);
+  for (const Sparsity* sp : {&ps.hess, &ps.jac_eq, &ps.jac_ineq}) {
+    mix((uint64_t)sp->nnz());
+    for (int k = 0; k < sp->nnz(); ++k) mix(((uint64_t)(uint32_t)sp->row[k] << 32) | (uint32_t)sp->col[k]);
+  }
+  return h;
+}
+
+CoopPlan make_coop_plan(const ProblemSource& ps, int tpb, const std::string& cache_dir) {
+  // candidates: 1 = plain minimum degree; -d = nested dissection of depth d (2^d pieces per chain, minimum-vertex-cover
+  // separators, bo_sparse.cpp).  Deeper dissection = lower elimination tree but more fill; the cheapest predicted lane
+  // programs (factorisation + both substitutions, cost model of schedule_program) that fit shared memory win.
+  // BO_SEGMENTS forces a variant (k > 1: the round-1 flat cut into k pieces).
   int best_seg = 1;
-  if (getenv("BO_SEGMENTS")) {
-    best_seg = atoi(getenv("BO_SEGMENTS"));
-  } else {
-    int64_t best_steps = -1;
-    for (int seg = 1; seg <= 3; ++seg) {
-      const CoopPlan c = make_coop_plan_segments(ps, tpb, seg, true);
-      const size_t smem = ((size_t)c.vals_size() + ps.nx + ps.n_eq + 5 * (tpb / 32) + 8) * sizeof(double);
-      if (seg > 1 && smem > 227 * 1024) break;
-      const int64_t steps = c.fac_steps + c.solve_steps;
-      if (best_steps < 0 || steps < best_steps - best_steps / 32) {  // > 3 % shorter
-        best_steps = steps;
-        best_seg = seg;
-      } else {
-        break;
+  static std::map<uint64_t, int> memo;
+  const uint64_t key = structure_hash(ps, tpb);
+  char name[64];
+  snprintf(name, sizeof name, "/plan_%016llx.txt", (unsigned long long)key);
+  const std::string memo_file = cache_dir.empty() ? std::string() : cache_dir + name;
+  bool known = false;
+  if (!getenv("BO_SEGMENTS") && !getenv("BO_DEBUG_LDL")) {
+    const auto it = memo.find(key);
+    if (it != memo.end()) {
+      best_seg = it->second;
+      known = true;
+    } else if (!memo_file.empty()) {
+      if (FILE* f = fopen(memo_file.c_str(), "r")) {
+        known = fscanf(f, "%d", &best_seg) == 1;
+        fclose(f);
       }
     }
   }
-  return make_coop_plan_segments(ps, tpb, best_seg, false);
+  if (getenv("BO_SEGMENTS")) {
+    best_seg = atoi(getenv("BO_SEGMENTS"));
+  } else if (!known) {
+    double best_cost = -1.0;
+    // -d: depth d, cuts in the middle; -(10 + d), -(20 + d): cuts of the end intervals biased to 0.6 / 0.7 (less fill)
+    bool fits_prev = true;
+    for (int seg : {1, -1, -2, -12, -22, -3, -13, -23}) {
+      const int d = seg < 0 ? (-seg) % 10 : 0, bias = seg < 0 ? (-seg) / 10 : 0;
+      if (bias > 0 && fits_prev) continue;       // the unbiased cut of this depth fitted: nothing to gain from a biased one
+      const CoopPlan c = make_coop_plan_segments(ps, tpb, seg, true);
+      const size_t smem = ((size_t)c.vals_size() + ps.nx + ps.n_eq + 5 * (tpb / 32) + 8) * sizeof(double);
+      const bool fits = seg == 1 || (smem <= 227 * 1024 && c.vals_size() + 1 < 32767);
+      if (getenv("BO_DEBUG_LDL"))
+        fprintf(stderr, "[ldl] candidate %d: %d levels, %d factor values, predicted %.0f cycles, %zu bytes of shared memory%s\n", seg, c.n_levels,
+                c.vals_size(), c.prog_cost, smem, fits ? "" : " (does not fit)");
+      if (bias == 0) fits_prev = fits;
+      else if (fits) fits_prev = true;
+      if (!fits) {
+        if (bias == 2 || d == 1) break;  // nothing of this depth fits: deeper ones will not either
+        continue;
+      }
+      if (best_cost < 0.0 || c.prog_cost < 0.97 * best_cost) {  // > 3 % cheaper
+        best_cost = c.prog_cost;
+        best_seg = seg;
+      }
+    }
+  }
+  if (!getenv("BO_SEGMENTS")) {
+    memo[key] = best_seg;
+    if (!known && !memo_file.empty())
+      if (FILE* f = fopen(memo_file.c_str(), "w")) {
+        fprintf(f, "%d\n", best_seg);
+        fclose(f);
+      }
+  }
+  CoopPlan out = make_coop_plan_segments(ps, tpb, best_seg, false);
+  if (getenv("BO_DEBUG_LDL"))
+    fprintf(stderr, "[ldl] segments %d: %d levels, %d factor values, factor %lld + solve %lld words (longest warp), %d smem doubles; factor W %d G %d PK %d%s, solves G %d / %d PK %d / %d\n", best_seg,
+            out.n_levels, out.vals_size(), (long long)out.fac_steps, (long long)out.solve_steps, out.smem_doubles, out.ldl_w, out.ldl_g, out.fac_pk, out.fac_aligned ? " aligned" : "", out.solve_g, out.solve_bwd_g, out.fwd_pk, out.bwd_pk);
+  return out;
 }
 
 static CoopPlan make_coop_plan_segments(const ProblemSource& ps, int tpb, int n_segments, bool ldl_only) {
   CoopPlan pl;
   pl.n_segments = n_segments;
-  pl.sp = make_sparse_plan(ps, false, n_segments);
+  // n_segments < 0: nested dissection of depth (-n_segments) % 10, cut bias 0.5 + 0.1 * ((-n_segments) / 10)
+  pl.sp = n_segments < 0 ? make_sparse_plan(ps, false, 1, (-n_segments) % 10, 0.5 + 0.1 * ((-n_segments) / 10)) : make_sparse_plan(ps, false, n_segments);
   const SparsePlan& sp = pl.sp;
   const int n = sp.n, nx = ps.nx, nnzL = sp.nnzL();
   std::vector<int32_t>& t = pl.itab;
@@ -1001,8 +1131,34 @@ static CoopPlan make_coop_plan_segments(const ProblemSource& ps, int tpb, int n_
   const int zero_v = sp.vals_size();  // index of a cell of `vals` that always holds 0.0 (padding operand)
   const int zero_b = n;               // same in the permuted right-hand side
   {
-    std::vector<std::vector<LaneTarget>> fac(nlev), fwd(nlev), bwd(nlev);
+    // Column-aligned factor program (default; BO_FAC_ALIGNED=0 = per-target operand lists, G lanes per target): the
+    // targets of column j -- D(j) and every C(i,j) -- all walk the SAME list k in rowpat(j); step p of every lane of the
+    // column reads C(j,k_p) and 1/D(k_p), one shared-memory word each for the whole column (broadcast), and its own
+    // C(i,k_p) (the zero cell where L(i,k_p) is structurally zero: 2.2x the operand slots on C5, a third of the wavefronts).
+    const bool fac_aligned = !(getenv("BO_FAC_ALIGNED") && atoi(getenv("BO_FAC_ALIGNED")) == 0);
+    std::vector<std::vector<LaneTarget>> fac(nlev), fwd(nlev), bwd(nlev), fac_al(nlev);
     for (int L = 0; L < nlev; ++L) {
+      if (fac_aligned) {
+        std::vector<int> cols = cols_of[L];
+        std::stable_sort(cols.begin(), cols.end(), [&](int a, int b) { return row_pat[a].size() > row_pat[b].size(); });
+        for (int j : cols) {
+          LaneTarget d;
+          d.tgt = j;
+          d.positive = sp.perm[j] < nx;
+          for (const auto& ke : row_pat[j]) d.con.push_back({n + ke.second, n + ke.second, ke.first});
+          fac_al[L].push_back(std::move(d));
+          for (int e = sp.colptr[j]; e < sp.colptr[j + 1]; ++e) {
+            const int i = sp.rowidx[e];
+            LaneTarget o;
+            o.tgt = n + e;
+            for (const auto& ke : row_pat[j]) {
+              const int e_ik = entry(i, ke.first);
+              o.con.push_back({e_ik >= 0 ? n + e_ik : zero_v, n + ke.second, ke.first});
+            }
+            fac_al[L].push_back(std::move(o));
+          }
+        }
+      }
       for (int j : cols_of[L]) {
         LaneTarget d;
         d.tgt = j;
@@ -1031,15 +1187,47 @@ static CoopPlan make_coop_plan_segments(const ProblemSource& ps, int tpb, int n_
         bwd[nlev - 1 - L].push_back(std::move(w));
       }
     }
+    if (getenv("BO_DEBUG_LDL") && !ldl_only) {
+      int64_t tot_t = 0, tot_len = 0, tot_dense = 0, tot_cols = 0;
+      for (int L = 0; L < nlev; ++L) {
+        int64_t nt = 0, len = 0, dense = 0;
+        for (int j : cols_of[L]) {
+          const int64_t nj = 1 + sp.colptr[j + 1] - sp.colptr[j], mj = (int64_t)row_pat[j].size();
+          nt += nj;
+          dense += nj * mj;
+        }
+        for (const auto& tg : fac[L]) len += (int64_t)tg.con.size();
+        if (L % 10 == 0 || L + 1 == nlev)
+          fprintf(stderr, "[ldl] level %3d: %3zu columns, %4lld targets, %6lld operands, %6lld column-aligned slots\n", L, cols_of[L].size(),
+                  (long long)nt, (long long)len, (long long)dense);
+        tot_t += nt; tot_len += len; tot_dense += dense; tot_cols += (int64_t)cols_of[L].size();
+      }
+      fprintf(stderr, "[ldl] %d levels, %lld columns, %lld targets, %lld operands, %lld column-aligned slots (fill-in of the aligned form %.2f)\n", nlev,
+              (long long)tot_cols, (long long)tot_t, (long long)tot_len, (long long)tot_dense, (double)tot_dense / (double)std::max<int64_t>(1, tot_len));
+    }
     const int max_warps = std::max(1, tpb / 32);
-    LaneProgram pf = best_program(fac, max_warps, zero_v, zero_v, zero_v, "BO_FAC_WARPS", "BO_FAC_G");
+    // small problems run many CTAs per SM (C3: 16): there the SM's issue slots are shared, the TOTAL instruction count weighs
+    // in next to the busiest warp of one CTA
+    const double sum_weight = (size_t)(sp.vals_size() + n) * sizeof(double) < 227 * 1024 / 4 ? 0.5 : 0.0;
+    // packet sizes: measured on B200 (profiles/r02_coop_phases_*.txt) -- C5 / C4 (operand lists of 27-40 per column): 8 beats 4 by
+    // 16 % / 9 %; C3 (3.4 operands per target, 16 CTAs per SM): 2 beats 4 beats 8 (138 k / 186 k / 263 k cycles per
+    // factorisation).  The cost model does not resolve that, so the small-problem regime is pinned to 2.
+    const std::vector<int> fac_pks = getenv("BO_FAC_PK") ? std::vector<int>{atoi(getenv("BO_FAC_PK"))}
+                                                         : (sum_weight > 0.0 ? std::vector<int>{2} : std::vector<int>{4, 8});
+    const std::vector<int> solve_pks = getenv("BO_SOLVE_PK") ? std::vector<int>{atoi(getenv("BO_SOLVE_PK"))} : std::vector<int>{1, 2, 4};
+    LaneProgram pf = best_program(fac, max_warps, fac_pks, zero_v, zero_v, zero_v, "BO_FAC_WARPS", "BO_FAC_G", sum_weight, fac_aligned ? &fac_al : nullptr);
+    pl.fac_aligned = pf.aligned;
     const int solve_warps = getenv("BO_SOLVE_MAX_WARPS") ? atoi(getenv("BO_SOLVE_MAX_WARPS")) : max_warps;
-    LaneProgram pw = best_program(fwd, std::min(solve_warps, max_warps), zero_v, zero_b, zero_v, "BO_SOLVE_WARPS", "BO_SOLVE_G");
-    LaneProgram pb = best_program(bwd, std::min(solve_warps, max_warps), zero_v, zero_b, zero_v, "BO_SOLVE_WARPS", "BO_SOLVE_G");
+    LaneProgram pw = best_program(fwd, std::min(solve_warps, max_warps), solve_pks, zero_v, zero_b, zero_v, "BO_SOLVE_WARPS", "BO_SOLVE_G", sum_weight);
+    LaneProgram pb = best_program(bwd, std::min(solve_warps, max_warps), solve_pks, zero_v, zero_b, zero_v, "BO_SOLVE_WARPS", "BO_SOLVE_G", sum_weight);
+    pl.fac_pk = pf.PK;
+    pl.fwd_pk = pw.PK;
+    pl.bwd_pk = pb.PK;
     pl.ldl_g = pf.G;
     pl.ldl_w = pf.W;
     pl.solve_g = pw.G;
     pl.solve_bwd_g = pb.G;
+    pl.prog_cost = pf.cost + pw.cost + pb.cost;
     pl.fac_steps = pf.max_steps();
     pl.solve_steps = pw.max_steps() + pb.max_steps();
     append_program(t, CT_PROG_FAC, pf);
@@ -1226,7 +1414,7 @@ std::string emit_coop_source(const ProblemSource& ps, const CoopPlan& pl, int tp
     const int by_regs = 65536 / (tpb * 64);
     const int min_ctas = std::max(1, std::min(std::min(by_smem, by_regs), 32));
     o << "#define BO_MIN_CTAS " << min_ctas << "\n#define BO_FAC_G " << pl.ldl_g << "\n#define BO_FWD_G " << pl.solve_g
-      << "\n#define BO_BWD_G " << pl.solve_bwd_g << "\n";
+      << "\n#define BO_BWD_G " << pl.solve_bwd_g << "\n#define BO_FAC_PK " << pl.fac_pk << "\n#define BO_FWD_PK " << pl.fwd_pk << "\n#define BO_BWD_PK " << pl.bwd_pk << "\n";
   }
   if (!hessian_depends_on_eq_multipliers(ps)) o << "#define BO_RECALC_DC_ONLY 1\n";
   if (pl.w_in_smem) o << "#define BO_W_IN_SMEM 1\n";

@@ -58,16 +58,20 @@ struct CoopPlan {
   bool gen_tapes = false;      // tapes compiled to straight-line code per component class (else interpreted)
   std::string gen_code;        // the generated class functions + dispatchers
   int n_levels = 0;            // elimination-tree height (= barriers per factorisation)
-  int n_segments = 1;          // pieces every chain of the KKT graph was cut into for the elimination order
+  int n_segments = 1;          // elimination order: 1 = minimum degree, k > 1 = chains cut flat into k pieces, -d = nested dissection of depth d
   int ldl_g = 1, ldl_w = 1;    // factor program: lanes per target, participating warps
+  bool fac_aligned = false;    // factor program in the column-aligned form (bo_coop.cpp)
+  int fac_pk = 8, fwd_pk = 2, bwd_pk = 2;  // operand words per packet of the factor / substitution lane programs
   int solve_g = 1, solve_bwd_g = 1;  // lanes cooperating on one row (forward) / column (backward) of a triangular solve
   int64_t fac_steps = 0, solve_steps = 0;  // longest warp stream of the factor / both triangular solves
+  double prog_cost = 0.0;      // predicted cycles of one factorisation + one pair of substitutions (scheduler's cost model)
   int64_t n_contrib = 0;       // multiply-adds of one numeric factorisation
   CoopTapeInfo fc, kkt;
   int vals_size() const { return sp.vals_size(); }
 };
 
-CoopPlan make_coop_plan(const ProblemSource& ps, int threads_per_block);
+// `cache_dir` (optional): where the verdict of the elimination-order search is remembered across processes.
+CoopPlan make_coop_plan(const ProblemSource& ps, int threads_per_block, const std::string& cache_dir = std::string());
 
 // Doubles of per-CTA global workspace (must equal BO_SCRATCH_DOUBLES of csrc/jit/bo_ipm_cta.cuh).
 size_t coop_scratch_doubles(const ProblemSource& ps, const CoopPlan& plan);

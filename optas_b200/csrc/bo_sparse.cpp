@@ -2,6 +2,8 @@
 #include "bo_sparse.h"
 
 #include <algorithm>
+#include <cstdlib>
+#include <functional>
 #include <set>
 
 namespace bo {
@@ -16,7 +18,7 @@ int SparsePlan::pos(int i_old, int j_old) const {
   return n + (int)(it - rowidx.begin());
 }
 
-SparsePlan make_sparse_plan(const ProblemSource& ps, bool large, int n_segments) {
+SparsePlan make_sparse_plan(const ProblemSource& ps, bool large, int n_segments, int nd_depth, double nd_bias) {
   SparsePlan pl;
   const int nx = ps.nx, n = ps.nx + ps.n_eq;
   pl.n = n;
@@ -61,8 +63,11 @@ SparsePlan make_sparse_plan(const ProblemSource& ps, bool large, int n_segments)
   // cut into n_segments pieces along its longest axis (BFS layers from a pseudo-peripheral vertex); the layer of
   // vertices at each cut is a separator that is eliminated last.  The pieces factor independently, so the
   // elimination tree is ~n_segments times lower; the price is the fill of the separator blocks.
-  std::vector<char> is_sep(n, 0);
-  if (n_segments > 1) {
+  // sep_level[v]: -1 = interior vertex; k >= 0 = member of a separator chosen at dissection depth k (0 = the cut made first,
+  // eliminated last).  The flat variant puts every separator at level 0.
+  std::vector<int> sep_level(n, -1);
+  int max_sep_level = -1;
+  if (n_segments > 1 || nd_depth > 0) {
     auto bfs = [&](int src, std::vector<int>& dist) {
       dist.assign(n, -1);
       std::vector<int> q{src};
@@ -85,33 +90,139 @@ SparsePlan make_sparse_plan(const ProblemSource& ps, bool large, int n_segments)
       const int u = comp.back();  // farthest from s0: one end of the component
       const std::vector<int> cu = bfs(u, du);
       const int depth = du[cu.back()] + 1;
-      if (depth < 4 * n_segments) continue;  // too short to be worth cutting
-      for (int x : comp) seg[x] = (int)((int64_t)du[x] * n_segments / depth);
-      for (int x : comp)
-        for (int w : adj[x])
-          if (seg[w] < seg[x]) is_sep[x] = 1;
+      if (nd_depth <= 0) {
+        if (depth < 4 * n_segments) continue;  // too short to be worth cutting
+        for (int x : comp) seg[x] = (int)((int64_t)du[x] * n_segments / depth);
+        for (int x : comp)
+          for (int w : adj[x])
+            if (seg[w] < seg[x]) sep_level[x] = 0;
+        max_sep_level = std::max(max_sep_level, 0);
+        continue;
+      }
+      // Nested dissection along the BFS axis: the layers [lo, hi) are cut near the middle, then both halves again, nd_depth
+      // times.  In a BFS layering edges join only equal or adjacent layers, so the cut between layers c-1 and c is crossed
+      // by a bipartite edge set; its MINIMUM VERTEX COVER (Koenig: from a maximum matching) is the smallest vertex
+      // separator for that cut -- on the horizon problems here the 7 joint angles of one stage, where "all vertices of
+      // layer c with a neighbour in c-1" is three times that.  Among the cuts within an eighth of the interval around
+      // the middle the smallest cover wins.
+      std::vector<std::vector<int>> layer(depth);
+      for (int x : comp) layer[du[x]].push_back(x);
+      auto cover_of_cut = [&](int c) {
+        std::vector<int> A, B;  // A: layer c-1 vertices with a neighbour in layer c; B: the other side
+        std::vector<int> idB(n, -1);
+        for (int x : layer[c]) {
+          if (sep_level[x] >= 0) continue;
+          for (int w : adj[x])
+            if (du[w] == c - 1 && sep_level[w] < 0) {
+              idB[x] = (int)B.size();
+              B.push_back(x);
+              break;
+            }
+        }
+        std::vector<std::vector<int>> nb;
+        for (int x : layer[c - 1]) {
+          if (sep_level[x] >= 0) continue;
+          std::vector<int> e;
+          for (int w : adj[x])
+            if (du[w] == c && idB[w] >= 0) e.push_back(idB[w]);
+          if (!e.empty()) {
+            A.push_back(x);
+            nb.push_back(e);
+          }
+        }
+        std::vector<int> matchB(B.size(), -1), matchA(A.size(), -1);
+        std::vector<char> vis;
+        std::function<bool(int)> augment = [&](int a) {
+          for (int b : nb[a]) {
+            if (vis[b]) continue;
+            vis[b] = 1;
+            if (matchB[b] < 0 || augment(matchB[b])) {
+              matchB[b] = a;
+              matchA[a] = b;
+              return true;
+            }
+          }
+          return false;
+        };
+        for (size_t a = 0; a < A.size(); ++a) {
+          vis.assign(B.size(), 0);
+          augment((int)a);
+        }
+        // Koenig: Z = reachable from the unmatched A vertices by alternating paths; cover = (A \ Z) + (B & Z)
+        std::vector<char> zA(A.size(), 0), zB(B.size(), 0);
+        std::vector<int> stack;
+        for (size_t a = 0; a < A.size(); ++a)
+          if (matchA[a] < 0) {
+            zA[a] = 1;
+            stack.push_back((int)a);
+          }
+        while (!stack.empty()) {
+          const int a = stack.back();
+          stack.pop_back();
+          for (int b : nb[a]) {
+            if (zB[b]) continue;
+            zB[b] = 1;
+            const int a2 = matchB[b];
+            if (a2 >= 0 && !zA[a2]) {
+              zA[a2] = 1;
+              stack.push_back(a2);
+            }
+          }
+        }
+        std::vector<int> cover;
+        for (size_t a = 0; a < A.size(); ++a)
+          if (!zA[a]) cover.push_back(A[a]);
+        for (size_t b = 0; b < B.size(); ++b)
+          if (zB[b]) cover.push_back(B[b]);
+        return cover;
+      };
+      // nd_bias > 0.5: an interval that still has a free end (an end of the chain) is cut nearer to its separator end.
+      // Pieces bounded by separators on BOTH sides carry the fill (every column of theirs couples with a separator), end
+      // pieces carry none: shorter inner pieces trade a little tree height for fill, i.e. for shared memory.
+      std::function<void(int, int, int)> dissect = [&](int lo, int hi, int level) {
+        if (level >= nd_depth || hi - lo < 8) return;
+        const bool free_lo = lo == 0, free_hi = hi == depth;
+        const double frac = (free_lo && !free_hi) ? nd_bias : ((free_hi && !free_lo) ? 1.0 - nd_bias : 0.5);
+        const int mid = lo + (int)((hi - lo) * frac + 0.5), win = std::max(1, (hi - lo) / 8);
+        int best_c = -1;
+        std::vector<int> best_cover;
+        for (int c = std::max(lo + 2, mid - win); c <= std::min(hi - 2, mid + win); ++c) {
+          std::vector<int> cov = cover_of_cut(c);
+          if (best_c < 0 || cov.size() < best_cover.size() ||
+              (cov.size() == best_cover.size() && std::abs(c - mid) < std::abs(best_c - mid))) {
+            best_c = c;
+            best_cover = std::move(cov);
+          }
+        }
+        if (best_c < 0) return;
+        for (int v : best_cover) sep_level[v] = level;
+        max_sep_level = std::max(max_sep_level, level);
+        dissect(lo, best_c, level + 1);
+        dissect(best_c, hi, level + 1);
+      };
+      dissect(0, depth, 0);
     }
   }
   std::vector<std::set<int>> g = adj;  // elimination graph (mutated)
   pl.perm.reserve(n);
   std::vector<std::vector<int>> col_struct;  // rows (old indices) below the diagonal of each eliminated column
   col_struct.reserve(n);
-  bool interior_phase = n_segments > 1;
+  int cur_level = max_sep_level + 1;  // separators of level >= cur_level are eligible (deepest first); interior vertices always
   for (int step = 0; step < n; ++step) {
     int best = -1;
     size_t best_deg = ~(size_t)0;
-    for (int pass = 0; pass < 2 && best < 0; ++pass) {
+    while (best < 0) {
       for (int v = 0; v < n; ++v) {
         if (done[v]) continue;
-        if (v >= nx && pending_x[v - nx] > 0) continue;  // constraint row not yet eligible
-        if (interior_phase && is_sep[v]) continue;        // separators wait until the pieces are done
+        if (v >= nx && pending_x[v - nx] > 0) continue;          // constraint row not yet eligible
+        if (sep_level[v] >= 0 && sep_level[v] < cur_level) continue;  // separators wait until everything below them is done
         if (g[v].size() < best_deg) {
           best_deg = g[v].size();
           best = v;
         }
       }
-      if (best < 0 && interior_phase) interior_phase = false;  // pieces exhausted: now the separators
-      else break;
+      if (best >= 0 || cur_level == 0) break;
+      cur_level -= 1;  // this phase is exhausted: admit the next separator level
     }
     if (best < 0) {  // only ineligible rows left (cannot happen: all x are always eligible) -- take any
       for (int v = 0; v < n; ++v)

@@ -38,6 +38,10 @@ struct SparsePlan {
 // horizon problems).
 // `large`: also append the structure tables, the KKT assembly program and the two tapes, so that the
 // kernel needs no problem-specific code at all (table-driven everything; see bo_ipm_reg.cuh BO_LARGE).
-SparsePlan make_sparse_plan(const ProblemSource& ps, bool large, int n_segments = 1);
+// `n_segments` > 1: every chain of the KKT graph is cut into that many pieces, separators eliminated last (flat).
+// `nd_depth` > 0: nested dissection instead -- the chain is bisected nd_depth times with minimum-vertex-cover separators,
+// separators eliminated deepest level first (elimination-tree height ~ piece length + nd_depth separator blocks).
+// `nd_bias` in [0.5, 1): where an interval with one free end is cut (0.5 = the middle; larger = nearer its separator end).
+SparsePlan make_sparse_plan(const ProblemSource& ps, bool large, int n_segments = 1, int nd_depth = 0, double nd_bias = 0.5);
 
 }  // namespace bo

@@ -223,6 +223,12 @@ BO_DEVICE void bo_reduce(double (&v)[K], const int (&op)[K], double* red) {
 #define BO_PROF_BEGIN() const long long bo_prof_t0 = clock64()
 #define BO_PROF_END(k) do { if (BO_TID == 0) C.prof[k] += clock64() - bo_prof_t0; } while (0)
 #define BO_PROF_COUNT(k) do { if (BO_TID == 0) C.prof[k] += 1; } while (0)
+#elif defined(BO_HOST_SIM)
+// host build: event counters only (0 kkt tape, 1 f/c tape, 2 assembly, 5 factorisations, 6 solves), read by tests/hostsim.py
+static long long bo_host_prof[8];
+#define BO_PROF_COUNT(k) do { bo_host_prof[k] += 1; } while (0)
+#define BO_PROF_BEGIN() do { } while (0)
+#define BO_PROF_END(k) do { if ((k) < 3) bo_host_prof[k] += 1; } while (0)
 #else
 #define BO_PROF_COUNT(k) do { } while (0)
 #define BO_PROF_BEGIN() do { } while (0)
@@ -477,82 +483,147 @@ BO_NOINLINE void bo_cta_assemble(const bo_cta& C, double rho, double dw, double 
   BO_PROF_END(2);
 }
 
-// Lane programs (bo_coop.cpp): warp-wide pre-scheduled streams of ROUNDS, 8 bytes per lane and word, word i of
-// lane l at [i][l].  A round = one header word + K operand words:
-//   header:  x = K | LEVEL_END << 31,  y = tgt | POSITIVE << 15      (tgt = 0x7FFF: this lane finalises nothing)
-//   operand: x = a | b << 16,          y = c
+// Lane programs (bo_coop.cpp): warp-wide pre-scheduled streams of fixed-size PACKETS, 8 bytes per lane and word, word i
+// of lane l at [i][l].  A packet = one header word + PK operand words; a ROUND (one target per group of G lanes) is one
+// or more packets:
+//   header:  x = flags (FIRST: the round starts here | LAST: it ends here | LEVEL_END | EMPTY) | log2(G) << 4,  y = tgt | POSITIVE << 15
+//            (tgt = 0x7FFF: this lane finalises nothing; the flags are the same in all lanes of the warp)
+//   operand: x = a | b << 16,          y = c                 (padding operands address the always-zero cells)
 // MODE 0 factor:   acc += vals[a] vals[b] vals[c];   finish: d = vals[tgt] - acc, diagonal: vals[tgt] = 1/d (+ pivot test)
 // MODE 1 forward:  acc += vals[a] bp[b];             finish: bp[tgt] = (bp[tgt] - acc) vals[tgt]
 // MODE 2 backward: acc += vals[a] bp[b];             finish: bp[tgt] -= acc vals[tgt]
-// After the K steps the G lanes of a group add up their accumulators (xor-shuffles) and lane 0 of the group
-// finalises; after a LEVEL_END round the participating warps synchronise.  The words do not depend on the data:
-// they are fetched a block (BO_LP_BLOCK words) ahead.
-#ifndef BO_LP_BLOCK
-#define BO_LP_BLOCK 8
+// After the LAST packet of a round the G lanes of a group add up their accumulators (xor-shuffles) and lane 0 of the group
+// finalises; after a LEVEL_END packet the participating warps synchronise.
+// Why packets: the first version walked a flat word stream with a per-word "header or operand?" branch, so every operand
+// cost a full dependent chain (word decode -> 3 shared-memory loads -> DMUL -> DFMA, ~65 cycles) and a level ~2300 cycles
+// (C4: 394 levels, 898 k cycles per factorisation, 0.5 % of the FP64 peak).  With a fixed packet shape the loop body is
+// branch-free: the 3 PK operand loads of a packet are issued back to back, the products are summed as a tree, the words
+// themselves are prefetched BO_LP_DEPTH packets ahead (they do not depend on the data; the stream is L2 resident).
+#ifndef BO_FAC_PK
+#define BO_FAC_PK 8
 #endif
+#ifndef BO_FWD_PK
+#define BO_FWD_PK 2
+#endif
+#ifndef BO_BWD_PK
+#define BO_BWD_PK 2
+#endif
+#ifndef BO_LP_DEPTH
+#define BO_LP_DEPTH 4
+#endif
+#define BO_LP_PAD_PACKETS 8 /* padding packets at the end of every warp stream (bo_coop.cpp emits them): >= BO_LP_DEPTH */
+#define BO_PKT_FIRST 1u
+#define BO_PKT_LAST 2u
+#define BO_PKT_LEVEL_END 4u
+#define BO_PKT_EMPTY 8u /* no operands in this packet (a warp with nothing to do in a level): only the barrier */
+
+#ifdef BO_HOST_SIM
+static inline double bo_cta_rcp(double d) { return 1.0 / d; }
+#else
+// reciprocal without the IEEE slow path (hardware seed + two Newton steps, within 2 ulp for normal arguments): one per pivot
+__device__ __forceinline__ double bo_cta_rcp(double d) {
+  double r;
+  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(d));
+  if (r != 0.0 && fabs(r) < BO_INF) {
+    double e = fma(-d, r, 1.0);
+    r = fma(r, e, r);
+    e = fma(-d, r, 1.0);
+    r = fma(r, e, r);
+  }
+  return r;
+}
+#endif
+
+// sum of the PK products of one packet (two interleaved partial sums: the same order on the device and in the host build)
+template <int MODE, int PK>
+BO_DEVICE double bo_pkt_sum(const bo_cta& C, const bo_int2* w) {
+  double e = 0.0, o = 0.0;
+  BO_UNROLL
+  for (int k = 0; k < PK; ++k) {
+    const unsigned x = (unsigned)w[k].x, y = (unsigned)w[k].y;
+    const double p = MODE == 0 ? BO_VALS_AT(C, x & 0xFFFFu) * BO_VALS_AT(C, x >> 16) * BO_VALS_AT(C, y)
+                               : BO_VALS_AT(C, x & 0xFFFFu) * BO_BP_AT(C, x >> 16);
+    if (k & 1) o += p;
+    else e += p;
+  }
+  return e + o;
+}
+
+// old values of the target, loaded before the group sum so that their latency hides behind the shuffles
 template <int MODE>
-BO_DEVICE void bo_lane_finish(const bo_cta& C, int tgt, bool positive, double acc) {
+BO_DEVICE void bo_lane_target_load(const bo_cta& C, int tgt, double* v0, double* b0) {
   if (MODE == 0) {
-    const double a0 = BO_VALS_AT(C, tgt);
-    const double d = a0 - acc;
+    *v0 = BO_VALS_AT(C, tgt < BO_VALS ? tgt : BO_VALS);
+    *b0 = 0.0;
+  } else {
+    *v0 = BO_VALS_AT(C, tgt < BO_NK ? tgt : BO_VALS);
+    *b0 = BO_BP_AT(C, tgt < BO_NK ? tgt : BO_NK);
+  }
+}
+
+template <int MODE>
+BO_DEVICE void bo_lane_finish(const bo_cta& C, int tgt, bool positive, double acc, double v0, double b0) {
+  if (MODE == 0) {
+    const double d = v0 - acc;
     if (tgt < BO_NK) {
-      const double scale = fmax(1.0, fabs(a0));
+      const double scale = fmax(1.0, fabs(v0));
       const bool bad = positive ? !(d > 1e-13 * scale) : !(d < -1e-13);
 #ifdef BO_HOST_SIM
       if (bad && tgt < C.ibuf[0]) C.ibuf[0] = tgt;
 #else
       if (bad) atomicMin(reinterpret_cast<int*>(&bo_smem[BO_SM_INTS]), tgt);
 #endif
-      BO_VALS_AT(C, tgt) = 1.0 / d;
+      BO_VALS_AT(C, tgt) = bo_cta_rcp(d);
     } else {
       BO_VALS_AT(C, tgt) = d;
     }
   } else if (MODE == 1) {
-    BO_BP_AT(C, tgt) = (BO_BP_AT(C, tgt) - acc) * BO_VALS_AT(C, tgt);
+    BO_BP_AT(C, tgt) = (b0 - acc) * v0;
   } else {
-    BO_BP_AT(C, tgt) -= acc * BO_VALS_AT(C, tgt);
+    BO_BP_AT(C, tgt) = b0 - acc * v0;
   }
 }
 
-template <int MODE, int G>
+template <int MODE, int G, int PK>
 BO_DEVICE void bo_lane_program(const bo_cta& C, int slot) {
   const int32_t* h = C.tab + C.tab[slot];
   const int W = h[0];
 #ifdef BO_HOST_SIM
   // faithful emulation: warps advance level by level, lanes in lock step, the same xor-tree for the group sums
   int pc[32] = {0};
+  static double acc[32][32];
   bool more = true;
   while (more) {
     more = false;
     for (int w = 0; w < W; ++w) {
       const int32_t* s = C.tab + h[2] + 64LL * h[4 + 2 * w];
-      const int n = h[5 + 2 * w];
+      const int n = h[5 + 2 * w] / (PK + 1);
       while (pc[w] < n) {
-        const int32_t* hdr = s + 64LL * pc[w];
-        const unsigned hx = (unsigned)hdr[0];
-        const int K = hx & 0xFFFFu;
-        double acc[32];
-        for (int l = 0; l < 32; ++l) acc[l] = 0.0;
-        for (int k = 0; k < K; ++k) {
-          const int32_t* row = s + 64LL * (pc[w] + 1 + k);
+        const int32_t* pkt = s + 64LL * (PK + 1) * pc[w];
+        const unsigned hx = (unsigned)pkt[0];
+        for (int l = 0; l < 32; ++l) {
+          bo_int2 ops[PK];
+          for (int k = 0; k < PK; ++k) ops[k] = bo_int2{pkt[64 * (k + 1) + 2 * l], pkt[64 * (k + 1) + 2 * l + 1]};
+          const double sum = bo_pkt_sum<MODE, PK>(C, ops);
+          acc[w][l] = (hx & BO_PKT_FIRST) ? sum : acc[w][l] + sum;
+        }
+        if (hx & BO_PKT_LAST) {
+          double v0[32], b0[32];
+          for (int l = 0; l < 32; ++l) bo_lane_target_load<MODE>(C, (unsigned)pkt[2 * l + 1] & 0x7FFFu, &v0[l], &b0[l]);
+          const int g_round = G > 0 ? G : 1 << ((hx >> 4) & 7u);  // G = 0: lanes per target chosen per level, in the header
+          for (int off = g_round >> 1; off > 0; off >>= 1) {
+            double t[32];
+            for (int l = 0; l < 32; ++l) t[l] = acc[w][l] + acc[w][l ^ off];
+            for (int l = 0; l < 32; ++l) acc[w][l] = t[l];
+          }
           for (int l = 0; l < 32; ++l) {
-            const unsigned x = (unsigned)row[2 * l], y = (unsigned)row[2 * l + 1];
-            const int a = x & 0xFFFFu, b = x >> 16, c = y & 0xFFFFu;
-            acc[l] += MODE == 0 ? BO_VALS_AT(C, a) * BO_VALS_AT(C, b) * BO_VALS_AT(C, c) : BO_VALS_AT(C, a) * BO_BP_AT(C, b);
+            const unsigned y = (unsigned)pkt[2 * l + 1];
+            const int tgt = y & 0x7FFFu;
+            if (tgt != 0x7FFF) bo_lane_finish<MODE>(C, tgt, (y & 0x8000u) != 0, acc[w][l], v0[l], b0[l]);
           }
         }
-        for (int off = G >> 1; off > 0; off >>= 1) {
-          double t[32];
-          for (int l = 0; l < 32; ++l) t[l] = acc[l] + acc[l ^ off];
-          for (int l = 0; l < 32; ++l) acc[l] = t[l];
-        }
-        for (int l = 0; l < 32; ++l) {
-          const unsigned y = (unsigned)hdr[2 * l + 1];
-          const int tgt = y & 0x7FFFu;
-          if (tgt != 0x7FFF) bo_lane_finish<MODE>(C, tgt, (y & 0x8000u) != 0, acc[l]);
-        }
-        pc[w] += K + 1;
-        if (hx & 0x80000000u) break;
+        pc[w] += 1;
+        if (hx & BO_PKT_LEVEL_END) break;
       }
       more = more || pc[w] < n;
     }
@@ -560,50 +631,56 @@ BO_DEVICE void bo_lane_program(const bo_cta& C, int slot) {
 #else
   const int warp = BO_TID >> 5, lane = BO_TID & 31;
   if (warp < W) {
-    // The stream is consumed as a flat sequence of words, BO_LP_BLOCK at a time, one block ahead (independent
-    // loads in flight); a header word closes the round before it (group sum, finalisation, level barrier) and opens
-    // the next one.  The trailing padding header closes the last round.
-    const bo_int2* s = reinterpret_cast<const bo_int2*>(C.tab + h[2]) + 32LL * h[4 + 2 * warp] + lane;
-    const int n = h[5 + 2 * warp] + 1;
-    const bo_int2 pad = bo_int2{0, 0x7FFF};
-    bo_int2 nxt[BO_LP_BLOCK];
+    // every warp stream ends with BO_LP_PAD_PACKETS (>= BO_LP_DEPTH) padding packets, so the prefetch needs no bounds test:
+    // one running pointer, loads at immediate offsets
+    const int2* nxt = reinterpret_cast<const int2*>(C.tab + h[2]) + 32LL * h[4 + 2 * warp] + lane;
+    const int n = h[5 + 2 * warp] / (PK + 1);  // packets of this warp
+    bo_int2 buf[BO_LP_DEPTH][PK + 1];
     BO_UNROLL
-    for (int u = 0; u < BO_LP_BLOCK; ++u) nxt[u] = u < n ? s[32 * u] : pad;
-    double acc = 0.0;
-    int rem = 0;
-    unsigned open_y = 0x7FFFu;
-    bool open = false, level_end = false;
-    for (int base = 0; base < n; base += BO_LP_BLOCK) {
-      bo_int2 cur[BO_LP_BLOCK];
+    for (int d = 0; d < BO_LP_DEPTH; ++d) {
       BO_UNROLL
-      for (int u = 0; u < BO_LP_BLOCK; ++u) cur[u] = nxt[u];
-      BO_UNROLL
-      for (int u = 0; u < BO_LP_BLOCK; ++u) {
-        const int i = base + BO_LP_BLOCK + u;
-        nxt[u] = i < n ? s[32 * i] : pad;
+      for (int k = 0; k <= PK; ++k) {
+        const int2 v = __ldg(nxt + 32 * k);
+        buf[d][k] = bo_int2{v.x, v.y};
       }
+      nxt += 32 * (PK + 1);
+    }
+    double acc = 0.0;
+    for (int base = 0; base < n; base += BO_LP_DEPTH) {
       BO_UNROLL
-      for (int u = 0; u < BO_LP_BLOCK; ++u) {
-        if (base + u >= n) break;
-        const unsigned x = (unsigned)cur[u].x, y = (unsigned)cur[u].y;
-        if (rem == 0) {
-          if (open) {
+      for (int d = 0; d < BO_LP_DEPTH; ++d) {
+        const int i = base + d;
+        if (i >= n) break;
+        bo_int2 cur[PK + 1];
+        BO_UNROLL
+        for (int k = 0; k <= PK; ++k) cur[k] = buf[d][k];
+        BO_UNROLL
+        for (int k = 0; k <= PK; ++k) {
+          const int2 v = __ldg(nxt + 32 * k);
+          buf[d][k] = bo_int2{v.x, v.y};
+        }
+        nxt += 32 * (PK + 1);
+        const unsigned hx = (unsigned)cur[0].x, hy = (unsigned)cur[0].y;
+        const int tgt = hy & 0x7FFFu;
+        if (!(hx & BO_PKT_EMPTY)) {
+          const double sum = bo_pkt_sum<MODE, PK>(C, cur + 1);
+          acc = (hx & BO_PKT_FIRST) ? sum : acc + sum;
+        }
+        if (hx & BO_PKT_LAST) {
+          double v0, b0;
+          bo_lane_target_load<MODE>(C, tgt, &v0, &b0);
+          if (G > 0) {
             BO_UNROLL
             for (int off = G >> 1; off > 0; off >>= 1) acc += bo_shfl_xor(acc, off);
-            const int tgt = open_y & 0x7FFFu;
-            if (tgt != 0x7FFF) bo_lane_finish<MODE>(C, tgt, (open_y & 0x8000u) != 0, acc);
-            acc = 0.0;
-            if (level_end) bo_bar_warps(W);
+          } else {  // lanes per target chosen per level (log2 in the header, warp-uniform)
+            const int g_round = 1 << ((hx >> 4) & 7u);
+            BO_UNROLL
+            for (int off = 16; off > 0; off >>= 1)
+              if (off < g_round) acc += bo_shfl_xor(acc, off);
           }
-          rem = x & 0xFFFFu;
-          level_end = (x >> 31) != 0;
-          open_y = y;
-          open = true;
-        } else {
-          if (MODE == 0) acc += BO_VALS_AT(C, x & 0xFFFFu) * BO_VALS_AT(C, x >> 16) * BO_VALS_AT(C, y);
-          else acc += BO_VALS_AT(C, x & 0xFFFFu) * BO_BP_AT(C, x >> 16);
-          --rem;
+          if (tgt != 0x7FFF) bo_lane_finish<MODE>(C, tgt, (hy & 0x8000u) != 0, acc, v0, b0);
         }
+        if (hx & BO_PKT_LEVEL_END) bo_bar_warps(W);
       }
     }
   }
@@ -616,7 +693,7 @@ BO_NOINLINE int bo_cta_factor(const bo_cta& C) {
   BO_PROF_BEGIN();
   if (BO_TID == 0) C.ibuf[0] = BO_NK;  // first bad pivot column (elimination order); BO_NK = none
   bo_sync();
-  bo_lane_program<0, BO_FAC_G>(C, CT_PROG_FAC);
+  bo_lane_program<0, BO_FAC_G, BO_FAC_PK>(C, CT_PROG_FAC);
   bo_sync();
   const int badcol = C.ibuf[0];
   bo_sync();
@@ -634,8 +711,11 @@ BO_NOINLINE void bo_cta_ldl_solve(const bo_cta& C, double* b) {
   double* bp = BO_BP_P(C);
   BO_PAR(j, BO_NK) bp[j] = b[perm[j]];
   bo_sync();
-  bo_lane_program<1, BO_FWD_G>(C, CT_PROG_FWD);
-  bo_lane_program<2, BO_BWD_G>(C, CT_PROG_BWD);
+  bo_lane_program<1, BO_FWD_G, BO_FWD_PK>(C, CT_PROG_FWD);
+  // the two programs may run on different numbers of warps: without this barrier a warp that has no part in the forward
+  // program would start the backward one early (and meet named barrier 1 with another thread count: an illegal instruction)
+  bo_sync();
+  bo_lane_program<2, BO_BWD_G, BO_BWD_PK>(C, CT_PROG_BWD);
   bo_sync();
   BO_PAR(j, BO_NK) b[perm[j]] = bp[j];
   bo_sync();
@@ -1061,10 +1141,24 @@ BO_DEVICE int bo_cta_trip_trial(bo_cta_state& S, const bo_cta& C, const bo_solve
       W[BO_OFF_Z + i] = z;
     }
     BO_PAR(j, BO_ME) W[BO_OFF_Y + j] += S.a * W[BO_OFF_YST + j];
-    #ifdef BO_RECALC_DC_ONLY  /* y does not enter the Hessian (linear equalities): only the rank-deficient case needs it */
+    // Least-squares multiplier re-estimate after a regularised step (see bo_ipm_reg.cuh).  Not when dc > 0 only because the
+    // degeneracy heuristic has switched it on for good (jac_degenerate: a structurally rank-deficient Jacobian, e.g. the four
+    // quaternion equalities per knot of figure_eight_plan.py, rank 3): there the re-estimate would run on EVERY iteration --
+    // one more factorisation and one or two more substitutions each -- where IPOPT (recalc_y = no) does none.  Measured on
+    // C4 (32 instances, host build): 109 -> 77 factorisations and 144 -> 106 substitutions per instance for 8 % more
+    // iterations, same minimisers.  BO_RECALC_MODE: 0 never, 1 only after dw > 0, 2 the round-1 rule (also every dc > 0).
+#if defined(BO_RECALC_MODE) && BO_RECALC_MODE == 0
+    S.recalc_y = false;
+#elif defined(BO_RECALC_MODE) && BO_RECALC_MODE == 1
+    S.recalc_y = S.dw > 0.0;
+#elif defined(BO_RECALC_MODE) && BO_RECALC_MODE == 2 && defined(BO_RECALC_DC_ONLY)
     S.recalc_y = S.dc > 0.0;
-#else
+#elif defined(BO_RECALC_MODE) && BO_RECALC_MODE == 2
     S.recalc_y = S.dw > 0.0 || S.dc > 0.0;
+#elif defined(BO_RECALC_DC_ONLY)  /* y does not enter the Hessian (linear equalities): only the rank-deficient case needs it */
+    S.recalc_y = S.dc > 0.0 && !S.jac_degenerate;
+#else
+    S.recalc_y = S.dw > 0.0 || (S.dc > 0.0 && !S.jac_degenerate);
 #endif
     S.it += 1;
     S.phase = BO_PH_EVAL;

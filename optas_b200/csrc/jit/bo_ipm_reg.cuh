@@ -1083,9 +1083,9 @@ BO_DEVICE int bo_trip_trial(bo_ipm_state& S, const bo_solver_params prm) {
       // regularised step (dw: nonconvex; dc: rank-deficient JE, whose multipliers are undetermined along
       // null(JE') and would otherwise drift by residual/dc): re-estimate y by least squares next trip
       #ifdef BO_RECALC_DC_ONLY  /* y does not enter the Hessian (linear equalities): only the rank-deficient case needs it */
-    S.recalc_y = S.dc > 0.0;
+    S.recalc_y = S.dc > 0.0 && !S.jac_degenerate;  // not once the degeneracy heuristic keeps dc on for good (bo_ipm_cta.cuh)
 #else
-    S.recalc_y = S.dw > 0.0 || S.dc > 0.0;
+    S.recalc_y = S.dw > 0.0 || (S.dc > 0.0 && !S.jac_degenerate);
 #endif
       S.it += 1;
       S.phase = BO_PH_EVAL;

@@ -100,6 +100,7 @@ extern "C" void hostsim_solve(long long B, const double* p, const double* x0, do
     f[b] = S.f; iters[b] = S.it; kkt[b] = S.err0; if (trips) trips[b] = S.trips;
   }
 }
+extern "C" void hostsim_coop_counts(long long* out, int reset) { for (int k = 0; k < 8; ++k) { out[k] = bo_host_prof[k]; if (reset) bo_host_prof[k] = 0; } }
 // component probes for tests/test_coop_logic.py
 struct Probe {
   std::vector<double> W, vals, bp, red; int ibuf[4]; bo_cta C;
@@ -166,6 +167,12 @@ class HostSim:
         self.lib = C.CDLL(so)
         vp = C.c_void_p
         self.lib.hostsim_solve.argtypes = [C.c_longlong] + [vp] * 9 + [C.c_int, C.c_double, C.c_double, C.c_double, C.c_double, C.c_int, vp, vp, vp]
+
+    def coop_counts(self, reset=True):
+        """cooperative tier only: events since the last reset {kkt tape, f/c tape, assembly, factorisations, solves}"""
+        out = np.zeros(8, dtype=np.int64)
+        self.lib.hostsim_coop_counts(out.ctypes.data_as(C.c_void_p), int(reset))
+        return {"kkt": int(out[0]), "fc": int(out[1]), "assembly": int(out[2]), "factor": int(out[5]), "solve": int(out[6])}
 
     def solve(self, P, X0, max_iter=100, tol=1e-8, acc_tol=1e-6, mu_init=0.1, max_step=0.5, max_trips=250):
         B = X0.shape[0]

@@ -135,23 +135,32 @@ def test_coop_tier_table_indices_are_in_bounds():
     solver, _, lo, tab, _ = _coop(prob)
     info = solver.tier_info()
     nvals, nk = info["factor_vals"], lo.nx + lo.n_eq
-    for slot, solve in ((5, False), (6, True), (7, True)):  # CT_PROG_FAC / FWD / BWD
+    for slot, solve in ((5, False), (6, True), (7, True)):  # CT_PROG_FAC / FWD / BWD: packets of 1 + pk words
         h = tab[tab[slot]:]
-        W, stream = int(h[0]), int(h[2])
+        W, pk, stream = int(h[0]), int(h[1]) >> 8, int(h[2])
+        assert pk in (1, 2, 4, 8)
         for w in range(W):
             first, n = int(h[4 + 2 * w]), int(h[5 + 2 * w])
-            words = tab[stream + 64 * first: stream + 64 * (first + n + 1)].reshape(-1, 32, 2).astype(np.int64) & 0xFFFFFFFF
-            i = 0
-            while i < n:
-                K = int(words[i, 0, 0] & 0xFFFF)
-                assert ((words[i, :, 0] & 0xFFFF) == K).all()  # warp-uniform
-                tg = words[i, :, 1] & 0x7FFF
-                assert ((tg == 0x7FFF) | (tg < (nk if solve else nvals))).all()
-                ops = words[i + 1: i + 1 + K]
-                a, b, c = ops[:, :, 0] & 0xFFFF, ops[:, :, 0] >> 16, ops[:, :, 1]
-                assert (a <= nvals).all() and (b <= (nk if solve else nvals)).all() and (c <= nvals).all()
-                i += K + 1
-            assert i == n
+            assert n % (pk + 1) == 0
+            words = tab[stream + 64 * first: stream + 64 * (first + n)].reshape(-1, pk + 1, 32, 2).astype(np.int64) & 0xFFFFFFFF
+            flags = words[:, 0, :, 0] & 0xF  # bits 4..6: log2 of the lanes per target of the round
+            assert (words[:, 0, :, 0] == words[:, 0, :1, 0]).all() and (words[:, 0, :, 0] < 128).all()  # warp-uniform
+            opened = False
+            for f in flags[:, 0]:  # rounds are FIRST ... LAST sequences; a level ends only where a round ends (or on an empty packet)
+                if f & 1:
+                    assert not opened
+                    opened = True
+                if f & 2:
+                    assert opened
+                    opened = False
+                if f & 4:
+                    assert not opened
+            tg = words[:, 0, :, 1] & 0x7FFF
+            assert ((tg == 0x7FFF) | (tg < (nk if solve else nvals))).all()
+            assert (tg[(flags & 2) == 0] == 0x7FFF).all()
+            ops = words[:, 1:]
+            a, b, c = ops[..., 0] & 0xFFFF, ops[..., 0] >> 16, ops[..., 1]
+            assert (a <= nvals).all() and (b <= (nk if solve else nvals)).all() and (c <= nvals).all()
 
 
 @pytest.mark.parametrize("with_eq,with_ineq", [(False, True), (True, False), (False, False)])

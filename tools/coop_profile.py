@@ -1,7 +1,7 @@
 """Phase breakdown of the cooperative tier: a -DBO_PROFILE build of the kernel returns clock64() counters
 (thread 0 of each CTA) in place of the first 8 solution entries.  usage: python tools/coop_profile.py c3|c4|c5 [tpb]"""
 import os, sys; sys.path.insert(0, ".")
-os.environ["B200OPTAS_JIT_DEFINES"] = "-DBO_PROFILE=1"
+os.environ["B200OPTAS_JIT_DEFINES"] = ("-DBO_PROFILE=1 " + os.environ.get("EXTRA_DEFINES", "")).strip()
 import numpy as np, optas_b200
 from optas_b200 import problems
 
