@@ -637,3 +637,35 @@ def test_smoke_entry_point(torch_cuda):
     import __graft_entry__
 
     __graft_entry__.smoke()
+
+
+def test_seed_infeasibility_schedule_changes_the_order_not_the_results(torch_cuda):
+    """``setup(schedule="seed_infeasibility")``: the device-resident batch goes to the kernel most-infeasible-seed first
+    (longest-processing-time-first with theta(x0) as the predictor); instances are independent, so every output must be
+    bitwise what the natural order gives."""
+    import optas_b200
+    from optas_b200 import problems
+
+    torch = torch_cuda
+    prob = problems.lwr_ik()
+    B = 4096
+    P, X0 = prob.sample(B, seed=5)
+    outs = {}
+    for sched in (None, "seed_infeasibility"):
+        solver = optas_b200.B200Solver(prob.opt).setup("ipopt", schedule=sched)
+        lo = solver._lowered
+        Pd, X0d = torch.from_numpy(P).cuda(), torch.from_numpy(X0).cuda()
+        X = torch.empty_like(X0d)
+        lam = torch.empty((B, lo.n_eq + lo.n_ineq), dtype=torch.float64, device="cuda")
+        f, kkt = torch.empty(B, dtype=torch.float64, device="cuda"), torch.empty(B, dtype=torch.float64, device="cuda")
+        st, it = torch.empty(B, dtype=torch.int32, device="cuda"), torch.empty(B, dtype=torch.int32, device="cuda")
+        solver.solve_raw(Pd, X0d, X, lam, f, st, it, kkt)
+        torch.cuda.synchronize()
+        outs[sched] = [t.cpu().numpy() for t in (X, lam, f, st, it, kkt)]
+        if sched:
+            theta = solver._sched["theta"].cpu().numpy().ravel()
+            v = np.asarray(prob.opt.v(X0[7], P[7])).ravel()
+            assert abs(theta[7] - (np.maximum(0.0, -v) ** 2).sum()) < 1e-12  # the predictor is the seed's constraint violation
+    for a, b in zip(outs[None], outs["seed_infeasibility"]):
+        assert np.array_equal(a, b)
+    assert (outs[None][3] == 0).mean() > 0.99
