@@ -414,7 +414,20 @@ class B200Solver(Solver):
         lo = self._lowered
         sc = self._sched
         if sc is None or sc["B"] != B or sc["device"] != X.device:
-            fun = self.seed_infeasibility_function() if sc is None else sc["fun"]
+            if sc is None:
+                from ._capi import BoError
+
+                try:
+                    fun = self.seed_infeasibility_function()
+                except BoError as err:  # e.g. more doubles per instance than the streaming kernel's shared-memory pipeline takes
+                    import warnings
+
+                    warnings.warn(f"schedule='seed_infeasibility' is not available for this problem ({err}); using the caller's order")
+                    self._schedule = None
+                    self._handle.solve(B, P, X0, X, lam, f, status, iters, kkt, stream)
+                    return
+            else:
+                fun = sc["fun"]
             kw = dict(device=X.device)
             sc = self._sched = {
                 "B": B, "device": X.device, "fun": fun, "theta": torch.empty((B, 1), dtype=torch.float64, **kw),
