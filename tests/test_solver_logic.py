@@ -498,3 +498,27 @@ def test_result_buffers_are_recycled_only_when_nobody_holds_them():
     assert id(d["x"]) in [id(st["arrays"]["x"]) for st in s._pool] and len(s._pool) == 3
     e = s._result_buffers(7)
     assert e["x"].shape == (7, 2)                 # another batch size gets its own set
+
+
+def test_seed_infeasibility_predictor_is_the_constraint_violation_of_the_seed():
+    """The function behind ``setup(schedule="seed_infeasibility")`` (which instance goes to the GPU first), evaluated by the
+    oracle's tape interpreter: theta(x0, p) = sum max(0, -v(x0, p))^2 with v the reference's stacked constraint vector
+    (optas/optimization.py:27-51); zero at a feasible seed, growing with the distance of the goal."""
+    import tape_vm
+    from optas_b200 import sym as cs
+    from optas_b200.tape import Tape
+
+    prob = problems.lwr_ik()
+    opt = prob.opt
+    theta = cs.sumsqr(cs.fmax(0.0, -opt.v(opt.x, opt.p)))
+    tape = Tape.from_function(cs.Function("seed_infeasibility", [opt.x, opt.p], [theta]))
+    assert list(tape.in_sizes) == [opt.nx, opt.np] and list(tape.out_sizes) == [1]
+    P, X0 = prob.sample(16, seed=3)
+    got = tape_vm.CTape(tape)(X0, P)[0].ravel()
+    for i in range(16):
+        v = np.asarray(opt.v(X0[i], P[i])).ravel()
+        assert abs(got[i] - (np.maximum(0.0, -v) ** 2).sum()) < 1e-12
+    assert (got > 0).all()  # the sampled goals are not at the seed
+    # scheduling order = decreasing theta: a permutation of the batch
+    order = np.argsort(-got)
+    assert sorted(order.tolist()) == list(range(16))
