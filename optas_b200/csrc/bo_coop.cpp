@@ -1417,6 +1417,7 @@ std::string emit_coop_source(const ProblemSource& ps, const CoopPlan& pl, int tp
       << "\n#define BO_BWD_G " << pl.solve_bwd_g << "\n#define BO_FAC_PK " << pl.fac_pk << "\n#define BO_FWD_PK " << pl.fwd_pk << "\n#define BO_BWD_PK " << pl.bwd_pk << "\n";
   }
   if (!hessian_depends_on_eq_multipliers(ps)) o << "#define BO_RECALC_DC_ONLY 1\n";
+  if (ps.nx + ps.n_eq >= 600) o << "#define BO_RECALC_SKIP_DEGENERATE 1\n";  // measured threshold, see bo_ipm_cta.cuh
   if (pl.w_in_smem) o << "#define BO_W_IN_SMEM 1\n";
   o << "#include \"bo_common.cuh\"\n";
   if (pl.gen_tapes) o << "#define BO_GEN_TAPES 1\n" << pl.gen_code;

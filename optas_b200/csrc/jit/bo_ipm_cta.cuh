@@ -1141,24 +1141,31 @@ BO_DEVICE int bo_cta_trip_trial(bo_cta_state& S, const bo_cta& C, const bo_solve
       W[BO_OFF_Z + i] = z;
     }
     BO_PAR(j, BO_ME) W[BO_OFF_Y + j] += S.a * W[BO_OFF_YST + j];
-    // Least-squares multiplier re-estimate after a regularised step (see bo_ipm_reg.cuh).  Not when dc > 0 only because the
-    // degeneracy heuristic has switched it on for good (jac_degenerate: a structurally rank-deficient Jacobian, e.g. the four
-    // quaternion equalities per knot of figure_eight_plan.py, rank 3): there the re-estimate would run on EVERY iteration --
-    // one more factorisation and one or two more substitutions each -- where IPOPT (recalc_y = no) does none.  Measured on
-    // C4 (32 instances, host build): 109 -> 77 factorisations and 144 -> 106 substitutions per instance for 8 % more
-    // iterations, same minimisers.  BO_RECALC_MODE: 0 never, 1 only after dw > 0, 2 the round-1 rule (also every dc > 0).
+    // Least-squares multiplier re-estimate after a regularised step (see bo_ipm_reg.cuh).  With BO_RECALC_SKIP_DEGENERATE
+    // (bo_coop.cpp defines it for KKT systems of 600 rows and more) not when dc > 0 only because the degeneracy heuristic has
+    // switched it on for good (jac_degenerate: a structurally rank-deficient Jacobian, e.g. the four quaternion equalities
+    // per knot of figure_eight_plan.py, rank 3): there the re-estimate would run on EVERY iteration -- one more
+    // factorisation and one or two more substitutions each -- where IPOPT (recalc_y = no) does none.  Measured: C4 (1250
+    // rows; 32 instances, host build) 109 -> 77 factorisations and 144 -> 106 substitutions per instance for 8 % more
+    // iterations, same minimisers, 1037 -> 1685 inst/s on B200; the joint-space planner (434 rows) 5.4 -> 7.4 iterations
+    // and 51.0 k -> 48.6 k inst/s, i.e. below that size the re-estimate pays for itself and stays.
+    // BO_RECALC_MODE (experiments): 0 never, 1 only after dw > 0, 2 also on every dc > 0, 3 skip under jac_degenerate.
 #if defined(BO_RECALC_MODE) && BO_RECALC_MODE == 0
     S.recalc_y = false;
 #elif defined(BO_RECALC_MODE) && BO_RECALC_MODE == 1
     S.recalc_y = S.dw > 0.0;
-#elif defined(BO_RECALC_MODE) && BO_RECALC_MODE == 2 && defined(BO_RECALC_DC_ONLY)
-    S.recalc_y = S.dc > 0.0;
-#elif defined(BO_RECALC_MODE) && BO_RECALC_MODE == 2
-    S.recalc_y = S.dw > 0.0 || S.dc > 0.0;
 #elif defined(BO_RECALC_DC_ONLY)  /* y does not enter the Hessian (linear equalities): only the rank-deficient case needs it */
+#if (defined(BO_RECALC_SKIP_DEGENERATE) && !(defined(BO_RECALC_MODE) && BO_RECALC_MODE == 2)) || (defined(BO_RECALC_MODE) && BO_RECALC_MODE == 3)
     S.recalc_y = S.dc > 0.0 && !S.jac_degenerate;
 #else
+    S.recalc_y = S.dc > 0.0;
+#endif
+#else
+#if (defined(BO_RECALC_SKIP_DEGENERATE) && !(defined(BO_RECALC_MODE) && BO_RECALC_MODE == 2)) || (defined(BO_RECALC_MODE) && BO_RECALC_MODE == 3)
     S.recalc_y = S.dw > 0.0 || (S.dc > 0.0 && !S.jac_degenerate);
+#else
+    S.recalc_y = S.dw > 0.0 || S.dc > 0.0;
+#endif
 #endif
     S.it += 1;
     S.phase = BO_PH_EVAL;

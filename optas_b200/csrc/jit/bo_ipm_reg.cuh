@@ -1082,10 +1082,13 @@ BO_DEVICE int bo_trip_trial(bo_ipm_state& S, const bo_solver_params prm) {
       for (int j = 0; j < BO_ME; ++j) S.y[j] += S.a * S.y_step[j];
       // regularised step (dw: nonconvex; dc: rank-deficient JE, whose multipliers are undetermined along
       // null(JE') and would otherwise drift by residual/dc): re-estimate y by least squares next trip
+      // (The cooperative tier skips the re-estimate once the degeneracy heuristic keeps dc on for good, bo_ipm_cta.cuh: there a
+      // factorisation costs more than the iterations it saves.  Here it does not: position + axis IK needs 6.0 iterations
+      // with it and 7.8 without, 15.9 M against 8.8 M inst/s on B200.)
       #ifdef BO_RECALC_DC_ONLY  /* y does not enter the Hessian (linear equalities): only the rank-deficient case needs it */
-    S.recalc_y = S.dc > 0.0 && !S.jac_degenerate;  // not once the degeneracy heuristic keeps dc on for good (bo_ipm_cta.cuh)
+    S.recalc_y = S.dc > 0.0;
 #else
-    S.recalc_y = S.dw > 0.0 || (S.dc > 0.0 && !S.jac_degenerate);
+    S.recalc_y = S.dw > 0.0 || S.dc > 0.0;
 #endif
       S.it += 1;
       S.phase = BO_PH_EVAL;

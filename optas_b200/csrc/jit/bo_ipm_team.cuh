@@ -732,9 +732,9 @@ BO_DEVICE int bo_tm_m2(bo_tm& M, double* BO_RESTRICT sm, const bo_solver_params&
     BO_UNROLL
     for (int j = 0; j < BO_ME; ++j) SM(BO_OFF_Y, j) += M.a * SM(BO_OFF_YST, j);
 #ifdef BO_RECALC_DC_ONLY
-    M.recalc_y = M.dc > 0.0 && !M.jac_degenerate;  // not once the degeneracy heuristic keeps dc on for good (bo_ipm_cta.cuh)
+    M.recalc_y = M.dc > 0.0;
 #else
-    M.recalc_y = M.dw > 0.0 || (M.dc > 0.0 && !M.jac_degenerate);
+    M.recalc_y = M.dw > 0.0 || M.dc > 0.0;
 #endif
     M.it += 1;
     M.phase = BO_PH_EVAL;
