@@ -661,7 +661,7 @@ int bo_problem_create(const bo_problem_desc* desc, const bo_options* opts_in, bo
     //   MPC tick T = 20     nx 80, 42 eq, 180 ineq                     0.12 M vs 0.81 M
     const bool big_enough = ps.nx + ps.n_eq + ps.n_ineq > 64;
     const bool wanted = pr->large || (pr->opts.flags & BO_FLAG_COOP) || (cp.kkt.n_components >= 16 && big_enough);
-    if (wanted && cp.vals_size() + 1 < 32767 && ps.nx + ps.n_eq + 1 < 32767 && smem <= 227 * 1024) {
+    if (wanted && cp.vals_size() + ps.nx + ps.n_eq + 2 < 32767 && smem <= 227 * 1024) {  // 15-bit target indices reach into bp
       pr->coop = true;
       pr->large = false;
       pr->tpb = tpb;

@@ -1060,7 +1060,7 @@ CoopPlan make_coop_plan(const ProblemSource& ps, int tpb, const std::string& cac
       if (bias > 0 && fits_prev) continue;       // the unbiased cut of this depth fitted: nothing to gain from a biased one
       const CoopPlan c = make_coop_plan_segments(ps, tpb, seg, true);
       const size_t smem = ((size_t)c.vals_size() + ps.nx + ps.n_eq + 5 * (tpb / 32) + 8) * sizeof(double);
-      const bool fits = seg == 1 || (smem <= 227 * 1024 && c.vals_size() + 1 < 32767);
+      const bool fits = seg == 1 || (smem <= 227 * 1024 && c.vals_size() + ps.nx + ps.n_eq + 2 < 32767);
       if (getenv("BO_DEBUG_LDL"))
         fprintf(stderr, "[ldl] candidate %d: %d levels, %d factor values, predicted %.0f cycles, %zu bytes of shared memory%s\n", seg, c.n_levels,
                 c.vals_size(), c.prog_cost, smem, fits ? "" : " (does not fit)");
@@ -1157,6 +1157,12 @@ static CoopPlan make_coop_plan_segments(const ProblemSource& ps, int tpb, int n_
             }
             fac_al[L].push_back(std::move(o));
           }
+          if (!row_pat[j].empty()) {  // the right-hand side rides along (see below)
+            LaneTarget r;
+            r.tgt = zero_v + 1 + j;
+            for (const auto& ke : row_pat[j]) r.con.push_back({zero_v + 1 + ke.first, n + ke.second, ke.first});
+            fac_al[L].push_back(std::move(r));
+          }
         }
       }
       for (int j : cols_of[L]) {
@@ -1176,6 +1182,16 @@ static CoopPlan make_coop_plan_segments(const ProblemSource& ps, int tpb, int n_
           }
           pl.n_contrib += (int64_t)o.con.size();
           fac[L].push_back(std::move(o));
+        }
+        // The forward substitution rides along with the factorisation: the right-hand side b (the array bp, which sits right
+        // behind vals in shared memory: index vals_size + 1 + j) is one more "row" of the matrix, z(j) = b(j) - sum_k
+        // C(j,k) (1/D(k)) z(k) one more target of column j's level.  Every factorisation is followed by a solve whose
+        // right-hand side is known beforehand, so that solve needs only the scaling by 1/D and the backward program.
+        if (!row_pat[j].empty()) {
+          LaneTarget r;
+          r.tgt = zero_v + 1 + j;
+          for (const auto& ke : row_pat[j]) r.con.push_back({zero_v + 1 + ke.first, n + ke.second, ke.first});
+          fac[L].push_back(std::move(r));
         }
         LaneTarget f;  // forward: z(j) = b(j) - sum_k C(j,k) u(k)
         f.tgt = j;

@@ -254,6 +254,7 @@ struct bo_cta_state {
   double f, mu, tau, dw_last, err0, theta_max, theta_min;
   int nf, it, n_acceptable, phase, trips;
   bool recalc_y, ls_mode;
+  bool rhs_ready;       // sol holds the right-hand side of the coming solve (computed once per entry into the factor phase, not per inertia retry)
   double phi0, theta0, dw, dc, rho;
   int attempt, heavy;
   int n_singular;       // consecutive iterations whose unperturbed KKT matrix was singular (rank-deficient JE)
@@ -553,7 +554,7 @@ BO_DEVICE double bo_pkt_sum(const bo_cta& C, const bo_int2* w) {
 template <int MODE>
 BO_DEVICE void bo_lane_target_load(const bo_cta& C, int tgt, double* v0, double* b0) {
   if (MODE == 0) {
-    *v0 = BO_VALS_AT(C, tgt < BO_VALS ? tgt : BO_VALS);
+    *v0 = BO_VALS_AT(C, tgt != 0x7FFF ? tgt : BO_VALS);  // targets beyond BO_VALS are right-hand-side entries (bp follows vals)
     *b0 = 0.0;
   } else {
     *v0 = BO_VALS_AT(C, tgt < BO_NK ? tgt : BO_VALS);
@@ -703,6 +704,29 @@ BO_NOINLINE int bo_cta_factor(const bo_cta& C) {
   return (C.tab + C.tab[CT_SIGN])[badcol] > 0 ? 1 : 2;
 }
 
+// The factor program carries a right-hand side along (bo_coop.cpp): what is in bp when it starts comes out as L^-1 bp.
+// bo_cta_load_rhs puts b there (before bo_cta_factor); after a successful factorisation bo_cta_ldl_solve_tail finishes
+// K^-1 b with the scaling by 1/D and the backward program only.
+BO_NOINLINE void bo_cta_load_rhs(const bo_cta& C, const double* b) {
+  const int32_t* perm = C.tab + C.tab[CT_PERM];
+  double* bp = BO_BP_P(C);
+  BO_PAR(j, BO_NK) bp[j] = b[perm[j]];
+  bo_sync();
+}
+BO_NOINLINE void bo_cta_ldl_solve_tail(const bo_cta& C, double* b) {
+  BO_PROF_BEGIN();
+  const int32_t* perm = C.tab + C.tab[CT_PERM];
+  double* bp = BO_BP_P(C);
+  BO_PAR(j, BO_NK) bp[j] *= BO_VALS_AT(C, j);
+  bo_sync();
+  bo_lane_program<2, BO_BWD_G, BO_BWD_PK>(C, CT_PROG_BWD);
+  bo_sync();
+  BO_PAR(j, BO_NK) b[perm[j]] = bp[j];
+  bo_sync();
+  BO_PROF_END(4);
+  BO_PROF_COUNT(6);
+}
+
 // Solve K b = b (b indexed by original row: x then y) with the factorisation in vals.  The substitutions run
 // on warp 0 (a level holds a couple of rows); ends with a CTA barrier.
 BO_NOINLINE void bo_cta_ldl_solve(const bo_cta& C, double* b) {
@@ -755,6 +779,7 @@ BO_DEVICE void bo_cta_init(bo_cta_state& S, const bo_cta& C, const bo_solver_par
   S.n_singular = 0;
   S.jac_degenerate = false;
   S.phase = BO_PH_EVAL;
+  S.rhs_ready = false;
   S.trips = 0;
   S.resto = 0;
   S.n_resto = 0;
@@ -798,7 +823,8 @@ BO_NOINLINE double bo_cta_resto_prepare(const bo_cta& C) {
 
 // Step for the residuals (rE, rI) with the current factorisation: fills sol (dx, -dy), dx, ds; returns the
 // fraction-to-the-boundary primal step length.
-BO_NOINLINE double bo_cta_step(bo_cta_state& S, const bo_cta& C) {
+// ... its right-hand side into sol (needs S.rho, the residuals rE / rI, sigma, rd); ends with a CTA barrier
+BO_NOINLINE void bo_cta_step_rhs(bo_cta_state& S, const bo_cta& C) {
   double* W = C.W;
   BO_PAR(i, BO_MI) W[BO_OFF_TV + i] = -(W[BO_OFF_Z + i] - S.mu / W[BO_OFF_S + i] + W[BO_OFF_SIG + i] * W[BO_OFF_RI + i]);
   BO_PAR(j, BO_ME) {
@@ -808,7 +834,17 @@ BO_NOINLINE double bo_cta_step(bo_cta_state& S, const bo_cta& C) {
   bo_sync();
   BO_PAR(c, BO_NX) W[BO_OFF_SOL + c] = -W[BO_OFF_RD + c] + BO_JI_T(c, W + BO_OFF_TV) + BO_JE_T(c, W + BO_OFF_T2);
   bo_sync();
-  bo_cta_ldl_solve(C, W + BO_OFF_SOL);
+}
+// `with_factor`: the right-hand side went through the factor program (bo_cta_load_rhs before bo_cta_factor): only the tail
+// of the solve is left
+BO_NOINLINE double bo_cta_step(bo_cta_state& S, const bo_cta& C, bool with_factor = false) {
+  double* W = C.W;
+  if (with_factor) {
+    bo_cta_ldl_solve_tail(C, W + BO_OFF_SOL);
+  } else {
+    bo_cta_step_rhs(S, C);
+    bo_cta_ldl_solve(C, W + BO_OFF_SOL);
+  }
   const double undo = 1.0 / (1.0 - S.rho * S.dc);
   BO_PAR(j, BO_ME) W[BO_OFF_SOL + BO_NX + j] *= undo;
   BO_PAR(i, BO_NX) W[BO_OFF_DX + i] = W[BO_OFF_SOL + i];
@@ -848,6 +884,7 @@ BO_DEVICE int bo_cta_trip_eval(bo_cta_state& S, const bo_cta& C, const bo_solver
     S.heavy = 0;
     S.ls_mode = false;
     S.phase = BO_PH_FACTOR;
+    S.rhs_ready = false;
     return -1;
   }
   if (S.recalc_y && BO_ME > 0 && !over) {
@@ -860,6 +897,7 @@ BO_DEVICE int bo_cta_trip_eval(bo_cta_state& S, const bo_cta& C, const bo_solver
     S.dw = 1.0;
     S.dc = 1e-10;
     S.phase = BO_PH_FACTOR;
+    S.rhs_ready = false;
     return -1;
   }
   // residuals and the scaled optimality error
@@ -927,6 +965,7 @@ BO_DEVICE int bo_cta_trip_eval(bo_cta_state& S, const bo_cta& C, const bo_solver
   S.heavy = 0;
   S.ls_mode = false;
   S.phase = BO_PH_FACTOR;
+  S.rhs_ready = false;
   bo_sync();
   return -1;
 }
@@ -936,15 +975,31 @@ BO_DEVICE int bo_cta_trip_factor(bo_cta_state& S, const bo_cta& C, const bo_solv
   if (S.phase != BO_PH_FACTOR) return -1;
   const double rho = S.ls_mode ? 0.0 : (S.resto > 0 ? 1.0 : BO_STATIC_RHO);
   S.rho = rho;
+  // the right-hand side of the solve that follows goes through the factor program (forward substitution for free); it does
+  // not depend on the regularisation, so inertia retries reuse it
+  if (!S.rhs_ready) {
+    if (S.ls_mode) {
+      BO_PAR(c, BO_NX) W[BO_OFF_SOL + c] = W[BO_OFF_G + c] - BO_JI_T(c, W + BO_OFF_Z);
+      BO_PAR(j, BO_ME) W[BO_OFF_SOL + BO_NX + j] = 0.0;
+      bo_sync();
+    } else {
+      if (S.resto == 0) {
+        BO_PAR(j, BO_ME) W[BO_OFF_RE + j] = W[BO_OFF_CE + j];
+        BO_PAR(i, BO_MI) W[BO_OFF_RI + i] = W[BO_OFF_CI + i] - W[BO_OFF_S + i];
+        bo_sync();
+      }
+      bo_cta_step_rhs(S, C);
+    }
+    S.rhs_ready = true;
+  }
   bo_cta_assemble(C, rho, S.dw, S.dc / (1.0 - rho * S.dc));
+  bo_cta_load_rhs(C, W + BO_OFF_SOL);
   const int bad = bo_cta_factor(C);
   const int inertia = bad == 0 ? 0 : (bad == 1 ? 1 : -1);
   if (S.ls_mode) {
     if (inertia == 0) {
-      BO_PAR(c, BO_NX) W[BO_OFF_SOL + c] = W[BO_OFF_G + c] - BO_JI_T(c, W + BO_OFF_Z);
-      BO_PAR(j, BO_ME) W[BO_OFF_SOL + BO_NX + j] = 0.0;
-      bo_sync();
-      bo_cta_ldl_solve(C, W + BO_OFF_SOL);
+      S.rhs_ready = false;
+      bo_cta_ldl_solve_tail(C, W + BO_OFF_SOL);
       double v[1] = {0.0};
       BO_PAR(j, BO_ME) v[0] = fmax(v[0], bo_isfinite(W[BO_OFF_SOL + BO_NX + j]) ? 0.0 : 1.0);
       const int op[1] = {BO_RED_MAX};
@@ -997,12 +1052,8 @@ BO_DEVICE int bo_cta_trip_factor(bo_cta_state& S, const bo_cta& C, const bo_solv
     S.n_singular = S.first_singular ? S.n_singular + 1 : 0;
     if (S.n_singular >= 3) S.jac_degenerate = true;
   }
-  if (S.resto == 0) {
-    BO_PAR(j, BO_ME) W[BO_OFF_RE + j] = W[BO_OFF_CE + j];
-    BO_PAR(i, BO_MI) W[BO_OFF_RI + i] = W[BO_OFF_CI + i] - W[BO_OFF_S + i];
-  }
-  bo_sync();
-  const double a_p = bo_cta_step(S, C);
+  S.rhs_ready = false;  // the solve below overwrites sol
+  const double a_p = bo_cta_step(S, C, true);
   BO_PAR(j, BO_ME) W[BO_OFF_YST + j] = -W[BO_OFF_SOL + BO_NX + j];
   double v[3] = {0.0, 0.0, 0.0};  // g'dx, sum ds/s, max |dx|
   BO_PAR(i, BO_NX) {
@@ -1077,6 +1128,7 @@ BO_DEVICE int bo_cta_trip_trial(bo_cta_state& S, const bo_cta& C, const bo_solve
       S.attempt += 1;
       S.dw *= 100.0;
       S.phase = BO_PH_FACTOR;
+      S.rhs_ready = false;
       return -1;
     }
     S.a *= 0.5;
@@ -1148,14 +1200,16 @@ BO_DEVICE int bo_cta_trip_trial(bo_cta_state& S, const bo_cta& C, const bo_solve
     // factorisation and one or two more substitutions each -- where IPOPT (recalc_y = no) does none.  Measured: C4 (1250
     // rows; 32 instances, host build) 109 -> 77 factorisations and 144 -> 106 substitutions per instance for 8 % more
     // iterations, same minimisers, 1037 -> 1685 inst/s on B200; the joint-space planner (434 rows) 5.4 -> 7.4 iterations
-    // and 51.0 k -> 48.6 k inst/s, i.e. below that size the re-estimate pays for itself and stays.
+    // and 51.0 k -> 48.6 k inst/s, i.e. below that size the re-estimate pays for itself and stays (when y enters the Hessian).
     // BO_RECALC_MODE (experiments): 0 never, 1 only after dw > 0, 2 also on every dc > 0, 3 skip under jac_degenerate.
 #if defined(BO_RECALC_MODE) && BO_RECALC_MODE == 0
     S.recalc_y = false;
 #elif defined(BO_RECALC_MODE) && BO_RECALC_MODE == 1
     S.recalc_y = S.dw > 0.0;
 #elif defined(BO_RECALC_DC_ONLY)  /* y does not enter the Hessian (linear equalities): only the rank-deficient case needs it */
-#if (defined(BO_RECALC_SKIP_DEGENERATE) && !(defined(BO_RECALC_MODE) && BO_RECALC_MODE == 2)) || (defined(BO_RECALC_MODE) && BO_RECALC_MODE == 3)
+    // ... and there the estimate buys little once dc is on for good, whatever the size (C3 from the zero seed: 72 ms per
+    // 16384 without it, 79 ms with it)
+#if !(defined(BO_RECALC_MODE) && BO_RECALC_MODE == 2)
     S.recalc_y = S.dc > 0.0 && !S.jac_degenerate;
 #else
     S.recalc_y = S.dc > 0.0;
@@ -1213,12 +1267,14 @@ BO_DEVICE int bo_cta_trip_trial(bo_cta_state& S, const bo_cta& C, const bo_solve
     S.attempt = 0;
     S.heavy = 0;
     S.phase = BO_PH_FACTOR;
+    S.rhs_ready = false;
     return -1;
   }
   if (S.ls >= BO_LS_MAX || S.a < BO_ALPHA_MIN) {
     if (++S.heavy >= BO_HEAVY_MAX) return S.err0 <= prm.acceptable_tol ? BO_ST_ACCEPTABLE : BO_ST_LINE_SEARCH;  // IPOPT: a failed step at an acceptable point ends "solved to acceptable level"
     S.dw = fmax(S.dw * 100.0, 1.0);
     S.phase = BO_PH_FACTOR;
+    S.rhs_ready = false;
   }
   return -1;
 }

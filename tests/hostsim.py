@@ -85,10 +85,10 @@ extern "C" void hostsim_solve(long long B, const double* p, const double* x0, do
                               double mu_init, double max_step, int max_trips, const int* ldl_tab, const double* dtab, double* scratch) {
   bo_solver_params prm;
   prm.max_iter = max_iter; prm.tol = tol; prm.acceptable_tol = acc_tol; prm.mu_init = mu_init; prm.max_step = max_step; prm.max_trips = max_trips; prm.ldl_tab = ldl_tab; prm.dtab = dtab; prm.scratch = scratch; prm.scratch_stride = 1;
-  std::vector<double> W(BO_SCRATCH_DOUBLES), vals(BO_VALS + 1), bp(BO_NK + 1), red(64);
+  std::vector<double> W(BO_SCRATCH_DOUBLES), vals(BO_VALS + 1 + BO_NK + 1), red(64);  // bp right behind vals, as in shared memory
   int ibuf[4];
   bo_cta C;
-  C.W = W.data(); C.vals = vals.data(); C.bp = bp.data(); C.red = red.data(); C.ibuf = ibuf; C.tab = ldl_tab; C.dtab = dtab; C.prof = nullptr; C.wkkt = nullptr; C.wfc = nullptr;
+  C.W = W.data(); C.vals = vals.data(); C.bp = vals.data() + BO_VALS + 1; C.red = red.data(); C.ibuf = ibuf; C.tab = ldl_tab; C.dtab = dtab; C.prof = nullptr; C.wkkt = nullptr; C.wfc = nullptr;
   for (long long b = 0; b < B; ++b) {
     bo_cta_state S;
     for (int i = 0; i < BO_NP; ++i) W[BO_OFF_P + i] = p[b * BO_NP + i];
@@ -103,9 +103,9 @@ extern "C" void hostsim_solve(long long B, const double* p, const double* x0, do
 extern "C" void hostsim_coop_counts(long long* out, int reset) { for (int k = 0; k < 8; ++k) { out[k] = bo_host_prof[k]; if (reset) bo_host_prof[k] = 0; } }
 // component probes for tests/test_coop_logic.py
 struct Probe {
-  std::vector<double> W, vals, bp, red; int ibuf[4]; bo_cta C;
-  Probe(const int* tab, const double* dtab) : W(BO_SCRATCH_DOUBLES), vals(BO_VALS + 1), bp(BO_NK + 1), red(64) {
-    C.W = W.data(); C.vals = vals.data(); C.bp = bp.data(); C.red = red.data(); C.ibuf = ibuf; C.tab = tab; C.dtab = dtab; C.prof = nullptr; C.wkkt = nullptr; C.wfc = nullptr;
+  std::vector<double> W, vals, red; int ibuf[4]; bo_cta C;
+  Probe(const int* tab, const double* dtab) : W(BO_SCRATCH_DOUBLES), vals(BO_VALS + 1 + BO_NK + 1), red(64) {
+    C.W = W.data(); C.vals = vals.data(); C.bp = vals.data() + BO_VALS + 1; C.red = red.data(); C.ibuf = ibuf; C.tab = tab; C.dtab = dtab; C.prof = nullptr; C.wkkt = nullptr; C.wfc = nullptr;
   }
 };
 static void cp(double* dst, const double* src, int n) { for (int i = 0; i < n; ++i) dst[i] = src[i]; }
@@ -126,14 +126,17 @@ extern "C" void hostsim_coop_fc(const int* tab, const double* dtab, const double
   cp(cE, W + BO_OFF_CET, BO_ME); cp(cI, W + BO_OFF_CIT, BO_MI);
 }
 // assemble K(H, JE, JI, sigma, rho) + diag(dw, -dcp), factor, solve K sol = rhs (in place).  Returns the factor's verdict.
+// merged != 0: the right-hand side rides through the factor program (forward substitution folded in), then only the tail.
 extern "C" int hostsim_coop_linsolve(const int* tab, const double* dtab, const double* H, const double* JE, const double* JI,
-                                     const double* sigma, double rho, double dw, double dcp, double* rhs) {
+                                     const double* sigma, double rho, double dw, double dcp, double* rhs, int merged) {
   Probe P(tab, dtab); double* W = P.W.data();
   cp(W + BO_OFF_H, H, BO_NNZ_H); cp(W + BO_OFF_JE, JE, BO_NNZ_JE); cp(W + BO_OFF_JI, JI, BO_NNZ_JI); cp(W + BO_OFF_SIG, sigma, BO_MI);
-  bo_cta_assemble(P.C, rho, dw, dcp);
-  const int bad = bo_cta_factor(P.C);
   cp(W + BO_OFF_SOL, rhs, BO_NK);
-  bo_cta_ldl_solve(P.C, W + BO_OFF_SOL);
+  bo_cta_assemble(P.C, rho, dw, dcp);
+  if (merged) bo_cta_load_rhs(P.C, W + BO_OFF_SOL);
+  const int bad = bo_cta_factor(P.C);
+  if (merged) bo_cta_ldl_solve_tail(P.C, W + BO_OFF_SOL);
+  else bo_cta_ldl_solve(P.C, W + BO_OFF_SOL);
   cp(rhs, W + BO_OFF_SOL, BO_NK);
   return bad;
 }

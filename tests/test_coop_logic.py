@@ -92,8 +92,9 @@ def test_lane_program_factorisation_and_solve(segments, monkeypatch):
     nx, me = lo.nx, lo.n_eq
     Hd = lo.hess.dense(H, (nx, nx), symmetric=True)
     JEd, JId = lo.jac_eq.dense(JE, (me, nx)), lo.jac_ineq.dense(JI, (lo.n_ineq, nx))
-    sim.lib.hostsim_coop_linsolve.argtypes = [C.c_void_p] * 6 + [C.c_double] * 3 + [C.c_void_p]
-    for rho, dw, dcp, hscale in ((1e3, 0.5, 1e-3, 1.0), (1e6, 0.0, 0.0, 1.0), (10.0, 0.0, 0.0, -50.0)):
+    sim.lib.hostsim_coop_linsolve.argtypes = [C.c_void_p] * 6 + [C.c_double] * 3 + [C.c_void_p, C.c_int]
+    # merged: the right-hand side goes through the factor program (forward substitution folded into the factorisation)
+    for (rho, dw, dcp, hscale), merged in [(c, m) for c in ((1e3, 0.5, 1e-3, 1.0), (1e6, 0.0, 0.0, 1.0), (10.0, 0.0, 0.0, -50.0)) for m in (0, 1)]:
         K = np.zeros((nx + me, nx + me))
         K[:nx, :nx] = hscale * Hd + JId.T @ np.diag(sigma) @ JId + rho * JEd.T @ JEd + dw * np.eye(nx)
         K[nx:, :nx], K[:nx, nx:] = JEd, JEd.T
@@ -102,7 +103,7 @@ def test_lane_program_factorisation_and_solve(segments, monkeypatch):
         sol = rhs.copy()
         Hs = np.ascontiguousarray(hscale * H)
         bad = sim.lib.hostsim_coop_linsolve(_vp(tab), _vp(dtab), _vp(Hs), _vp(np.ascontiguousarray(JE)),
-                                            _vp(np.ascontiguousarray(JI)), _vp(sigma), rho, dw, dcp, _vp(sol))
+                                            _vp(np.ascontiguousarray(JI)), _vp(sigma), rho, dw, dcp, _vp(sol), merged)
         pd = np.linalg.eigvalsh(K[:nx, :nx]).min() > 0
         if dcp == 0.0 and pd:
             # -dc = 0: the y pivots are -JE (..)^-1 JE' < 0 for full-rank JE
@@ -156,11 +157,13 @@ def test_coop_tier_table_indices_are_in_bounds():
                 if f & 4:
                     assert not opened
             tg = words[:, 0, :, 1] & 0x7FFF
-            assert ((tg == 0x7FFF) | (tg < (nk if solve else nvals))).all()
+            # factor targets beyond the factor values are right-hand-side entries (bp sits right behind vals: nvals + 1 + j)
+            assert ((tg == 0x7FFF) | (tg < (nk if solve else nvals + 1 + nk))).all()
+            assert solve or ((tg == 0x7FFF) | (tg != nvals)).all()
             assert (tg[(flags & 2) == 0] == 0x7FFF).all()
             ops = words[:, 1:]
             a, b, c = ops[..., 0] & 0xFFFF, ops[..., 0] >> 16, ops[..., 1]
-            assert (a <= nvals).all() and (b <= (nk if solve else nvals)).all() and (c <= nvals).all()
+            assert (a <= (nvals if solve else nvals + 1 + nk)).all() and (b <= (nk if solve else nvals)).all() and (c <= nvals).all()
 
 
 @pytest.mark.parametrize("with_eq,with_ineq", [(False, True), (True, False), (False, False)])
