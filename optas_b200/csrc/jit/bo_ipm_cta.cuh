@@ -439,8 +439,28 @@ BO_DEVICE double bo_cta_eval_kkt(const bo_cta& C) {
 // sum over the entries of list `r` of J[nz] * v[other]
 BO_DEVICE double bo_gather(const int32_t* BO_RESTRICT ptr, const int32_t* BO_RESTRICT ent, int r, const double* BO_RESTRICT J,
                            const double* BO_RESTRICT v) {
+  // J, v and the index lists live in the per-CTA global workspace / the tables (L2): four entries' loads are issued
+  // together (the list is a chain of dependent L2 round trips otherwise); the sum keeps its order
   double acc = 0.0;
-  for (int e = ptr[r]; e < ptr[r + 1]; ++e) acc += J[ent[2 * e]] * v[ent[2 * e + 1]];
+  int e = ptr[r];
+  const int end = ptr[r + 1];
+  for (; e + 4 <= end; e += 4) {
+    int ia[4], ib[4];
+    double a[4], b[4];
+    BO_UNROLL
+    for (int u = 0; u < 4; ++u) {
+      ia[u] = ent[2 * (e + u)];
+      ib[u] = ent[2 * (e + u) + 1];
+    }
+    BO_UNROLL
+    for (int u = 0; u < 4; ++u) {
+      a[u] = J[ia[u]];
+      b[u] = v[ib[u]];
+    }
+    BO_UNROLL
+    for (int u = 0; u < 4; ++u) acc += a[u] * b[u];
+  }
+  for (; e < end; ++e) acc += J[ent[2 * e]] * v[ent[2 * e + 1]];
   return acc;
 }
 #define BO_JE_T(c, v) bo_gather(C.tab + C.tab[CT_JE_CPTR], C.tab + C.tab[CT_JE_CENT], c, C.W + BO_OFF_JE, v)
@@ -466,7 +486,26 @@ BO_NOINLINE void bo_cta_assemble(const bo_cta& C, double rho, double dw, double 
   BO_PAR(k, nt) {
     const int pos = apos[k];
     double acc = 0.0;
-    for (int e = aptr[k]; e < aptr[k + 1]; ++e) {
+    int e = aptr[k];
+    const int end = aptr[k + 1];
+    // four terms at a time: their table rows, then their operands, are loaded together (everything here is an L2 round
+    // trip); every term has the form (c a) b with c = sigma | rho | 1 and b = 1 for the plain entries, summed in order
+    for (; e + 4 <= end; e += 4) {
+      bo_int4 q[4];
+      double a[4], b[4], c[4];
+      BO_UNROLL
+      for (int u = 0; u < 4; ++u) q[u] = term[e + u];
+      BO_UNROLL
+      for (int u = 0; u < 4; ++u) {
+        const double* src = q[u].x == 0 ? H : (q[u].x == 2 ? JI : JE);
+        a[u] = src[q[u].y];
+        b[u] = q[u].x >= 2 ? src[q[u].z] : 1.0;
+        c[u] = q[u].x == 2 ? sigma[q[u].w] : (q[u].x == 3 ? rho : 1.0);
+      }
+      BO_UNROLL
+      for (int u = 0; u < 4; ++u) acc += c[u] * a[u] * b[u];
+    }
+    for (; e < end; ++e) {
       const bo_int4 q = term[e];
       if (q.x == 0) acc += H[q.y];
       else if (q.x == 1) acc += JE[q.y];
