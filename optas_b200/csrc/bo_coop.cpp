@@ -1434,6 +1434,9 @@ std::string emit_coop_source(const ProblemSource& ps, const CoopPlan& pl, int tp
   }
   if (!hessian_depends_on_eq_multipliers(ps)) o << "#define BO_RECALC_DC_ONLY 1\n";
   if (ps.nx + ps.n_eq >= 600) o << "#define BO_RECALC_SKIP_DEGENERATE 1\n";  // measured threshold, see bo_ipm_cta.cuh
+  // a failing factorisation is abandoned at the level of its first bad pivot -- where the factor fills shared memory (one
+  // CTA per SM); small problems (many CTAs per SM, few failures) keep the plain level barrier
+  if ((size_t)(pl.vals_size() + ps.nx + ps.n_eq) * sizeof(double) >= 227 * 1024 / 4) o << "#define BO_FAC_ABANDON 1\n";
   if (pl.w_in_smem) o << "#define BO_W_IN_SMEM 1\n";
   o << "#include \"bo_common.cuh\"\n";
   if (pl.gen_tapes) o << "#define BO_GEN_TAPES 1\n" << pl.gen_code;

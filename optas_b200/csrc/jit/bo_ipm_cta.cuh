@@ -120,6 +120,17 @@ __device__ __forceinline__ void bo_bar_warps(int n_warps) {  // barrier among wa
   if (n_warps > 1) asm volatile("bar.sync 1, %0;" ::"r"(n_warps * 32) : "memory");
   else __syncwarp();
 }
+// level barrier of the factor program that also tells every participating thread whether ANY of them saw a bad pivot in
+// the level (one decision for all warps: the program is abandoned at the same level everywhere)
+__device__ __forceinline__ bool bo_bar_warps_or(int n_warps, bool flag) {
+  if (n_warps > 1) {
+    unsigned out;
+    asm volatile("{\n\t.reg .pred p, q;\n\tsetp.ne.u32 q, %1, 0;\n\tbar.red.or.pred p, 1, %2, q;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                 : "=r"(out) : "r"((unsigned)flag), "r"(n_warps * 32) : "memory");
+    return out != 0;
+  }
+  return __any_sync(0xffffffffu, flag);
+}
 __device__ __forceinline__ void bo_syncwarp() { __syncwarp(); }
 __device__ __forceinline__ double bo_shfl_xor(double v, int m) { return __shfl_xor_sync(0xffffffffu, v, m); }
 #endif
@@ -602,12 +613,13 @@ BO_DEVICE void bo_lane_target_load(const bo_cta& C, int tgt, double* v0, double*
 }
 
 template <int MODE>
-BO_DEVICE void bo_lane_finish(const bo_cta& C, int tgt, bool positive, double acc, double v0, double b0) {
+BO_DEVICE bool bo_lane_finish(const bo_cta& C, int tgt, bool positive, double acc, double v0, double b0) {
+  bool bad = false;
   if (MODE == 0) {
     const double d = v0 - acc;
     if (tgt < BO_NK) {
       const double scale = fmax(1.0, fabs(v0));
-      const bool bad = positive ? !(d > 1e-13 * scale) : !(d < -1e-13);
+      bad = positive ? !(d > 1e-13 * scale) : !(d < -1e-13);
 #ifdef BO_HOST_SIM
       if (bad && tgt < C.ibuf[0]) C.ibuf[0] = tgt;
 #else
@@ -622,6 +634,7 @@ BO_DEVICE void bo_lane_finish(const bo_cta& C, int tgt, bool positive, double ac
   } else {
     BO_BP_AT(C, tgt) = b0 - acc * v0;
   }
+  return bad;
 }
 
 template <int MODE, int G, int PK>
@@ -667,6 +680,13 @@ BO_DEVICE void bo_lane_program(const bo_cta& C, int slot) {
       }
       more = more || pc[w] < n;
     }
+    // A factorisation with a bad pivot is thrown away (the caller regularises and starts over), so the program is
+    // abandoned at the end of the level in which the first one turns up: 44 % (C5) / 22 % (C4) of the way on average
+    // (BO_FAC_ABANDON: only for the one-CTA-per-SM problems; on C3, 16 CTAs per SM and 3 % failing factorisations, the vote
+    // at every level costs more than it saves: 893 k -> 849 k inst/s)
+#ifdef BO_FAC_ABANDON
+    if (MODE == 0 && C.ibuf[0] < BO_NK) break;
+#endif
   }
 #else
   const int warp = BO_TID >> 5, lane = BO_TID & 31;
@@ -686,11 +706,12 @@ BO_DEVICE void bo_lane_program(const bo_cta& C, int slot) {
       nxt += 32 * (PK + 1);
     }
     double acc = 0.0;
-    for (int base = 0; base < n; base += BO_LP_DEPTH) {
+    bool bad_seen = false, abandon = false;
+    for (int base = 0; base < n && !abandon; base += BO_LP_DEPTH) {
       BO_UNROLL
       for (int d = 0; d < BO_LP_DEPTH; ++d) {
         const int i = base + d;
-        if (i >= n) break;
+        if (i >= n || abandon) break;
         bo_int2 cur[PK + 1];
         BO_UNROLL
         for (int k = 0; k <= PK; ++k) cur[k] = buf[d][k];
@@ -718,9 +739,17 @@ BO_DEVICE void bo_lane_program(const bo_cta& C, int slot) {
             for (int off = 16; off > 0; off >>= 1)
               if (off < g_round) acc += bo_shfl_xor(acc, off);
           }
-          if (tgt != 0x7FFF) bo_lane_finish<MODE>(C, tgt, (hy & 0x8000u) != 0, acc, v0, b0);
+          if (tgt != 0x7FFF) bad_seen |= bo_lane_finish<MODE>(C, tgt, (hy & 0x8000u) != 0, acc, v0, b0);
         }
-        if (hx & BO_PKT_LEVEL_END) bo_bar_warps(W);
+        if (hx & BO_PKT_LEVEL_END) {
+          // factor: a bad pivot anywhere in this level ends the program for every warp (see the host branch above)
+#ifdef BO_FAC_ABANDON
+          if (MODE == 0) abandon = bo_bar_warps_or(W, bad_seen);
+          else bo_bar_warps(W);
+#else
+          bo_bar_warps(W);
+#endif
+        }
       }
     }
   }
@@ -728,7 +757,9 @@ BO_DEVICE void bo_lane_program(const bo_cta& C, int slot) {
 }
 
 // In-place factorisation.  On exit vals[j] = 1/D(j), vals[n+e] = C(i,j) = L(i,j) D(j).
-// Returns 0 ok, 1 = first bad pivot is in the x block (non-positive), 2 = in the y block (non-negative).
+// Returns 0 ok, 1 = first bad pivot is in the x block (non-positive), 2 = in the y block (non-negative); "first" = the
+// smallest column among the bad pivots of the levels done when the program was abandoned (it stops at the end of the level
+// in which a bad pivot turns up: the factor is thrown away anyway).
 BO_NOINLINE int bo_cta_factor(const bo_cta& C) {
   BO_PROF_BEGIN();
   if (BO_TID == 0) C.ibuf[0] = BO_NK;  // first bad pivot column (elimination order); BO_NK = none
