@@ -1283,6 +1283,11 @@ static CoopPlan make_coop_plan_segments(const ProblemSource& ps, int tpb, int n_
     pairs(ps.jac_ineq, ps.n_ineq, 2);
     pairs(ps.jac_eq, ps.n_eq, 3);
     t[CT_ANT] = (int32_t)terms.size();
+    {
+      size_t n_terms = 0;
+      for (const auto& kv : terms) n_terms += kv.second.size() / 4;
+      pl.asm_terms_per_position = terms.empty() ? 0.0 : (double)n_terms / (double)terms.size();
+    }
     std::vector<int32_t> apos, aptr{0}, aterm;
     for (const auto& kv : terms) {
       apos.push_back(kv.first);
@@ -1437,6 +1442,10 @@ std::string emit_coop_source(const ProblemSource& ps, const CoopPlan& pl, int tp
   // a failing factorisation is abandoned at the level of its first bad pivot -- where the factor fills shared memory (one
   // CTA per SM); small problems (many CTAs per SM, few failures) keep the plain level barrier
   if ((size_t)(pl.vals_size() + ps.nx + ps.n_eq) * sizeof(double) >= 227 * 1024 / 4) o << "#define BO_FAC_ABANDON 1\n";
+  // KKT assembly: four positions per thread in flight where the term lists are short (C5: 117 k -> 66 k cycles per
+  // iteration), four terms of one position where they are long (C4, C3: the interleaved form is 14 % / 50 % slower there)
+  if (pl.asm_terms_per_position < 2.0 && (size_t)(pl.vals_size() + ps.nx + ps.n_eq) * sizeof(double) >= 227 * 1024 / 4)
+    o << "#define BO_ASM_INTERLEAVE 1\n";
   if (pl.w_in_smem) o << "#define BO_W_IN_SMEM 1\n";
   o << "#include \"bo_common.cuh\"\n";
   if (pl.gen_tapes) o << "#define BO_GEN_TAPES 1\n" << pl.gen_code;

@@ -64,6 +64,7 @@ struct CoopPlan {
   int fac_pk = 8, fwd_pk = 2, bwd_pk = 2;  // operand words per packet of the factor / substitution lane programs
   int solve_g = 1, solve_bwd_g = 1;  // lanes cooperating on one row (forward) / column (backward) of a triangular solve
   int64_t fac_steps = 0, solve_steps = 0;  // longest warp stream of the factor / both triangular solves
+  double asm_terms_per_position = 0.0;  // KKT assembly: mean number of terms per assembled position
   double prog_cost = 0.0;      // predicted cycles of one factorisation + one pair of substitutions (scheduler's cost model)
   int64_t n_contrib = 0;       // multiply-adds of one numeric factorisation
   CoopTapeInfo fc, kkt;

@@ -494,6 +494,51 @@ BO_NOINLINE void bo_cta_assemble(const bo_cta& C, double rho, double dw, double 
   const bo_int4* term = reinterpret_cast<const bo_int4*>(t + t[CT_ATERM]);
   const int32_t* sign = t + t[CT_SIGN];
   const double *H = C.W + BO_OFF_H, *JE = C.W + BO_OFF_JE, *JI = C.W + BO_OFF_JI, *sigma = C.W + BO_OFF_SIG;
+#ifdef BO_ASM_INTERLEAVE  /* short term lists (C5: 1.7 per position): bo_coop.cpp decides */
+  // Everything read here (tables, H, JE, JI, sigma) is an L2 round trip, and a position's terms are a chain of them (its
+  // list bounds -> a table row -> that row's operands).  Each thread therefore walks FOUR positions at once, step by step,
+  // so that four independent chains are in flight; every position still adds its terms in list order.  A term has the form
+  // (c a) b with c = sigma | rho | 1 and b = 1 for the plain entries.
+  for (int k0 = BO_TID; k0 < nt; k0 += 4 * BO_NT) {
+    int pos[4], e[4], end[4];
+    double acc[4];
+    int longest = 0;
+    BO_UNROLL
+    for (int u = 0; u < 4; ++u) {
+      const int k = k0 + u * BO_NT;
+      const bool valid = k < nt;
+      pos[u] = valid ? apos[k] : -1;
+      e[u] = valid ? aptr[k] : 0;
+      end[u] = valid ? aptr[k + 1] : 0;
+      acc[u] = 0.0;
+      longest = end[u] - e[u] > longest ? end[u] - e[u] : longest;
+    }
+    for (int step = 0; step < longest; ++step) {
+      bo_int4 q[4];
+      double a[4], b[4], c[4];
+      BO_UNROLL
+      for (int u = 0; u < 4; ++u) q[u] = e[u] < end[u] ? term[e[u]] : bo_int4{-1, 0, 0, 0};
+      BO_UNROLL
+      for (int u = 0; u < 4; ++u) {
+        const double* src = q[u].x == 0 ? H : (q[u].x == 2 ? JI : JE);
+        a[u] = q[u].x >= 0 ? src[q[u].y] : 0.0;
+        b[u] = q[u].x >= 2 ? src[q[u].z] : 1.0;
+        c[u] = q[u].x == 2 ? sigma[q[u].w] : (q[u].x == 3 ? rho : 1.0);
+      }
+      BO_UNROLL
+      for (int u = 0; u < 4; ++u) {
+        if (q[u].x >= 0) acc[u] += c[u] * a[u] * b[u];
+        e[u] += 1;
+      }
+    }
+    BO_UNROLL
+    for (int u = 0; u < 4; ++u)
+      if (pos[u] >= 0) {
+        if (pos[u] < BO_NK) acc[u] += sign[pos[u]] > 0 ? dw : -dcp;
+        vals[pos[u]] = acc[u];
+      }
+  }
+#else  /* long term lists (C4: the J_I' Sigma J_I products; C3): four terms of ONE position at a time */
   BO_PAR(k, nt) {
     const int pos = apos[k];
     double acc = 0.0;
@@ -526,6 +571,7 @@ BO_NOINLINE void bo_cta_assemble(const bo_cta& C, double rho, double dw, double 
     if (pos < BO_NK) acc += sign[pos] > 0 ? dw : -dcp;
     vals[pos] = acc;
   }
+#endif
   if (BO_TID == 0) {  // padding operands of the lane programs
     vals[BO_VALS] = 0.0;
     BO_BP_P(C)[BO_NK] = 0.0;
